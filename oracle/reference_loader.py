@@ -1,0 +1,120 @@
+"""Import the UNMODIFIED reference python packages (TEST INFRASTRUCTURE, build container only).
+
+``/root/reference`` exists only in the build container, never on the GPU box, so
+this module is used by ``oracle/gen_golden.py`` (to make ``tests/golden``) and by
+the CPU tests that pin ``oracle/port.py`` against the reference itself.  Those
+tests skip when the directory is absent.
+
+What is done to make the reference importable, none of which
+edits a reference file:
+
+* ``torchdiffeq`` (absent, ancde.yml:245) -> ``oracle.torchdiffeq_shim``.
+* ``torch.nn.Module.cuda`` is neutralised on CUDA-less hosts because the
+  reference hard-codes ``.cuda()`` (cdeint_module.py:163,253).
+* the reference packages are imported under their own names (``controldiffeq``,
+  ``models``) with ``sys.modules`` restored afterwards, so they never shadow (or
+  get shadowed by) this repo's drop-in ``controldiffeq`` package.
+* Q7 repair: ``ANCDE`` with ``timewise=True`` crashes as shipped because
+  metamodel.py:330 overwrites ``h_prime`` with ``time_attention.weight``; the
+  loader wraps ``controldiffeq.ancde_bottom`` / ``controldiffeq.ancde`` (looked
+  up by attribute at call time, metamodel.py:320,350) so that a 2-D tensor
+  ``h_prime`` is replaced by the file the bottom solve just wrote -- exactly what
+  ``ANCDE_forecasting`` (metamodel.py:650-652) already does.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import torchdiffeq_shim
+
+REFERENCE_ROOT = os.environ.get('ANCDE_REFERENCE_ROOT', '/root/reference')
+
+_cache = {}
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, 'controldiffeq'))
+
+
+def _purge(prefixes):
+    saved = {}
+    for k in list(sys.modules):
+        if any(k == p or k.startswith(p + '.') for p in prefixes):
+            saved[k] = sys.modules.pop(k)
+    return saved
+
+
+def load():
+    """Returns ``(ref_controldiffeq, ref_models)`` module objects of the reference."""
+    if 'mods' in _cache:
+        return _cache['mods']
+    if not available():
+        raise RuntimeError('reference tree not present at %s' % REFERENCE_ROOT)
+    if not torch.cuda.is_available():
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+    prefixes = ('controldiffeq', 'models', 'torchdiffeq')
+    saved = _purge(prefixes)
+    old_path = list(sys.path)
+    torchdiffeq_shim.install()
+    sys.path.insert(0, os.path.join(REFERENCE_ROOT, 'experiments'))
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ref_cde = importlib.import_module('controldiffeq')
+            ref_models = importlib.import_module('models')
+    finally:
+        sys.path[:] = old_path
+        _purge(prefixes)
+        sys.modules.update(saved)
+    assert ref_cde.__file__.startswith(REFERENCE_ROOT), ref_cde.__file__
+    _install_q7_repair(ref_cde)
+    _cache['mods'] = (ref_cde, ref_models)
+    return _cache['mods']
+
+
+def _install_q7_repair(ref_cde):
+    orig_bottom, orig_top = ref_cde.ancde_bottom, ref_cde.ancde
+    state = {}
+
+    def ancde_bottom(*args, **kwargs):
+        state['file'] = kwargs.get('file', args[4] if len(args) > 4 else None)
+        return orig_bottom(*args, **kwargs)
+
+    def ancde(*args, **kwargs):
+        hp = kwargs.get('h_prime')
+        if torch.is_tensor(hp) and hp.dim() == 2:
+            kwargs['h_prime'] = np.load(state['file'])
+        return orig_top(*args, **kwargs)
+
+    ref_cde.ancde_bottom = ancde_bottom
+    ref_cde.ancde = ancde
+
+
+def make_reference_model(cfg, file):
+    """Builds the reference model exactly as experiments/common.py:863-924 (make_model) does.
+
+    ``cfg`` keys: kind ('ancde'|'ancde_forecasting'), C, H, HH, A, AA, nl, out, output_time,
+    soft, slope_check, timewise, initial.
+    """
+    _, models = load()
+    f = models.FinalTanh_ff6(input_channels=cfg['C'], hidden_atten_channels=cfg['A'],
+                             hidden_hidden_atten_channels=cfg['AA'], num_hidden_layers=cfg['nl'])
+    g = models.FinalTanh(input_channels=cfg['C'], hidden_channels=cfg['H'],
+                         hidden_hidden_channels=cfg['HH'], num_hidden_layers=cfg['nl'])
+    if cfg['kind'] == 'ancde':
+        model = models.ANCDE(func=f, func_g=g, input_channels=cfg['C'], hidden_channels=cfg['H'],
+                             output_channels=cfg['out'], attention_channel=cfg['A'],
+                             slope_check=cfg['slope_check'], soft=cfg['soft'], timewise=cfg['timewise'],
+                             file=file, initial=cfg.get('initial', True))
+    else:
+        model = models.ANCDE_forecasting(func=f, func_g=g, input_channels=cfg['C'],
+                                         output_time=cfg['output_time'], hidden_channels=cfg['H'],
+                                         output_channels=cfg['out'], attention_channel=cfg['A'],
+                                         slope_check=cfg['slope_check'], soft=cfg['soft'],
+                                         timewise=cfg['timewise'], file=file, initial=cfg.get('initial', True))
+    return model
