@@ -1,0 +1,115 @@
+"""ctypes binding of libancde_b200.so (the C ABI declared in include/ancde_b200.h).
+
+There is no fallback: if the library is missing or a kernel reports an error this raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libancde_b200.so')
+
+MAX_LAYERS = 8
+MODE_PLAIN, MODE_BOTTOM, MODE_TOP = 0, 1, 2
+ABI_VERSION = 1
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+
+
+class NcdeDesc(ctypes.Structure):
+    """Mirror of `ancde_ncde_desc`."""
+    _fields_ = [
+        ('B', ctypes.c_int32), ('L', ctypes.c_int32), ('C', ctypes.c_int32), ('Hd', ctypes.c_int32),
+        ('n_hidden', ctypes.c_int32), ('width', ctypes.c_int32 * MAX_LAYERS), ('mode', ctypes.c_int32),
+        ('att_C', ctypes.c_int32), ('att_L', ctypes.c_int32), ('n_hp', ctypes.c_int32),
+        ('t_start', ctypes.c_float), ('t_end', ctypes.c_float), ('step', ctypes.c_float),
+        ('n_steps', ctypes.c_int32), ('n_out', ctypes.c_int32),
+        ('times', ctypes.c_void_p), ('t_out', ctypes.c_void_p),
+        ('coeff_b', ctypes.c_void_p), ('coeff_c2', ctypes.c_void_p), ('coeff_d3', ctypes.c_void_p),
+        ('z0', ctypes.c_void_p),
+        ('W', ctypes.c_void_p * (MAX_LAYERS + 1)), ('bias', ctypes.c_void_p * (MAX_LAYERS + 1)),
+        ('attention', ctypes.c_void_p), ('h_prime', ctypes.c_void_p),
+        ('z_out', ctypes.c_void_p), ('k_out', ctypes.c_void_p),
+        ('wpack', ctypes.c_void_p), ('save_act', ctypes.c_void_p), ('save_G', ctypes.c_void_p),
+        ('grad_z_out', ctypes.c_void_p), ('grad_z0', ctypes.c_void_p),
+        ('grad_W', ctypes.c_void_p * (MAX_LAYERS + 1)), ('grad_bias', ctypes.c_void_p * (MAX_LAYERS + 1)),
+        ('grad_attention', ctypes.c_void_p),
+        ('samples_per_cta', ctypes.c_int32), ('reserved', ctypes.c_int32),
+    ]
+
+
+_lib = None
+
+EXPORTS = ['ancde_abi_version', 'ancde_last_error', 'ancde_spline_coeffs_f32', 'ancde_spline_coeffs_f64',
+           'ancde_ncde_wpack_floats', 'ancde_ncde_save_act_floats', 'ancde_ncde_save_G_floats',
+           'ancde_ncde_forward', 'ancde_ncde_backward', 'ancde_last_launch_count', 'ancde_fp32_peak_kernel']
+
+
+def lib():
+    """Loads the shared library (once). Raises if it has not been built -- there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'libancde_b200.so is missing (%s). Build it with `python -m ancde_b200.build` '
+            '(nvcc, sm_100a). There is no CPU or PyTorch fallback for the kernels.' % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(L, name):
+            raise RuntimeError('libancde_b200.so does not export %s' % name)
+    L.ancde_abi_version.restype = ctypes.c_int
+    if L.ancde_abi_version() != ABI_VERSION:
+        raise RuntimeError('libancde_b200.so has ABI %d, python expects %d; rebuild' % (L.ancde_abi_version(), ABI_VERSION))
+    L.ancde_last_error.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    L.ancde_spline_coeffs_f32.argtypes = [vp] * 6 + [i64, ci, ci, vp]
+    L.ancde_spline_coeffs_f64.argtypes = [vp] * 6 + [i64, ci, ci, ci, vp]
+    for n in ('ancde_ncde_wpack_floats', 'ancde_ncde_save_act_floats', 'ancde_ncde_save_G_floats'):
+        getattr(L, n).argtypes = [ctypes.POINTER(NcdeDesc)]
+        getattr(L, n).restype = i64
+    L.ancde_ncde_forward.argtypes = [ctypes.POINTER(NcdeDesc), vp]
+    L.ancde_ncde_backward.argtypes = [ctypes.POINTER(NcdeDesc), vp]
+    L.ancde_fp32_peak_kernel.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double), vp]
+    _lib = L
+    return L
+
+
+def last_error():
+    buf = ctypes.create_string_buffer(512)
+    lib().ancde_last_error(buf, 512)
+    return buf.value.decode()
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = last_error()
+        if rc == -3:
+            raise NotImplementedError('%s: %s' % (what, msg))
+        if rc == -1:
+            raise ValueError('%s: %s' % (what, msg))
+        raise RuntimeError('%s failed (code %d): %s' % (what, rc, msg))
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError('%s must be a CUDA tensor: the ANCDE B200 kernels have no CPU path (got device %s)'
+                           % (name, t.device))
+
+
+_launches = {'total': 0}
+
+
+def note_launches():
+    n = lib().ancde_last_launch_count()
+    _launches['total'] += n
+    return n
+
+
+def launches_total():
+    return _launches['total']

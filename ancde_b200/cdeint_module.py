@@ -1,0 +1,163 @@
+"""Drop-in for controldiffeq/cdeint_module.py: cdeint, ancde_bottom, ancde on the fused B200 solver.
+
+The reference builds a python vector-field object and hands it to torchdiffeq (one python call and
+~40 kernel launches per RK4 stage, a `.item()` sync and a host->device copy of h' per stage,
+cdeint_module.py:56-72,103-138).  Here each of the three entry points is ONE kernel launch that
+integrates every sample over every step (csrc/ncde_fwd.cu).  A fused kernel cannot call back into
+python, so the opaque callables of the reference API are recognised structurally:
+
+* `dX_dt` must be the bound `derivative` method of a NaturalCubicSpline (its coefficient tensors
+  are what the kernel reads);
+* `func` / `func_g` must be FinalTanh / FinalTanh_ff6 shaped modules (vector_fields.py:185-250).
+
+Anything else raises NotImplementedError -- there is no eager fallback.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .solver import SolvePlan, solve
+
+# h' of the latest bottom solve, keyed by the `file` argument.  The reference round-trips h'
+# through that .npy file on disk (cdeint_module.py:69-70, metamodel.py:326); here it stays in HBM.
+_H_PRIME = {}
+
+
+def load_h_prime(file):
+    """Device tensor (4*steps, B, C) written by the latest `ancde_bottom(..., file=file)`."""
+    if file not in _H_PRIME:
+        raise FileNotFoundError("no bottom solve has produced h' for %r yet" % (file,))
+    return _H_PRIME[file]
+
+
+def _spline_of(dX_dt):
+    sp = getattr(dX_dt, '__self__', None)
+    ok = sp is not None and all(hasattr(sp, n) for n in ('_times', '_b', '_two_c', '_three_d'))
+    if not ok or getattr(dX_dt, '__name__', '') != 'derivative':
+        raise NotImplementedError(
+            'dX_dt must be the `derivative` method of a NaturalCubicSpline: the fused B200 kernel reads the '
+            'spline coefficients directly and cannot call an arbitrary python control (no eager fallback)')
+    if sp._b.dim() != 3:
+        raise NotImplementedError('the fused solver expects coefficients of shape (batch, length-1, channels)')
+    return sp
+
+
+def _rk4_step(kwargs, default_step):
+    """Resolves (method, step_size) the way the reference entry points do."""
+    kwargs = dict(kwargs)
+    method = kwargs.pop('method', None)
+    options = dict(kwargs.pop('options', None) or {})
+    kwargs.pop('rtol', None)
+    kwargs.pop('atol', None)
+    if kwargs:
+        raise TypeError('unexpected solver arguments: %s' % sorted(kwargs))
+    if method is None:
+        # torchdiffeq's own default is dopri5 (adaptive); the ANCDE entry points switch it to rk4
+        method = 'rk4' if default_step is not None else 'dopri5'
+    if method != 'rk4':
+        raise NotImplementedError("method=%r: the fused B200 solver implements the fixed-grid 'rk4' (3/8 rule) "
+                                  "path the ANCDE experiments use" % (method,))
+    if 'grid_constructor' in options:
+        raise NotImplementedError("options['grid_constructor'] is not supported; pass options['step_size']")
+    step = options.get('step_size', default_step)
+    if step is None:
+        raise NotImplementedError("rk4 needs options['step_size'] (a grid equal to `t` is not implemented)")
+    return float(step)
+
+
+class VectorField(torch.nn.Module):
+    """Descriptor of f(z) dX/dt (reference: cdeint_module.py:9-32). Evaluated inside the fused kernel."""
+
+    def __init__(self, dX_dt, func):
+        super(VectorField, self).__init__()
+        if not isinstance(func, torch.nn.Module):
+            raise ValueError("func must be a torch.nn.Module.")
+        self.dX_dt = dX_dt
+        self.func = func
+
+    def forward(self, t, z):
+        raise NotImplementedError('vector fields are evaluated inside the fused kernel; call cdeint()')
+
+
+class VectorField_stack(VectorField):
+    """Bottom field that also records h' (reference: cdeint_module.py:34-72)."""
+
+    def __init__(self, dX_dt, func, final_time, file):
+        super(VectorField_stack, self).__init__(dX_dt, func)
+        self.final_time = final_time
+        self.file = file
+
+
+class AttentiveVectorField(torch.nn.Module):
+    """Top field g(z) dY/dt with attention (reference: cdeint_module.py:74-138)."""
+
+    def __init__(self, dX_dt, func_g, X_s, h_prime, time, attention):
+        super(AttentiveVectorField, self).__init__()
+        if not isinstance(func_g, torch.nn.Module):
+            raise ValueError("func must be a torch.nn.Module.")
+        self.dX_dt, self.func_g, self.X_s = dX_dt, func_g, X_s
+        self.h_prime, self.timewise, self.attention = h_prime, time, attention
+
+    def forward(self, t, z):
+        raise NotImplementedError('vector fields are evaluated inside the fused kernel; call ancde()')
+
+
+def cdeint(dX_dt, z0, func, t, adjoint=True, **kwargs):
+    """Solves z' = func(z) dX/dt and returns z at the times `t`: (len(t), batch, hidden).
+
+    Reference: cdeint_module.py:141-151.  `adjoint` selects torchdiffeq's adjoint in the reference;
+    here both settings backpropagate through the discrete solver (same forward, gradients agree to
+    the solver's O(h^4)), see DESIGN.md.
+    """
+    sp = _spline_of(dX_dt)
+    step = _rk4_step(kwargs, None)
+    plan = SolvePlan(_lib.MODE_PLAIN, sp._times, (sp._b, sp._two_c, sp._three_d), t, step)
+    z_out, _ = solve(plan, func, z0)
+    return z_out
+
+
+def ancde_bottom(dX_dt, z0, func, t, file, adjoint=True, **kwargs):
+    """Bottom (attention) NCDE over all of `t`; returns (len(t), batch, C) and keeps h' for `file`.
+
+    Reference: cdeint_module.py:168-243.
+    """
+    sp = _spline_of(dX_dt)
+    if 'method' not in kwargs:
+        kwargs['method'] = 'rk4'
+    step = _rk4_step(kwargs, 1.0)
+    if adjoint and any(c.requires_grad for c in (sp._b, sp._two_c, sp._three_d)):
+        raise ValueError("Gradients do not backpropagate through the control with adjoint=True. (This is a limitation "
+                         "of the underlying torchdiffeq library.)")
+    plan = SolvePlan(_lib.MODE_BOTTOM, sp._times, (sp._b, sp._two_c, sp._three_d), t, step, want_k=True)
+    z_out, k_out = solve(plan, func, z0)
+    _H_PRIME[file] = k_out
+    return z_out
+
+
+def ancde(dX_dt, attention, z0, X_s, func_g, h_prime, t, timewise, adjoint=True, **kwargs):
+    """Top NCDE driven by dY = dX*a + a(1-a)*dX*h'; returns (len(t), batch, hidden).
+
+    Reference: cdeint_module.py:247-254 + AttentiveVectorField (:103-138).  `h_prime` may be the device
+    tensor from `load_h_prime`, a numpy array (as np.load returns in the reference) or -- the reference's
+    timewise ANCDE passes `time_attention.weight` here and crashes -- a 2-D tensor, in which
+    case the h' of the latest bottom solve is used (what ANCDE_forecasting does).
+    With adjoint=True the attention receives no gradient through this solve (torchdiffeq's adjoint
+    only differentiates func parameters and z0).
+    """
+    sp = _spline_of(dX_dt)
+    step = _rk4_step(kwargs, None)
+    if isinstance(h_prime, np.ndarray):
+        h_prime = torch.from_numpy(h_prime).to(z0.device)
+    if torch.is_tensor(h_prime) and h_prime.dim() == 2:
+        if not _H_PRIME:
+            raise IndexError('too many indices for tensor of dimension 2')   # what the reference raises
+        h_prime = next(reversed(_H_PRIME.values()))
+    if h_prime.dim() != 3:
+        raise ValueError("h_prime must have shape (calls, batch, channels)")
+    att = attention
+    if att.dim() == 2:
+        att = att.unsqueeze(-1)
+    plan = SolvePlan(_lib.MODE_TOP, sp._times, (sp._b, sp._two_c, sp._three_d), t, step,
+                     h_prime=h_prime.detach(), att_grad=not adjoint)
+    z_out, _ = solve(plan, func_g, z0, att)
+    return z_out

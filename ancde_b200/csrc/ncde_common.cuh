@@ -1,0 +1,90 @@
+// Device helpers shared by the forward and backward NCDE kernels.
+#pragma once
+#include "ncde_layout.cuh"
+
+namespace ancde {
+
+// ---- small vectors of samples: a CTA integrates TS samples, activations are stored
+// [feature][TS] so one LDS.128 broadcasts 4 samples of one feature to every lane.
+template <int VW> struct Vec;
+template <> struct Vec<4> {
+    static __device__ __forceinline__ void ld(const float* p, float* v) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void st(float* p, const float* v) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Vec<2> {
+    static __device__ __forceinline__ void ld(const float* p, float* v) {
+        float2 t = *reinterpret_cast<const float2*>(p);
+        v[0] = t.x; v[1] = t.y;
+    }
+    static __device__ __forceinline__ void st(float* p, const float* v) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    }
+};
+template <> struct Vec<1> {
+    static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = *p; }
+    static __device__ __forceinline__ void st(float* p, const float* v) { *p = v[0]; }
+};
+
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the MUFU pipe (ex2 + rcp): 5 issue slots, |abs err| < 4e-7
+// (tanh.approx.f32 is ~5e-4 relative and fails the 1e-4 parity bar after hundreds of stages).
+__device__ __forceinline__ float tanh_mufu(float x)
+{
+#ifdef ANCDE_TANH_LIBM
+    return tanhf(x);
+#else
+    float e, r;
+    float a = x * 2.885390081777927f;   // 2 * log2(e)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
+    float d = e + 1.0f;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return fmaf(-2.0f, r, 1.0f);
+#endif
+}
+
+// Time of grid point k: arange(k) * step + t_start, last point clipped (torchdiffeq
+// _grid_constructor_from_step_size), in float32 without contraction.
+__device__ __forceinline__ float grid_time(int k, int n_steps, float t_start, float t_end, float step)
+{
+    float t = __fadd_rn(__fmul_rn((float)k, step), t_start);
+    if (k == n_steps && t > t_end) t = t_end;
+    return t;
+}
+
+// Stage times of torchdiffeq's rk4_alt_step_func: t, t + dt/3, t + dt*2/3, t + dt.
+__device__ __forceinline__ float stage_time(float t0, float dt, int s)
+{
+    if (s == 0) return t0;
+    if (s == 1) return __fadd_rn(t0, __fdiv_rn(dt, 3.0f));
+    if (s == 2) return __fadd_rn(t0, __fdiv_rn(__fmul_rn(dt, 2.0f), 3.0f));
+    return __fadd_rn(t0, dt);
+}
+
+struct SolveArgs {
+    NcdeLayout lo;
+    float t_start, t_end, step;
+    const float* times;
+    const float* t_out;
+    const float* cb;
+    const float* cc2;
+    const float* cd3;
+    const float* z0;
+    const float* attention;
+    const float* h_prime;
+    const float* wpack;
+    float* z_out;
+    float* k_out;
+    float* save_act;
+    float* save_G;
+    // backward
+    const float* grad_z_out;
+    float* grad_z0;
+    float* grad_attention;
+    float* grad_hidden;     // packed like the hidden part of wpack (Wt layout), accumulated with atomics
+};
+
+}  // namespace ancde

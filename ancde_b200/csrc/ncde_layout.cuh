@@ -1,0 +1,39 @@
+// Host+device description of how one fused NCDE solve is laid out: packed weights, shared
+// memory carve-up and the buffers saved for the backward pass.
+#pragma once
+#include "common.cuh"
+
+namespace ancde {
+
+struct NcdeLayout {
+    // ---- problem ----
+    int B, L, C, Hd, n_hidden, mode, att_C, att_L, n_hp, n_steps, n_out;
+    int width[ANCDE_MAX_LAYERS];
+    // ---- derived ----
+    int TS;            // samples per CTA
+    int ntiles;        // CTAs
+    int C4;            // C rounded up to 4: the output layer's columns are (i, j) -> i*C4 + j
+    int NCH;           // C4 / 4 column chunks per row
+    int NCG;           // Hd * NCH column groups of 4
+    int NCP;           // Hd * C4 padded columns
+    int K;             // width of the last hidden layer = reduction size of the output layer
+    int Hmax;          // widest activation
+    // packed weights (floats from the start of wpack); hidden layer l is stored transposed
+    // Wt[k][o] with an odd row stride so that both o-major and k-major walks are conflict free.
+    int in_dim[ANCDE_MAX_LAYERS], stride[ANCDE_MAX_LAYERS];
+    int off_w[ANCDE_MAX_LAYERS], off_b[ANCDE_MAX_LAYERS];
+    int hidden_floats;  // all hidden layers (weights + biases)
+    int off_wo, off_bo; // output layer Wt_out[k][NCP], bias_out[NCP]
+    int64_t wpack_floats;
+    // saved activations per (stage, tile): z_s | h_1 .. h_n | dU | dU/da   (each [feature][TS])
+    int act_off_h[ANCDE_MAX_LAYERS];
+    int act_off_du, act_off_duda, act_floats;
+    int n_stages;       // 4 * n_steps
+};
+
+__host__ __device__ static inline int pad4(int x) { return (x + 3) & ~3; }
+
+// Fills the layout from a descriptor; returns 0 or an ANCDE_E* code (message set).
+int make_layout(const ancde_ncde_desc* d, NcdeLayout* lo);
+
+}  // namespace ancde

@@ -1,0 +1,204 @@
+"""Host side of the fused NCDE solve: builds the C-ABI descriptor and wraps it in autograd.
+
+The solve itself (all time steps, all RK4 stages, MLP + tanh + contraction) is ONE CUDA kernel
+(csrc/ncde_fwd.cu); the backward is the matching pair of kernels in csrc/ncde_bwd.cu.  This module
+only moves pointers around -- it contains no arithmetic of the path.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+
+_grid_cache = {}
+FORCE_SAMPLES_PER_CTA = 0   # tests set this to 1/2/4/8 to exercise every kernel instantiation
+
+
+class SolvePlan:
+    """Everything about one solve that is not a differentiable tensor."""
+
+    def __init__(self, mode, times, coeffs, t_out, step_size, h_prime=None, want_k=False, att_grad=True):
+        b, c2, d3 = coeffs
+        _lib.require_cuda(b, 'spline coefficients')
+        dev = b.device
+        self.mode = mode
+        self.device = dev
+        self.B, self.Lm1, self.C = b.shape[0], b.shape[1], b.shape[2]
+        self.times = _f32(times, dev)
+        self.t_out = _f32(t_out, dev)
+        self.b, self.c2, self.d3 = (_f32(x, dev) for x in (b, c2, d3))
+        self.h_prime = None if h_prime is None else _f32(h_prime, dev)
+        self.want_k = want_k
+        self.att_grad = att_grad
+        self.grid = fixed_grid_meta(t_out, step_size)
+        if self.times.numel() != self.Lm1 + 1:
+            raise ValueError('times has %d entries but the coefficients have %d pieces' % (self.times.numel(), self.Lm1))
+
+
+def _f32(x, dev):
+    return x.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def fixed_grid_meta(t_out, step_size):
+    """(t_start, t_end, step, n_steps) of torchdiffeq's _grid_constructor_from_step_size, float32."""
+    key = (t_out.data_ptr(), t_out._version, t_out.numel(), str(t_out.device), float(step_size))
+    hit = _grid_cache.get(key)
+    if hit is not None:
+        return hit
+    th = t_out.detach().to('cpu', torch.float32)
+    if th.numel() < 2:
+        raise ValueError('t must contain at least two times')
+    if not bool((th[1:] > th[:-1]).all()):
+        if bool((th[1:] < th[:-1]).all()):
+            raise NotImplementedError('decreasing integration times are not supported by the fused solver')
+        raise AssertionError('t must be strictly increasing or decreasing')
+    step = torch.tensor(float(step_size), dtype=torch.float32)
+    niters = int(torch.ceil((th[-1] - th[0]) / step + 1).item())
+    meta = (float(th[0]), float(th[-1]), float(step), niters - 1)
+    if len(_grid_cache) > 256:
+        _grid_cache.clear()
+    _grid_cache[key] = meta
+    return meta
+
+
+def mlp_params(func):
+    """Extracts (hidden [(W, b)...], (W_out, b_out), Hd, C) from a FinalTanh / FinalTanh_ff6-shaped module.
+
+    Layout contract (experiments/models/vector_fields.py:185-250): linear_in, optional linear_test,
+    linears[*] all followed by ReLU, then linear_out -> view(Hd, C) -> tanh.
+    """
+    if not isinstance(func, torch.nn.Module):
+        raise ValueError("func must be a torch.nn.Module.")
+    try:
+        layers = [func.linear_in]
+        if hasattr(func, 'linear_test'):
+            layers.append(func.linear_test)
+        layers += list(func.linears)
+        out = func.linear_out
+    except AttributeError:
+        raise NotImplementedError(
+            'the fused B200 solver only understands FinalTanh / FinalTanh_ff6 shaped vector fields '
+            '(linear_in[, linear_test], linears, linear_out + tanh); got %s' % type(func).__name__)
+    if len(layers) > _lib.MAX_LAYERS:
+        raise NotImplementedError('at most %d hidden layers are supported' % _lib.MAX_LAYERS)
+    Hd = layers[0].in_features
+    if out.out_features % Hd != 0:
+        raise ValueError('linear_out has %d outputs, not a multiple of the state size %d' % (out.out_features, Hd))
+    C = out.out_features // Hd
+    tensors = []
+    for lin in layers + [out]:
+        tensors += [lin.weight, lin.bias]
+    return tensors, [l.out_features for l in layers], Hd, C
+
+
+def _desc(plan, z0, attention, wb, widths, Hd):
+    d = _lib.NcdeDesc()
+    d.B, d.L, d.C, d.Hd = plan.B, plan.Lm1 + 1, plan.C, Hd
+    d.n_hidden = len(widths)
+    for i, w in enumerate(widths):
+        d.width[i] = w
+    d.mode = plan.mode
+    t_start, t_end, step, n_steps = plan.grid
+    d.t_start, d.t_end, d.step, d.n_steps = t_start, t_end, step, n_steps
+    d.n_out = plan.t_out.numel()
+    d.times, d.t_out = plan.times.data_ptr(), plan.t_out.data_ptr()
+    d.coeff_b, d.coeff_c2, d.coeff_d3 = plan.b.data_ptr(), plan.c2.data_ptr(), plan.d3.data_ptr()
+    d.z0 = z0.data_ptr()
+    for i in range(len(widths) + 1):
+        d.W[i] = wb[2 * i].data_ptr()
+        d.bias[i] = wb[2 * i + 1].data_ptr()
+    if plan.mode == _lib.MODE_TOP:
+        d.att_L, d.att_C = attention.shape[0], attention.shape[2]
+        d.n_hp = plan.h_prime.shape[0]
+        d.attention = attention.data_ptr()
+        d.h_prime = plan.h_prime.data_ptr()
+    d.samples_per_cta = FORCE_SAMPLES_PER_CTA
+    return d
+
+
+class _NcdeSolve(torch.autograd.Function):
+    """z_out, k_out = solve(plan, widths, z0, attention, W0, b0, ..., W_out, b_out)."""
+
+    @staticmethod
+    def forward(ctx, plan, widths, z0, attention, *wb):
+        L_ = _lib.lib()
+        dev = plan.device
+        _lib.require_cuda(z0, 'z0')
+        Hd = z0.shape[-1]
+        z0c = z0.detach().float().contiguous()
+        wbc = [w.detach().float().contiguous() for w in wb]
+        attc = None
+        if plan.mode == _lib.MODE_TOP:
+            attc = attention.detach().float().contiguous()
+            if attc.dim() != 3 or attc.shape[1] != plan.B:
+                raise ValueError('attention must have shape (knots, batch, channels|1), got %s' % (tuple(attc.shape),))
+        d = _desc(plan, z0c, attc, wbc, widths, Hd)
+        n_out = plan.t_out.numel()
+        n_steps = plan.grid[3]
+        z_out = torch.empty(n_out, plan.B, Hd, dtype=torch.float32, device=dev)
+        k_out = torch.empty(4 * n_steps if plan.want_k else 0, plan.B, Hd, dtype=torch.float32, device=dev)
+        d.z_out = z_out.data_ptr()
+        d.k_out = k_out.data_ptr() if plan.want_k else None
+        wpack = torch.empty(L_.ancde_ncde_wpack_floats(ctypes.byref(d)), dtype=torch.float32, device=dev)
+        d.wpack = wpack.data_ptr()
+        need_grad = any(ctx.needs_input_grad)
+        save_act = save_G = None
+        if need_grad:
+            save_act = torch.empty(L_.ancde_ncde_save_act_floats(ctypes.byref(d)), dtype=torch.float32, device=dev)
+            save_G = torch.empty(L_.ancde_ncde_save_G_floats(ctypes.byref(d)), dtype=torch.float32, device=dev)
+            d.save_act, d.save_G = save_act.data_ptr(), save_G.data_ptr()
+        with torch.cuda.device(dev):
+            rc = L_.ancde_ncde_forward(ctypes.byref(d), _lib.stream_ptr(dev))
+        _lib.check(rc, 'ancde_ncde_forward')
+        _lib.note_launches()
+        ctx.plan, ctx.widths, ctx.Hd = plan, widths, Hd
+        ctx.keep = (z0c, attc, wbc, wpack, save_act, save_G)
+        ctx.mark_non_differentiable(k_out)
+        return z_out, k_out
+
+    @staticmethod
+    def backward(ctx, g_z_out, g_k_out):
+        L_ = _lib.lib()
+        plan, widths, Hd = ctx.plan, ctx.widths, ctx.Hd
+        z0c, attc, wbc, wpack, save_act, save_G = ctx.keep
+        dev = plan.device
+        d = _desc(plan, z0c, attc, wbc, widths, Hd)
+        d.wpack, d.save_act, d.save_G = wpack.data_ptr(), save_act.data_ptr(), save_G.data_ptr()
+        g = g_z_out.detach().float().contiguous()
+        grad_z0 = torch.empty_like(z0c)
+        grads = [torch.zeros_like(w) for w in wbc]
+        d.grad_z_out, d.grad_z0 = g.data_ptr(), grad_z0.data_ptr()
+        for i in range(len(widths) + 1):
+            d.grad_W[i] = grads[2 * i].data_ptr()
+            d.grad_bias[i] = grads[2 * i + 1].data_ptr()
+        grad_att = None
+        if plan.mode == _lib.MODE_TOP and plan.att_grad and ctx.needs_input_grad[3]:
+            grad_att = torch.zeros_like(attc)
+            d.grad_attention = grad_att.data_ptr()
+        # z_out / k_out are not needed by the backward kernels
+        d.z_out = save_act.data_ptr()
+        with torch.cuda.device(dev):
+            rc = L_.ancde_ncde_backward(ctypes.byref(d), _lib.stream_ptr(dev))
+        _lib.check(rc, 'ancde_ncde_backward')
+        _lib.note_launches()
+        ctx.keep = None
+        return (None, None, grad_z0, grad_att) + tuple(grads)
+
+
+def solve(plan, func, z0, attention=None):
+    """Runs the fused solve. Returns (z_out (n_out, B, Hd), k_out (4*steps, B, Hd) or None)."""
+    wb, widths, Hd, C = mlp_params(func)
+    if C != plan.C:
+        raise ValueError("func did not return a tensor with the same number of input channels as dX_dt returned. "
+                         "func has %d channels, whilst dX_dt returned %d channels." % (C, plan.C))
+    if z0.shape[-1] != Hd:
+        raise ValueError("func did not return a tensor with the same number of hidden channels as z0. func has "
+                         "%d channels, whilst z0 has %d channels." % (Hd, z0.shape[-1]))
+    if z0.dim() != 2 or z0.shape[0] != plan.B:
+        raise ValueError("dX_dt did not return a tensor with the same number of batch dimensions as z0. dX_dt "
+                         "returned batch shape (%d,), whilst z0 has shape %s." % (plan.B, tuple(z0.shape)))
+    if attention is None:
+        attention = z0.new_zeros(())
+    z_out, k_out = _NcdeSolve.apply(plan, widths, z0, attention, *wb)
+    return z_out, (k_out if plan.want_k else None)

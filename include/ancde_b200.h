@@ -1,0 +1,137 @@
+/*
+ * ancde_b200.h -- C ABI of libancde_b200.so (hand-written sm_100a kernels for the
+ * ANCDE dual-NCDE hot path).  Plain pointers and sizes only; no torch types.
+ *
+ * Ownership: the caller allocates every input, output and workspace buffer (device
+ * memory, contiguous); the library never allocates or frees device memory, never
+ * synchronises the host, and launches on the stream it is given.  Every entry point
+ * returns 0 on success or a negative ANCDE_E* code; the message of the last error of
+ * the calling thread is available through ancde_last_error().
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference repository sheoyon-jhin/ANCDE).
+ */
+#ifndef ANCDE_B200_H
+#define ANCDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANCDE_OK            0
+#define ANCDE_EINVAL       -1   /* bad argument (shape, null pointer, unsupported size) */
+#define ANCDE_ECUDA        -2   /* a CUDA runtime call failed */
+#define ANCDE_EUNSUPPORTED -3   /* valid request the kernels do not cover (no fallback exists) */
+
+#define ANCDE_MAX_LAYERS 8      /* hidden (ReLU) layers in a vector-field MLP */
+
+/* ABI version; bumped when a struct below changes. */
+int ancde_abi_version(void);
+
+/* Copies the calling thread's last error message into buf (NUL terminated). Returns its length. */
+int ancde_last_error(char* buf, size_t len);
+
+/* ---------------------------------------------------------------------------------------------
+ * Natural cubic spline coefficients with missing values.
+ * Replaces controldiffeq.natural_cubic_spline_coeffs (controldiffeq/interpolate.py:159-226),
+ * i.e. _natural_cubic_spline_coeffs_without_missing_values (:7-53), the per-scalar-path NaN
+ * routine (:78-153) and misc.tridiagonal_solve (controldiffeq/misc.py:12-66).
+ *
+ *   times : (L)        knot times, strictly increasing
+ *   X     : (N, L, C)  values, NaN = missing
+ *   a, b, two_c, three_d : (N, L-1, C) outputs
+ * times_were_f32 (f64 entry only): the reference keeps `times` in float32 while X is float64
+ * (Stock); reciprocals of time differences are then rounded through float32 like it does.
+ * ------------------------------------------------------------------------------------------- */
+int ancde_spline_coeffs_f32(const float* times, const float* X, float* a, float* b, float* two_c,
+                            float* three_d, int64_t N, int L, int C, void* stream);
+int ancde_spline_coeffs_f64(const double* times, const double* X, double* a, double* b, double* two_c,
+                            double* three_d, int64_t N, int L, int C, int times_were_f32, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused neural-CDE solve: z' = tanh(MLP(z)).view(Hd, C) @ dU/dt, fixed-grid RK4 (3/8 rule).
+ *
+ * One descriptor covers the three reference operators:
+ *   mode ANCDE_MODE_PLAIN   controldiffeq.cdeint  + VectorField          (cdeint_module.py:9-32,141-151)
+ *   mode ANCDE_MODE_BOTTOM  controldiffeq.ancde_bottom + VectorField_stack (:34-72,168-243); also
+ *                           emits h' = every stage derivative in call order (the reference's .npy file)
+ *   mode ANCDE_MODE_TOP     controldiffeq.ancde   + AttentiveVectorField  (:74-138,247-254):
+ *                           dU = dX*a + a(1-a)*dX*h'[call counter], a = attention[floor(t)-1]
+ * The MLP is FinalTanh_ff6 / FinalTanh (experiments/models/vector_fields.py:185-250): n_hidden
+ * ReLU layers then a linear layer to Hd*C followed by tanh.  The solver arithmetic is
+ * torchdiffeq==0.0.1's FixedGridODESolver with rk4_alt_step_func.
+ * ------------------------------------------------------------------------------------------- */
+#define ANCDE_MODE_PLAIN  0
+#define ANCDE_MODE_BOTTOM 1
+#define ANCDE_MODE_TOP    2
+
+typedef struct ancde_ncde_desc {
+    /* ---- shapes ---- */
+    int32_t B;                 /* samples */
+    int32_t L;                 /* spline knots; coefficient tensors are (B, L-1, C) */
+    int32_t C;                 /* control channels */
+    int32_t Hd;                /* state size */
+    int32_t n_hidden;          /* hidden layers, 1..ANCDE_MAX_LAYERS */
+    int32_t width[ANCDE_MAX_LAYERS];   /* output width of hidden layer l */
+    int32_t mode;              /* ANCDE_MODE_* */
+    int32_t att_C;             /* TOP: 1 (timewise) or C (elementwise) */
+    int32_t att_L;             /* TOP: leading size of attention (knots) */
+    int32_t n_hp;              /* TOP: leading size of h_prime (4 * bottom steps) */
+    /* ---- the fixed grid: t_k = t_start + k*step (last clipped to t_end) ---- */
+    float   t_start, t_end, step;
+    int32_t n_steps;           /* grid intervals */
+    int32_t n_out;             /* requested output times (t_out[0] == t_start) */
+    /* ---- inputs (device pointers, float32) ---- */
+    const float* times;        /* (L) */
+    const float* t_out;        /* (n_out) increasing */
+    const float* coeff_b;      /* (B, L-1, C) */
+    const float* coeff_c2;     /* (B, L-1, C) */
+    const float* coeff_d3;     /* (B, L-1, C) */
+    const float* z0;           /* (B, Hd) */
+    const float* W[ANCDE_MAX_LAYERS + 1];     /* torch Linear weights, (out, in) row-major; [n_hidden] = output layer (Hd*C, width[n_hidden-1]) */
+    const float* bias[ANCDE_MAX_LAYERS + 1];
+    const float* attention;    /* TOP: (att_L, B, att_C) */
+    const float* h_prime;      /* TOP: (n_hp, B, C) */
+    /* ---- outputs ---- */
+    float* z_out;              /* (n_out, B, Hd) */
+    float* k_out;              /* BOTTOM (or NULL): (4*n_steps, B, Hd) stage derivatives in call order */
+    /* ---- workspace ---- */
+    float* wpack;              /* packed/transposed weights, ancde_ncde_wpack_floats() floats */
+    float* save_act;           /* NULL for inference; else ancde_ncde_save_act_floats() floats */
+    float* save_G;             /* NULL for inference; else ancde_ncde_save_G_floats() floats */
+    /* ---- backward only ---- */
+    const float* grad_z_out;   /* (n_out, B, Hd) cotangents of z_out */
+    float* grad_z0;            /* (B, Hd) written */
+    float* grad_W[ANCDE_MAX_LAYERS + 1];      /* accumulated into (caller zeroes), same layout as W */
+    float* grad_bias[ANCDE_MAX_LAYERS + 1];
+    float* grad_attention;     /* TOP, or NULL (adjoint-mode gradient flow): (att_L, B, att_C) accumulated into */
+    int32_t samples_per_cta;   /* 0 = let the library choose (8, 4, 2 or 1) */
+    int32_t reserved;
+} ancde_ncde_desc;
+
+/* Workspace sizes (in floats) for a descriptor whose shape fields are filled in. */
+int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d);
+int64_t ancde_ncde_save_act_floats(const ancde_ncde_desc* d);
+int64_t ancde_ncde_save_G_floats(const ancde_ncde_desc* d);
+
+/* Forward solve.  Writes z_out (and k_out, save_act, save_G when non-NULL). */
+int ancde_ncde_forward(const ancde_ncde_desc* d, void* stream);
+
+/* Backprop through the solver (discrete adjoint of the RK4 recurrence), using save_act / save_G
+ * written by ancde_ncde_forward with the same descriptor.  Overwrites save_G. */
+int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream);
+
+/* Number of kernel launches the last forward / backward call of this thread issued. */
+int ancde_last_launch_count(void);
+
+/* FP32 FMA throughput microbenchmark (roofline denominator): launches a kernel of
+ * dependent-free FFMA chains; returns the FLOP count it executes in *flops. */
+int ancde_fp32_peak_kernel(float* scratch, int iters, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANCDE_B200_H */

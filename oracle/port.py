@@ -334,7 +334,7 @@ def dual_ncde_forward(sd, cfg, times, coeffs, final_index, slope, stream=False, 
         dX = Xt.float()                                                    # :106
         q = int(math.floor(float(tt))) - 1                                 # cdeint_module.py:108-110 (Q3)
         a_t = att_solve[q]
-        m = n if n <= n_hp - 2 else 0                                      # :134-137 (Q5), counter + reset rule
+        m = n % (n_hp - 1)                                                 # :134-137 (Q5), counter + reset rule
         dY = (dX * a_t + (a_t * (1 - a_t) * Xt) * h_prime[m]).float()      # :113-129
         return (G @ dY.unsqueeze(-1)).squeeze(-1)                          # :133
 

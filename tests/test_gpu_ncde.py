@@ -1,0 +1,204 @@
+"""GPU parity of the fused dual-NCDE path (csrc/ncde_fwd.cu, csrc/ncde_bwd.cu) through the public API.
+
+Golden vectors come from the UNMODIFIED reference (oracle/gen_golden.py); seeded cases are checked against
+the CPU restatement oracle/port.py.  Bars (north star): FP32 predictions / hidden states within 1e-4
+relative (max-norm), gradients (backprop through the solver) within 2e-3 relative.
+"""
+import pytest
+import torch
+
+from tests.helpers import DUAL_CASES, dual_case, loss_weights, rel_err, load_golden
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 1e-4
+GRAD_TOL = 2e-3
+
+
+def _build(case_or_cfg, sd=None):
+    import ancde_b200
+    from ancde_b200 import metamodel
+    cfg = case_or_cfg
+    model, g, f = metamodel.model_from_config(cfg, file='test_h_prime')
+    if sd is not None:
+        model.load_state_dict(sd, strict=True)
+    return model.cuda()
+
+
+def _forward(model, g, adjoint=False, stream=None):
+    cfg = g['cfg']
+    coeffs = tuple(c.cuda() for c in g['coeffs'])
+    times = g['times'].cuda()
+    fi = g['final_index'].cuda()
+    kw = dict(stream=cfg['stream'] if stream is None else stream, adjoint=adjoint)
+    if g['static'] is not None:
+        return model(times, coeffs + (g['static'].cuda(),), fi, g['slope'], **kw)
+    return model(times, coeffs, fi, g['slope'], **kw)
+
+
+@pytest.mark.parametrize('case', DUAL_CASES)
+def test_forward_matches_reference_golden(case):
+    import ancde_b200
+    g = dual_case(case)
+    model = _build(g['cfg'], g['sd'])
+    with torch.no_grad():
+        pred = _forward(model, g)
+    torch.cuda.synchronize()
+    assert pred.shape == g['pred'].shape
+    e = rel_err(pred, g['pred'])
+    hp = ancde_b200.load_h_prime('test_h_prime')
+    eh = rel_err(hp, g['h_prime'])
+    print('%s: pred rel err %.3e, h_prime rel err %.3e' % (case, e, eh))
+    assert eh < FWD_TOL, (case, 'h_prime', eh)
+    assert e < FWD_TOL, (case, 'pred', e)
+
+
+@pytest.mark.parametrize('case', DUAL_CASES)
+def test_gradients_match_reference_golden(case):
+    g = dual_case(case)
+    model = _build(g['cfg'], g['sd'])
+    pred = _forward(model, g)
+    (pred * loss_weights(pred.shape).cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(pred, g['pred']) < FWD_TOL
+    params = dict(model.named_parameters())
+    worst = ('', 0.0)
+    for k, ref in g['grads'].items():
+        assert params[k].grad is not None, (case, k)
+        e = rel_err(params[k].grad, ref)
+        if e > worst[1]:
+            worst = (k, e)
+    print('%s: worst grad rel err %.3e (%s)' % (case, worst[1], worst[0]))
+    assert worst[1] < GRAD_TOL, (case,) + worst
+    for k, p in params.items():
+        if k not in g['grads']:
+            assert p.grad is None or p.grad.abs().max().item() == 0.0, (case, k)
+
+
+@pytest.mark.parametrize('ts', [1, 2, 4, 8])
+@pytest.mark.parametrize('case', ['mujoco', 'sepsis'])
+def test_every_tile_size_gives_the_same_answer(case, ts):
+    from ancde_b200 import solver
+    g = dual_case(case)
+    model = _build(g['cfg'], g['sd'])
+    solver.FORCE_SAMPLES_PER_CTA = ts
+    try:
+        pred = _forward(model, g)
+        (pred * loss_weights(pred.shape).cuda()).sum().backward()
+        torch.cuda.synchronize()
+    finally:
+        solver.FORCE_SAMPLES_PER_CTA = 0
+    assert rel_err(pred, g['pred']) < FWD_TOL, (case, ts)
+    params = dict(model.named_parameters())
+    for k, ref in g['grads'].items():
+        assert rel_err(params[k].grad, ref) < GRAD_TOL, (case, ts, k)
+
+
+def test_cdeint_matches_reference_golden():
+    import ancde_b200
+    z = load_golden('cdeint_small')
+    C, H, HH, nl = (int(v) for v in z['dims'])
+    func = ancde_b200.FinalTanh(C, H, HH, nl)
+    model = ancde_b200.NeuralCDE(func, C, H, 3, initial=True)
+    model.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd.')}, strict=True)
+    model = model.cuda()
+    times = torch.from_numpy(z['times']).cuda()
+    coeffs = tuple(torch.from_numpy(z['coeff_' + k]).cuda() for k in 'abcd')
+    fi = torch.from_numpy(z['final_index']).cuda()
+    pred_stream = model(times, coeffs, fi, stream=True, method='rk4', options=dict(step_size=1.0))
+    assert rel_err(pred_stream, torch.from_numpy(z['pred_stream'])) < FWD_TOL
+    pred = model(times, coeffs, fi, method='rk4', options=dict(step_size=1.0))
+    assert rel_err(pred, torch.from_numpy(z['pred'])) < FWD_TOL
+    (pred * loss_weights(pred.shape).cuda()).sum().backward()
+    for k, p in model.named_parameters():
+        assert rel_err(p.grad, torch.from_numpy(z['grad.' + k])) < GRAD_TOL, k
+
+
+def test_adjoint_mode_gradient_flow_matches_oracle():
+    """adjoint=True: attention / h' are constants of the top solve."""
+    from oracle import port
+    g = dual_case('mujoco_soft_tw')
+    model = _build(g['cfg'], g['sd'])
+    pred = _forward(model, g, adjoint=True)
+    pred.sum().backward()
+    sd = {k: v.clone().requires_grad_(True) for k, v in g['sd'].items()}
+    res = port.dual_ncde_forward(sd, g['cfg'], g['times'], g['coeffs'], g['final_index'], g['slope'],
+                                 stream=True, adjoint=True)
+    res['pred'].sum().backward()
+    assert rel_err(pred, res['pred']) < FWD_TOL
+    for k, p in model.named_parameters():
+        ref = sd[k].grad
+        if ref is None or ref.abs().max() == 0:
+            assert p.grad is None or p.grad.abs().max().item() == 0.0, k
+        else:
+            assert rel_err(p.grad, ref) < GRAD_TOL, k
+
+
+def test_general_grid_and_interpolated_outputs_against_oracle():
+    """step_size that does not divide the knot spacing + output times between grid points."""
+    import ancde_b200
+    from oracle import port
+    torch.manual_seed(3)
+    C, H, HH, nl, L, B = 5, 7, 9, 2, 9, 6
+    func = ancde_b200.FinalTanh(C, H, HH, nl)
+    times = torch.linspace(0.0, 4.0, L)
+    X = 0.3 * torch.randn(B, L, C).cumsum(1)
+    coeffs = port.natural_cubic_spline_coeffs(times, X)
+    z0 = torch.randn(B, H)
+    t = torch.tensor([0.0, 0.7, 1.5, 3.0, 4.0])
+    sd = {'func.' + k: v.detach().clone().requires_grad_(True) for k, v in func.state_dict().items()}
+    z0r = z0.clone().requires_grad_(True)
+    ref = port.cdeint_port(sd, times, coeffs, z0r, t, 0.3, H, C, prefix='func')
+    w = loss_weights(ref.shape)
+    (ref * w).sum().backward()
+    func = func.cuda()
+    sp = ancde_b200.NaturalCubicSpline(times.cuda(), tuple(c.cuda() for c in coeffs))
+    z0g = z0.cuda().requires_grad_(True)
+    got = ancde_b200.cdeint(sp.derivative, z0g, func, t.cuda(), adjoint=False, method='rk4',
+                            options=dict(step_size=0.3))
+    (got * w.cuda()).sum().backward()
+    assert rel_err(got, ref) < FWD_TOL
+    assert rel_err(z0g.grad, z0r.grad) < GRAD_TOL
+    for k, p in func.named_parameters():
+        assert rel_err(p.grad, sd['func.' + k].grad) < GRAD_TOL, k
+
+
+def test_full_size_sepsis_batch_sharding_property():
+    """BASELINE size (B=1024 Sepsis shape): the result of a batch equals the results of its shards."""
+    from ancde_b200 import synthetic, metamodel
+    import ancde_b200
+    cfg = synthetic.CONFIGS['sepsis']
+    torch.manual_seed(2021)
+    model, _, _ = metamodel.model_from_config(cfg, file='full')
+    model = model.cuda()
+    bt = synthetic.make_batch('sepsis', B=1024)
+    times = bt['times'].cuda()
+    coeffs = ancde_b200.natural_cubic_spline_coeffs(times, bt['X'].cuda())
+    fi, st = bt['final_index'].cuda(), bt['static'].cuda()
+    with torch.no_grad():
+        full = model(times, coeffs + (st,), fi, 1.0)
+        lo = model(times, tuple(c[:512] for c in coeffs) + (st[:512],), fi[:512], 1.0)
+        hi = model(times, tuple(c[512:] for c in coeffs) + (st[512:],), fi[512:], 1.0)
+    assert torch.isfinite(full).all()
+    assert torch.equal(full, torch.cat([lo, hi]))
+
+
+def test_api_errors():
+    import ancde_b200
+    func = ancde_b200.FinalTanh(3, 4, 5, 2).cuda()
+    times = torch.arange(5.).cuda()
+    coeffs = ancde_b200.natural_cubic_spline_coeffs(times, torch.randn(2, 5, 3).cuda())
+    sp = ancde_b200.NaturalCubicSpline(times, coeffs)
+    z0 = torch.randn(2, 4).cuda()
+    with pytest.raises(NotImplementedError):
+        ancde_b200.cdeint(lambda t: None, z0, func, times, method='rk4', options=dict(step_size=1.0))
+    with pytest.raises(NotImplementedError):
+        ancde_b200.cdeint(sp.derivative, z0, func, times, method='dopri5')
+    with pytest.raises(ValueError):
+        ancde_b200.cdeint(sp.derivative, z0, lambda z: z, times, method='rk4', options=dict(step_size=1.0))
+    with pytest.raises(ValueError):
+        ancde_b200.cdeint(sp.derivative, torch.randn(2, 7).cuda(), func, times, method='rk4',
+                          options=dict(step_size=1.0))
+    with pytest.raises(ValueError):
+        ancde_b200.cdeint(sp.derivative, torch.randn(3, 4).cuda(), func, times, method='rk4',
+                          options=dict(step_size=1.0))
