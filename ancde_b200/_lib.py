@@ -43,7 +43,8 @@ _lib = None
 
 EXPORTS = ['ancde_abi_version', 'ancde_last_error', 'ancde_spline_coeffs_f32', 'ancde_spline_coeffs_f64',
            'ancde_ncde_wpack_floats', 'ancde_ncde_save_act_floats', 'ancde_ncde_save_G_floats',
-           'ancde_ncde_forward', 'ancde_ncde_backward', 'ancde_last_launch_count', 'ancde_fp32_peak_kernel']
+           'ancde_ncde_forward', 'ancde_ncde_backward', 'ancde_last_launch_count', 'ancde_fp32_peak_kernel',
+           'ancde_profile_enable', 'ancde_profile_count', 'ancde_profile_get']
 
 
 def lib():
@@ -72,6 +73,7 @@ def lib():
     L.ancde_ncde_forward.argtypes = [ctypes.POINTER(NcdeDesc), vp]
     L.ancde_ncde_backward.argtypes = [ctypes.POINTER(NcdeDesc), vp]
     L.ancde_fp32_peak_kernel.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double), vp]
+    L.ancde_profile_get.argtypes = [ci, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_float)]
     _lib = L
     return L
 
@@ -113,3 +115,37 @@ def note_launches():
 
 def launches_total():
     return _launches['total']
+
+
+def profile_enable(on=True):
+    lib().ancde_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """Per-kernel (name, ms) of every launch since profile_enable(); synchronise the device first."""
+    L = lib()
+    out = []
+    buf = ctypes.create_string_buffer(64)
+    ms = ctypes.c_float()
+    for i in range(L.ancde_profile_count()):
+        check(L.ancde_profile_get(i, buf, 64, ctypes.byref(ms)), 'ancde_profile_get')
+        out.append((buf.value.decode(), float(ms.value)))
+    return out
+
+
+def fp32_peak_tflops(device, iters=4096, reps=5):
+    """Measured FP32 FMA peak of this GPU (TFLOP/s) from the library's FFMA microbenchmark."""
+    L = lib()
+    scratch = torch.empty(148 * 8 * 256, dtype=torch.float32, device=device)
+    flops = ctypes.c_double()
+    best = 0.0
+    with torch.cuda.device(device):
+        sp = stream_ptr(device)
+        for _ in range(reps + 2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(L.ancde_fp32_peak_kernel(scratch.data_ptr(), iters, ctypes.byref(flops), sp), 'fp32_peak')
+            e1.record()
+            e1.synchronize()
+            best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best

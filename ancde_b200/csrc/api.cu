@@ -19,6 +19,32 @@ void set_error(const char* fmt, ...)
 void count_launch() { ++g_launches; }
 void reset_launch_count() { g_launches = 0; }
 
+// ---- per-kernel timing: event pairs recorded around every launch while profiling is enabled
+constexpr int PROF_MAX = 8192;
+struct ProfEntry { const char* name; cudaEvent_t e0, e1; };
+static ProfEntry g_prof[PROF_MAX];
+static int g_prof_n = 0, g_prof_made = 0;
+static bool g_prof_on = false;
+
+void prof_begin(const char* name, cudaStream_t stream)
+{
+    if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+    ProfEntry& e = g_prof[g_prof_n];
+    if (g_prof_n >= g_prof_made) {
+        cudaEventCreate(&e.e0);
+        cudaEventCreate(&e.e1);
+        g_prof_made = g_prof_n + 1;
+    }
+    e.name = name;
+    cudaEventRecord(e.e0, stream);
+}
+void prof_end(cudaStream_t stream)
+{
+    if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+    cudaEventRecord(g_prof[g_prof_n].e1, stream);
+    ++g_prof_n;
+}
+
 // 8 independent FFMA chains per thread: the issue-bound FP32 peak of the SM (128 FMA/clk).
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters)
 {
@@ -54,11 +80,31 @@ extern "C" int ancde_last_error(char* buf, size_t len)
 
 extern "C" int ancde_last_launch_count(void) { return ancde::g_launches; }
 
+extern "C" int ancde_profile_enable(int on)
+{
+    ancde::g_prof_on = on != 0;
+    ancde::g_prof_n = 0;
+    return ANCDE_OK;
+}
+
+extern "C" int ancde_profile_count(void) { return ancde::g_prof_n; }
+
+extern "C" int ancde_profile_get(int i, char* name, size_t len, float* ms)
+{
+    ANCDE_CHECK_ARG(i >= 0 && i < ancde::g_prof_n && name && ms, "profile_get: bad index %d", i);
+    strncpy(name, ancde::g_prof[i].name, len - 1);
+    name[len - 1] = 0;
+    ANCDE_CUDA(cudaEventElapsedTime(ms, ancde::g_prof[i].e0, ancde::g_prof[i].e1));
+    return ANCDE_OK;
+}
+
 extern "C" int ancde_fp32_peak_kernel(float* scratch, int iters, double* flops, void* stream)
 {
     ANCDE_CHECK_ARG(scratch && iters > 0, "fp32_peak: bad arguments");
     const int blocks = 148 * 8, threads = 256;
+    ancde::prof_begin("fp32_peak", (cudaStream_t)stream);
     ancde::fp32_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(scratch, iters);
+    ancde::prof_end((cudaStream_t)stream);
     ANCDE_CUDA(cudaGetLastError());
     if (flops) *flops = 2.0 * 64.0 * (double)iters * blocks * threads;
     return ANCDE_OK;

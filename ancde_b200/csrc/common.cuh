@@ -11,6 +11,9 @@ namespace ancde {
 void set_error(const char* fmt, ...);
 void count_launch();
 void reset_launch_count();
+// Optional per-kernel timing (CUDA events on the launching stream), see ancde_profile_* in the header.
+void prof_begin(const char* name, cudaStream_t stream);
+void prof_end(cudaStream_t stream);
 
 #define ANCDE_CHECK_ARG(cond, ...)                 \
     do {                                           \

@@ -543,13 +543,18 @@ static int launch_bwd(const ancde_ncde_desc* d, SolveArgs& a, cudaStream_t strea
     // hidden-gradient scratch lives behind the packed weights
     a.grad_hidden = d->wpack + lo.wpack_floats;
     ANCDE_CUDA(cudaMemsetAsync(a.grad_hidden, 0, sizeof(float) * pad4(lo.hidden_floats), stream));
+    static const char* names[3] = {"ncde_bwd_plain", "ncde_bwd_bottom", "ncde_bwd_top"};
+    static const char* wnames[3] = {"ncde_wgrad_plain", "ncde_wgrad_bottom", "ncde_wgrad_top"};
     if (wo_smem) {
         ANCDE_CUDA(cudaFuncSetAttribute(ncde_bwd_kernel<TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prof_begin(names[lo.mode], stream);
         ncde_bwd_kernel<TS, true><<<lo.ntiles, nt, smem, stream>>>(a);
     } else {
         ANCDE_CUDA(cudaFuncSetAttribute(ncde_bwd_kernel<TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prof_begin(names[lo.mode], stream);
         ncde_bwd_kernel<TS, false><<<lo.ntiles, nt, smem, stream>>>(a);
     }
+    prof_end(stream);
     count_launch();
     ANCDE_CUDA(cudaGetLastError());
 
@@ -569,8 +574,10 @@ static int launch_bwd(const ancde_ncde_desc* d, SolveArgs& a, cudaStream_t strea
         const int per = (int)((nblocks + gy - 1) / gy);
         gy = (nblocks + per - 1) / per;
         const size_t sm = sizeof(float) * ((size_t)TS * WG_CG * 4 + (size_t)TS * KP + pad4(lo.Hd * TS) + (size_t)lo.C4 * TS);
+        prof_begin(wnames[lo.mode], stream);
         ncde_wgrad_kernel<TS><<<dim3(gx, (unsigned)gy), nthreads, sm, stream>>>(a, d->grad_W[lo.n_hidden],
                                                                                d->grad_bias[lo.n_hidden], per);
+        prof_end(stream);
         count_launch();
         ANCDE_CUDA(cudaGetLastError());
     }
@@ -579,7 +586,9 @@ static int launch_bwd(const ancde_ncde_desc* d, SolveArgs& a, cudaStream_t strea
         ua.lo = lo;
         ua.packed = a.grad_hidden;
         for (int l = 0; l < lo.n_hidden; ++l) { ua.gW[l] = d->grad_W[l]; ua.gB[l] = d->grad_bias[l]; }
+        prof_begin("unpack_hidden_grads", stream);
         unpack_hidden_grads_kernel<<<32, 256, 0, stream>>>(ua);
+        prof_end(stream);
         count_launch();
         ANCDE_CUDA(cudaGetLastError());
     }

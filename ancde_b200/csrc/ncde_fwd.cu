@@ -460,13 +460,17 @@ static int launch_fwd(const SolveArgs& a, cudaStream_t stream)
         set_error("ncde_forward: hidden layers need %zu bytes of shared memory (max %zu)", smem, max_smem);
         return ANCDE_EUNSUPPORTED;
     }
+    static const char* names[3] = {"ncde_fwd_plain", "ncde_fwd_bottom", "ncde_fwd_top"};
     if (wo_smem) {
         ANCDE_CUDA(cudaFuncSetAttribute(ncde_fwd_kernel<TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prof_begin(names[lo.mode], stream);
         ncde_fwd_kernel<TS, true><<<lo.ntiles, nt, smem, stream>>>(a);
     } else {
         ANCDE_CUDA(cudaFuncSetAttribute(ncde_fwd_kernel<TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prof_begin(names[lo.mode], stream);
         ncde_fwd_kernel<TS, false><<<lo.ntiles, nt, smem, stream>>>(a);
     }
+    prof_end(stream);
     count_launch();
     ANCDE_CUDA(cudaGetLastError());
     return ANCDE_OK;
@@ -482,7 +486,9 @@ int pack_weights(const ancde_ncde_desc* d, const NcdeLayout& lo, cudaStream_t st
         pa.bias[l] = d->bias[l];
     }
     pa.wpack = d->wpack;
+    prof_begin("pack_weights", stream);
     pack_weights_kernel<<<64, 256, 0, stream>>>(pa);
+    prof_end(stream);
     count_launch();
     ANCDE_CUDA(cudaGetLastError());
     return ANCDE_OK;

@@ -200,7 +200,9 @@ static int launch_spline(const T* times, const T* X, T* a, T* b, T* c2, T* d3, i
                                     (int)smem));
     const int64_t grid = (P + nt - 1) / nt;
     ANCDE_CHECK_ARG(grid <= 0x7fffffffLL, "spline_coeffs: too many paths");
+    prof_begin(sizeof(T) == 4 ? "spline_coeffs_f32" : "spline_coeffs_f64", stream);
     spline_coeffs_kernel<T><<<(unsigned)grid, nt, smem, stream>>>(times, X, a, b, c2, d3, P, L, C, tf32);
+    prof_end(stream);
     count_launch();
     ANCDE_CUDA(cudaGetLastError());
     return ANCDE_OK;

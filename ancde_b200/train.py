@@ -1,0 +1,57 @@
+"""One training step of the dual-NCDE models the way the reference harness runs it.
+
+Reference: experiments/common.py:_train_loop (:378-614) / _train_loop_forecasting (:205-375):
+pred = model(times, coeffs, final_index, slope); loss = task loss + 0.03 * sum ||theta_g||
+(:47-58, regularisation over func_g only); loss.backward(); optimizer.step().  Data-parallel runs
+add one flat-gradient all-reduce between backward and the optimizer step (ancde_b200/dp.py).
+"""
+import torch
+
+from . import metamodel, synthetic
+from .dp import FlatGradBucket
+
+
+def task_loss(cfg, pred, y):
+    if cfg['kind'] == 'ancde_forecasting':
+        return torch.nn.functional.mse_loss(pred, y)                          # common.py:766
+    if cfg['out'] == 1:                                                       # Sepsis: BCE, pos_weight 10
+        pw = torch.tensor(10.0, device=pred.device)
+        return torch.nn.functional.binary_cross_entropy_with_logits(pred.squeeze(-1), y, pos_weight=pw)
+    return torch.nn.functional.cross_entropy(pred, y)
+
+
+class DualNcdeTrainer:
+    """Model + Adam + flat gradient bucket for one of `synthetic.CONFIGS`."""
+
+    def __init__(self, workload, device, seed=2021, lr=1e-4, adjoint=False, file='train_h_prime'):
+        self.cfg = synthetic.CONFIGS[workload]
+        self.workload = workload
+        self.device = torch.device(device)
+        self.adjoint = adjoint
+        torch.manual_seed(seed)                       # same initial weights on every rank
+        self.model, self.func_g, self.func_f = metamodel.model_from_config(self.cfg, file=file)
+        self.model = self.model.to(self.device)
+        self.bucket = FlatGradBucket(self.model.parameters())
+        fused = self.device.type == 'cuda'
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, weight_decay=1e-4, fused=fused)
+        self.reg_params = [p for p in self.func_g.parameters()]
+
+    def forward(self, batch, slope=1.0):
+        cfg = self.cfg
+        coeffs = batch['coeffs']
+        kw = dict(stream=cfg['stream'], adjoint=self.adjoint)
+        if cfg['static']:
+            return self.model(batch['times'], tuple(coeffs) + (batch['static'],), batch['final_index'], slope, **kw)
+        return self.model(batch['times'], tuple(coeffs), batch['final_index'], slope, **kw)
+
+    def step(self, batch, slope=1.0):
+        """forward + loss + backward + gradient all-reduce + Adam. Returns the (detached) loss."""
+        self.bucket.zero()
+        pred = self.forward(batch, slope)
+        loss = task_loss(self.cfg, pred, batch['y'])
+        for p in self.reg_params:
+            loss = loss + 0.03 * p.norm()
+        loss.backward()
+        self.bucket.all_reduce_mean()
+        self.opt.step()
+        return loss.detach()

@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the fused dual-NCDE training step (BASELINE.json metric: fwd+bwd samples/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sepsis] [--impl ours|reference]
+
+A step = one pass of the hot path over one batch: dual-NCDE forward, loss, backward through the solver,
+(N>1: flat-gradient all-reduce over NCCL) and the Adam update.  Default workload: PhysioNet-Sepsis (no OI)
+shape, 1024 samples per GPU (weak scaling), synthetic data, random-init weights.
+Prints ONE JSON line on rank 0 (see the keys below).  `--impl reference` times the CPU restatement of the
+reference (oracle/port.py; /root/reference itself does not exist on the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'dual_ncde_fwd_bwd_samples_per_sec'
+WORKLOAD_TEXT = {
+    'sepsis': 'PhysioNet Sepsis no-OI shape: ANCDE, 35 ch (34+time), 72 knots (times 1..72), h=hh=49, 4 layers, '
+              'attention 20/20, soft timewise attention, rk4 step 1, backprop through the solver, batch 1024/GPU',
+    'sepsis_oi': 'PhysioNet Sepsis OI shape: ANCDE, 69 ch, 72 knots, h=hh=49, 4 layers, soft timewise attention, '
+                 'rk4 step 1, batch 1024/GPU',
+    'mujoco': 'Mujoco shape: ANCDE_forecasting, 14 ch, 20 knots -> 5 steps, h=12, 2 layers, hard STE attention',
+    'stock': 'Google-Stock shape: ANCDE_forecasting, 6 ch, 24 knots -> 1 step, h=12, 2 layers, hard STE attention',
+    'uea': 'UEA CharacterTrajectories shape: ANCDE, 4 ch, 182 knots, h=40, 3 layers, soft timewise attention',
+}
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def algorithmic_macs(cfg):
+    """MACs per sample per RK4 stage."""
+    C, H, HH, A, AA, nl = cfg['C'], cfg['H'], cfg['HH'], cfg['A'], cfg['AA'], cfg['nl']
+    f_hidden = C * AA + AA * A + (nl - 1) * A * A
+    f_out = A * C * C
+    g_hidden = H * HH + (nl - 1) * HH * HH
+    g_out = HH * H * C
+    return dict(f_hidden=f_hidden, f_out=f_out, f_contract=C * C, g_hidden=g_hidden, g_out=g_out,
+                g_contract=H * C)
+
+
+def kernel_flops(cfg, B):
+    """Algorithmic FLOPs of one launch of each kernel (2 * MACs * stages * samples)."""
+    m = algorithmic_macs(cfg)
+    stages = 4 * (cfg['L'] - 1)
+    bot = m['f_hidden'] + m['f_out'] + m['f_contract']
+    top = m['g_hidden'] + m['g_out'] + m['g_contract']
+    s = 2.0 * stages * B
+    return {
+        'ncde_fwd_bottom': s * bot, 'ncde_fwd_top': s * top,
+        # recurrent backward: input-gradient pass of every layer + the hidden layers' weight gradients
+        'ncde_bwd_bottom': s * (bot + m['f_hidden']), 'ncde_bwd_top': s * (top + m['g_hidden']),
+        # output-layer weight gradient
+        'ncde_wgrad_bottom': s * m['f_out'], 'ncde_wgrad_top': s * m['g_out'],
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_device_batch(workload, B, seed, device):
+    import ancde_b200
+    from ancde_b200 import synthetic
+    bt = synthetic.make_batch(workload, B=B, seed=seed)
+    times = bt['times'].to(device)
+    coeffs = ancde_b200.natural_cubic_spline_coeffs(times, bt['X'].to(device))
+    out = dict(times=times, coeffs=tuple(coeffs), final_index=bt['final_index'].to(device), y=bt['y'].to(device))
+    if bt['static'] is not None:
+        out['static'] = bt['static'].to(device)
+    return out
+
+
+def to_pinned_host(batch):
+    host = {}
+    for k, v in batch.items():
+        if k == 'coeffs':
+            host[k] = tuple(c.cpu().pin_memory() for c in v)
+        else:
+            host[k] = v.cpu().pin_memory()
+    return host
+
+
+def h2d(host, device):
+    dev = {}
+    nbytes = 0
+    for k, v in host.items():
+        if k == 'coeffs':
+            dev[k] = tuple(c.to(device, non_blocking=True) for c in v)
+            nbytes += sum(c.numel() * c.element_size() for c in v)
+        else:
+            dev[k] = v.to(device, non_blocking=True)
+            nbytes += v.numel() * v.element_size()
+    return dev, nbytes
+
+
+# ------------------------------------------------------------------------------------------ CPU reference
+def cpu_reference_samples_per_sec(workload, sample_B, steps, warmup):
+    """fwd+bwd of the CPU restatement of the reference (oracle/port.py) with every host thread."""
+    from oracle import port
+    from ancde_b200 import synthetic, metamodel
+    cfg = synthetic.CONFIGS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(2021)
+    model, _, _ = metamodel.model_from_config(cfg, file='cpu')
+    bt = synthetic.make_batch(workload, B=sample_B, seed=2021)
+    coeffs = port.natural_cubic_spline_coeffs(bt['times'], bt['X'])
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    sdm = {k[len('model.'):]: v for k, v in sd.items() if k.startswith('model.')} if cfg['static'] else sd
+
+    def one():
+        for v in sd.values():
+            v.grad = None
+        z0 = port.ivn_z0(sd, bt['static']) if cfg['static'] else None
+        res = port.dual_ncde_forward(sdm, cfg, bt['times'], coeffs, bt['final_index'], 1.0, stream=cfg['stream'],
+                                     z0=z0, adjoint=False)
+        from ancde_b200.train import task_loss
+        loss = task_loss(cfg, res['pred'], bt['y'])
+        loss.backward()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        one()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one()
+        ts.append(time.perf_counter() - t0)
+    sec = statistics.median(ts)
+    return sample_B / sec, sec, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    sample_B = args.cpu_sample
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 2))
+    value, sec, cores = cpu_reference_samples_per_sec(args.workload, sample_B, steps, warmup)
+    sample = '%d samples of the %s workload per step (bounded sample of the %d-sample batch), fwd+bwd, ' \
+             'median of %d steps after %d warm-up' % (sample_B, args.workload, args.batch, steps, warmup)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD_TEXT[args.workload], 'name': args.workload, 'batch_per_step': sample_B},
+        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+    import ancde_b200
+    from ancde_b200 import _lib, synthetic
+    from ancde_b200.train import DualNcdeTrainer
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the ANCDE B200 path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    if world != args.gpus and rank == 0:
+        sys.stderr.write('warning: --gpus %d but WORLD_SIZE=%d\n' % (args.gpus, world))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    cfg = synthetic.CONFIGS[args.workload]
+    B = args.batch
+    trainer = DualNcdeTrainer(args.workload, device, seed=2021, adjoint=args.adjoint)
+    # several distinct resident batches, cycled, so no step re-reads inputs the previous one left in L2
+    n_res = 4
+    batches = [make_device_batch(args.workload, B, 2021 + 1000 * rank + i, device) for i in range(n_res)]
+    host_batches = [to_pinned_host(b) for b in batches[:2]]
+    fp32_peak = _lib.fp32_peak_tflops(device)
+
+    def timed(fn, steps, warmup, profile=False):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        if profile:
+            _lib.profile_enable(True)
+        launches0 = _lib.launches_total()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof = _lib.profile_read() if profile else []
+        if profile:
+            _lib.profile_enable(False)
+        t = torch.tensor([ms], device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), _lib.launches_total() - launches0, prof
+
+    # ---- value: inputs resident in HBM
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms, launches, prof = timed(lambda i: trainer.step(batches[i % n_res]), args.steps, args.warmup, profile=True)
+    clk = clocks.stop() if rank == 0 else {}
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host (pinned) inputs through the public API, H2D + D2H inside the timed region
+    h2d_bytes = [0]
+    d2h_bytes = [0]
+
+    def e2e_step(i):
+        dev_batch, nb = h2d(host_batches[i % len(host_batches)], device)
+        h2d_bytes[0] = nb
+        loss = trainer.step(dev_batch)
+        loss_host = loss.to('cpu')                # device -> host read of the step's result
+        d2h_bytes[0] = loss_host.numel() * loss_host.element_size()
+        return loss_host
+
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e, _, _ = timed(e2e_step, e2e_steps, 2)
+    e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- per-kernel roofline from the CUDA-event timings taken inside the timed region
+    flops = kernel_flops(cfg, B)
+    agg = {}
+    for name, t in prof:
+        a = agg.setdefault(name, [0.0, 0])
+        a[0] += t
+        a[1] += 1
+    total_kernel_ms = sum(a[0] for a in agg.values())
+    kernels = []
+    for name, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        avg = t / n
+        k = {'name': name, 'launches': n, 'avg_ms': round(avg, 4), 'share_of_kernel_time': round(t / total_kernel_ms, 4)}
+        if name in flops:
+            k['algorithmic_gflop_per_launch'] = round(flops[name] / 1e9, 3)
+            k['achieved_tflops'] = round(flops[name] / (avg * 1e-3) / 1e12, 3)
+            k['frac_of_fp32_peak'] = round(flops[name] / (avg * 1e-3) / 1e12 / fp32_peak, 4)
+        kernels.append(k)
+    dom = next((k for k in kernels if 'achieved_tflops' in k), None)
+    total_flops = sum(flops.values())
+    roofline = None
+    if dom is not None:
+        roofline = {'bound': 'fp32', 'kernel': dom['name'], 'achieved': dom['achieved_tflops'],
+                    'peak': round(fp32_peak, 2), 'unit': 'TFLOP/s', 'frac': dom['frac_of_fp32_peak'],
+                    'peak_source': 'FFMA microbenchmark (ancde_fp32_peak_kernel) measured in this run; '
+                                   'MEASURED_PEAKS.json holds no FP32 figure',
+                    'traffic': None,
+                    'step_frac': round(total_flops * args.steps / (ms * 1e-3) / 1e12 / fp32_peak, 4),
+                    'step_algorithmic_gflop': round(total_flops / 1e9, 2)}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, sec, cores = cpu_reference_samples_per_sec(args.workload, args.cpu_sample, 3, 1)
+        cpu = {'value': round(v, 2), 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+               'sample': '%d samples of the same workload, fwd+bwd, median of 3 after 1 warm-up (%.2f s each)'
+                         % (args.cpu_sample, sec)}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD_TEXT[args.workload], 'name': args.workload, 'batch_per_gpu': B,
+                   'global_batch': B * world, 'adjoint': bool(args.adjoint), 'optimizer': 'Adam (fused) inside the step',
+                   'parallelism': 'dp%d' % world,
+                   'l2': '%d distinct resident batches cycled; each step streams ~%.1f GB of saved activations '
+                         'through HBM (>> 126 MB L2)' % (n_res, saved_gb(cfg, B))},
+        'clocks': clk,
+        'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes[0],
+                'd2h_bytes_per_step': d2h_bytes[0], 'ms_per_step': ms_e2e / e2e_steps, 'steps': e2e_steps},
+        'gpu_launches': launches,
+        'roofline': roofline,
+        'kernels': kernels,
+        'cpu_baseline': cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def saved_gb(cfg, B):
+    stages = 4 * (cfg['L'] - 1)
+    c4 = lambda c: (c + 3) // 4 * 4
+    return stages * B * 4 * (cfg['H'] * c4(cfg['C']) + cfg['C'] * c4(cfg['C'])) / 1e9
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', default='sepsis', choices=sorted(WORKLOAD_TEXT))
+    ap.add_argument('--batch', type=int, default=None, help='samples per GPU (default: the workload\'s batch)')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--adjoint', action='store_true', help="reference's adjoint=True gradient flow")
+    ap.add_argument('--cpu-sample', type=int, default=512, help='samples per CPU-baseline step')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3
+    from ancde_b200 import synthetic
+    if args.batch is None:
+        args.batch = synthetic.CONFIGS[args.workload]['B']
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -127,6 +127,13 @@ int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream);
 /* Number of kernel launches the last forward / backward call of this thread issued. */
 int ancde_last_launch_count(void);
 
+/* Per-kernel timing for the roofline report: while enabled, every kernel launch of this library is
+ * bracketed by CUDA events on its stream.  After the caller has synchronised the stream,
+ * ancde_profile_get(i, ...) returns the name and duration (ms) of the i-th launch since enabling. */
+int ancde_profile_enable(int on);
+int ancde_profile_count(void);
+int ancde_profile_get(int i, char* name, size_t len, float* ms);
+
 /* FP32 FMA throughput microbenchmark (roofline denominator): launches a kernel of
  * dependent-free FFMA chains; returns the FLOP count it executes in *flops. */
 int ancde_fp32_peak_kernel(float* scratch, int iters, double* flops, void* stream);

@@ -180,7 +180,8 @@ def test_full_size_sepsis_batch_sharding_property():
         lo = model(times, tuple(c[:512] for c in coeffs) + (st[:512],), fi[:512], 1.0)
         hi = model(times, tuple(c[512:] for c in coeffs) + (st[512:],), fi[512:], 1.0)
     assert torch.isfinite(full).all()
-    assert torch.equal(full, torch.cat([lo, hi]))
+    # the torch linear layers in front of the solver are not batch-invariant to the last bit
+    assert (full - torch.cat([lo, hi])).abs().max().item() < 1e-6
 
 
 def test_api_errors():
