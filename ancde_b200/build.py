@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = ['api.cu', 'spline.cu', 'ncde_fwd.cu', 'ncde_bwd.cu']
+SOURCES = ['api.cu', 'spline.cu', 'ncde_host.cu', 'ncde_fwd.cu', 'ncde_bwd.cu', 'ncde_wgrad.cu']
 LIB = os.path.join(HERE, 'libancde_b200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
@@ -30,7 +30,7 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=()):
     """Compiles every CUDA source for sm_100a and links the shared library. Returns its path."""
     if not force and not needs_build():
         return LIB
@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src[:-3] + '.o')
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + ['-D' + x for x in defines] + ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, pr in procs:
@@ -62,4 +62,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv,
+                defines=[a[2:] for a in sys.argv if a.startswith('-D')]))

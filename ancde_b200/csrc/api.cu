@@ -45,6 +45,9 @@ void prof_end(cudaStream_t stream)
     ++g_prof_n;
 }
 
+static long long* g_dbg = nullptr;
+long long* debug_buffer() { return g_dbg; }
+
 // 8 independent FFMA chains per thread: the issue-bound FP32 peak of the SM (128 FMA/clk).
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters)
 {
@@ -68,6 +71,9 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters)
 }  // namespace ancde
 
 extern "C" int ancde_abi_version(void) { return 1; }
+
+// development aid: device buffer of 64 int64 counters for -DANCDE_PHASE_TIMING builds
+extern "C" int ancde_debug_set_buffer(long long* dev_ptr) { ancde::g_dbg = dev_ptr; return ANCDE_OK; }
 
 extern "C" int ancde_last_error(char* buf, size_t len)
 {

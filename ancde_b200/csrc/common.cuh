@@ -14,6 +14,7 @@ void reset_launch_count();
 // Optional per-kernel timing (CUDA events on the launching stream), see ancde_profile_* in the header.
 void prof_begin(const char* name, cudaStream_t stream);
 void prof_end(cudaStream_t stream);
+long long* debug_buffer();
 
 #define ANCDE_CHECK_ARG(cond, ...)                 \
     do {                                           \

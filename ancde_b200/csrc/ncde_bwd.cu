@@ -8,19 +8,22 @@
 //    (nothing is recomputed).  Hidden-layer weight gradients accumulate in shared memory; the
 //    cotangent of the attention (top NCDE, backprop mode) is reduced in shared memory and added
 //    to grad_attention.  The stage cotangent is written back over the saved stage input.
-//  * ncde_wgrad_kernel -- the non-recurrent part: dW_out[col][k] = sum over all (stage, sample)
-//    of pre_bar[col] * h_last[k] as a register-tiled FP32 GEMM over the saved tanh outputs
-//    (read exactly once), with the bias gradient folded in as an extra k column.
+//    Data movement: the saved activations of the next stage arrive by cp.async into a second
+//    buffer, the next tile of tanh outputs is pulled into L2 with a bulk prefetch, and an output
+//    layer that does not fit in shared memory is streamed through a TMA ring (k-contiguous copy).
+//  * ncde_wgrad_kernel (ncde_wgrad.cu) -- the non-recurrent output-layer weight gradient.
 //  * unpack_hidden_grads_kernel -- packed (transposed) hidden gradients -> torch layout.
 //
 // Matches autograd through torchdiffeq's rk4_alt_step_func + the reference vector fields
 // (cdeint_module.py:25-32,56-72,103-138; vector_fields.py:205-218,237-250) to FP32 round-off.
 #include "ncde_common.cuh"
+#include "pipeline.cuh"
 
 namespace ancde {
 
 int fill_args(const ancde_ncde_desc* d, const NcdeLayout& lo, SolveArgs* a);
 int pack_weights(const ancde_ncde_desc* d, const NcdeLayout& lo, cudaStream_t stream);
+int launch_wgrad(const SolveArgs& a, float* gW, float* gB, cudaStream_t stream);   // ncde_wgrad.cu
 
 // Sum of v[idx] over the 32 lanes of a warp for V values per lane in V/2 + V/4 + ... shuffles:
 // afterwards lane l holds the totals of idx = l*(V/32) .. +V/32-1 in v[0 .. V/32-1]  (V >= 32), or
@@ -48,30 +51,46 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&v)[V], int lane)
     }
 }
 
+__device__ __forceinline__ void cp_async16_b(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// WO_SMEM: the k-contiguous output-layer copy W_out[col][KPS] is resident in shared memory; otherwise it is
+// streamed from L2 through a ring of slots (32*NSPLIT columns each) by a producer warp.
 template <int TS, bool WO_SMEM>
 __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant__ SolveArgs p)
 {
     constexpr int VW = (TS >= 4) ? 4 : TS;
     constexpr int NQ = TS / VW;
     const NcdeLayout& lo = p.lo;
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NT = p.ntc;
+    const int NW = NT / 32;
     const int tile = blockIdx.x;
     const int b0 = tile * TS;
-    const int Hd = lo.Hd, C4 = lo.C4, NCH = lo.NCH, NCG = lo.NCG, NCP = lo.NCP, K = lo.K;
+    const int Hd = lo.Hd, C4 = lo.C4, NCH = lo.NCH, NCG = lo.NCG, NCP = lo.NCP, K = lo.K, KPS = lo.KPS, DUS = lo.DUS;
     const int NKG = (K + 7) / 8;
-    int NSPLIT = (NT / 32) / NKG;
+    int NSPLIT = NW / NKG;
     if (NSPLIT < 1) NSPLIT = 1;
+    const int CC = 32 * NSPLIT;                        // columns per phase-2 chunk
+    const int nchunks = (NCP + CC - 1) / CC;
+    const int NSLOT = p.ring_slots;
     const int HT = pad4(Hd * TS);
     const bool need_att = (lo.mode == ANCDE_MODE_TOP) && (p.grad_attention != nullptr);
+    const int64_t g_tile_f4 = (int64_t)TS * NCG;        // float4 per (stage, tile) block of saved tanh outputs
 
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* bar_empty = bar_full + 8;
+    float* smem = reinterpret_cast<float*>(smem_raw + 128);
     float* sHW = smem;                                   // hidden weights (packed, transposed)
     float* sGW = sHW + pad4(lo.hidden_floats);           // hidden weight-gradient accumulators
     float* sp = sGW + pad4(lo.hidden_floats);
-    float* sWo = sp;
-    if (WO_SMEM) sp += (size_t)K * NCP + NCP;
+    float* sWoT = sp;                                    // resident W_out[col][KPS], or the ring
+    sp += WO_SMEM ? (size_t)NCP * KPS : (size_t)NSLOT * CC * KPS;
     float* sPre = sp;   sp += (size_t)NCP * TS;          // [q][col][VW]
-    float* sAct = sp;   sp += lo.act_floats;             // saved activations of the stage
+    float* sActBuf = sp; sp += 2 * (size_t)lo.act_floats;   // saved activations, double buffered
     float* sG = sp;     sp += HT;                        // cotangent of the stage derivative
     float* sLam = sp;   sp += HT;                        // cotangent of z at the end of the step
     float* sMu = sp;    sp += HT;                        // pending cotangent of z at the start
@@ -83,6 +102,46 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     float* sHbPart = sp; sp += (size_t)NSPLIT * NKG * 8 * TS;
     float* sTmp = sp;                                    // [C4][TS]
 
+    if (!WO_SMEM) {
+        if (tid == 0) {
+            for (int s = 0; s < NSLOT; ++s) {
+                mbar_init(bar_full + s, 1);
+                mbar_init(bar_empty + s, NKG * NSPLIT);  // the warps that take part in phase 2
+            }
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (tid >= NT) {
+            // ---- producer warp: W_out[col][KPS] chunks through the ring + L2 prefetch of the tanh outputs
+            if (lane == 0) {
+                const float* Wg = p.wpack + lo.off_wot;
+                int slot = 0;
+                uint32_t phase = 1;
+                for (int n = lo.n_stages - 1; n >= 0; --n) {
+                    if (n >= 1)
+                        bulk_prefetch_l2(reinterpret_cast<const float4*>(p.save_G) + ((int64_t)(n - 1) * lo.ntiles + tile) * g_tile_f4,
+                                         (uint32_t)(g_tile_f4 * 16));
+                    for (int c = 0; c < nchunks; ++c) {
+                        mbar_wait(bar_empty + slot, phase);
+                        const int cols = (NCP - c * CC < CC) ? NCP - c * CC : CC;
+                        const uint32_t bytes = (uint32_t)(cols * KPS * 4);
+                        mbar_arrive_expect_tx(bar_full + slot, bytes);
+                        bulk_g2s(sWoT + (size_t)slot * CC * KPS, Wg + (size_t)c * CC * KPS, bytes, bar_full + slot);
+                        if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+                    }
+                }
+            }
+            return;
+        }
+    }
+    auto cta_sync = [&]() { named_bar_sync(1, NT); };
+    auto act_block = [&](int n) { return p.save_act + ((int64_t)n * lo.ntiles + tile) * lo.act_floats; };
+    auto issue_act = [&](int n, float* dst) {
+        const float* src = act_block(n);
+        for (int i = tid; i < lo.act_floats / 4; i += NT) cp_async16_b(dst + i * 4, src + i * 4);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+
     {
         const float4* src = reinterpret_cast<const float4*>(p.wpack);
         float4* dst = reinterpret_cast<float4*>(sHW);
@@ -92,16 +151,19 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
             dz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (WO_SMEM) {
-            const float4* s2 = reinterpret_cast<const float4*>(p.wpack + lo.off_wo);
-            float4* d2 = reinterpret_cast<float4*>(sWo);
-            for (int i = tid; i < (K * NCP + NCP) / 4; i += NT) d2[i] = __ldg(s2 + i);
+            const float4* s2 = reinterpret_cast<const float4*>(p.wpack + lo.off_wot);
+            float4* d2 = reinterpret_cast<float4*>(sWoT);
+            for (int i = tid; i < NCP * KPS / 4; i += NT) d2[i] = __ldg(s2 + i);
         }
         for (int item = tid; item < Hd * TS; item += NT) { sLam[item] = 0.f; sMu[item] = 0.f; }
+        issue_act(lo.n_stages - 1, sActBuf);
     }
-    __syncthreads();
-    const float* Wo = WO_SMEM ? sWo : (p.wpack + lo.off_wo);
+    cta_sync();
 
     int jb = lo.n_out - 1;   // last output time whose cotangent has not been consumed yet
+    int rslot = 0;           // ring slot / phase parity of the next fill to consume
+    uint32_t rphase = 0;
+    int abuf = 0;            // which half of sActBuf holds the current stage
 
     for (int k = lo.n_steps - 1; k >= 0; --k) {
         const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step);
@@ -109,12 +171,11 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
         const float dt = __fsub_rn(t1, t0);
         // ---- cotangents of the outputs emitted during this step: t_out[j] in (t0, t1]
         {
-            int j = jb;
             for (int item = tid; item < Hd * TS; item += NT) {
                 const int i = item / TS, b = item - i * TS;
                 const int bg = b0 + b;
                 float lam = sLam[item], mu = sMu[item];
-                for (j = jb; j >= 1; --j) {
+                for (int j = jb; j >= 1; --j) {
                     const float tj = __ldg(p.t_out + j);
                     if (!(tj > t0)) break;
                     const float g = (bg < lo.B) ? __ldg(p.grad_z_out + ((int64_t)j * lo.B + bg) * Hd + i) : 0.f;
@@ -130,12 +191,14 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
             }
             while (jb >= 1 && __ldg(p.t_out + jb) > t0) --jb;
         }
-        __syncthreads();
+        cta_sync();
 
 #pragma unroll 1
         for (int s = 3; s >= 0; --s) {
             const int n = 4 * k + s;
-            float* act = p.save_act + ((int64_t)n * lo.ntiles + tile) * lo.act_floats;
+            float* act = act_block(n);
+            float* sAct = sActBuf + (size_t)abuf * lo.act_floats;
+            PHASE_T0();
             // ---- cotangent of the stage derivative k_{s+1}  (transpose of rk4_alt_step_func)
             for (int item = tid; item < Hd * TS; item += NT) {
                 const float lam = sLam[item];
@@ -146,20 +209,21 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                 else g = dt * (0.125f * lam + sV4[item] + (sV2[item] - sV3[item]) * (1.0f / 3.0f));
                 sG[item] = g;
             }
-            // ---- saved activations of this stage -> shared memory
-            {
-                const float4* src = reinterpret_cast<const float4*>(act);
-                float4* dst = reinterpret_cast<float4*>(sAct);
-                for (int i = tid; i < lo.act_floats / 4; i += NT) dst[i] = __ldg(src + i);
-            }
-            __syncthreads();
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");     // saved activations of this stage have landed
+            cta_sync();
+            // prefetch the next stage's activations (this kernel walks n downwards); pull its tanh outputs into L2
+            if (n >= 1) issue_act(n - 1, sActBuf + (size_t)(abuf ^ 1) * lo.act_floats);
+            if (WO_SMEM && tid == 0 && n >= 1)
+                bulk_prefetch_l2(reinterpret_cast<const float4*>(p.save_G) + ((int64_t)(n - 1) * lo.ntiles + tile) * g_tile_f4,
+                                 (uint32_t)(g_tile_f4 * 16));
             // the stage cotangent replaces the saved stage input in HBM (read by the wgrad kernel);
             // the copy in sAct stays valid for the first hidden layer's weight gradient
             for (int item = tid; item < Hd * TS; item += NT) act[item] = sG[item];
 
             const float* sDU = sAct + lo.act_off_du;
-            // ---- phase 1: tanh outputs from HBM, pre-activation cotangent into shared memory
-            const float4* gbase = reinterpret_cast<const float4*>(p.save_G) + (((int64_t)n * lo.ntiles + tile) * TS) * NCG;
+            PHASE_MARK(8);    // stage cotangent + saved activations
+            // ---- phase 1: tanh outputs, pre-activation cotangent into shared memory
+            const float4* gbase = reinterpret_cast<const float4*>(p.save_G) + ((int64_t)n * lo.ntiles + tile) * g_tile_f4;
             if (need_att) {
                 // cotangent of dU: dUbar[j][b] = sum_i gbar[i][b] * G[i][j][b]; the products go through
                 // shared memory (same layout as pre_bar) and are reduced over the rows i
@@ -184,7 +248,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                             Vec<VW>::st(sPre + ((size_t)q * NCP + cg * 4 + c) * VW, v);
                         }
                 }
-                __syncthreads();
+                cta_sync();
                 for (int item = tid; item < C4 * NQ; item += NT) {
                     const int q = item / C4, j = item - q * C4;
                     float acc[VW];
@@ -197,12 +261,12 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                         for (int e = 0; e < VW; ++e) acc[e] += v[e];
                     }
                     float du[VW];
-                    Vec<VW>::ld(sAct + lo.act_off_duda + j * TS + q * VW, du);
+                    Vec<VW>::ld(sAct + lo.act_off_duda + du_index(j, q * VW, TS, DUS), du);
 #pragma unroll
                     for (int e = 0; e < VW; ++e) acc[e] *= du[e];
                     Vec<VW>::st(sTmp + j * TS + q * VW, acc);
                 }
-                __syncthreads();
+                cta_sync();
             }
             for (int cg = tid; cg < NCG; cg += NT) {
                 const int i = cg / NCH, chunk = cg - i * NCH;
@@ -220,7 +284,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         float du[VW], v[VW];
-                        Vec<VW>::ld(sDU + (chunk * 4 + c) * TS + q * VW, du);
+                        Vec<VW>::ld(sDU + chunk * DUS + c * TS + q * VW, du);
 #pragma unroll
                         for (int e = 0; e < VW; ++e) {
                             const float gg = g[q * VW + e][c];
@@ -229,7 +293,8 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                         Vec<VW>::st(sPre + ((size_t)q * NCP + cg * 4 + c) * VW, v);
                     }
             }
-            __syncthreads();
+            cta_sync();
+            PHASE_MARK(9);    // phase 1: G -> pre_bar (+ attention products)
             // ---- cotangent of the attention: a[q] += dUbar * dU/da   
             if (need_att) {
                 const float ts = stage_time(t0, dt, s);
@@ -250,23 +315,40 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                     }
                 }
             }
-            // ---- phase 2: hbar[k][b] = sum_col pre_bar[col][b] * Wt_out[k][col]
+            PHASE_MARK(10);   // attention atomics
+            // ---- phase 2: hbar[k][b] = sum_col pre_bar[col][b] * W_out[col][k]; warp = (k group, column split)
             if (warp < NKG * NSPLIT) {
                 const int kg = warp % NKG, split = warp / NKG;
                 float acc[8 * TS];
 #pragma unroll
                 for (int i = 0; i < 8 * TS; ++i) acc[i] = 0.f;
-                for (int col = split * 32 + lane; col < NCP; col += 32 * NSPLIT) {
-                    float pv[TS];
+                for (int c = 0; c < nchunks; ++c) {
+                    const int col = c * CC + split * 32 + lane;
+                    const float* wrow;
+                    int slot = 0;
+                    if (WO_SMEM) {
+                        wrow = sWoT + (size_t)(col < NCP ? col : 0) * KPS + kg * 8;
+                    } else {
+                        slot = rslot;
+                        mbar_wait(bar_full + slot, rphase);
+                        wrow = sWoT + ((size_t)slot * CC + split * 32 + lane) * KPS + kg * 8;
+                    }
+                    if (col < NCP) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(wrow);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wrow + 4);
+                        float pv[TS];
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) Vec<VW>::ld(sPre + ((size_t)q * NCP + col) * VW, pv + q * VW);
+                        for (int q = 0; q < NQ; ++q) Vec<VW>::ld(sPre + ((size_t)q * NCP + col) * VW, pv + q * VW);
+                        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        const int kr = kg * 8 + kk;
-                        float w = 0.f;
-                        if (kr < K) w = WO_SMEM ? Wo[(size_t)kr * NCP + col] : __ldg(Wo + (size_t)kr * NCP + col);
+                        for (int kk = 0; kk < 8; ++kk)
 #pragma unroll
-                        for (int b = 0; b < TS; ++b) acc[kk * TS + b] = fmaf(w, pv[b], acc[kk * TS + b]);
+                            for (int b = 0; b < TS; ++b) acc[kk * TS + b] = fmaf(wv[kk], pv[b], acc[kk * TS + b]);
+                    }
+                    if (!WO_SMEM) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_empty + slot);
+                        if (++rslot == NSLOT) { rslot = 0; rphase ^= 1; }
                     }
                 }
                 warp_reduce_scatter<8 * TS>(acc, lane);
@@ -281,8 +363,13 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                     constexpr int per = 32 / V;
                     if (lane % per == 0) sHbPart[((size_t)split * NKG + kg) * V + lane / per] = acc[0];
                 }
+            } else if (!WO_SMEM) {
+                // warps without a phase-2 role still track the ring position
+                for (int c = 0; c < nchunks; ++c)
+                    if (++rslot == NSLOT) { rslot = 0; rphase ^= 1; }
             }
-            __syncthreads();
+            cta_sync();
+            PHASE_MARK(11);   // phase 2: pre_bar x W_out + reduce + barrier
             // ---- phase 3: hidden layers backwards
             float* hb = sHb0;
             float* hb_next = sHb1;
@@ -302,49 +389,82 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                     }
                     hb[item] = (hl[item] > 0.f) ? v : 0.f;
                 }
-                __syncthreads();
+                cta_sync();
                 const float* inl = (l == 0) ? sAct : sAct + lo.act_off_h[l - 1];
-                // weight / bias gradient accumulators: dWt[k][o] += sum_b delta[o][b] * in[k][b]
-                for (int item = tid; item < Kin * N; item += NT) {
-                    const int kk = item / N, o = item - kk * N;
-                    float acc = 0.f;
+                const int NWA = (NW >= 2) ? NW / 2 : NW;     // warps [0, NWA): input gradient; the rest: weight gradient
+                if (warp < NWA || NW < 2) {
+                    // cotangent of the layer input: hb_next[k][b] = sum_o Wt[k][o] * delta[o][b]; KS adjacent lanes
+                    // split the sum over o and combine with shuffles
+                    const int nitems = Kin * NQ;
+                    int KS = 4;
+                    while (KS > 1 && nitems * KS > NWA * 32) KS >>= 1;
+                    const int ks = tid & (KS - 1);
+                    const int per = (NWA * 32) / KS;
+                    const int OL = (N + KS - 1) / KS;
+                    const int obeg = ks * OL;
+                    int ocnt = N - obeg;
+                    ocnt = ocnt > OL ? OL : ocnt;
+                    const float* Wt = sHW + lo.off_w[l];
+                    for (int base = 0; base < nitems; base += per) {
+                        const int item = base + tid / KS;
+                        const bool valid = item < nitems;
+                        int q = 0, kk = valid ? item : 0;
+                        if (NQ > 1 && kk >= Kin) { q = 1; kk -= Kin; }
+                        float acc[VW];
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        float dv[VW], iv[VW];
-                        Vec<VW>::ld(hb + o * TS + q * VW, dv);
-                        Vec<VW>::ld(inl + kk * TS + q * VW, iv);
-#pragma unroll
-                        for (int e = 0; e < VW; ++e) acc = fmaf(dv[e], iv[e], acc);
-                    }
-                    sGW[lo.off_w[l] + kk * S + o] += acc;
-                }
-                for (int o = tid; o < N; o += NT) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int b = 0; b < TS; ++b) acc += hb[o * TS + b];
-                    sGW[lo.off_b[l] + o] += acc;
-                }
-                // cotangent of the layer input: hb_next[k][b] = sum_o Wt[k][o] * delta[o][b]
-                const float* Wt = sHW + lo.off_w[l];
-                for (int item = tid; item < Kin * NQ; item += NT) {
-                    const int q = item / Kin, kk = item - q * Kin;
-                    float acc[VW];
-#pragma unroll
-                    for (int e = 0; e < VW; ++e) acc[e] = 0.f;
-                    const float* wp = Wt + kk * S;
+                        for (int e = 0; e < VW; ++e) acc[e] = 0.f;
+                        if (valid) {
+                            const float* wp = Wt + kk * S + obeg;
+                            const float* dp = hb + obeg * TS + q * VW;
 #pragma unroll 4
-                    for (int o = 0; o < N; ++o) {
-                        const float w = wp[o];
-                        float dv[VW];
-                        Vec<VW>::ld(hb + o * TS + q * VW, dv);
+                            for (int o = 0; o < ocnt; ++o) {
+                                const float w = *wp;
+                                float dv[VW];
+                                Vec<VW>::ld(dp, dv);
+                                ++wp;
+                                dp += TS;
 #pragma unroll
-                        for (int e = 0; e < VW; ++e) acc[e] = fmaf(w, dv[e], acc[e]);
+                                for (int e = 0; e < VW; ++e) acc[e] = fmaf(w, dv[e], acc[e]);
+                            }
+                        }
+                        for (int m = KS >> 1; m >= 1; m >>= 1)
+#pragma unroll
+                            for (int e = 0; e < VW; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], m);
+                        if (valid && ks == 0) Vec<VW>::st(hb_next + kk * TS + q * VW, acc);
                     }
-                    Vec<VW>::st(hb_next + kk * TS + q * VW, acc);
                 }
-                __syncthreads();
+                if (warp >= NWA || NW < 2) {
+                    // weight / bias gradient accumulators: dWt[k][o] += sum_b delta[o][b] * in[k][b]
+                    const int w0 = (NW < 2) ? 0 : NWA, nw = (NW < 2) ? 1 : NW - NWA;
+                    for (int kk = warp - w0; kk < Kin; kk += nw) {
+                        float iv[TS];
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) Vec<VW>::ld(inl + kk * TS + q * VW, iv + q * VW);
+                        for (int o = lane; o < N; o += 32) {
+                            float acc = 0.f;
+#pragma unroll
+                            for (int q = 0; q < NQ; ++q) {
+                                float dv[VW];
+                                Vec<VW>::ld(hb + o * TS + q * VW, dv);
+#pragma unroll
+                                for (int e = 0; e < VW; ++e) acc = fmaf(dv[e], iv[q * VW + e], acc);
+                            }
+                            sGW[lo.off_w[l] + kk * S + o] += acc;
+                        }
+                    }
+                    if (warp == w0) {
+                        for (int o = lane; o < N; o += 32) {
+                            float acc = 0.f;
+#pragma unroll
+                            for (int b = 0; b < TS; ++b) acc += hb[o * TS + b];
+                            sGW[lo.off_b[l] + o] += acc;
+                        }
+                    }
+                }
+                cta_sync();
                 float* t = hb; hb = hb_next; hb_next = t;
             }
+            PHASE_MARK(12);   // phase 3: hidden layers
             // hb now holds the cotangent of the stage input
             for (int item = tid; item < Hd * TS; item += NT) {
                 const float v = hb[item];
@@ -356,7 +476,9 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                     sMu[item] = 0.f;
                 }
             }
-            __syncthreads();
+            abuf ^= 1;
+            cta_sync();
+            PHASE_MARK(13);   // RK4 adjoint combine + barrier
         }
     }
     // ---- results
@@ -368,109 +490,6 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     for (int i = tid; i < lo.hidden_floats; i += NT) {
         const float v = sGW[i];
         if (v != 0.f) atomicAdd(p.grad_hidden + i, v);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Output-layer weight gradient: a GEMM whose reduction runs over every (stage, tile, sample) row.
-// CTA = 32 column groups (128 columns) x all k; thread = 4 columns x 8 k; rows are staged through
-// shared memory in chunks of one (stage, tile) block at a time.
-// ---------------------------------------------------------------------------------------------
-constexpr int WG_CG = 32;        // column groups per CTA
-constexpr int WG_MAXKG = 16;     // k groups of 8 (K + 1 bias column <= 128)
-
-template <int TS>
-__global__ void __launch_bounds__(512) ncde_wgrad_kernel(const __grid_constant__ SolveArgs p, float* gW, float* gB,
-                                                         int blocks_per_cta)
-{
-    constexpr int VW = (TS >= 4) ? 4 : TS;
-    constexpr int NQ = TS / VW;
-    const NcdeLayout& lo = p.lo;
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, kg = tid >> 5;
-    const int Hd = lo.Hd, C4 = lo.C4, NCH = lo.NCH, NCG = lo.NCG, K = lo.K, C = lo.C;
-    const int NKG = (K + 1 + 7) / 8;        // + the bias column
-    const int KP = NKG * 8;
-    const int cg0 = blockIdx.x * WG_CG;
-    const int cg = cg0 + lane;
-    const bool cg_ok = cg < NCG;
-    const int i_row = cg_ok ? cg / NCH : 0;
-    const int chunk = cg_ok ? cg - i_row * NCH : 0;
-
-    extern __shared__ __align__(16) float smem[];
-    float* sP = smem;                         // [TS][WG_CG*4] pre_bar of this block
-    float* sH = sP + TS * WG_CG * 4;          // [TS][KP] last hidden activation (+1.0 bias column)
-    float* sGb = sH + TS * KP;                // [Hd][TS] stage cotangent
-    float* sDU = sGb + pad4(Hd * TS);         // [C4][TS]
-
-    float acc[4][8];
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) acc[c][kk] = 0.f;
-
-    const int64_t nblocks = (int64_t)lo.n_stages * lo.ntiles;
-    const int64_t blk0 = (int64_t)blockIdx.y * blocks_per_cta;
-    int64_t blk1 = blk0 + blocks_per_cta;
-    if (blk1 > nblocks) blk1 = nblocks;
-    const float* hl_off = nullptr;
-    for (int64_t blk = blk0; blk < blk1; ++blk) {
-        const float* act = p.save_act + blk * lo.act_floats;
-        // stage cotangent, dU, last hidden activation
-        for (int item = tid; item < Hd * TS; item += NT) sGb[item] = __ldg(act + item);
-        for (int item = tid; item < C4 * TS; item += NT) sDU[item] = __ldg(act + lo.act_off_du + item);
-        hl_off = act + lo.act_off_h[lo.n_hidden - 1];
-        for (int item = tid; item < TS * KP; item += NT) {
-            const int b = item / KP, kk = item - b * KP;
-            float v = 0.f;
-            if (kk < K) v = __ldg(hl_off + kk * TS + b);
-            else if (kk == K) v = 1.0f;
-            sH[item] = v;
-        }
-        __syncthreads();
-        // pre_bar for this CTA's 128 columns (warp 0..: every warp computes a share of the samples)
-        for (int b = kg; b < TS; b += NT / 32) {
-            float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (cg_ok) {
-                const float4 g = __ldg(reinterpret_cast<const float4*>(p.save_G) + (blk * TS + b) * NCG + cg);
-                const float gb = sGb[i_row * TS + b];
-                pv.x = gb * sDU[(chunk * 4 + 0) * TS + b] * fmaf(-g.x, g.x, 1.0f);
-                pv.y = gb * sDU[(chunk * 4 + 1) * TS + b] * fmaf(-g.y, g.y, 1.0f);
-                pv.z = gb * sDU[(chunk * 4 + 2) * TS + b] * fmaf(-g.z, g.z, 1.0f);
-                pv.w = gb * sDU[(chunk * 4 + 3) * TS + b] * fmaf(-g.w, g.w, 1.0f);
-            }
-            *reinterpret_cast<float4*>(sP + (b * WG_CG + lane) * 4) = pv;
-        }
-        __syncthreads();
-        if (kg < NKG) {
-#pragma unroll
-            for (int b = 0; b < TS; ++b) {
-                const float4 pv = *reinterpret_cast<const float4*>(sP + (b * WG_CG + lane) * 4);
-                const float4 h0 = *reinterpret_cast<const float4*>(sH + b * KP + kg * 8);
-                const float4 h1 = *reinterpret_cast<const float4*>(sH + b * KP + kg * 8 + 4);
-                const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                const float pc[4] = {pv.x, pv.y, pv.z, pv.w};
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) acc[c][kk] = fmaf(pc[c], hv[kk], acc[c][kk]);
-            }
-        }
-        __syncthreads();
-    }
-    (void)NQ;
-    if (cg_ok && kg < NKG) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int j = chunk * 4 + c;
-            if (j >= C) continue;
-            const int row = i_row * C + j;           // row of the torch (Hd*C, K) weight
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-                const int kr = kg * 8 + kk;
-                if (kr < K) atomicAdd(gW + (int64_t)row * K + kr, acc[c][kk]);
-                else if (kr == K) atomicAdd(gB + row, acc[c][kk]);
-            }
-        }
     }
 }
 
@@ -497,7 +516,7 @@ __global__ void unpack_hidden_grads_kernel(const __grid_constant__ UnpackArgs a)
 
 static int bwd_threads(const NcdeLayout& lo)
 {
-    int per = (lo.NCG + 511) / 512;
+    int per = (lo.NCG + 447) / 448;
     int nt = round_up((lo.NCG + per - 1) / per, 32);
     const int NKG = (lo.K + 7) / 8;
     if (nt < NKG * 32) nt = NKG * 32;
@@ -505,23 +524,31 @@ static int bwd_threads(const NcdeLayout& lo)
     return nt;
 }
 
-size_t bwd_smem_floats(const NcdeLayout& lo, bool wo_smem, int nt)
+// shared memory (bytes) of the backward without the output-layer weights / ring
+static size_t bwd_smem_base(const NcdeLayout& lo, int nt)
 {
     const int NKG = (lo.K + 7) / 8;
     int nsplit = (nt / 32) / NKG;
     if (nsplit < 1) nsplit = 1;
     size_t f = 2 * (size_t)pad4(lo.hidden_floats);
-    if (wo_smem) f += (size_t)lo.K * lo.NCP + lo.NCP;
-    f += (size_t)lo.NCP * lo.TS + lo.act_floats + 6 * (size_t)pad4(lo.Hd * lo.TS) + 2 * (size_t)pad4(lo.Hmax * lo.TS) +
-         (size_t)nsplit * NKG * 8 * lo.TS + (size_t)lo.C4 * lo.TS;
-    return f;
+    f += (size_t)lo.NCP * lo.TS + 2 * (size_t)lo.act_floats + 6 * (size_t)pad4(lo.Hd * lo.TS) +
+         2 * (size_t)pad4(lo.Hmax * lo.TS) + (size_t)nsplit * NKG * 8 * lo.TS + (size_t)lo.C4 * lo.TS;
+    return f * 4 + 128;
+}
+
+static size_t bwd_ring_bytes(const NcdeLayout& lo, int nt, int slots)
+{
+    const int NKG = (lo.K + 7) / 8;
+    int nsplit = (nt / 32) / NKG;
+    if (nsplit < 1) nsplit = 1;
+    return (size_t)slots * 32 * nsplit * lo.KPS * 4;
 }
 
 // Used by make_layout's tile-size choice: does the backward fit with this many samples per CTA?
 bool bwd_fits(const NcdeLayout& lo)
 {
     const int nt = bwd_threads(lo);
-    return nt <= 512 && bwd_smem_floats(lo, false, nt) * 4 <= 227 * 1024;
+    return nt <= 480 && bwd_smem_base(lo, nt) + bwd_ring_bytes(lo, nt, 2) <= 227 * 1024;
 }
 
 template <int TS>
@@ -530,56 +557,51 @@ static int launch_bwd(const ancde_ncde_desc* d, SolveArgs& a, cudaStream_t strea
     const NcdeLayout& lo = a.lo;
     const int nt = bwd_threads(lo);
     const size_t max_smem = 227 * 1024;
-    if (nt > 512) {
-        set_error("ncde_backward: needs %d threads per CTA (max 512)", nt);
+    if (nt > 480) {
+        set_error("ncde_backward: needs %d threads per CTA (max 480)", nt);
         return ANCDE_EUNSUPPORTED;
     }
-    const bool wo_smem = bwd_smem_floats(lo, true, nt) * 4 <= max_smem;
-    const size_t smem = bwd_smem_floats(lo, wo_smem, nt) * 4;
-    if (smem > max_smem) {
-        set_error("ncde_backward: needs %zu bytes of shared memory per CTA (max %zu)", smem, max_smem);
-        return ANCDE_EUNSUPPORTED;
+    const size_t base = bwd_smem_base(lo, nt);
+    const bool wo_smem = base + (size_t)lo.NCP * lo.KPS * 4 <= max_smem;
+    size_t smem;
+    int threads = nt;
+    a.ntc = nt;
+    a.ring_kc = 0; a.ring_pw = 0;
+    if (wo_smem) {
+        a.ring_slots = 1;
+        smem = base + (size_t)lo.NCP * lo.KPS * 4;
+    } else {
+        int slots = 4;
+        while (slots > 2 && base + bwd_ring_bytes(lo, nt, slots) > max_smem) --slots;
+        smem = base + bwd_ring_bytes(lo, nt, slots);
+        if (smem > max_smem) {
+            set_error("ncde_backward: needs %zu bytes of shared memory per CTA (max %zu)", smem, max_smem);
+            return ANCDE_EUNSUPPORTED;
+        }
+        a.ring_slots = slots;
+        threads = nt + 32;
     }
     // hidden-gradient scratch lives behind the packed weights
     a.grad_hidden = d->wpack + lo.wpack_floats;
     ANCDE_CUDA(cudaMemsetAsync(a.grad_hidden, 0, sizeof(float) * pad4(lo.hidden_floats), stream));
     static const char* names[3] = {"ncde_bwd_plain", "ncde_bwd_bottom", "ncde_bwd_top"};
-    static const char* wnames[3] = {"ncde_wgrad_plain", "ncde_wgrad_bottom", "ncde_wgrad_top"};
     if (wo_smem) {
         ANCDE_CUDA(cudaFuncSetAttribute(ncde_bwd_kernel<TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         prof_begin(names[lo.mode], stream);
-        ncde_bwd_kernel<TS, true><<<lo.ntiles, nt, smem, stream>>>(a);
+        ncde_bwd_kernel<TS, true><<<lo.ntiles, threads, smem, stream>>>(a);
     } else {
         ANCDE_CUDA(cudaFuncSetAttribute(ncde_bwd_kernel<TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         prof_begin(names[lo.mode], stream);
-        ncde_bwd_kernel<TS, false><<<lo.ntiles, nt, smem, stream>>>(a);
+        ncde_bwd_kernel<TS, false><<<lo.ntiles, threads, smem, stream>>>(a);
     }
     prof_end(stream);
     count_launch();
     ANCDE_CUDA(cudaGetLastError());
 
-    // output-layer weight gradient
+    // output-layer weight gradient (reads the stage cotangents the kernel above left in save_act)
     {
-        const int NKG = (lo.K + 1 + 7) / 8;
-        if (NKG > WG_MAXKG) {
-            set_error("ncde_backward: last hidden width %d too large for the wgrad kernel", lo.K);
-            return ANCDE_EUNSUPPORTED;
-        }
-        const int KP = NKG * 8;
-        const int nthreads = NKG * 32 < 64 ? 64 : NKG * 32;
-        const int gx = (lo.NCG + WG_CG - 1) / WG_CG;
-        const int64_t nblocks = (int64_t)lo.n_stages * lo.ntiles;
-        int64_t gy = (148 * 4 + gx - 1) / gx;
-        if (gy > nblocks) gy = nblocks;
-        const int per = (int)((nblocks + gy - 1) / gy);
-        gy = (nblocks + per - 1) / per;
-        const size_t sm = sizeof(float) * ((size_t)TS * WG_CG * 4 + (size_t)TS * KP + pad4(lo.Hd * TS) + (size_t)lo.C4 * TS);
-        prof_begin(wnames[lo.mode], stream);
-        ncde_wgrad_kernel<TS><<<dim3(gx, (unsigned)gy), nthreads, sm, stream>>>(a, d->grad_W[lo.n_hidden],
-                                                                               d->grad_bias[lo.n_hidden], per);
-        prof_end(stream);
-        count_launch();
-        ANCDE_CUDA(cudaGetLastError());
+        const int rc = launch_wgrad(a, d->grad_W[lo.n_hidden], d->grad_bias[lo.n_hidden], stream);
+        if (rc != ANCDE_OK) return rc;
     }
     {
         UnpackArgs ua;

@@ -64,6 +64,9 @@ __device__ __forceinline__ float stage_time(float t0, float dt, int s)
     return __fadd_rn(t0, dt);
 }
 
+// Index of control channel j, sample b inside a dU block (see NcdeLayout::DUS).
+__device__ __forceinline__ int du_index(int j, int b, int TS, int DUS) { return (j >> 2) * DUS + (j & 3) * TS + b; }
+
 struct SolveArgs {
     NcdeLayout lo;
     float t_start, t_end, step;
@@ -85,6 +88,28 @@ struct SolveArgs {
     float* grad_z0;
     float* grad_attention;
     float* grad_hidden;     // packed like the hidden part of wpack (Wt layout), accumulated with atomics
+    // launch-time tiling of the output-layer weight stream (filled by the launchers)
+    int ntc;                // consumer threads per CTA (a TMA producer warp may sit behind them)
+    int ring_kc;            // k rows per ring slot
+    int ring_slots;         // ring depth
+    int ring_pw;            // floats per row in a slot (columns of one pass)
+    long long* dbg;         // phase timing buffer (only read when built with -DANCDE_PHASE_TIMING)
 };
+
+// Phase timing for kernel development: thread 0 of CTA 0 accumulates clock64() deltas per phase.
+#ifdef ANCDE_PHASE_TIMING
+#define PHASE_T0() long long pt__ = clock64()
+#define PHASE_MARK(i)                                                      \
+    do {                                                                   \
+        if (threadIdx.x == 0 && blockIdx.x == 0 && p.dbg) {                \
+            const long long now__ = clock64();                             \
+            p.dbg[i] += now__ - pt__;                                      \
+            pt__ = now__;                                                  \
+        }                                                                  \
+    } while (0)
+#else
+#define PHASE_T0() do { } while (0)
+#define PHASE_MARK(i) do { } while (0)
+#endif
 
 }  // namespace ancde

@@ -8,10 +8,13 @@
 //   3. runs the output layer in register tiles (4 columns x TS samples per thread), applies
 //      tanh and contracts the (Hd x C) field with dU,          [vector_fields.py:216-218, cdeint_module.py:61,133]
 //   4. combines the stage into the RK4 recurrence              [torchdiffeq rk4_alt_step_func]
-// Weights are packed once per call (transposed, padded) and kept in shared memory; only an
-// output layer too large for the 227 KB of one SM (Sepsis: 1715x49, 3381x49) is streamed from
-// L2 with coalesced 128-bit loads.  Plain FP32 FMA throughout (north-star tolerance 1e-4).
+// Hidden-layer weights are packed once per call (transposed, padded) and stay in shared memory.
+// The output-layer weights stay there too when they fit; the Sepsis-size layers (1715x49 / 3381x49
+// floats > 227 KB) are streamed from L2 instead: a producer warp keeps a ring of shared-memory
+// slots full with TMA bulk copies (cp.async.bulk + mbarrier) that run ahead of the consumers, so
+// the FMA loop only ever reads shared memory.  Plain FP32 FMA (north-star tolerance 1e-4).
 #include "ncde_common.cuh"
+#include "pipeline.cuh"
 
 namespace ancde {
 
@@ -41,7 +44,7 @@ __device__ __forceinline__ void ctl_issue(const SolveArgs& p, const float* sTime
     int q = (int)floorf(ts) - 1;                      // attention[int(floor(t)) - 1], python wrap
     if (q < 0) q += lo.att_L;
     q = q < 0 ? 0 : (q >= lo.att_L ? lo.att_L - 1 : q);
-    const int m = n % (lo.n_hp - 1);                  // call counter with the reset rule (:134-137)
+    const int m = (lo.mode == ANCDE_MODE_TOP) ? n % (lo.n_hp - 1) : 0;   // call counter + reset rule (:134-137)
 #pragma unroll
     for (int it = 0; it < CTL_ITEMS; ++it) {
         const int item = tid + it * NT;
@@ -85,16 +88,18 @@ __device__ __forceinline__ void ctl_finish(const SolveArgs& p, const CtlRegs& r,
                                __fmul_rn(__fmul_rn(__fmul_rn(a, __fsub_rn(1.0f, a)), dX), hp));
                 duda = dX * (1.0f + (1.0f - 2.0f * a) * hp);
             }
-            sDU[j * TS + b] = dU;
+            const int di = du_index(j, b, TS, lo.DUS);
+            sDU[di] = dU;
             if (act) {
-                act[lo.act_off_du + j * TS + b] = dU;
-                if (lo.mode == ANCDE_MODE_TOP) act[lo.act_off_duda + j * TS + b] = duda;
+                act[lo.act_off_du + di] = dU;
+                if (lo.mode == ANCDE_MODE_TOP) act[lo.act_off_duda + di] = duda;
             }
         }
     }
 }
 
-// out[o][.] = relu(bias[o] + sum_k Wt[k][o] * in[k][.]) for all TS samples.
+// out[o][.] = relu(bias[o] + sum_k Wt[k][o] * in[k][.]) for all TS samples; one (output, group of VW samples)
+// per thread.  The layers are tiny (<= 49x49) and latency bound: few threads, no index arithmetic.
 template <int TS>
 __device__ __forceinline__ void dense_relu(const float* __restrict__ Wt, const float* __restrict__ bias, int K,
                                            int N, int S, const float* __restrict__ in, float* __restrict__ out,
@@ -102,45 +107,57 @@ __device__ __forceinline__ void dense_relu(const float* __restrict__ Wt, const f
 {
     constexpr int VW = (TS >= 4) ? 4 : TS;
     constexpr int NQ = TS / VW;
-    for (int item = tid; item < N * NQ; item += NT) {
-        const int q = item / N, o = item - q * N;
+    for (int o = tid; o < N * NQ; o += NT) {
+        int q = 0, oo = o;
+        if (NQ > 1 && oo >= N) { q = 1; oo -= N; }
         float acc[VW];
-        const float bv = bias[o];
+        const float bv = bias[oo];
 #pragma unroll
         for (int e = 0; e < VW; ++e) acc[e] = bv;
-        const float* wp = Wt + o;
+        const float* wp = Wt + oo;
         const float* ip = in + q * VW;
-#pragma unroll 4
+#pragma unroll 7
         for (int k = 0; k < K; ++k) {
-            const float w = wp[k * S];
+            const float w = *wp;
             float v[VW];
-            Vec<VW>::ld(ip + k * TS, v);
+            Vec<VW>::ld(ip, v);
+            wp += S;
+            ip += TS;
 #pragma unroll
             for (int e = 0; e < VW; ++e) acc[e] = fmaf(w, v[e], acc[e]);
         }
 #pragma unroll
         for (int e = 0; e < VW; ++e) acc[e] = fmaxf(acc[e], 0.f);
-        Vec<VW>::st(out + o * TS + q * VW, acc);
-        if (gsave) Vec<VW>::st(gsave + o * TS + q * VW, acc);
+        Vec<VW>::st(out + oo * TS + q * VW, acc);
+        if (gsave) Vec<VW>::st(gsave + oo * TS + q * VW, acc);
     }
 }
 
+// WO_SMEM: output-layer weights resident in shared memory; otherwise streamed through the TMA ring.
 template <int TS, bool WO_SMEM>
 __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant__ SolveArgs p)
 {
     constexpr int VW = (TS >= 4) ? 4 : TS;
     constexpr int NQ = TS / VW;
     const NcdeLayout& lo = p.lo;
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int NT = p.ntc;                         // consumer threads (the producer warp, if any, sits behind them)
     const int tile = blockIdx.x;
     const int b0 = tile * TS;
     const int Hd = lo.Hd, C4 = lo.C4, NCH = lo.NCH, NCG = lo.NCG, NCP = lo.NCP, K = lo.K;
+    const int KC = p.ring_kc, NSLOT = p.ring_slots, PW = p.ring_pw;
+    const int npass = (NCG + NT - 1) / NT;        // column groups are walked NT at a time
+    const int nchunks = (K + KC - 1) / KC;
 
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw);      // [NSLOT]
+    uint64_t* bar_empty = bar_full + 8;                              // [NSLOT]
+    float* smem = reinterpret_cast<float*>(smem_raw + 128);
     float* sHW = smem;                                   // hidden weights + biases (packed)
     float* sp = sHW + pad4(lo.hidden_floats);
-    float* sWo = sp;                                     // output layer (only if it fits)
-    if (WO_SMEM) sp += (size_t)K * NCP + NCP;
+    float* sBo = sp;    sp += NCP;                       // output-layer bias
+    float* sWo = sp;                                     // output-layer weights, or the streaming ring
+    sp += WO_SMEM ? (size_t)K * NCP : (size_t)NSLOT * KC * PW;
     float* sTimes = sp; sp += pad4(lo.L);
     float* sIn = sp;    sp += pad4(Hd * TS);             // stage input z_s      [i][TS]
     float* sA0 = sp;    sp += pad4(lo.Hmax * TS);        // activations ping
@@ -149,18 +166,56 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
     float* sK1 = sp;    sp += pad4(Hd * TS);
     float* sK2 = sp;    sp += pad4(Hd * TS);
     float* sK3 = sp;    sp += pad4(Hd * TS);
-    float* sDU = sp;    sp += 2 * pad4(C4 * TS);         // control increment, double buffered [j][TS]
+    float* sDU = sp;    sp += 2 * lo.du_floats;          // control increment, double buffered [chunk][4][TS]
     float* sPart = sp;                                   // per column-group partial dot products
+
+    if (!WO_SMEM) {
+        if (tid == 0) {
+            for (int s = 0; s < NSLOT; ++s) {
+                mbar_init(bar_full + s, 1);              // one arrive.expect_tx per fill
+                mbar_init(bar_empty + s, NT / 32);       // one arrive per consumer warp
+            }
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (tid >= NT) {
+            // ---- producer warp: streams Wt_out[k][pass columns] through the ring, always ahead
+            if (lane == 0) {
+                const float* Wg = p.wpack + lo.off_wo;
+                int slot = 0;
+                uint32_t phase = 1;
+                for (int n = 0; n < lo.n_stages; ++n)
+                    for (int pass = 0; pass < npass; ++pass) {
+                        const int col0 = pass * NT * 4;
+                        const int pw = (NCP - col0 < PW) ? NCP - col0 : PW;
+                        for (int c = 0; c < nchunks; ++c) {
+                            mbar_wait(bar_empty + slot, phase);
+                            const int rows = (K - c * KC < KC) ? K - c * KC : KC;
+                            mbar_arrive_expect_tx(bar_full + slot, (uint32_t)(rows * pw * 4));
+                            float* dst = sWo + (size_t)slot * KC * PW;
+                            for (int r = 0; r < rows; ++r)
+                                bulk_g2s(dst + (size_t)r * PW, Wg + (size_t)(c * KC + r) * NCP + col0, (uint32_t)(pw * 4),
+                                         bar_full + slot);
+                            if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+                        }
+                    }
+            }
+            return;
+        }
+    }
+    auto cta_sync = [&]() { named_bar_sync(1, NT); };
 
     // ---- prologue: weights, knot times, initial state
     {
         const float4* src = reinterpret_cast<const float4*>(p.wpack);
         float4* dst = reinterpret_cast<float4*>(sHW);
         for (int i = tid; i < pad4(lo.hidden_floats) / 4; i += NT) dst[i] = __ldg(src + i);
+        const float4* sb = reinterpret_cast<const float4*>(p.wpack + lo.off_bo);
+        for (int i = tid; i < NCP / 4; i += NT) reinterpret_cast<float4*>(sBo)[i] = __ldg(sb + i);
         if (WO_SMEM) {
             const float4* s2 = reinterpret_cast<const float4*>(p.wpack + lo.off_wo);
             float4* d2 = reinterpret_cast<float4*>(sWo);
-            for (int i = tid; i < (K * NCP + NCP) / 4; i += NT) d2[i] = __ldg(s2 + i);
+            for (int i = tid; i < K * NCP / 4; i += NT) d2[i] = __ldg(s2 + i);
         }
         for (int i = tid; i < lo.L; i += NT) sTimes[i] = p.times[i];
         for (int item = tid; item < Hd * TS; item += NT) {
@@ -173,18 +228,18 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
             if (p.save_act) p.save_act[(int64_t)tile * lo.act_floats + item] = v;
         }
     }
-    __syncthreads();
-    const float* Wo = WO_SMEM ? sWo : (p.wpack + lo.off_wo);
-    const float* bo = Wo + (size_t)K * NCP;
+    cta_sync();
 
     int cnt = 0;        // knots strictly below the current stage time (monotone)
     int jout = 1;       // next requested output time
+    int rslot = 0;      // ring slot / phase parity of the next fill to consume
+    uint32_t rphase = 0;
     {
         CtlRegs r;
         ctl_issue<TS>(p, sTimes, cnt, 0, 0, b0, tid, NT, r);
         ctl_finish<TS>(p, r, sDU, p.save_act ? p.save_act + (int64_t)tile * lo.act_floats : nullptr, tid, NT);
     }
-    __syncthreads();
+    cta_sync();
 
     for (int k = 0; k < lo.n_steps; ++k) {
         const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step);
@@ -196,9 +251,10 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
             float* act = p.save_act ? p.save_act + ((int64_t)n * lo.ntiles + tile) * lo.act_floats : nullptr;
             float* act_next = (p.save_act && n + 1 < lo.n_stages)
                                   ? p.save_act + ((int64_t)(n + 1) * lo.ntiles + tile) * lo.act_floats : nullptr;
-            const float* sDUcur = sDU + (n & 1) * pad4(C4 * TS);
-            float* sDUnext = sDU + ((n + 1) & 1) * pad4(C4 * TS);
+            const float* sDUcur = sDU + (n & 1) * lo.du_floats;
+            float* sDUnext = sDU + ((n + 1) & 1) * lo.du_floats;
 
+            PHASE_T0();
             // (1) control of the NEXT stage: loads in flight while this stage's MLP runs
             CtlRegs ctl;
             const bool have_next = (n + 1 < lo.n_stages);
@@ -210,66 +266,96 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
             for (int l = 0; l < lo.n_hidden; ++l) {
                 dense_relu<TS>(sHW + lo.off_w[l], sHW + lo.off_b[l], lo.in_dim[l], lo.width[l], lo.stride[l], in,
                                outb, act ? act + lo.act_off_h[l] : nullptr, tid, NT);
-                __syncthreads();
+                cta_sync();
                 in = outb;
                 outb = (outb == sA0) ? sA1 : sA0;
             }
+            PHASE_MARK(0);   // ctl issue + hidden layers
 
             // (3) output layer, tanh, contraction with dU: thread = 4 columns x TS samples
-            for (int cg = tid; cg < NCG; cg += NT) {
+            for (int pass = 0; pass < npass; ++pass) {
+                const int cg = pass * NT + tid;
+                const bool active = cg < NCG;
                 float acc[TS][4];
                 {
-                    const float4 bv = WO_SMEM ? *reinterpret_cast<const float4*>(bo + cg * 4)
-                                              : __ldg(reinterpret_cast<const float4*>(bo + cg * 4));
+                    const float4 bv = *reinterpret_cast<const float4*>(sBo + (active ? cg : 0) * 4);
 #pragma unroll
                     for (int b = 0; b < TS; ++b) { acc[b][0] = bv.x; acc[b][1] = bv.y; acc[b][2] = bv.z; acc[b][3] = bv.w; }
                 }
-                const float* wp = Wo + cg * 4;
+                for (int c = 0; c < nchunks; ++c) {
+                    const float* wp;
+                    int wstride;
+                    int slot = 0;
+                    if (WO_SMEM) {
+                        wp = sWo + (size_t)(c * KC) * NCP + (active ? cg : 0) * 4;
+                        wstride = NCP;
+                    } else {
+                        slot = rslot;
+                        mbar_wait(bar_full + slot, rphase);
+                        wp = sWo + (size_t)slot * KC * PW + tid * 4;
+                        wstride = PW;
+                    }
+                    const int rows = (K - c * KC < KC) ? K - c * KC : KC;
+                    if (active) {
+                        const float* ip = in + (c * KC) * TS;
 #pragma unroll 7
-                for (int kk = 0; kk < K; ++kk) {
-                    const float4 w = WO_SMEM ? *reinterpret_cast<const float4*>(wp + (size_t)kk * NCP)
-                                             : __ldg(reinterpret_cast<const float4*>(wp + (size_t)kk * NCP));
+                        for (int kk = 0; kk < rows; ++kk) {
+                            const float4 w = *reinterpret_cast<const float4*>(wp);
+                            wp += wstride;
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        float v[VW];
-                        Vec<VW>::ld(in + kk * TS + q * VW, v);
+                            for (int q = 0; q < NQ; ++q) {
+                                float v[VW];
+                                Vec<VW>::ld(ip + q * VW, v);
 #pragma unroll
-                        for (int e = 0; e < VW; ++e) {
-                            acc[q * VW + e][0] = fmaf(v[e], w.x, acc[q * VW + e][0]);
-                            acc[q * VW + e][1] = fmaf(v[e], w.y, acc[q * VW + e][1]);
-                            acc[q * VW + e][2] = fmaf(v[e], w.z, acc[q * VW + e][2]);
-                            acc[q * VW + e][3] = fmaf(v[e], w.w, acc[q * VW + e][3]);
+                                for (int e = 0; e < VW; ++e) {
+                                    acc[q * VW + e][0] = fmaf(v[e], w.x, acc[q * VW + e][0]);
+                                    acc[q * VW + e][1] = fmaf(v[e], w.y, acc[q * VW + e][1]);
+                                    acc[q * VW + e][2] = fmaf(v[e], w.z, acc[q * VW + e][2]);
+                                    acc[q * VW + e][3] = fmaf(v[e], w.w, acc[q * VW + e][3]);
+                                }
+                            }
+                            ip += TS;
                         }
                     }
-                }
-                const int chunk = cg % NCH;
-                float part[TS];
-#pragma unroll
-                for (int b = 0; b < TS; ++b) part[b] = 0.f;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float dy[TS];
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) Vec<VW>::ld(sDUcur + (chunk * 4 + c) * TS + q * VW, dy + q * VW);
-#pragma unroll
-                    for (int b = 0; b < TS; ++b) {
-                        const float g = tanh_mufu(acc[b][c]);
-                        acc[b][c] = g;
-                        part[b] = fmaf(g, dy[b], part[b]);
+                    if (!WO_SMEM) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_empty + slot);
+                        if (++rslot == NSLOT) { rslot = 0; rphase ^= 1; }
                     }
                 }
-                if (p.save_G) {
-                    float4* gp = reinterpret_cast<float4*>(p.save_G) +
-                                 (((int64_t)n * lo.ntiles + tile) * TS) * NCG + cg;
+                PHASE_MARK(1);   // output-layer FMA loop
+                if (active) {
+                    const int chunk = cg % NCH;
+                    float part[TS];
 #pragma unroll
-                    for (int b = 0; b < TS; ++b)
-                        gp[(int64_t)b * NCG] = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
+                    for (int b = 0; b < TS; ++b) part[b] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float dy[TS];
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) Vec<VW>::ld(sDUcur + chunk * lo.DUS + c * TS + q * VW, dy + q * VW);
+#pragma unroll
+                        for (int b = 0; b < TS; ++b) {
+                            const float gt = tanh_mufu(acc[b][c]);
+                            acc[b][c] = gt;
+                            part[b] = fmaf(gt, dy[b], part[b]);
+                        }
+                    }
+                    if (p.save_G) {
+                        float4* gp = reinterpret_cast<float4*>(p.save_G) +
+                                     (((int64_t)n * lo.ntiles + tile) * TS) * NCG + cg;
+#pragma unroll
+                        for (int b = 0; b < TS; ++b)
+                            gp[(int64_t)b * NCG] = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) Vec<VW>::st(sPart + cg * TS + q * VW, part + q * VW);
                 }
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) Vec<VW>::st(sPart + cg * TS + q * VW, part + q * VW);
             }
+            PHASE_MARK(2);   // tanh, contraction, G store
             if (have_next) ctl_finish<TS>(p, ctl, sDUnext, act_next, tid, NT);
-            __syncthreads();
+            cta_sync();
+            PHASE_MARK(3);   // control finish + barrier
 
             // (4) finish the contraction and advance the RK4 recurrence (rk4_alt_step_func)
             for (int item = tid; item < Hd * TS; item += NT) {
@@ -314,120 +400,16 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
             if (s == 3) {
                 while (jout < lo.n_out && t1 >= __ldg(p.t_out + jout)) ++jout;
             }
-            __syncthreads();
+            cta_sync();
+            PHASE_MARK(4);   // RK4 combine + barrier
         }
     }
 }
 
-// ---- weight packing: torch (out, in) row-major -> transposed, padded layout of NcdeLayout
-struct PackArgs {
-    NcdeLayout lo;
-    const float* W[ANCDE_MAX_LAYERS + 1];
-    const float* bias[ANCDE_MAX_LAYERS + 1];
-    float* wpack;
-};
-
-__global__ void pack_weights_kernel(const __grid_constant__ PackArgs a)
-{
-    const NcdeLayout& lo = a.lo;
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    for (int l = 0; l < lo.n_hidden; ++l) {
-        const int in = lo.in_dim[l], out = lo.width[l], S = lo.stride[l];
-        for (int idx = gtid; idx < in * S; idx += gsz) {
-            const int k = idx / S, o = idx - k * S;
-            a.wpack[lo.off_w[l] + idx] = (o < out) ? a.W[l][(int64_t)o * in + k] : 0.f;
-        }
-        for (int o = gtid; o < pad4(out); o += gsz) a.wpack[lo.off_b[l] + o] = (o < out) ? a.bias[l][o] : 0.f;
-    }
-    const int K = lo.K, NCP = lo.NCP, C4 = lo.C4, C = lo.C;
-    const float* Wout = a.W[lo.n_hidden];
-    const float* bout = a.bias[lo.n_hidden];
-    for (int64_t idx = gtid; idx < (int64_t)K * NCP; idx += gsz) {
-        const int k = (int)(idx / NCP), col = (int)(idx - (int64_t)k * NCP);
-        const int i = col / C4, j = col - i * C4;
-        a.wpack[lo.off_wo + idx] = (j < C) ? Wout[((int64_t)i * C + j) * K + k] : 0.f;
-    }
-    for (int col = gtid; col < NCP; col += gsz) {
-        const int i = col / C4, j = col - i * C4;
-        a.wpack[lo.off_bo + col] = (j < C) ? bout[i * C + j] : 0.f;
-    }
-}
-
-// ---- host side -------------------------------------------------------------------------------
-bool bwd_fits(const NcdeLayout& lo);
-
-static void fill_layout(const ancde_ncde_desc* d, int TS, NcdeLayout* lo)
-{
-    *lo = NcdeLayout();
-    lo->B = d->B; lo->L = d->L; lo->C = d->C; lo->Hd = d->Hd; lo->n_hidden = d->n_hidden; lo->mode = d->mode;
-    lo->att_C = d->att_C; lo->att_L = d->att_L; lo->n_hp = d->n_hp; lo->n_steps = d->n_steps; lo->n_out = d->n_out;
-    lo->n_stages = 4 * d->n_steps;
-    lo->Hmax = d->Hd;
-    for (int l = 0; l < d->n_hidden; ++l) {
-        lo->width[l] = d->width[l];
-        lo->in_dim[l] = (l == 0) ? d->Hd : d->width[l - 1];
-        lo->stride[l] = d->width[l] | 1;
-        if (d->width[l] > lo->Hmax) lo->Hmax = d->width[l];
-    }
-    lo->TS = TS;
-    lo->ntiles = (d->B + TS - 1) / TS;
-    lo->C4 = pad4(d->C);
-    lo->NCH = lo->C4 / 4;
-    lo->NCG = d->Hd * lo->NCH;
-    lo->NCP = d->Hd * lo->C4;
-    lo->K = d->width[d->n_hidden - 1];
-    int off = 0;
-    for (int l = 0; l < d->n_hidden; ++l) {
-        lo->off_w[l] = off; off += pad4(lo->in_dim[l] * lo->stride[l]);
-        lo->off_b[l] = off; off += pad4(lo->width[l]);
-    }
-    lo->hidden_floats = off;
-    lo->off_wo = off; off += lo->K * lo->NCP;
-    lo->off_bo = off; off += lo->NCP;
-    lo->wpack_floats = off;
-    int a = d->Hd * TS;
-    for (int l = 0; l < d->n_hidden; ++l) { lo->act_off_h[l] = a; a += d->width[l] * TS; }
-    lo->act_off_du = a; a += lo->C4 * TS;
-    lo->act_off_duda = a;
-    if (d->mode == ANCDE_MODE_TOP) a += lo->C4 * TS;
-    lo->act_floats = pad4(a);
-}
-
-int make_layout(const ancde_ncde_desc* d, NcdeLayout* lo)
-{
-    ANCDE_CHECK_ARG(d != nullptr, "ncde: null descriptor");
-    ANCDE_CHECK_ARG(d->B >= 1 && d->L >= 2 && d->C >= 1 && d->Hd >= 1, "ncde: bad shape B=%d L=%d C=%d Hd=%d",
-                    d->B, d->L, d->C, d->Hd);
-    ANCDE_CHECK_ARG(d->n_hidden >= 1 && d->n_hidden <= ANCDE_MAX_LAYERS, "ncde: n_hidden=%d out of range",
-                    d->n_hidden);
-    ANCDE_CHECK_ARG(d->mode >= ANCDE_MODE_PLAIN && d->mode <= ANCDE_MODE_TOP, "ncde: bad mode %d", d->mode);
-    ANCDE_CHECK_ARG(d->n_steps >= 1 && d->n_out >= 1, "ncde: n_steps=%d n_out=%d", d->n_steps, d->n_out);
-    ANCDE_CHECK_ARG(d->step > 0.f, "ncde: step must be positive");
-    if (d->mode == ANCDE_MODE_TOP) {
-        ANCDE_CHECK_ARG(d->att_C == 1 || d->att_C == d->C, "ncde: attention channels %d (need 1 or C=%d)", d->att_C, d->C);
-        ANCDE_CHECK_ARG(d->att_L >= 1 && d->n_hp >= 2, "ncde: att_L=%d n_hp=%d", d->att_L, d->n_hp);
-    }
-    for (int l = 0; l < d->n_hidden; ++l) ANCDE_CHECK_ARG(d->width[l] >= 1, "ncde: width[%d]=%d", l, d->width[l]);
-    int TS = d->samples_per_cta;
-    if (TS == 0) {
-        // the largest tile that still gives every SM work (148 SMs); weight reuse grows with TS.
-        // The backward's shared-memory footprint grows with TS too, so shrink until it fits.
-        TS = 8;
-        while (TS > 1 && (d->B + TS - 1) / TS < 120) TS /= 2;
-        for (;;) {
-            fill_layout(d, TS, lo);
-            if (TS == 1 || bwd_fits(*lo)) break;
-            TS /= 2;
-        }
-    }
-    ANCDE_CHECK_ARG(TS == 8 || TS == 4 || TS == 2 || TS == 1, "ncde: samples_per_cta=%d (need 8, 4, 2 or 1)", TS);
-    fill_layout(d, TS, lo);
-    return ANCDE_OK;
-}
-
+// ---- launch -----------------------------------------------------------------------------------
 static int fwd_threads(const NcdeLayout& lo)
 {
-    int per = (lo.NCG + 511) / 512;
+    int per = (lo.NCG + 447) / 448;
     int nt = round_up((lo.NCG + per - 1) / per, 32);
     int need = (lo.C4 * lo.TS + CTL_ITEMS - 1) / CTL_ITEMS;
     if (nt < need) nt = round_up(need, 32);
@@ -435,40 +417,63 @@ static int fwd_threads(const NcdeLayout& lo)
     return nt;
 }
 
-static size_t fwd_smem_floats(const NcdeLayout& lo, bool wo_smem)
+// shared memory (bytes) without the output-layer weights / ring
+static size_t fwd_smem_base(const NcdeLayout& lo)
 {
-    size_t f = pad4(lo.hidden_floats);
-    if (wo_smem) f += (size_t)lo.K * lo.NCP + lo.NCP;
+    size_t f = pad4(lo.hidden_floats) + lo.NCP;
     f += pad4(lo.L) + pad4(lo.Hd * lo.TS) + 2 * pad4(lo.Hmax * lo.TS) + 4 * pad4(lo.Hd * lo.TS) +
-         2 * pad4(lo.C4 * lo.TS) + (size_t)lo.NCG * lo.TS;
-    return f;
+         2 * (size_t)lo.du_floats + (size_t)lo.NCG * lo.TS;
+    return f * 4 + 128;
 }
 
 template <int TS>
-static int launch_fwd(const SolveArgs& a, cudaStream_t stream)
+static int launch_fwd_ts(SolveArgs a, cudaStream_t stream)
 {
     const NcdeLayout& lo = a.lo;
     const int nt = fwd_threads(lo);
-    if (nt > 512) {
-        set_error("ncde_forward: C=%d with %d samples per CTA needs %d threads (max 512)", lo.C, lo.TS, nt);
+    if (nt > 480) {
+        set_error("ncde_forward: C=%d with %d samples per CTA needs %d threads (max 480)", lo.C, lo.TS, nt);
         return ANCDE_EUNSUPPORTED;
     }
     const size_t max_smem = 227 * 1024;
-    bool wo_smem = fwd_smem_floats(lo, true) * 4 <= max_smem;
-    const size_t smem = fwd_smem_floats(lo, wo_smem) * 4;
-    if (smem > max_smem) {
-        set_error("ncde_forward: hidden layers need %zu bytes of shared memory (max %zu)", smem, max_smem);
+    const size_t base = fwd_smem_base(lo);
+    if (base > max_smem) {
+        set_error("ncde_forward: hidden layers need %zu bytes of shared memory (max %zu)", base, max_smem);
         return ANCDE_EUNSUPPORTED;
+    }
+    const bool wo_smem = base + (size_t)lo.K * lo.NCP * 4 <= max_smem;
+    a.ntc = nt;
+    size_t smem;
+    int threads = nt;
+    if (wo_smem) {
+        a.ring_kc = lo.K; a.ring_slots = 1; a.ring_pw = lo.NCP;
+        smem = base + (size_t)lo.K * lo.NCP * 4;
+    } else {
+        // ring of NSLOT slots, each KC rows of the pass width; as deep as the remaining shared memory allows
+        const int pw = (lo.NCP < nt * 4) ? lo.NCP : nt * 4;
+        const size_t avail = max_smem - base;
+        int slots = 3;
+        int kc = (int)(avail / ((size_t)slots * pw * 4));
+        if (kc < 1) { slots = 2; kc = (int)(avail / ((size_t)slots * pw * 4)); }
+        if (kc < 1) {
+            set_error("ncde_forward: no shared memory left for the weight ring (%zu bytes free)", avail);
+            return ANCDE_EUNSUPPORTED;
+        }
+        if (kc > 8) kc = 8;
+        if (kc > lo.K) kc = lo.K;
+        a.ring_kc = kc; a.ring_slots = slots; a.ring_pw = pw;
+        smem = base + (size_t)slots * kc * pw * 4;
+        threads = nt + 32;
     }
     static const char* names[3] = {"ncde_fwd_plain", "ncde_fwd_bottom", "ncde_fwd_top"};
     if (wo_smem) {
         ANCDE_CUDA(cudaFuncSetAttribute(ncde_fwd_kernel<TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         prof_begin(names[lo.mode], stream);
-        ncde_fwd_kernel<TS, true><<<lo.ntiles, nt, smem, stream>>>(a);
+        ncde_fwd_kernel<TS, true><<<lo.ntiles, threads, smem, stream>>>(a);
     } else {
         ANCDE_CUDA(cudaFuncSetAttribute(ncde_fwd_kernel<TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         prof_begin(names[lo.mode], stream);
-        ncde_fwd_kernel<TS, false><<<lo.ntiles, nt, smem, stream>>>(a);
+        ncde_fwd_kernel<TS, false><<<lo.ntiles, threads, smem, stream>>>(a);
     }
     prof_end(stream);
     count_launch();
@@ -476,81 +481,14 @@ static int launch_fwd(const SolveArgs& a, cudaStream_t stream)
     return ANCDE_OK;
 }
 
-int pack_weights(const ancde_ncde_desc* d, const NcdeLayout& lo, cudaStream_t stream)
+int launch_fwd(const SolveArgs& a, cudaStream_t stream)
 {
-    PackArgs pa;
-    pa.lo = lo;
-    for (int l = 0; l <= d->n_hidden; ++l) {
-        ANCDE_CHECK_ARG(d->W[l] && d->bias[l], "ncde: null weight/bias pointer for layer %d", l);
-        pa.W[l] = d->W[l];
-        pa.bias[l] = d->bias[l];
+    switch (a.lo.TS) {
+        case 8: return launch_fwd_ts<8>(a, stream);
+        case 4: return launch_fwd_ts<4>(a, stream);
+        case 2: return launch_fwd_ts<2>(a, stream);
+        default: return launch_fwd_ts<1>(a, stream);
     }
-    pa.wpack = d->wpack;
-    prof_begin("pack_weights", stream);
-    pack_weights_kernel<<<64, 256, 0, stream>>>(pa);
-    prof_end(stream);
-    count_launch();
-    ANCDE_CUDA(cudaGetLastError());
-    return ANCDE_OK;
-}
-
-int fill_args(const ancde_ncde_desc* d, const NcdeLayout& lo, SolveArgs* a)
-{
-    ANCDE_CHECK_ARG(d->times && d->t_out && d->coeff_b && d->coeff_c2 && d->coeff_d3 && d->z0 && d->z_out && d->wpack,
-                    "ncde: null input/output pointer");
-    if (d->mode == ANCDE_MODE_TOP) ANCDE_CHECK_ARG(d->attention && d->h_prime, "ncde: TOP mode needs attention and h_prime");
-    *a = SolveArgs();
-    a->lo = lo;
-    a->t_start = d->t_start; a->t_end = d->t_end; a->step = d->step;
-    a->times = d->times; a->t_out = d->t_out; a->cb = d->coeff_b; a->cc2 = d->coeff_c2; a->cd3 = d->coeff_d3;
-    a->z0 = d->z0; a->attention = d->attention; a->h_prime = d->h_prime; a->wpack = d->wpack;
-    a->z_out = d->z_out; a->k_out = d->k_out; a->save_act = d->save_act; a->save_G = d->save_G;
-    a->grad_z_out = d->grad_z_out; a->grad_z0 = d->grad_z0; a->grad_attention = d->grad_attention;
-    return ANCDE_OK;
 }
 
 }  // namespace ancde
-
-using namespace ancde;
-
-extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
-{
-    NcdeLayout lo;
-    if (make_layout(d, &lo) != ANCDE_OK) return -1;
-    return lo.wpack_floats + pad4(lo.hidden_floats);   // + hidden-gradient scratch used by the backward
-}
-
-extern "C" int64_t ancde_ncde_save_act_floats(const ancde_ncde_desc* d)
-{
-    NcdeLayout lo;
-    if (make_layout(d, &lo) != ANCDE_OK) return -1;
-    return (int64_t)lo.n_stages * lo.ntiles * lo.act_floats;
-}
-
-extern "C" int64_t ancde_ncde_save_G_floats(const ancde_ncde_desc* d)
-{
-    NcdeLayout lo;
-    if (make_layout(d, &lo) != ANCDE_OK) return -1;
-    return (int64_t)lo.n_stages * lo.ntiles * lo.TS * lo.NCP;
-}
-
-extern "C" int ancde_ncde_forward(const ancde_ncde_desc* d, void* stream_)
-{
-    reset_launch_count();
-    cudaStream_t stream = (cudaStream_t)stream_;
-    NcdeLayout lo;
-    int rc = make_layout(d, &lo);
-    if (rc != ANCDE_OK) return rc;
-    ANCDE_CHECK_ARG((d->save_act == nullptr) == (d->save_G == nullptr), "ncde_forward: save_act and save_G go together");
-    SolveArgs a;
-    rc = fill_args(d, lo, &a);
-    if (rc != ANCDE_OK) return rc;
-    rc = pack_weights(d, lo, stream);
-    if (rc != ANCDE_OK) return rc;
-    switch (lo.TS) {
-        case 8: return launch_fwd<8>(a, stream);
-        case 4: return launch_fwd<4>(a, stream);
-        case 2: return launch_fwd<2>(a, stream);
-        default: return launch_fwd<1>(a, stream);
-    }
-}

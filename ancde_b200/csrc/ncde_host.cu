@@ -1,0 +1,198 @@
+// Host side of the fused NCDE solve: layout of packed weights / saved activations, weight packing,
+// argument marshalling and the C-ABI entry points for the forward.
+#include "ncde_common.cuh"
+
+namespace ancde {
+
+int launch_fwd(const SolveArgs& a, cudaStream_t stream);   // ncde_fwd.cu
+
+// ---- weight packing: torch (out, in) row-major -> transposed, padded layout of NcdeLayout
+struct PackArgs {
+    NcdeLayout lo;
+    const float* W[ANCDE_MAX_LAYERS + 1];
+    const float* bias[ANCDE_MAX_LAYERS + 1];
+    float* wpack;
+};
+
+__global__ void pack_weights_kernel(const __grid_constant__ PackArgs a)
+{
+    const NcdeLayout& lo = a.lo;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (int l = 0; l < lo.n_hidden; ++l) {
+        const int in = lo.in_dim[l], out = lo.width[l], S = lo.stride[l];
+        for (int idx = gtid; idx < in * S; idx += gsz) {
+            const int k = idx / S, o = idx - k * S;
+            a.wpack[lo.off_w[l] + idx] = (o < out) ? a.W[l][(int64_t)o * in + k] : 0.f;
+        }
+        for (int o = gtid; o < pad4(out); o += gsz) a.wpack[lo.off_b[l] + o] = (o < out) ? a.bias[l][o] : 0.f;
+    }
+    const int K = lo.K, NCP = lo.NCP, C4 = lo.C4, C = lo.C;
+    const float* Wout = a.W[lo.n_hidden];
+    const float* bout = a.bias[lo.n_hidden];
+    for (int64_t idx = gtid; idx < (int64_t)K * NCP; idx += gsz) {
+        const int k = (int)(idx / NCP), col = (int)(idx - (int64_t)k * NCP);
+        const int i = col / C4, j = col - i * C4;
+        a.wpack[lo.off_wo + idx] = (j < C) ? Wout[((int64_t)i * C + j) * K + k] : 0.f;
+    }
+    for (int col = gtid; col < NCP; col += gsz) {
+        const int i = col / C4, j = col - i * C4;
+        a.wpack[lo.off_bo + col] = (j < C) ? bout[i * C + j] : 0.f;
+    }
+    for (int64_t idx = gtid; idx < (int64_t)NCP * lo.KPS; idx += gsz) {
+        const int col = (int)(idx / lo.KPS), k = (int)(idx - (int64_t)col * lo.KPS);
+        const int i = col / C4, j = col - i * C4;
+        a.wpack[lo.off_wot + idx] = (j < C && k < K) ? Wout[((int64_t)i * C + j) * K + k] : 0.f;
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+bool bwd_fits(const NcdeLayout& lo);
+
+static void fill_layout(const ancde_ncde_desc* d, int TS, NcdeLayout* lo)
+{
+    *lo = NcdeLayout();
+    lo->B = d->B; lo->L = d->L; lo->C = d->C; lo->Hd = d->Hd; lo->n_hidden = d->n_hidden; lo->mode = d->mode;
+    lo->att_C = d->att_C; lo->att_L = d->att_L; lo->n_hp = d->n_hp; lo->n_steps = d->n_steps; lo->n_out = d->n_out;
+    lo->n_stages = 4 * d->n_steps;
+    lo->Hmax = d->Hd;
+    for (int l = 0; l < d->n_hidden; ++l) {
+        lo->width[l] = d->width[l];
+        lo->in_dim[l] = (l == 0) ? d->Hd : d->width[l - 1];
+        lo->stride[l] = d->width[l] | 1;
+        if (d->width[l] > lo->Hmax) lo->Hmax = d->width[l];
+    }
+    lo->TS = TS;
+    lo->ntiles = (d->B + TS - 1) / TS;
+    lo->C4 = pad4(d->C);
+    lo->NCH = lo->C4 / 4;
+    lo->NCG = d->Hd * lo->NCH;
+    lo->NCP = d->Hd * lo->C4;
+    lo->K = d->width[d->n_hidden - 1];
+    int off = 0;
+    for (int l = 0; l < d->n_hidden; ++l) {
+        lo->off_w[l] = off; off += pad4(lo->in_dim[l] * lo->stride[l]);
+        lo->off_b[l] = off; off += pad4(lo->width[l]);
+    }
+    lo->hidden_floats = off;
+    lo->off_wo = off; off += lo->K * lo->NCP;
+    lo->off_bo = off; off += lo->NCP;
+    lo->KPS = 8 * ((lo->K + 7) / 8) + 4;   // +4: 16-byte rows whose stride is bank-conflict free for LDS.128
+    lo->off_wot = off; off += lo->NCP * lo->KPS;
+    lo->wpack_floats = off;
+    int a = d->Hd * TS;
+    for (int l = 0; l < d->n_hidden; ++l) { lo->act_off_h[l] = a; a += d->width[l] * TS; }
+    lo->DUS = 4 * TS + 4;
+    lo->du_floats = pad4(lo->NCH * lo->DUS);
+    a = pad4(a);
+    lo->act_off_du = a; a += lo->du_floats;
+    lo->act_off_duda = a;
+    if (d->mode == ANCDE_MODE_TOP) a += lo->du_floats;
+    lo->act_floats = pad4(a);
+}
+
+int make_layout(const ancde_ncde_desc* d, NcdeLayout* lo)
+{
+    ANCDE_CHECK_ARG(d != nullptr, "ncde: null descriptor");
+    ANCDE_CHECK_ARG(d->B >= 1 && d->L >= 2 && d->C >= 1 && d->Hd >= 1, "ncde: bad shape B=%d L=%d C=%d Hd=%d",
+                    d->B, d->L, d->C, d->Hd);
+    ANCDE_CHECK_ARG(d->n_hidden >= 1 && d->n_hidden <= ANCDE_MAX_LAYERS, "ncde: n_hidden=%d out of range",
+                    d->n_hidden);
+    ANCDE_CHECK_ARG(d->mode >= ANCDE_MODE_PLAIN && d->mode <= ANCDE_MODE_TOP, "ncde: bad mode %d", d->mode);
+    ANCDE_CHECK_ARG(d->n_steps >= 1 && d->n_out >= 1, "ncde: n_steps=%d n_out=%d", d->n_steps, d->n_out);
+    ANCDE_CHECK_ARG(d->step > 0.f, "ncde: step must be positive");
+    if (d->mode == ANCDE_MODE_TOP) {
+        ANCDE_CHECK_ARG(d->att_C == 1 || d->att_C == d->C, "ncde: attention channels %d (need 1 or C=%d)", d->att_C, d->C);
+        ANCDE_CHECK_ARG(d->att_L >= 1 && d->n_hp >= 2, "ncde: att_L=%d n_hp=%d", d->att_L, d->n_hp);
+    }
+    for (int l = 0; l < d->n_hidden; ++l) ANCDE_CHECK_ARG(d->width[l] >= 1, "ncde: width[%d]=%d", l, d->width[l]);
+    int TS = d->samples_per_cta;
+    if (TS == 0) {
+        // the largest tile that still gives every SM work (148 SMs); weight reuse grows with TS.
+        // The backward's shared-memory footprint grows with TS too, so shrink until it fits.
+        TS = 8;
+        while (TS > 1 && (d->B + TS - 1) / TS < 120) TS /= 2;
+        for (;;) {
+            fill_layout(d, TS, lo);
+            if (TS == 1 || bwd_fits(*lo)) break;
+            TS /= 2;
+        }
+    }
+    ANCDE_CHECK_ARG(TS == 8 || TS == 4 || TS == 2 || TS == 1, "ncde: samples_per_cta=%d (need 8, 4, 2 or 1)", TS);
+    fill_layout(d, TS, lo);
+    return ANCDE_OK;
+}
+
+int pack_weights(const ancde_ncde_desc* d, const NcdeLayout& lo, cudaStream_t stream)
+{
+    PackArgs pa;
+    pa.lo = lo;
+    for (int l = 0; l <= d->n_hidden; ++l) {
+        ANCDE_CHECK_ARG(d->W[l] && d->bias[l], "ncde: null weight/bias pointer for layer %d", l);
+        pa.W[l] = d->W[l];
+        pa.bias[l] = d->bias[l];
+    }
+    pa.wpack = d->wpack;
+    prof_begin("pack_weights", stream);
+    pack_weights_kernel<<<64, 256, 0, stream>>>(pa);
+    prof_end(stream);
+    count_launch();
+    ANCDE_CUDA(cudaGetLastError());
+    return ANCDE_OK;
+}
+
+int fill_args(const ancde_ncde_desc* d, const NcdeLayout& lo, SolveArgs* a)
+{
+    ANCDE_CHECK_ARG(d->times && d->t_out && d->coeff_b && d->coeff_c2 && d->coeff_d3 && d->z0 && d->z_out && d->wpack,
+                    "ncde: null input/output pointer");
+    if (d->mode == ANCDE_MODE_TOP) ANCDE_CHECK_ARG(d->attention && d->h_prime, "ncde: TOP mode needs attention and h_prime");
+    *a = SolveArgs();
+    a->lo = lo;
+    a->t_start = d->t_start; a->t_end = d->t_end; a->step = d->step;
+    a->times = d->times; a->t_out = d->t_out; a->cb = d->coeff_b; a->cc2 = d->coeff_c2; a->cd3 = d->coeff_d3;
+    a->z0 = d->z0; a->attention = d->attention; a->h_prime = d->h_prime; a->wpack = d->wpack;
+    a->z_out = d->z_out; a->k_out = d->k_out; a->save_act = d->save_act; a->save_G = d->save_G;
+    a->grad_z_out = d->grad_z_out; a->grad_z0 = d->grad_z0; a->grad_attention = d->grad_attention;
+    a->dbg = debug_buffer();
+    return ANCDE_OK;
+}
+
+}  // namespace ancde
+
+using namespace ancde;
+
+extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
+{
+    NcdeLayout lo;
+    if (make_layout(d, &lo) != ANCDE_OK) return -1;
+    return lo.wpack_floats + pad4(lo.hidden_floats);   // + hidden-gradient scratch used by the backward
+}
+
+extern "C" int64_t ancde_ncde_save_act_floats(const ancde_ncde_desc* d)
+{
+    NcdeLayout lo;
+    if (make_layout(d, &lo) != ANCDE_OK) return -1;
+    return (int64_t)lo.n_stages * lo.ntiles * lo.act_floats;
+}
+
+extern "C" int64_t ancde_ncde_save_G_floats(const ancde_ncde_desc* d)
+{
+    NcdeLayout lo;
+    if (make_layout(d, &lo) != ANCDE_OK) return -1;
+    return (int64_t)lo.n_stages * lo.ntiles * lo.TS * lo.NCP;
+}
+
+extern "C" int ancde_ncde_forward(const ancde_ncde_desc* d, void* stream_)
+{
+    reset_launch_count();
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NcdeLayout lo;
+    int rc = make_layout(d, &lo);
+    if (rc != ANCDE_OK) return rc;
+    ANCDE_CHECK_ARG((d->save_act == nullptr) == (d->save_G == nullptr), "ncde_forward: save_act and save_G go together");
+    SolveArgs a;
+    rc = fill_args(d, lo, &a);
+    if (rc != ANCDE_OK) return rc;
+    rc = pack_weights(d, lo, stream);
+    if (rc != ANCDE_OK) return rc;
+    return launch_fwd(a, stream);
+}

@@ -24,10 +24,13 @@ struct NcdeLayout {
     int off_w[ANCDE_MAX_LAYERS], off_b[ANCDE_MAX_LAYERS];
     int hidden_floats;  // all hidden layers (weights + biases)
     int off_wo, off_bo; // output layer Wt_out[k][NCP], bias_out[NCP]
+    int off_wot, KPS;   // second copy for the backward: W_out[col][KPS] (k contiguous, KPS = 8*ceil(K/8) + 4)
     int64_t wpack_floats;
     // saved activations per (stage, tile): z_s | h_1 .. h_n | dU | dU/da   (each [feature][TS])
     int act_off_h[ANCDE_MAX_LAYERS];
     int act_off_du, act_off_duda, act_floats;
+    int DUS, du_floats; // dU is stored per column chunk: [chunk][4][TS] with a chunk stride of DUS = 4*TS + 4 floats
+                        // (bank-conflict free 128-bit reads by lanes that own consecutive chunks)
     int n_stages;       // 4 * n_steps
 };
 
