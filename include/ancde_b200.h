@@ -121,7 +121,8 @@ int64_t ancde_ncde_save_G_floats(const ancde_ncde_desc* d);
 int ancde_ncde_forward(const ancde_ncde_desc* d, void* stream);
 
 /* Backprop through the solver (discrete adjoint of the RK4 recurrence), using save_act / save_G
- * written by ancde_ncde_forward with the same descriptor.  Overwrites save_G. */
+ * written by ancde_ncde_forward with the same descriptor.  Overwrites the stage-input slots of save_act
+ * with the stage cotangents (consumed by the weight-gradient kernel launched from the same call). */
 int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream);
 
 /* Number of kernel launches the last forward / backward call of this thread issued. */
@@ -133,6 +134,10 @@ int ancde_last_launch_count(void);
 int ancde_profile_enable(int on);
 int ancde_profile_count(void);
 int ancde_profile_get(int i, char* name, size_t len, float* ms);
+
+/* Development aid: 64 int64 counters in device memory that kernels built with -DANCDE_PHASE_TIMING
+ * fill with per-phase clock64() totals (normal builds never touch the buffer). NULL disables. */
+int ancde_debug_set_buffer(long long* dev_counters);
 
 /* FP32 FMA throughput microbenchmark (roofline denominator): launches a kernel of
  * dependent-free FFMA chains; returns the FLOP count it executes in *flops. */

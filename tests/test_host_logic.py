@@ -1,0 +1,91 @@
+"""Host-side logic of the drop-in API that needs no GPU: grids, structural recognition, errors, models."""
+import pytest
+import torch
+
+import ancde_b200
+from ancde_b200 import solver, cdeint_module, metamodel, synthetic
+from oracle import port
+
+
+def test_fixed_grid_meta_matches_torchdiffeq_grid_constructor():
+    for t, step in ((torch.arange(24.), 1.0), (torch.arange(72.) + 1, 1.0), (torch.tensor([0.0, 0.7, 1.5, 4.0]), 0.3),
+                    (torch.linspace(0, 1, 11), 0.1)):
+        t0, t1, h, n = solver.fixed_grid_meta(t, step)
+        grid = port.fixed_grid(t, step)
+        assert n == len(grid) - 1 and t0 == float(t[0]) and t1 == float(t[-1])
+    with pytest.raises(NotImplementedError):
+        solver.fixed_grid_meta(torch.tensor([2.0, 1.0, 0.0]), 1.0)
+    with pytest.raises(AssertionError):
+        solver.fixed_grid_meta(torch.tensor([0.0, 2.0, 1.0]), 1.0)
+
+
+def test_mlp_params_recognises_both_vector_fields():
+    g = ancde_b200.FinalTanh(35, 49, 49, 4)
+    wb, widths, Hd, C = solver.mlp_params(g)
+    assert (widths, Hd, C, len(wb)) == ([49, 49, 49, 49], 49, 35, 10)
+    f = ancde_b200.FinalTanh_ff6(35, 20, 20, 4)
+    wb, widths, Hd, C = solver.mlp_params(f)
+    assert (widths, Hd, C, len(wb)) == ([20, 20, 20, 20, 20], 35, 35, 12)
+    with pytest.raises(ValueError):
+        solver.mlp_params(lambda z: z)
+    with pytest.raises(NotImplementedError):
+        solver.mlp_params(torch.nn.Linear(3, 3))
+
+
+def test_reference_state_dict_names_load_into_the_models():
+    from tests.helpers import dual_case
+    for case in ('stock', 'sepsis', 'uea'):
+        g = dual_case(case)
+        model, _, _ = metamodel.model_from_config(g['cfg'])
+        model.load_state_dict(g['sd'], strict=True)
+
+
+def test_entry_points_reject_opaque_callables_and_other_solvers():
+    times = torch.arange(5.)
+    coeffs = tuple(torch.randn(2, 4, 3) for _ in range(4))
+    sp = ancde_b200.NaturalCubicSpline(times, coeffs)
+    func = ancde_b200.FinalTanh(3, 4, 5, 2)
+    z0 = torch.randn(2, 4)
+    with pytest.raises(NotImplementedError):
+        ancde_b200.cdeint(lambda t: None, z0, func, times, method='rk4', options=dict(step_size=1.0))
+    with pytest.raises(NotImplementedError):
+        ancde_b200.cdeint(sp.evaluate, z0, func, times, method='rk4', options=dict(step_size=1.0))
+    with pytest.raises(NotImplementedError):
+        ancde_b200.cdeint(sp.derivative, z0, func, times, method='dopri5')
+    with pytest.raises(NotImplementedError):
+        ancde_b200.cdeint(sp.derivative, z0, func, times)     # torchdiffeq's default is dopri5
+    with pytest.raises(ValueError):                            # adjoint + control that requires grad (cdeint_module.py:218-220)
+        c2 = tuple(c.clone().requires_grad_(True) for c in coeffs)
+        ancde_b200.ancde_bottom(ancde_b200.NaturalCubicSpline(times, c2).derivative, torch.randn(2, 3),
+                                ancde_b200.FinalTanh_ff6(3, 4, 4, 2), times, file='x', adjoint=True)
+    with pytest.raises(FileNotFoundError):
+        cdeint_module.load_h_prime('never-written.npy')
+
+
+def test_spline_evaluate_and_derivative_match_reference_port():
+    times = torch.sort(torch.rand(9) * 3)[0]
+    X = torch.randn(3, 9, 2, dtype=torch.float64)
+    coeffs = port.natural_cubic_spline_coeffs(times, X)
+    sp = ancde_b200.NaturalCubicSpline(times, coeffs)
+    for t in (times[0], times[3], times[3] + 0.01, times[-1], times[-1] + 1.0, times[0] - 1.0):
+        assert torch.equal(sp.evaluate(t), port.spline_evaluate(times, coeffs, t))
+        assert torch.equal(sp.derivative(t), port.spline_derivative(times, coeffs, t))
+
+
+def test_solve_times_and_readout_follow_the_reference():
+    times = torch.arange(6.) + 1
+    fi = torch.tensor([5, 2, 2, 0, 3])
+    t, idx = metamodel._solve_times(times, fi, stream=False)
+    assert t.tolist() == [1.0, 3.0, 4.0, 6.0] and idx.tolist() == [3, 1, 1, 0, 2]
+    z = torch.arange(4 * 5 * 2, dtype=torch.float32).view(4, 5, 2)
+    out = metamodel._readout(z, idx, stream=False)
+    assert torch.equal(out, torch.stack([z[3, 0], z[1, 1], z[1, 2], z[0, 3], z[2, 4]]))
+
+
+def test_synthetic_batches_have_the_baseline_shapes():
+    for name, cfg in synthetic.CONFIGS.items():
+        bt = synthetic.make_batch(name, B=5)
+        assert bt['X'].shape == (5, cfg['L'], cfg['C'])
+        assert bt['times'].shape == (cfg['L'],) and float(bt['times'][0]) == cfg['t0']
+        assert torch.isnan(bt['X']).any()
+        assert (bt['static'] is None) == (cfg['static'] == 0)
