@@ -24,6 +24,8 @@ namespace ancde {
 int fill_args(const ancde_ncde_desc* d, const NcdeLayout& lo, SolveArgs* a);
 int pack_weights(const ancde_ncde_desc* d, const NcdeLayout& lo, cudaStream_t stream);
 int launch_wgrad(const SolveArgs& a, float* gW, float* gB, cudaStream_t stream);   // ncde_wgrad.cu
+struct HiddenGradPtrs { float* gW[ANCDE_MAX_LAYERS]; float* gB[ANCDE_MAX_LAYERS]; };
+int launch_hidden_wgrad(const SolveArgs& a, const HiddenGradPtrs& hp, cudaStream_t stream);
 
 // Sum of v[idx] over the 32 lanes of a warp for V values per lane in V/2 + V/4 + ... shuffles:
 // afterwards lane l holds the totals of idx = l*(V/32) .. +V/32-1 in v[0 .. V/32-1]  (V >= 32), or
@@ -73,7 +75,8 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     const int NKG = (K + 7) / 8;
     int NSPLIT = NW / NKG;
     if (NSPLIT < 1) NSPLIT = 1;
-    const int CC = 32 * NSPLIT;                        // columns per phase-2 chunk
+    const int CS = p.ring_kc;                          // column steps (of 32*NSPLIT columns) per phase-2 chunk
+    const int CC = 32 * NSPLIT * CS;                   // columns per phase-2 chunk
     const int nchunks = (NCP + CC - 1) / CC;
     const int NSLOT = p.ring_slots;
     const int HT = pad4(Hd * TS);
@@ -85,12 +88,11 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     uint64_t* bar_empty = bar_full + 8;
     float* smem = reinterpret_cast<float*>(smem_raw + 128);
     float* sHW = smem;                                   // hidden weights (packed, transposed)
-    float* sGW = sHW + pad4(lo.hidden_floats);           // hidden weight-gradient accumulators
-    float* sp = sGW + pad4(lo.hidden_floats);
+    float* sp = sHW + pad4(lo.hidden_floats);
     float* sWoT = sp;                                    // resident W_out[col][KPS], or the ring
     sp += WO_SMEM ? (size_t)NCP * KPS : (size_t)NSLOT * CC * KPS;
     float* sPre = sp;   sp += (size_t)NCP * TS;          // [q][col][VW]
-    float* sActBuf = sp; sp += 2 * (size_t)lo.act_floats;   // saved activations, double buffered
+    float* sActBuf = sp; sp += 2 * (size_t)lo.act_fwd_floats;   // saved activations, double buffered
     float* sG = sp;     sp += HT;                        // cotangent of the stage derivative
     float* sLam = sp;   sp += HT;                        // cotangent of z at the end of the step
     float* sMu = sp;    sp += HT;                        // pending cotangent of z at the start
@@ -138,18 +140,14 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     auto act_block = [&](int n) { return p.save_act + ((int64_t)n * lo.ntiles + tile) * lo.act_floats; };
     auto issue_act = [&](int n, float* dst) {
         const float* src = act_block(n);
-        for (int i = tid; i < lo.act_floats / 4; i += NT) cp_async16_b(dst + i * 4, src + i * 4);
+        for (int i = tid; i < lo.act_fwd_floats / 4; i += NT) cp_async16_b(dst + i * 4, src + i * 4);
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
 
     {
         const float4* src = reinterpret_cast<const float4*>(p.wpack);
         float4* dst = reinterpret_cast<float4*>(sHW);
-        float4* dz = reinterpret_cast<float4*>(sGW);
-        for (int i = tid; i < pad4(lo.hidden_floats) / 4; i += NT) {
-            dst[i] = __ldg(src + i);
-            dz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int i = tid; i < pad4(lo.hidden_floats) / 4; i += NT) dst[i] = __ldg(src + i);
         if (WO_SMEM) {
             const float4* s2 = reinterpret_cast<const float4*>(p.wpack + lo.off_wot);
             float4* d2 = reinterpret_cast<float4*>(sWoT);
@@ -197,7 +195,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
         for (int s = 3; s >= 0; --s) {
             const int n = 4 * k + s;
             float* act = act_block(n);
-            float* sAct = sActBuf + (size_t)abuf * lo.act_floats;
+            float* sAct = sActBuf + (size_t)abuf * lo.act_fwd_floats;
             PHASE_T0();
             // ---- cotangent of the stage derivative k_{s+1}  (transpose of rk4_alt_step_func)
             for (int item = tid; item < Hd * TS; item += NT) {
@@ -212,13 +210,12 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");     // saved activations of this stage have landed
             cta_sync();
             // prefetch the next stage's activations (this kernel walks n downwards); pull its tanh outputs into L2
-            if (n >= 1) issue_act(n - 1, sActBuf + (size_t)(abuf ^ 1) * lo.act_floats);
+            if (n >= 1) issue_act(n - 1, sActBuf + (size_t)(abuf ^ 1) * lo.act_fwd_floats);
             if (WO_SMEM && tid == 0 && n >= 1)
                 bulk_prefetch_l2(reinterpret_cast<const float4*>(p.save_G) + ((int64_t)(n - 1) * lo.ntiles + tile) * g_tile_f4,
                                  (uint32_t)(g_tile_f4 * 16));
-            // the stage cotangent replaces the saved stage input in HBM (read by the wgrad kernel);
-            // the copy in sAct stays valid for the first hidden layer's weight gradient
-            for (int item = tid; item < Hd * TS; item += NT) act[item] = sG[item];
+            // the stage cotangent goes to HBM for the weight-gradient kernels
+            for (int item = tid; item < Hd * TS; item += NT) act[lo.act_off_gbar + item] = sG[item];
 
             const float* sDU = sAct + lo.act_off_du;
             PHASE_MARK(8);    // stage cotangent + saved activations
@@ -323,27 +320,31 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 8 * TS; ++i) acc[i] = 0.f;
                 for (int c = 0; c < nchunks; ++c) {
-                    const int col = c * CC + split * 32 + lane;
-                    const float* wrow;
                     int slot = 0;
+                    const float* wbase;
                     if (WO_SMEM) {
-                        wrow = sWoT + (size_t)(col < NCP ? col : 0) * KPS + kg * 8;
+                        wbase = sWoT + (size_t)c * CC * KPS;
                     } else {
                         slot = rslot;
                         mbar_wait(bar_full + slot, rphase);
-                        wrow = sWoT + ((size_t)slot * CC + split * 32 + lane) * KPS + kg * 8;
+                        wbase = sWoT + (size_t)slot * CC * KPS;
                     }
-                    if (col < NCP) {
-                        const float4 w0 = *reinterpret_cast<const float4*>(wrow);
-                        const float4 w1 = *reinterpret_cast<const float4*>(wrow + 4);
-                        float pv[TS];
+                    for (int cs = 0; cs < CS; ++cs) {
+                        const int lcol = (cs * NSPLIT + split) * 32 + lane;
+                        const int col = c * CC + lcol;
+                        if (col < NCP) {
+                            const float* wrow = wbase + (size_t)lcol * KPS + kg * 8;
+                            const float4 w0 = *reinterpret_cast<const float4*>(wrow);
+                            const float4 w1 = *reinterpret_cast<const float4*>(wrow + 4);
+                            float pv[TS];
 #pragma unroll
-                        for (int q = 0; q < NQ; ++q) Vec<VW>::ld(sPre + ((size_t)q * NCP + col) * VW, pv + q * VW);
-                        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                            for (int q = 0; q < NQ; ++q) Vec<VW>::ld(sPre + ((size_t)q * NCP + col) * VW, pv + q * VW);
+                            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                        for (int kk = 0; kk < 8; ++kk)
+                            for (int kk = 0; kk < 8; ++kk)
 #pragma unroll
-                            for (int b = 0; b < TS; ++b) acc[kk * TS + b] = fmaf(wv[kk], pv[b], acc[kk * TS + b]);
+                                for (int b = 0; b < TS; ++b) acc[kk * TS + b] = fmaf(wv[kk], pv[b], acc[kk * TS + b]);
+                        }
                     }
                     if (!WO_SMEM) {
                         __syncwarp();
@@ -387,19 +388,19 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                     } else {
                         v = hb[item];
                     }
-                    hb[item] = (hl[item] > 0.f) ? v : 0.f;
+                    v = (hl[item] > 0.f) ? v : 0.f;
+                    hb[item] = v;
+                    act[lo.act_off_delta[l] + item] = v;     // for the hidden weight-gradient kernel
                 }
                 cta_sync();
-                const float* inl = (l == 0) ? sAct : sAct + lo.act_off_h[l - 1];
-                const int NWA = (NW >= 2) ? NW / 2 : NW;     // warps [0, NWA): input gradient; the rest: weight gradient
-                if (warp < NWA || NW < 2) {
+                {
                     // cotangent of the layer input: hb_next[k][b] = sum_o Wt[k][o] * delta[o][b]; KS adjacent lanes
                     // split the sum over o and combine with shuffles
                     const int nitems = Kin * NQ;
                     int KS = 4;
-                    while (KS > 1 && nitems * KS > NWA * 32) KS >>= 1;
+                    while (KS > 1 && nitems * KS > NT) KS >>= 1;
                     const int ks = tid & (KS - 1);
-                    const int per = (NWA * 32) / KS;
+                    const int per = NT / KS;
                     const int OL = (N + KS - 1) / KS;
                     const int obeg = ks * OL;
                     int ocnt = N - obeg;
@@ -433,34 +434,6 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                         if (valid && ks == 0) Vec<VW>::st(hb_next + kk * TS + q * VW, acc);
                     }
                 }
-                if (warp >= NWA || NW < 2) {
-                    // weight / bias gradient accumulators: dWt[k][o] += sum_b delta[o][b] * in[k][b]
-                    const int w0 = (NW < 2) ? 0 : NWA, nw = (NW < 2) ? 1 : NW - NWA;
-                    for (int kk = warp - w0; kk < Kin; kk += nw) {
-                        float iv[TS];
-#pragma unroll
-                        for (int q = 0; q < NQ; ++q) Vec<VW>::ld(inl + kk * TS + q * VW, iv + q * VW);
-                        for (int o = lane; o < N; o += 32) {
-                            float acc = 0.f;
-#pragma unroll
-                            for (int q = 0; q < NQ; ++q) {
-                                float dv[VW];
-                                Vec<VW>::ld(hb + o * TS + q * VW, dv);
-#pragma unroll
-                                for (int e = 0; e < VW; ++e) acc = fmaf(dv[e], iv[q * VW + e], acc);
-                            }
-                            sGW[lo.off_w[l] + kk * S + o] += acc;
-                        }
-                    }
-                    if (warp == w0) {
-                        for (int o = lane; o < N; o += 32) {
-                            float acc = 0.f;
-#pragma unroll
-                            for (int b = 0; b < TS; ++b) acc += hb[o * TS + b];
-                            sGW[lo.off_b[l] + o] += acc;
-                        }
-                    }
-                }
                 cta_sync();
                 float* t = hb; hb = hb_next; hb_next = t;
             }
@@ -487,31 +460,6 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
         const int bg = b0 + b;
         if (bg < lo.B) p.grad_z0[(int64_t)bg * Hd + i] = sLam[item] + __ldg(p.grad_z_out + (int64_t)bg * Hd + i);
     }
-    for (int i = tid; i < lo.hidden_floats; i += NT) {
-        const float v = sGW[i];
-        if (v != 0.f) atomicAdd(p.grad_hidden + i, v);
-    }
-}
-
-struct UnpackArgs {
-    NcdeLayout lo;
-    const float* packed;
-    float* gW[ANCDE_MAX_LAYERS];
-    float* gB[ANCDE_MAX_LAYERS];
-};
-
-__global__ void unpack_hidden_grads_kernel(const __grid_constant__ UnpackArgs a)
-{
-    const NcdeLayout& lo = a.lo;
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    for (int l = 0; l < lo.n_hidden; ++l) {
-        const int in = lo.in_dim[l], out = lo.width[l], S = lo.stride[l];
-        for (int idx = gtid; idx < in * out; idx += gsz) {
-            const int o = idx / in, k = idx - o * in;
-            a.gW[l][idx] += a.packed[lo.off_w[l] + k * S + o];
-        }
-        for (int o = gtid; o < out; o += gsz) a.gB[l][o] += a.packed[lo.off_b[l] + o];
-    }
 }
 
 static int bwd_threads(const NcdeLayout& lo)
@@ -530,25 +478,25 @@ static size_t bwd_smem_base(const NcdeLayout& lo, int nt)
     const int NKG = (lo.K + 7) / 8;
     int nsplit = (nt / 32) / NKG;
     if (nsplit < 1) nsplit = 1;
-    size_t f = 2 * (size_t)pad4(lo.hidden_floats);
-    f += (size_t)lo.NCP * lo.TS + 2 * (size_t)lo.act_floats + 6 * (size_t)pad4(lo.Hd * lo.TS) +
+    size_t f = (size_t)pad4(lo.hidden_floats);
+    f += (size_t)lo.NCP * lo.TS + 2 * (size_t)lo.act_fwd_floats + 6 * (size_t)pad4(lo.Hd * lo.TS) +
          2 * (size_t)pad4(lo.Hmax * lo.TS) + (size_t)nsplit * NKG * 8 * lo.TS + (size_t)lo.C4 * lo.TS;
     return f * 4 + 128;
 }
 
-static size_t bwd_ring_bytes(const NcdeLayout& lo, int nt, int slots)
+static size_t bwd_ring_bytes(const NcdeLayout& lo, int nt, int slots, int cs)
 {
     const int NKG = (lo.K + 7) / 8;
     int nsplit = (nt / 32) / NKG;
     if (nsplit < 1) nsplit = 1;
-    return (size_t)slots * 32 * nsplit * lo.KPS * 4;
+    return (size_t)slots * 32 * nsplit * cs * lo.KPS * 4;
 }
 
 // Used by make_layout's tile-size choice: does the backward fit with this many samples per CTA?
 bool bwd_fits(const NcdeLayout& lo)
 {
     const int nt = bwd_threads(lo);
-    return nt <= 480 && bwd_smem_base(lo, nt) + bwd_ring_bytes(lo, nt, 2) <= 227 * 1024;
+    return nt <= 480 && bwd_smem_base(lo, nt) + bwd_ring_bytes(lo, nt, 2, 1) <= 227 * 1024;
 }
 
 template <int TS>
@@ -566,24 +514,28 @@ static int launch_bwd(const ancde_ncde_desc* d, SolveArgs& a, cudaStream_t strea
     size_t smem;
     int threads = nt;
     a.ntc = nt;
-    a.ring_kc = 0; a.ring_pw = 0;
+    a.ring_kc = 1; a.ring_pw = 0;
     if (wo_smem) {
         a.ring_slots = 1;
         smem = base + (size_t)lo.NCP * lo.KPS * 4;
     } else {
-        int slots = 4;
-        while (slots > 2 && base + bwd_ring_bytes(lo, nt, slots) > max_smem) --slots;
-        smem = base + bwd_ring_bytes(lo, nt, slots);
+        // the deepest ring that fits: prefer two column steps per slot (fewer barrier waits), at least 3 slots
+        int slots = 4, cs = 2;
+        while (base + bwd_ring_bytes(lo, nt, slots, cs) > max_smem) {
+            if (slots > 3) --slots;
+            else if (cs > 1) { cs = 1; slots = 4; }
+            else if (slots > 2) --slots;
+            else break;
+        }
+        smem = base + bwd_ring_bytes(lo, nt, slots, cs);
         if (smem > max_smem) {
             set_error("ncde_backward: needs %zu bytes of shared memory per CTA (max %zu)", smem, max_smem);
             return ANCDE_EUNSUPPORTED;
         }
         a.ring_slots = slots;
+        a.ring_kc = cs;
         threads = nt + 32;
     }
-    // hidden-gradient scratch lives behind the packed weights
-    a.grad_hidden = d->wpack + lo.wpack_floats;
-    ANCDE_CUDA(cudaMemsetAsync(a.grad_hidden, 0, sizeof(float) * pad4(lo.hidden_floats), stream));
     static const char* names[3] = {"ncde_bwd_plain", "ncde_bwd_bottom", "ncde_bwd_top"};
     if (wo_smem) {
         ANCDE_CUDA(cudaFuncSetAttribute(ncde_bwd_kernel<TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -598,21 +550,14 @@ static int launch_bwd(const ancde_ncde_desc* d, SolveArgs& a, cudaStream_t strea
     count_launch();
     ANCDE_CUDA(cudaGetLastError());
 
-    // output-layer weight gradient (reads the stage cotangents the kernel above left in save_act)
+    // weight gradients (read the stage / layer cotangents the kernel above left in save_act)
     {
-        const int rc = launch_wgrad(a, d->grad_W[lo.n_hidden], d->grad_bias[lo.n_hidden], stream);
+        int rc = launch_wgrad(a, d->grad_W[lo.n_hidden], d->grad_bias[lo.n_hidden], stream);
         if (rc != ANCDE_OK) return rc;
-    }
-    {
-        UnpackArgs ua;
-        ua.lo = lo;
-        ua.packed = a.grad_hidden;
-        for (int l = 0; l < lo.n_hidden; ++l) { ua.gW[l] = d->grad_W[l]; ua.gB[l] = d->grad_bias[l]; }
-        prof_begin("unpack_hidden_grads", stream);
-        unpack_hidden_grads_kernel<<<32, 256, 0, stream>>>(ua);
-        prof_end(stream);
-        count_launch();
-        ANCDE_CUDA(cudaGetLastError());
+        HiddenGradPtrs hp;
+        for (int l = 0; l < lo.n_hidden; ++l) { hp.gW[l] = d->grad_W[l]; hp.gB[l] = d->grad_bias[l]; }
+        rc = launch_hidden_wgrad(a, hp, stream);
+        if (rc != ANCDE_OK) return rc;
     }
     return ANCDE_OK;
 }

@@ -98,8 +98,10 @@ __device__ __forceinline__ void ctl_finish(const SolveArgs& p, const CtlRegs& r,
     }
 }
 
-// out[o][.] = relu(bias[o] + sum_k Wt[k][o] * in[k][.]) for all TS samples; one (output, group of VW samples)
-// per thread.  The layers are tiny (<= 49x49) and latency bound: few threads, no index arithmetic.
+// out[o][.] = relu(bias[o] + sum_k Wt[k][o] * in[k][.]) for all TS samples.  The layers are tiny (<= 49x49): one
+// (output, group of VW samples) item per thread pair -- the two lanes of a pair split k and add with one
+// shuffle.  (Measured on B200: spreading a layer over all 14 warps costs more in index arithmetic and
+// shuffles than the shorter dependent chain gains; 1 lane per item leaves one warp per scheduler.)
 template <int TS>
 __device__ __forceinline__ void dense_relu(const float* __restrict__ Wt, const float* __restrict__ bias, int K,
                                            int N, int S, const float* __restrict__ in, float* __restrict__ out,
@@ -107,29 +109,42 @@ __device__ __forceinline__ void dense_relu(const float* __restrict__ Wt, const f
 {
     constexpr int VW = (TS >= 4) ? 4 : TS;
     constexpr int NQ = TS / VW;
-    for (int o = tid; o < N * NQ; o += NT) {
-        int q = 0, oo = o;
-        if (NQ > 1 && oo >= N) { q = 1; oo -= N; }
+    const int ks = tid & 1, slot = tid >> 1, nslots = NT >> 1;
+    const int KL = (K + 1) >> 1;
+    const int kbeg = ks * KL;
+    const int kcnt = ks ? K - KL : KL;
+    const int nitems = N * NQ;
+    for (int base = 0; base < nitems; base += nslots) {
+        const int item = base + slot;
+        const bool valid = item < nitems;
+        int q = 0, o = valid ? item : 0;
+        if (NQ > 1 && o >= N) { q = 1; o -= N; }
         float acc[VW];
-        const float bv = bias[oo];
 #pragma unroll
-        for (int e = 0; e < VW; ++e) acc[e] = bv;
-        const float* wp = Wt + oo;
-        const float* ip = in + q * VW;
-#pragma unroll 7
-        for (int k = 0; k < K; ++k) {
-            const float w = *wp;
-            float v[VW];
-            Vec<VW>::ld(ip, v);
-            wp += S;
-            ip += TS;
+        for (int e = 0; e < VW; ++e) acc[e] = 0.f;
+        if (valid) {
+            const float* wp = Wt + kbeg * S + o;
+            const float* ip = in + kbeg * TS + q * VW;
+#pragma unroll 5
+            for (int k = 0; k < kcnt; ++k) {
+                const float w = *wp;
+                float v[VW];
+                Vec<VW>::ld(ip, v);
+                wp += S;
+                ip += TS;
 #pragma unroll
-            for (int e = 0; e < VW; ++e) acc[e] = fmaf(w, v[e], acc[e]);
+                for (int e = 0; e < VW; ++e) acc[e] = fmaf(w, v[e], acc[e]);
+            }
         }
 #pragma unroll
-        for (int e = 0; e < VW; ++e) acc[e] = fmaxf(acc[e], 0.f);
-        Vec<VW>::st(out + oo * TS + q * VW, acc);
-        if (gsave) Vec<VW>::st(gsave + oo * TS + q * VW, acc);
+        for (int e = 0; e < VW; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 1);
+        if (valid && ks == 0) {
+            const float bv = bias[o];
+#pragma unroll
+            for (int e = 0; e < VW; ++e) acc[e] = fmaxf(acc[e] + bv, 0.f);
+            Vec<VW>::st(out + o * TS + q * VW, acc);
+            if (gsave) Vec<VW>::st(gsave + o * TS + q * VW, acc);
+        }
     }
 }
 
@@ -259,6 +274,7 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
             CtlRegs ctl;
             const bool have_next = (n + 1 < lo.n_stages);
             if (have_next) ctl_issue<TS>(p, sTimes, cnt, s == 3 ? k + 1 : k, s == 3 ? 0 : s + 1, b0, tid, NT, ctl);
+            PHASE_MARK(5);   // control issue
 
             // (2) hidden layers
             const float* in = sIn;

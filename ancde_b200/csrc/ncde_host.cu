@@ -87,6 +87,10 @@ static void fill_layout(const ancde_ncde_desc* d, int TS, NcdeLayout* lo)
     lo->act_off_du = a; a += lo->du_floats;
     lo->act_off_duda = a;
     if (d->mode == ANCDE_MODE_TOP) a += lo->du_floats;
+    a = pad4(a);
+    lo->act_fwd_floats = a;
+    lo->act_off_gbar = a; a += pad4(d->Hd * TS);
+    for (int l = 0; l < d->n_hidden; ++l) { lo->act_off_delta[l] = a; a += pad4(d->width[l] * TS); }
     lo->act_floats = pad4(a);
 }
 
@@ -164,7 +168,7 @@ extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
 {
     NcdeLayout lo;
     if (make_layout(d, &lo) != ANCDE_OK) return -1;
-    return lo.wpack_floats + pad4(lo.hidden_floats);   // + hidden-gradient scratch used by the backward
+    return lo.wpack_floats;
 }
 
 extern "C" int64_t ancde_ncde_save_act_floats(const ancde_ncde_desc* d)

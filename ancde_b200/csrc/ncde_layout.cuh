@@ -29,6 +29,9 @@ struct NcdeLayout {
     // saved activations per (stage, tile): z_s | h_1 .. h_n | dU | dU/da   (each [feature][TS])
     int act_off_h[ANCDE_MAX_LAYERS];
     int act_off_du, act_off_duda, act_floats;
+    int act_fwd_floats;                   // floats of a block the forward writes (everything before gbar)
+    int act_off_gbar;                     // written by the backward: cotangent of the stage derivative [Hd][TS]
+    int act_off_delta[ANCDE_MAX_LAYERS];  // written by the backward: masked cotangent of hidden layer l [width][TS]
     int DUS, du_floats; // dU is stored per column chunk: [chunk][4][TS] with a chunk stride of DUS = 4*TS + 4 floats
                         // (bank-conflict free 128-bit reads by lanes that own consecutive chunks)
     int n_stages;       // 4 * n_steps

@@ -57,10 +57,11 @@ def kernel_flops(cfg, B):
     s = 2.0 * stages * B
     return {
         'ncde_fwd_bottom': s * bot, 'ncde_fwd_top': s * top,
-        # recurrent backward: input-gradient pass of every layer + the hidden layers' weight gradients
-        'ncde_bwd_bottom': s * (bot + m['f_hidden']), 'ncde_bwd_top': s * (top + m['g_hidden']),
-        # output-layer weight gradient
+        # recurrent backward: input-gradient pass of every layer (same MACs as the forward)
+        'ncde_bwd_bottom': s * bot, 'ncde_bwd_top': s * top,
+        # weight gradients: output layer, hidden layers
         'ncde_wgrad_bottom': s * m['f_out'], 'ncde_wgrad_top': s * m['g_out'],
+        'ncde_hidden_wgrad_bottom': s * m['f_hidden'], 'ncde_hidden_wgrad_top': s * m['g_hidden'],
     }
 
 

@@ -17,9 +17,9 @@ L.ancde_debug_set_buffer(ctypes.c_void_p(dbg.data_ptr()))
 tr.step(batch); torch.cuda.synchronize()
 d = dbg.cpu().tolist()
 stages = 4 * (tr.cfg['L'] - 1)
-names = {0: 'fwd ctl+hidden', 1: 'fwd out-layer loop', 2: 'fwd tanh/contract/G store', 3: 'fwd ctl finish+barrier', 4: 'fwd combine+barrier',
+names = {5: 'fwd ctl issue', 0: 'fwd hidden layers', 1: 'fwd out-layer loop', 2: 'fwd tanh/contract/G store', 3: 'fwd ctl finish+barrier', 4: 'fwd combine+barrier',
          8: 'bwd gbar+act load', 9: 'bwd phase1 G->pre_bar', 10: 'bwd attention', 11: 'bwd phase2 pre_bar x W', 12: 'bwd phase3 hidden', 13: 'bwd combine'}
 print('cycles per stage (CTA 0; bottom and top kernels summed):')
 for i, nm in names.items():
     print('  %-28s %9.0f' % (nm, d[i] / stages))
-print('  fwd total %.0f  bwd total %.0f' % (sum(d[0:5]) / stages, sum(d[8:14]) / stages))
+print('  fwd total %.0f  bwd total %.0f' % (sum(d[0:6]) / stages, sum(d[8:14]) / stages))
