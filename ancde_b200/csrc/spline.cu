@@ -9,19 +9,22 @@
 //
 // Memory: X is (N, L, C) and every output (N, L-1, C), channel innermost.  Consecutive threads
 // own consecutive channels of one sample, so at a fixed knot a warp touches one contiguous run
-// of 32 values: loads and stores are sector-coalesced without staging.  The three per-knot
-// scratch arrays (imputed x, modified diagonal, modified rhs -> knot derivative) live in shared
-// memory as [knot][thread] (bank-conflict free).  HBM-bound: algorithmic traffic is
-// (L + 4(L-1)) * sizeof(T) bytes per path.
+// of 32 values: loads and stores are sector-coalesced without staging.  HBM-bound: algorithmic
+// traffic is (L + 4(L-1)) * sizeof(T) bytes per path.
+//
+// SIMT efficiency: with 90 % of the entries missing (Sepsis) nearly every knot is observed by SOME
+// lane of a warp, so loops over knots with a per-lane "observed?" branch run at ~10 % lane
+// utilisation.  Instead pass 0 compacts the observed knot indices of each path into shared memory
+// ([ordinal][thread], 16 bit), the two Thomas sweeps iterate over ORDINALS (all lanes busy until
+// the shortest path ends) and the expansion pass walks the L-1 intervals in lock step.
 #include "common.cuh"
 
 namespace ancde {
 
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __restrict__ A,
-                     T* __restrict__ Bc, T* __restrict__ C2, T* __restrict__ D3, int64_t P, int L, int C,
-                     int tf32)
+                     T* Bc, T* __restrict__ C2, T* D3, int64_t P, int L, int C, int tf32)
 {
     typedef Ops<T> O;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -29,9 +32,7 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
     const int tid = threadIdx.x;
     T* sT = reinterpret_cast<T*>(smem_raw);
     const int Lp = (L + 3) & ~3;
-    T* sx = sT + Lp;                 // [L][NT] imputed values (NaN = unobserved)
-    T* sd = sx + (size_t)L * NT;     // [L][NT] modified diagonal at observed knots
-    T* sb = sd + (size_t)L * NT;     // [L][NT] modified rhs, then the knot derivative
+    unsigned short* sidx = reinterpret_cast<unsigned short*>(sT + Lp);   // [L+2][NT] knot index per ordinal
 
     for (int i = tid; i < L; i += NT) sT[i] = times[i];
     __syncthreads();
@@ -43,27 +44,39 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
     const T* xp = X + n * (int64_t)L * C + c;
     const int64_t obase = n * (int64_t)(L - 1) * C + c;
 
-    // ---- pass 0: load the path, find the first / last observation
-    int first = -1, last = -1;
+    // ---- pass 0: compact the observed knots (slot 0 is kept free for an imputed first knot)
+    int pos = 1, first = -1, last = -1;
+    T xfirst = T(0), xlast = T(0);
 #pragma unroll 8
     for (int i = 0; i < L; ++i) {
-        T v = xp[(int64_t)i * C];
-        sx[i * NT + tid] = v;
+        const T v = xp[(int64_t)i * C];
         if (v == v) {
-            if (first < 0) first = i;
+            if (first < 0) { first = i; xfirst = v; }
             last = i;
+            xlast = v;
+            sidx[pos * NT + tid] = (unsigned short)i;
+            ++pos;
         }
     }
     if (first < 0) {   // all NaN: zero coefficients (interpolate.py:93-101)
         for (int i = 0; i < L - 1; ++i) {
-            int64_t o = obase + (int64_t)i * C;
+            const int64_t o = obase + (int64_t)i * C;
             A[o] = T(0); Bc[o] = T(0); C2[o] = T(0); D3[o] = T(0);
         }
         return;
     }
-    // end-point imputation (interpolate.py:104-114)
-    if (first != 0) sx[tid] = sx[first * NT + tid];
-    if (last != L - 1) sx[(L - 1) * NT + tid] = sx[last * NT + tid];
+    // end-point imputation (interpolate.py:104-114): knot 0 takes the first observed value, knot L-1 the last
+    const bool imp_first = first != 0, imp_last = last != L - 1;
+    int base = 1;
+    if (imp_first) { sidx[tid] = 0; base = 0; }
+    if (imp_last) { sidx[pos * NT + tid] = (unsigned short)(L - 1); ++pos; }
+    const int m = pos - base;                        // observed knots after imputation, >= 2
+    const unsigned short* jx = sidx + base * NT + tid;     // jx[j*NT] = knot index of ordinal j
+    auto xval = [&](int j, int ij) -> T {
+        if (j == 0 && imp_first) return xfirst;
+        if (j == m - 1 && imp_last) return xlast;
+        return xp[(int64_t)ij * C];
+    };
 
     // reciprocal of a time difference in the dtype of `times` (float32 for the Stock fixtures)
     auto recip = [&](int i1, int i0, T& r, T& r2) {
@@ -79,85 +92,86 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
         }
     };
 
-    // ---- pass 1: forward sweep over the observed knots (misc.py:57-61).  Row j of the system
-    // (interpolate.py:31-43) is D_j = 2 (r_j + r_{j-1}), rhs_j = pds_j + pds_{j-1}; it is
-    // completed when the NEXT observed knot is reached.
-    int prev = -1, pprev = -1, m = 0;
-    T r_prev = T(0), pds_prev = T(0);
-    for (int i = 0; i < L; ++i) {
-        T v = sx[i * NT + tid];
-        if (!(v == v)) continue;
-        ++m;
-        if (prev >= 0) {
+    // Scratch of the Thomas solve: the modified diagonal / rhs of ordinal j live in interval slot j of this
+    // path's OWN output arrays (D3 / Bc, coalesced, L1/L2 resident) until pass 3 overwrites them; only m of the
+    // L-1 slots are touched.  The last ordinal (m-1 can be L-1, one past the slots) stays in registers.
+    T* sd = D3 + obase;
+    T* sb = Bc + obase;
+    const int64_t SC = C;       // stride between interval slots
+    T k_last;
+    // ---- pass 1: forward sweep over the ordinals (misc.py:57-61).  Row j of the system
+    // (interpolate.py:31-43) is D_j = 2 (r_j + r_{j-1}), rhs_j = pds_j + pds_{j-1}.
+    {
+        int iprev = jx[0];
+        T xprev = xval(0, iprev);
+        T r_prev = T(0), pds_prev = T(0), Dpp = T(0), bpp = T(0);
+        for (int j = 1; j < m; ++j) {
+            const int ij = jx[j * NT];
+            const T xj = xval(j, ij);
             T r, r2;
-            recip(i, prev, r, r2);
-            T pds = O::mul(O::mul(T(3), O::sub(v, sx[prev * NT + tid])), r2);
+            recip(ij, iprev, r, r2);
+            const T pds = O::mul(O::mul(T(3), O::sub(xj, xprev)), r2);
             T D = O::mul(O::add(r, r_prev), T(2));
             T rhs = O::add(pds, pds_prev);
-            if (pprev >= 0) {
-                T w = O::div(r_prev, sd[pprev * NT + tid]);
+            if (j >= 2) {
+                const T w = O::div(r_prev, Dpp);
                 D = O::sub(D, O::mul(w, r_prev));
-                rhs = O::sub(rhs, O::mul(w, sb[pprev * NT + tid]));
+                rhs = O::sub(rhs, O::mul(w, bpp));
             }
-            sd[prev * NT + tid] = D;
-            sb[prev * NT + tid] = rhs;
-            pprev = prev;
-            r_prev = r;
-            pds_prev = pds;
+            sd[(j - 1) * SC] = D;
+            sb[(j - 1) * SC] = rhs;
+            Dpp = D; bpp = rhs;
+            r_prev = r; pds_prev = pds;
+            iprev = ij; xprev = xj;
         }
-        prev = i;
-    }
-    {   // last row: D = 2 r_{m-2}, rhs = pds_{m-2}
+        // last row: D = 2 r_{m-2}, rhs = pds_{m-2}
         T D = O::mul(O::add(T(0), r_prev), T(2));
         T rhs = pds_prev;
-        if (pprev >= 0) {
-            T w = O::div(r_prev, sd[pprev * NT + tid]);
+        {
+            const T w = O::div(r_prev, Dpp);
             D = O::sub(D, O::mul(w, r_prev));
-            rhs = O::sub(rhs, O::mul(w, sb[pprev * NT + tid]));
+            rhs = O::sub(rhs, O::mul(w, bpp));
         }
-        sd[prev * NT + tid] = D;
-        sb[prev * NT + tid] = rhs;
-    }
-    // ---- pass 2: back substitution (misc.py:63-65); sb becomes the knot derivative
-    {
-        int nxt = -1;
-        for (int i = L - 1; i >= 0; --i) {
-            T v = sx[i * NT + tid];
-            if (!(v == v)) continue;
-            if (nxt < 0) {
-                sb[i * NT + tid] = O::div(sb[i * NT + tid], sd[i * NT + tid]);
-            } else {
-                T r, r2;
-                recip(nxt, i, r, r2);
-                sb[i * NT + tid] = O::div(O::sub(sb[i * NT + tid], O::mul(r, sb[nxt * NT + tid])),
-                                          sd[i * NT + tid]);
-            }
-            nxt = i;
+        // ---- pass 2: back substitution (misc.py:63-65); slot j of Bc becomes the knot derivative k_j
+        T knext = O::div(rhs, D);
+        k_last = knext;
+        int inext = iprev;
+        for (int j = m - 2; j >= 0; --j) {
+            const int ij = jx[j * NT];
+            T r, r2;
+            recip(inext, ij, r, r2);
+            knext = O::div(O::sub(sb[j * SC], O::mul(r, knext)), sd[j * SC]);
+            sb[j * SC] = knext;
+            inext = ij;
         }
     }
     // ---- pass 3: coefficients of each observed piece (interpolate.py:46-53), expanded to every
-    // interval with offset = t_observed - t_i (interpolate.py:136-148)
+    // interval with offset = t_observed - t_i (interpolate.py:136-148).  All lanes walk i in lock step,
+    // BACKWARDS: piece jj is entered at its last interval idx[jj+1]-1 >= jj, when slots jj+1.. are the only
+    // ones overwritten so far; k_{jj+1} is carried in a register from the piece above, k_jj is read from slot jj.
     const bool two_knots = (m == 2);   // a single linear piece (interpolate.py:17-21)
     T pa = T(0), pb = T(0), pc = T(0), pd = T(0);
-    int cur = 0;
-    for (int i = 0; i < L - 1; ++i) {
-        T v = sx[i * NT + tid];
-        if (v == v) {
-            cur = i;
-            int ni = i + 1;
-            while (!(sx[ni * NT + tid] == sx[ni * NT + tid])) ++ni;
-            T x1 = sx[ni * NT + tid];
+    int jj = m - 1, icur = L - 1;      // current piece ordinal (none yet) and its first knot
+    T k_hi = k_last;                   // derivative at the upper knot of the piece about to be entered
+    for (int i = L - 2; i >= 0; --i) {
+        if (i < icur) {
+            // enter piece jj-1: intervals [idx[jj-1], idx[jj])
+            --jj;
+            const int ni = icur;
+            icur = jx[jj * NT];
+            const T v = xval(jj, icur), x1 = xval(jj + 1, ni);
             pa = v;
+            const T k0 = sb[jj * SC], k1 = k_hi;
+            k_hi = k0;
             if (two_knots) {
-                T dt = tf32 ? (T)__fsub_rn((float)sT[ni], (float)sT[i]) : O::sub(sT[ni], sT[i]);
+                T dt = tf32 ? (T)__fsub_rn((float)sT[ni], (float)sT[icur]) : O::sub(sT[ni], sT[icur]);
                 pb = O::div(O::sub(x1, v), dt);
                 pc = T(0);
                 pd = T(0);
             } else {
                 T r, r2;
-                recip(ni, i, r, r2);
-                T k0 = sb[i * NT + tid], k1 = sb[ni * NT + tid];
-                T six_pd = O::mul(T(2), O::mul(T(3), O::sub(x1, v)));
+                recip(ni, icur, r, r2);
+                const T six_pd = O::mul(T(2), O::mul(T(3), O::sub(x1, v)));
                 pb = k0;
                 // two_c = (six_pd * r - 4 k0 - 2 k1) * r
                 pc = O::mul(O::sub(O::sub(O::mul(six_pd, r), O::mul(T(4), k0)), O::mul(T(2), k1)), r);
@@ -165,10 +179,10 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
                 pd = O::mul(O::add(O::mul(-six_pd, r), O::mul(T(3), O::add(k0, k1))), r2);
             }
         }
-        T off = tf32 ? (T)__fsub_rn((float)sT[cur], (float)sT[i]) : O::sub(sT[cur], sT[i]);
+        const T off = tf32 ? (T)__fsub_rn((float)sT[icur], (float)sT[i]) : O::sub(sT[icur], sT[i]);
         // a_inner = (0.5 two_c - three_d * off / 3) * off
-        T a_inner = O::mul(O::sub(O::mul(T(0.5), pc), O::div(O::mul(pd, off), T(3))), off);
-        int64_t o = obase + (int64_t)i * C;
+        const T a_inner = O::mul(O::sub(O::mul(T(0.5), pc), O::div(O::mul(pd, off), T(3))), off);
+        const int64_t o = obase + (int64_t)i * C;
         A[o] = O::add(pa, O::mul(O::sub(a_inner, pb), off));
         Bc[o] = O::add(pb, O::mul(O::sub(O::mul(pd, off), pc), off));
         C2[o] = O::sub(pc, O::mul(O::mul(T(2), pd), off));
@@ -186,11 +200,13 @@ static int launch_spline(const T* times, const T* X, T* a, T* b, T* c2, T* d3, i
     if (N == 0) return ANCDE_OK;
     const int64_t P = N * (int64_t)C;
     const int Lp = (L + 3) & ~3;
+    // the only shared scratch is the 16-bit ordinal -> knot index list; the Thomas scratch lives in the outputs
+    ANCDE_CHECK_ARG(L <= 65535, "spline_coeffs: L=%d too long (max 65535 knots)", L);
     int nt = 128;
     size_t smem = 0;
     for (;; nt /= 2) {
-        smem = ((size_t)3 * L * nt + Lp) * sizeof(T);
-        if (smem <= 200 * 1024 || nt == 32) break;
+        smem = (size_t)Lp * sizeof(T) + (size_t)(L + 2) * nt * sizeof(unsigned short);
+        if (smem <= 48 * 1024 || nt == 32) break;
     }
     if (smem > 227 * 1024) {
         set_error("spline_coeffs: L=%d needs %zu bytes of shared memory per CTA (max 227 KB)", L, smem);

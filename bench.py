@@ -348,6 +348,7 @@ def run_ours(args):
                 'd2h_bytes_per_step': d2h_bytes[0], 'ms_per_step': ms_e2e / e2e_steps, 'steps': e2e_steps},
         'gpu_launches': launches,
         'roofline': roofline,
+        'roofline_spline': spline_roofline(device, cfg) if world == 1 else None,
         'kernels': kernels,
         'cpu_baseline': cpu,
     }
@@ -355,6 +356,42 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def spline_roofline(device, cfg, n_paths_target=2 ** 20):
+    """HBM roofline of the spline-coefficient kernel on a dataset-split sized input of the workload's shape."""
+    import ancde_b200
+    from ancde_b200 import _lib
+    L, C = cfg['L'], cfg['C']
+    N = max(1024, n_paths_target // C)
+    g = torch.Generator(device='cpu').manual_seed(7)
+    X = (0.1 * torch.randn(N, L, C, generator=g)).cumsum(1)
+    X[torch.rand(N, L, C, generator=g) < 0.9] = float('nan')
+    X = X.to(device)
+    times = (torch.arange(L, dtype=torch.float32) + cfg['t0']).to(device)
+    for _ in range(3):
+        ancde_b200.natural_cubic_spline_coeffs(times, X)
+    torch.cuda.synchronize(device)
+    _lib.profile_enable(True)
+    reps = 10
+    for _ in range(reps):
+        ancde_b200.natural_cubic_spline_coeffs(times, X)
+    torch.cuda.synchronize(device)
+    ts = [t for name, t in _lib.profile_read() if name.startswith('spline_coeffs')]
+    _lib.profile_enable(False)
+    ms = sum(ts) / len(ts)
+    nbytes = N * C * (L + 4 * (L - 1)) * 4           # algorithmic: read X once, write a, b, two_c, three_d once
+    peak, src = 6650.0, 'fallback 6.65 TB/s (B200_PROFILING.md)'
+    try:
+        mp = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        peak, src = float(mp['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs'
+    except (OSError, KeyError, ValueError):
+        pass
+    achieved = nbytes / (ms * 1e-3) / 1e9
+    return {'bound': 'hbm', 'kernel': 'spline_coeffs_f32', 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s',
+            'frac': round(achieved / peak, 4), 'traffic': None, 'peak_source': src, 'avg_ms': round(ms, 4),
+            'paths': N * C, 'knots': L, 'algorithmic_bytes_per_launch': nbytes,
+            'input': '%d x %d x %d float32, 90%% of entries missing' % (N, L, C)}
 
 
 def saved_gb(cfg, B):
