@@ -206,10 +206,15 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
                         for (int c = 0; c < nchunks; ++c) {
                             mbar_wait(bar_empty + slot, phase);
                             const int rows = (K - c * KC < KC) ? K - c * KC : KC;
-                            mbar_arrive_expect_tx(bar_full + slot, (uint32_t)(rows * pw * 4));
+#ifdef ANCDE_EXPERIMENT_HALF_STREAM
+                            const int pwx = (pw / 8) * 4;     // timing experiment only: stream half of every row
+#else
+                            const int pwx = pw;
+#endif
+                            mbar_arrive_expect_tx(bar_full + slot, (uint32_t)(rows * pwx * 4));
                             float* dst = sWo + (size_t)slot * KC * PW;
                             for (int r = 0; r < rows; ++r)
-                                bulk_g2s(dst + (size_t)r * PW, Wg + (size_t)(c * KC + r) * NCP + col0, (uint32_t)(pw * 4),
+                                bulk_g2s(dst + (size_t)r * PW, Wg + (size_t)(c * KC + r) * NCP + col0, (uint32_t)(pwx * 4),
                                          bar_full + slot);
                             if (++slot == NSLOT) { slot = 0; phase ^= 1; }
                         }

@@ -32,7 +32,8 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
     const int tid = threadIdx.x;
     T* sT = reinterpret_cast<T*>(smem_raw);
     const int Lp = (L + 3) & ~3;
-    unsigned short* sidx = reinterpret_cast<unsigned short*>(sT + Lp);   // [L+2][NT] knot index per ordinal
+    T* sxv = sT + Lp;                                                     // [L+2][NT] observed value per ordinal
+    unsigned short* sidx = reinterpret_cast<unsigned short*>(sxv + (size_t)(L + 2) * NT);   // [L+2][NT] knot index per ordinal
 
     for (int i = tid; i < L; i += NT) sT[i] = times[i];
     __syncthreads();
@@ -55,6 +56,7 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
             last = i;
             xlast = v;
             sidx[pos * NT + tid] = (unsigned short)i;
+            sxv[pos * NT + tid] = v;
             ++pos;
         }
     }
@@ -68,15 +70,12 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
     // end-point imputation (interpolate.py:104-114): knot 0 takes the first observed value, knot L-1 the last
     const bool imp_first = first != 0, imp_last = last != L - 1;
     int base = 1;
-    if (imp_first) { sidx[tid] = 0; base = 0; }
-    if (imp_last) { sidx[pos * NT + tid] = (unsigned short)(L - 1); ++pos; }
+    if (imp_first) { sidx[tid] = 0; sxv[tid] = xfirst; base = 0; }
+    if (imp_last) { sidx[pos * NT + tid] = (unsigned short)(L - 1); sxv[pos * NT + tid] = xlast; ++pos; }
     const int m = pos - base;                        // observed knots after imputation, >= 2
     const unsigned short* jx = sidx + base * NT + tid;     // jx[j*NT] = knot index of ordinal j
-    auto xval = [&](int j, int ij) -> T {
-        if (j == 0 && imp_first) return xfirst;
-        if (j == m - 1 && imp_last) return xlast;
-        return xp[(int64_t)ij * C];
-    };
+    const T* jv = sxv + base * NT + tid;                    // jv[j*NT] = value of ordinal j (imputed ends included)
+    auto xval = [&](int j, int) -> T { return jv[j * NT]; };
 
     // reciprocal of a time difference in the dtype of `times` (float32 for the Stock fixtures)
     auto recip = [&](int i1, int i0, T& r, T& r2) {
@@ -136,6 +135,7 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
         T knext = O::div(rhs, D);
         k_last = knext;
         int inext = iprev;
+#pragma unroll 4
         for (int j = m - 2; j >= 0; --j) {
             const int ij = jx[j * NT];
             T r, r2;
@@ -205,8 +205,8 @@ static int launch_spline(const T* times, const T* X, T* a, T* b, T* c2, T* d3, i
     int nt = 128;
     size_t smem = 0;
     for (;; nt /= 2) {
-        smem = (size_t)Lp * sizeof(T) + (size_t)(L + 2) * nt * sizeof(unsigned short);
-        if (smem <= 48 * 1024 || nt == 32) break;
+        smem = (size_t)Lp * sizeof(T) + (size_t)(L + 2) * nt * (sizeof(unsigned short) + sizeof(T));
+        if (smem <= 56 * 1024 || nt == 32) break;
     }
     if (smem > 227 * 1024) {
         set_error("spline_coeffs: L=%d needs %zu bytes of shared memory per CTA (max 227 KB)", L, smem);

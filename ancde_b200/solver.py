@@ -12,7 +12,8 @@ import torch
 from . import _lib
 
 _grid_cache = {}
-FORCE_SAMPLES_PER_CTA = 0   # tests set this to 1/2/4/8 to exercise every kernel instantiation
+import os
+FORCE_SAMPLES_PER_CTA = int(os.environ.get('ANCDE_SAMPLES_PER_CTA', '0'))   # 0 = library default; tests set 1/2/4/8
 
 
 class SolvePlan:
