@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libancde_b200.so')
 
 MAX_LAYERS = 8
 MODE_PLAIN, MODE_BOTTOM, MODE_TOP = 0, 1, 2
+ENGINE_FFMA, ENGINE_MMA = 1, 2
 ABI_VERSION = 1
 
 _f32p = ctypes.POINTER(ctypes.c_float)
@@ -35,7 +36,7 @@ class NcdeDesc(ctypes.Structure):
         ('grad_z_out', ctypes.c_void_p), ('grad_z0', ctypes.c_void_p),
         ('grad_W', ctypes.c_void_p * (MAX_LAYERS + 1)), ('grad_bias', ctypes.c_void_p * (MAX_LAYERS + 1)),
         ('grad_attention', ctypes.c_void_p),
-        ('samples_per_cta', ctypes.c_int32), ('reserved', ctypes.c_int32),
+        ('samples_per_cta', ctypes.c_int32), ('engine', ctypes.c_int32),
     ]
 
 

@@ -1,0 +1,199 @@
+// Tensor-core ("v2") fused NCDE solve: shared definitions.
+//
+// Design: the vector field's output layer  G = tanh(W_out h + b).view(Hd, C)  is 88 % of the
+// path's FLOPs.  With the batch spread over all SMs an SM only owns ~8 samples, so a plain FFMA or UMMA formulation
+// re-reads all of W_out (84 k floats at the Sepsis shape) from shared memory for every 8 samples and is bound by
+// shared-memory bandwidth.  Here a thread-block CLUSTER of CS CTAs integrates NS = 8*NT samples together: every CTA
+// keeps a 1/CS slice of W_out's rows resident in shared memory for the whole solve (pre-split into FP16 hi/lo
+// fragments, 4 bytes per weight), multiplies it with the activations of all NS samples on the tensor cores
+// (mma.sync m16n8k16, 3 products per tile = FP32-grade accuracy: hi*hi + lo*hi + hi*lo), applies tanh and the
+// contraction with dU in the accumulator registers, and the CTAs exchange the 1/CS slices of the stage derivative
+// through distributed shared memory.  The small hidden layers are evaluated redundantly by every CTA of the cluster.
+//
+// Output-layer rows are grouped into TILES of 16 = 2 field rows (i-pair) x 8 control channels (j-chunk):
+//   tile (ip, jc), row r < 8  -> (i = 2*ip,     j = 8*jc + r)
+//                  row r >= 8 -> (i = 2*ip + 1, j = 8*jc + r - 8)
+// so that in the m16n8 accumulator fragment a thread holds the same j for both field rows and the contraction over
+// j is a reduction over the 8 lanes that share lane%4.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "ncde_common.cuh"
+#include "pipeline.cuh"
+
+namespace ancde {
+
+constexpr float V2_WSCALE = 64.0f;          // weights are stored as fp16(64*W): keeps the lo halves out of the subnormals
+constexpr float V2_WSCALE_INV = 1.0f / 64.0f;
+constexpr int V2_MAX_KSTEPS = 4;            // output-layer reduction size K <= 64
+constexpr int V2_RK_ITEMS = 6;              // (state element, sample) items a thread keeps in registers
+constexpr int V2_MAX_CS = 8;
+
+// A-operand pack of a matrix A[M][K]: m-tiles of 16 rows; per m-tile `full` k16 steps (64 uint4 each: 32 lanes of hi
+// fragments then 32 lanes of lo fragments) and an optional k8 tail (32 uint4: {hi a0, hi a1, lo a0, lo a1} per lane)
+// or k16 tail.
+struct APack {
+    int M, K;           // logical sizes
+    int mtiles;         // ceil(M / 16)
+    int full;           // k16 steps (including a k16 tail)
+    int tail8;          // 1 if a final k8 step follows
+    int stride;         // uint4 per m-tile = full*64 + tail8*32
+    int off;            // offset in uint4 units from the start of wpack
+};
+
+struct V2Layout {
+    // ---- problem ----
+    int B, L, C, Hd, n_hidden, mode, att_C, att_L, n_hp, n_steps, n_out, n_stages;
+    int width[ANCDE_MAX_LAYERS], in_dim[ANCDE_MAX_LAYERS];
+    int K;                      // width of the last hidden layer
+    // ---- output-layer tiling ----
+    int NIP, NJC, C8, ntiles;   // i-pairs, j-chunks, 8*NJC, NIP*NJC
+    // ---- packed weights (wpack, 16-byte units) ----
+    APack hf[ANCDE_MAX_LAYERS];     // hidden layer l forward:   A = 64*W_l      [width_l][in_l]
+    APack hb[ANCDE_MAX_LAYERS];     // hidden layer l backward:  A = 64*W_l^T    [in_l][width_l]
+    APack of;                       // output layer forward:     A = 64*W_out tiles, M = ntiles*16, K
+    APack ob;                       // output layer backward:    per tile A = 64*W_out^T [K][16 rows]; M = K, K = 16, `off` per tile = ob.off + tile*ob_tile
+    int ob_tile;                    // uint4 per tile of the backward pack = mtiles(K)*64
+    int off_hbias[ANCDE_MAX_LAYERS];    // float offsets (from wpack as float*): 64*bias_l padded to 16*mtiles
+    int off_obias;                      // 64*bias_out per tile row [ntiles][16]
+    int hidden_u4, hidden_b_u4;     // total uint4 of all hf / hb packs (contiguous from hf[0].off / hb[0].off)
+    int64_t wpack_floats;
+    int KSB;                        // k16 steps of the widest B-operand (activations) buffer
+    // ---- saved activations: [stage][feature row][B]; rows = z_s | h_1..h_L | dU | dU/da | gbar | delta_1..delta_L
+    int row_z, row_h[ANCDE_MAX_LAYERS], row_du, row_duda, row_gbar, row_delta[ANCDE_MAX_LAYERS], act_rows;
+    // tanh outputs: [stage][B][Hd][C8]
+};
+
+struct V2Launch {
+    int CS, NT, NS, nclusters, threads;
+    int ip_begin[V2_MAX_CS + 1];    // i-pair range of every cluster rank
+    size_t smem;
+};
+
+struct V2Args {
+    V2Layout lo;
+    V2Launch la;
+    float t_start, t_end, step;
+    const float* times;
+    const float* t_out;
+    const float* cb;
+    const float* cc2;
+    const float* cd3;
+    const float* z0;
+    const float* attention;
+    const float* h_prime;
+    const uint4* wpack;
+    float* z_out;
+    float* k_out;
+    float* save_act;
+    float* save_G;
+    const float* grad_z_out;
+    float* grad_z0;
+    float* grad_attention;
+    long long* dbg;
+};
+
+int make_layout2(const ancde_ncde_desc* d, V2Layout* lo);
+int pack_weights2(const ancde_ncde_desc* d, const V2Layout& lo, cudaStream_t stream);
+int fill_args2(const ancde_ncde_desc* d, const V2Layout& lo, V2Args* a);
+int launch_fwd2(V2Args& a, cudaStream_t stream);
+
+#ifdef __CUDACC__
+// ---- tensor-core primitives (legacy mma.sync path: the operands live in registers, M = 16 rows of weights,
+// N = 8 samples -- the shape of this problem; see DESIGN.md for why not tcgen05) ------------------------------
+__device__ __forceinline__ void mma16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0)
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0));
+}
+// d += (Ahi + Alo) * (Bhi + Blo) without the lo*lo term; small terms first.
+__device__ __forceinline__ void mma16x3(float (&d)[4], const uint4& ah, const uint4& al, uint32_t bh0, uint32_t bh1, uint32_t bl0,
+                                        uint32_t bl1)
+{
+    mma16(d, al.x, al.y, al.z, al.w, bh0, bh1);
+    mma16(d, ah.x, ah.y, ah.z, ah.w, bl0, bl1);
+    mma16(d, ah.x, ah.y, ah.z, ah.w, bh0, bh1);
+}
+// k8 tail: a = {hi a0, hi a1, lo a0, lo a1}
+__device__ __forceinline__ void mma8x3(float (&d)[4], const uint4& a, uint32_t bh0, uint32_t bl0)
+{
+    mma8(d, a.z, a.w, bh0);
+    mma8(d, a.x, a.y, bl0);
+    mma8(d, a.x, a.y, bh0);
+}
+
+// FP32 pair -> packed FP16 hi and lo halves (x = hi + lo up to 2^-22 |x|)
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo)
+{
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// B-operand (activations) buffer: [k16 step][n-tile][lane] uint4 = {hi b0, hi b1, lo b0, lo b1}; element (k, n) of the
+// K x N operand lives in lane (n%8)*4 + (k%8)/2, register (k%16)/8, half k%2.
+__device__ __forceinline__ void bfrag_store(uint4* buf, int NT, int k, int n, float v)
+{
+    const int kk = k & 15;
+    __half* base = reinterpret_cast<__half*>(buf + (((k >> 4) * NT + (n >> 3)) * 32 + (n & 7) * 4 + ((kk & 7) >> 1)));
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    const int e = (kk >> 3) * 2 + (kk & 1);
+    base[e] = hi;
+    base[4 + e] = lo;
+}
+
+// ---- cluster plumbing -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t rank)
+{
+    uint32_t d;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(d) : "r"(smem_addr), "r"(rank));
+    return d;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v)
+{
+    asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
+// Sum over the 8 lanes that share lane%4 of V values per lane, halving the live values at every step: afterwards
+// the lane with g = lane/4 holds, in v[0 .. V/8-1], the totals of indices base(g) .. base(g) + V/8 - 1 with
+// base(g) = (g>>2)*(V/2) + ((g>>1)&1)*(V/4) + (g&1)*(V/8).  For V = 4 the last step is a plain butterfly and both
+// lanes of a pair hold the total of index (g>>2)*2 + ((g>>1)&1).
+template <int V>
+__device__ __forceinline__ void reduce_scatter_g(float (&v)[V], int lane)
+{
+    int mask = 16;
+#pragma unroll
+    for (int half = V / 2; half >= 1 && mask >= 4; half /= 2) {
+        const bool up = (lane & mask) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? v[i] : v[i + half];
+            const float keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+        }
+        mask >>= 1;
+    }
+    if (V == 4) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 4);
+}
+#endif
+
+}  // namespace ancde

@@ -1,6 +1,6 @@
 // Host side of the fused NCDE solve: layout of packed weights / saved activations, weight packing,
 // argument marshalling and the C-ABI entry points for the forward.
-#include "ncde_common.cuh"
+#include "ncde2_common.cuh"
 
 namespace ancde {
 
@@ -164,8 +164,18 @@ int fill_args(const ancde_ncde_desc* d, const NcdeLayout& lo, SolveArgs* a)
 
 using namespace ancde;
 
+// Engine choice: the descriptor's `engine`, else the library default.
+static const int DEFAULT_ENGINE = ANCDE_ENGINE_FFMA;
+namespace ancde {
+int engine_of(const ancde_ncde_desc* d) { return (d && d->engine) ? d->engine : DEFAULT_ENGINE; }
+}
+
 extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
 {
+    if (engine_of(d) == ANCDE_ENGINE_MMA) {
+        V2Layout l2;
+        return make_layout2(d, &l2) == ANCDE_OK ? l2.wpack_floats : -1;
+    }
     NcdeLayout lo;
     if (make_layout(d, &lo) != ANCDE_OK) return -1;
     return lo.wpack_floats;
@@ -173,6 +183,10 @@ extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
 
 extern "C" int64_t ancde_ncde_save_act_floats(const ancde_ncde_desc* d)
 {
+    if (engine_of(d) == ANCDE_ENGINE_MMA) {
+        V2Layout l2;
+        return make_layout2(d, &l2) == ANCDE_OK ? (int64_t)l2.n_stages * l2.act_rows * l2.B : -1;
+    }
     NcdeLayout lo;
     if (make_layout(d, &lo) != ANCDE_OK) return -1;
     return (int64_t)lo.n_stages * lo.ntiles * lo.act_floats;
@@ -180,6 +194,10 @@ extern "C" int64_t ancde_ncde_save_act_floats(const ancde_ncde_desc* d)
 
 extern "C" int64_t ancde_ncde_save_G_floats(const ancde_ncde_desc* d)
 {
+    if (engine_of(d) == ANCDE_ENGINE_MMA) {
+        V2Layout l2;
+        return make_layout2(d, &l2) == ANCDE_OK ? (int64_t)l2.n_stages * l2.B * l2.Hd * l2.C8 : -1;
+    }
     NcdeLayout lo;
     if (make_layout(d, &lo) != ANCDE_OK) return -1;
     return (int64_t)lo.n_stages * lo.ntiles * lo.TS * lo.NCP;
@@ -189,10 +207,22 @@ extern "C" int ancde_ncde_forward(const ancde_ncde_desc* d, void* stream_)
 {
     reset_launch_count();
     cudaStream_t stream = (cudaStream_t)stream_;
+    ANCDE_CHECK_ARG(d != nullptr, "ncde_forward: null descriptor");
+    ANCDE_CHECK_ARG((d->save_act == nullptr) == (d->save_G == nullptr), "ncde_forward: save_act and save_G go together");
+    if (engine_of(d) == ANCDE_ENGINE_MMA) {
+        V2Layout l2;
+        int rc2 = make_layout2(d, &l2);
+        if (rc2 != ANCDE_OK) return rc2;
+        V2Args a2;
+        rc2 = fill_args2(d, l2, &a2);
+        if (rc2 != ANCDE_OK) return rc2;
+        rc2 = pack_weights2(d, l2, stream);
+        if (rc2 != ANCDE_OK) return rc2;
+        return launch_fwd2(a2, stream);
+    }
     NcdeLayout lo;
     int rc = make_layout(d, &lo);
     if (rc != ANCDE_OK) return rc;
-    ANCDE_CHECK_ARG((d->save_act == nullptr) == (d->save_G == nullptr), "ncde_forward: save_act and save_G go together");
     SolveArgs a;
     rc = fill_args(d, lo, &a);
     if (rc != ANCDE_OK) return rc;

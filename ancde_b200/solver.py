@@ -14,6 +14,7 @@ from . import _lib
 _grid_cache = {}
 import os
 FORCE_SAMPLES_PER_CTA = int(os.environ.get('ANCDE_SAMPLES_PER_CTA', '0'))   # 0 = library default; tests set 1/2/4/8
+ENGINE = int(os.environ.get('ANCDE_ENGINE', '0'))                           # 0 = library default; 1 = FFMA, 2 = tensor-core
 
 
 class SolvePlan:
@@ -115,6 +116,7 @@ def _desc(plan, z0, attention, wb, widths, Hd):
         d.attention = attention.data_ptr()
         d.h_prime = plan.h_prime.data_ptr()
     d.samples_per_cta = FORCE_SAMPLES_PER_CTA
+    d.engine = ENGINE
     return d
 
 
