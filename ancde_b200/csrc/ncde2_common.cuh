@@ -59,13 +59,19 @@ struct V2Layout {
     int hidden_u4, hidden_b_u4;     // total uint4 of all hf / hb packs (contiguous from hf[0].off / hb[0].off)
     int64_t wpack_floats;
     int KSB;                        // k16 steps of the widest B-operand (activations) buffer
-    // ---- saved activations: [stage][feature row][B]; rows = z_s | h_1..h_L | dU | dU/da | gbar | delta_1..delta_L
-    int row_z, row_h[ANCDE_MAX_LAYERS], row_du, row_duda, row_gbar, row_delta[ANCDE_MAX_LAYERS], act_rows;
-    // tanh outputs: [stage][B][Hd][C8]
+    int MTz;                        // m-tiles of the state (ceil(Hd / 16))
+    // ---- tiling of the batch (fixed per shape so that forward and backward agree on the saved layouts) ----
+    int NT, NS, nclusters;          // n-tiles (8 samples each) and samples per cluster, clusters
+    unsigned magicC;                // ceil(2^32 / C): item / C == __umulhi(item, magicC) for item * C < 2^32
+    // ---- saved activations, per (stage, cluster) a block of act_block floats; matrices [rows][NS] are stored in
+    // accumulator-FRAGMENT order: m-tile mt, n-tile nt, lane -> float4 {(g, 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1)}
+    int fo_z, fo_h[ANCDE_MAX_LAYERS], fo_du, fo_duda, fo_gbar, fo_delta[ANCDE_MAX_LAYERS], act_block;
+    // dU / dU/da blocks are [item = n*C + j]
+    // tanh outputs: [stage][cluster][tile][nt][lane] float4 in the same fragment order (rows = tile rows)
 };
 
 struct V2Launch {
-    int CS, NT, NS, nclusters, threads;
+    int CS, threads;
     int ip_begin[V2_MAX_CS + 1];    // i-pair range of every cluster rank
     size_t smem;
 };
@@ -97,6 +103,21 @@ int make_layout2(const ancde_ncde_desc* d, V2Layout* lo);
 int pack_weights2(const ancde_ncde_desc* d, const V2Layout& lo, cudaStream_t stream);
 int fill_args2(const ancde_ncde_desc* d, const V2Layout& lo, V2Args* a);
 int launch_fwd2(V2Args& a, cudaStream_t stream);
+int choose_launch2_fwd(V2Layout* lo, V2Launch* la);
+
+// Phase timing for kernel development (-DANCDE_PHASE_TIMING): clock64() deltas are accumulated in registers and
+// written once at the end, so that the probe itself does not stall the warp on a global round trip per phase.
+#ifdef ANCDE_PHASE_TIMING
+#define PH2_DECL() long long ph2_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long ph2_t = 0
+#define PH2_T0() ph2_t = clock64()
+#define PH2_MARK(i) do { const long long now__ = clock64(); ph2_acc[i] += now__ - ph2_t; ph2_t = now__; } while (0)
+#define PH2_FLUSH(base) do { if (threadIdx.x == 0 && blockIdx.x == 0 && p.dbg) { for (int i__ = 0; i__ < 8; ++i__) p.dbg[(base) + i__] += ph2_acc[i__]; } } while (0)
+#else
+#define PH2_DECL() do { } while (0)
+#define PH2_T0() do { } while (0)
+#define PH2_MARK(i) do { } while (0)
+#define PH2_FLUSH(base) do { } while (0)
+#endif
 
 #ifdef __CUDACC__
 // ---- tensor-core primitives (legacy mma.sync path: the operands live in registers, M = 16 rows of weights,
@@ -139,17 +160,30 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// B-operand (activations) buffer: [k16 step][n-tile][lane] uint4 = {hi b0, hi b1, lo b0, lo b1}; element (k, n) of the
-// K x N operand lives in lane (n%8)*4 + (k%8)/2, register (k%16)/8, half k%2.
-__device__ __forceinline__ void bfrag_store(uint4* buf, int NT, int k, int n, float v)
+// B-operand (activations) buffers: two FP16 matrices (hi, lo) [n][KP] with k contiguous and KP = 16*KSB + 8 halfs
+// (row stride = 16 bytes mod 128: ldmatrix / stmatrix rows fall into distinct bank groups).
+// Address of this lane's row for the x4 access of (k16 step ks, n-tile nt): matrices {hi k0-7, hi k8-15, lo k0-7, lo k8-15}.
+__device__ __forceinline__ uint32_t bmat_lane_addr(uint32_t hi_base, uint32_t lo_minus_hi, int KP, int lane)
 {
-    const int kk = k & 15;
-    __half* base = reinterpret_cast<__half*>(buf + (((k >> 4) * NT + (n >> 3)) * 32 + (n & 7) * 4 + ((kk & 7) >> 1)));
-    const __half hi = __float2half_rn(v);
-    const __half lo = __float2half_rn(v - __half2float(hi));
-    const int e = (kk >> 3) * 2 + (kk & 1);
-    base[e] = hi;
-    base[4 + e] = lo;
+    return hi_base + (uint32_t)(((lane & 7) * KP + ((lane >> 3) & 1) * 8) * 2) + ((lane >> 4) ? lo_minus_hi : 0u);
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+// Stores an accumulator tile (rows = features k, columns = samples n) transposed, i.e. as rows n of the [n][k] matrices.
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
+{
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1,%2,%3,%4};\n" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+// Splits an accumulator fragment {(g,2t),(g,2t+1),(g+8,2t),(g+8,2t+1)} into hi/lo halves and stores it as the B operand
+// of the next product.
+__device__ __forceinline__ void store_act_tile(uint32_t lane_addr, const float (&v)[4])
+{
+    uint32_t h0, l0, h1, l1;
+    split_pair(v[0], v[1], h0, l0);
+    split_pair(v[2], v[3], h1, l1);
+    stmatrix_x4_trans(lane_addr, h0, h1, l0, l1);
 }
 
 // ---- cluster plumbing -------------------------------------------------------------------------------------------

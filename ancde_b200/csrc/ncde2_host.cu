@@ -71,15 +71,23 @@ int make_layout2(const ancde_ncde_desc* d, V2Layout* lo)
     for (int l = 0; l < d->n_hidden; ++l) { lo->off_hbias[l] = foff; foff += lo->hf[l].mtiles * 16; }
     lo->off_obias = foff; foff += lo->ntiles * 16;
     lo->wpack_floats = pad4(foff);
-    int r = 0;
-    lo->row_z = r; r += d->Hd;
-    for (int l = 0; l < d->n_hidden; ++l) { lo->row_h[l] = r; r += d->width[l]; }
-    lo->row_du = r; r += d->C;
-    lo->row_duda = r;
-    if (d->mode == ANCDE_MODE_TOP) r += d->C;
-    lo->row_gbar = r; r += d->Hd;
-    for (int l = 0; l < d->n_hidden; ++l) { lo->row_delta[l] = r; r += d->width[l]; }
-    lo->act_rows = r;
+    lo->MTz = (d->Hd + 15) / 16;
+    // batch tiling: decided by the forward's shared-memory fit (ncde2_fwd.cu)
+    V2Launch la;
+    lo->NT = 0;
+    lo->magicC = (unsigned)((((uint64_t)1 << 32) + d->C - 1) / d->C);
+    const int rc = choose_launch2_fwd(lo, &la);
+    if (rc != ANCDE_OK) return rc;
+    int o = 0;
+    const int frag = lo->NT * 128;
+    lo->fo_z = o; o += lo->MTz * frag;
+    for (int l = 0; l < d->n_hidden; ++l) { lo->fo_h[l] = o; o += lo->hf[l].mtiles * frag; }
+    lo->fo_du = o; o += pad4(d->C * lo->NS);
+    lo->fo_duda = o;
+    if (d->mode == ANCDE_MODE_TOP) o += pad4(d->C * lo->NS);
+    lo->fo_gbar = o; o += lo->MTz * frag;
+    for (int l = 0; l < d->n_hidden; ++l) { lo->fo_delta[l] = o; o += lo->hf[l].mtiles * frag; }
+    lo->act_block = o;
     return ANCDE_OK;
 }
 

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     int rslot = 0;           // ring slot / phase parity of the next fill to consume
     uint32_t rphase = 0;
     int abuf = 0;            // which half of sActBuf holds the current stage
+    float gmax = 0.f;        // largest |stage cotangent| this thread wrote (scale of the FP16 weight-gradient operands)
 
     for (int k = lo.n_steps - 1; k >= 0; --k) {
         const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step);
@@ -215,7 +216,11 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                 bulk_prefetch_l2(reinterpret_cast<const float4*>(p.save_G) + ((int64_t)(n - 1) * lo.ntiles + tile) * g_tile_f4,
                                  (uint32_t)(g_tile_f4 * 16));
             // the stage cotangent goes to HBM for the weight-gradient kernels
-            for (int item = tid; item < Hd * TS; item += NT) act[lo.act_off_gbar + item] = sG[item];
+            for (int item = tid; item < Hd * TS; item += NT) {
+                const float gv = sG[item];
+                act[lo.act_off_gbar + item] = gv;
+                gmax = fmaxf(gmax, fabsf(gv));
+            }
 
             const float* sDU = sAct + lo.act_off_du;
             PHASE_MARK(8);    // stage cotangent + saved activations
@@ -455,6 +460,9 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
         }
     }
     // ---- results
+    for (int o = 16; o >= 1; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if (lane == 0 && gmax > 0.f && gmax < 3.0e38f)
+        atomicMax(reinterpret_cast<unsigned*>(const_cast<float*>(p.wpack) + lo.off_gscale), __float_as_uint(gmax));
     for (int item = tid; item < Hd * TS; item += NT) {
         const int i = item / TS, b = item - i * TS;
         const int bg = b0 + b;

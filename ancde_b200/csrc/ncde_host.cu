@@ -26,6 +26,7 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a)
         }
         for (int o = gtid; o < pad4(out); o += gsz) a.wpack[lo.off_b[l] + o] = (o < out) ? a.bias[l][o] : 0.f;
     }
+    if (gtid < 4) a.wpack[lo.off_gscale + gtid] = 0.f;
     const int K = lo.K, NCP = lo.NCP, C4 = lo.C4, C = lo.C;
     const float* Wout = a.W[lo.n_hidden];
     const float* bout = a.bias[lo.n_hidden];
@@ -78,6 +79,7 @@ static void fill_layout(const ancde_ncde_desc* d, int TS, NcdeLayout* lo)
     lo->off_bo = off; off += lo->NCP;
     lo->KPS = 8 * ((lo->K + 7) / 8) + 4;   // +4: 16-byte rows whose stride is bank-conflict free for LDS.128
     lo->off_wot = off; off += lo->NCP * lo->KPS;
+    lo->off_gscale = off; off += 4;
     lo->wpack_floats = off;
     int a = d->Hd * TS;
     for (int l = 0; l < d->n_hidden; ++l) { lo->act_off_h[l] = a; a += d->width[l] * TS; }
@@ -185,7 +187,7 @@ extern "C" int64_t ancde_ncde_save_act_floats(const ancde_ncde_desc* d)
 {
     if (engine_of(d) == ANCDE_ENGINE_MMA) {
         V2Layout l2;
-        return make_layout2(d, &l2) == ANCDE_OK ? (int64_t)l2.n_stages * l2.act_rows * l2.B : -1;
+        return make_layout2(d, &l2) == ANCDE_OK ? (int64_t)l2.n_stages * l2.nclusters * l2.act_block : -1;
     }
     NcdeLayout lo;
     if (make_layout(d, &lo) != ANCDE_OK) return -1;
@@ -196,7 +198,7 @@ extern "C" int64_t ancde_ncde_save_G_floats(const ancde_ncde_desc* d)
 {
     if (engine_of(d) == ANCDE_ENGINE_MMA) {
         V2Layout l2;
-        return make_layout2(d, &l2) == ANCDE_OK ? (int64_t)l2.n_stages * l2.B * l2.Hd * l2.C8 : -1;
+        return make_layout2(d, &l2) == ANCDE_OK ? (int64_t)l2.n_stages * l2.nclusters * l2.ntiles * l2.NT * 128 : -1;
     }
     NcdeLayout lo;
     if (make_layout(d, &lo) != ANCDE_OK) return -1;

@@ -25,6 +25,7 @@ struct NcdeLayout {
     int hidden_floats;  // all hidden layers (weights + biases)
     int off_wo, off_bo; // output layer Wt_out[k][NCP], bias_out[NCP]
     int off_wot, KPS;   // second copy for the backward: W_out[col][KPS] (k contiguous, KPS = 8*ceil(K/8) + 4)
+    int off_gscale;     // 4 floats of scratch: max |stage cotangent| of the running backward (bits, atomicMax)
     int64_t wpack_floats;
     // saved activations per (stage, tile): z_s | h_1 .. h_n | dU | dU/da   (each [feature][TS])
     int act_off_h[ANCDE_MAX_LAYERS];

@@ -11,6 +11,8 @@
 // Tiling: a CTA owns CBLK*128 columns and ALL k; warp = (k group of 8, column block), lane = one
 // column group of 4, so a thread accumulates a 4 x 8 register tile.  Rows arrive in chunks of 32
 // through a two-stage cp.async (LDGSTS) pipeline; the bias gradient is the extra k column h = 1.
+#include <stdlib.h>
+
 #include "ncde_common.cuh"
 
 namespace ancde {
@@ -408,8 +410,16 @@ int launch_hidden_wgrad(const SolveArgs& a, const HiddenGradPtrs& hp, cudaStream
     }
 }
 
+int launch_wgrad_mma(const SolveArgs& a, float* gW, float* gB, cudaStream_t stream);   // ncde_wgrad_mma.cu
+
 int launch_wgrad(const SolveArgs& a, float* gW, float* gB, cudaStream_t stream)
 {
+    static int ffma = -1;        // development switch: ANCDE_WGRAD_FFMA=1 selects the FP32-FMA kernel of this file
+    if (ffma < 0) {
+        const char* e = getenv("ANCDE_WGRAD_FFMA");
+        ffma = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!ffma) return launch_wgrad_mma(a, gW, gB, stream);
     switch (a.lo.TS) {
         case 8: return launch_wgrad_ts<8>(a, gW, gB, stream);
         case 4: return launch_wgrad_ts<4>(a, gW, gB, stream);
