@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(MAXTHR, 1) ncde2_fwd_kernel(const __grid_const
                 cb[it] = cc2[it] = cd3[it] = 0.f;
                 ca[it] = chp[it] = 0.f;
                 const int item = tid + it * NTHR;
-                const int n = (int)__umulhi((unsigned)item, lo.magicC), j = item - n * C;
+                const int n = (C == 1) ? item : (int)__umulhi((unsigned)item, lo.magicC), j = item - n * C;
                 const int bg = b0 + n;
                 if (item < n_ctl && bg < B) {
                     const int o = bg * rowlen + j;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(MAXTHR, 1) ncde2_fwd_kernel(const __grid_const
         for (int it = 0; it < V2_CTL_ITEMS; ++it) {
             const int item = tid + it * NTHR;
             if (it < n_ctl_it && item < n_ctl) {
-                const int n = (int)__umulhi((unsigned)item, lo.magicC), j = item - n * C;
+                const int n = (C == 1) ? item : (int)__umulhi((unsigned)item, lo.magicC), j = item - n * C;
                 // derivative = b + (two_c + three_d * frac) * frac   (interpolate.py:298-303)
                 const float dX = __fadd_rn(cb[it], __fmul_rn(__fadd_rn(cc2[it], __fmul_rn(cd3[it], cfrac)), cfrac));
                 float dU = dX, duda = 0.f;

@@ -16,8 +16,7 @@
 //
 // Matches autograd through torchdiffeq's rk4_alt_step_func + the reference vector fields
 // (cdeint_module.py:25-32,56-72,103-138; vector_fields.py:205-218,237-250) to FP32 round-off.
-#include "ncde_common.cuh"
-#include "pipeline.cuh"
+#include "ncde2_common.cuh"
 
 namespace ancde {
 
@@ -58,30 +57,34 @@ __device__ __forceinline__ void cp_async16_b(void* smem_dst, const void* gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 
-// WO_SMEM: the k-contiguous output-layer copy W_out[col][KPS] is resident in shared memory; otherwise it is
-// streamed from L2 through a ring of slots (32*NSPLIT columns each) by a producer warp.
-template <int TS, bool WO_SMEM>
+constexpr int BW_MTK_MAX = 4;      // output-layer reduction size K <= 64
+
+// The output layer's vector-Jacobian product runs on the tensor cores: per TILE of 16 output rows (2 field rows x 8
+// control channels, see NcdeLayout) a warp builds the pre-activation cotangent of its 8 samples directly in
+// B-fragment registers from the saved tanh outputs, splits it into FP16 hi/lo halves (scaled by a power of two taken
+// from the largest stage cotangent of the tile) and multiplies it with the W_out^T fragments that a producer warp
+// streams from L2 through a ring of shared-memory slots (TMA bulk copies).  CT tiles per slot, one per warp of a
+// group of CT warps; two groups work on alternate slots.
+template <int TS>
 __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant__ SolveArgs p)
 {
     constexpr int VW = (TS >= 4) ? 4 : TS;
     constexpr int NQ = TS / VW;
     const NcdeLayout& lo = p.lo;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
     const int NT = p.ntc;
     const int NW = NT / 32;
     const int tile = blockIdx.x;
     const int b0 = tile * TS;
-    const int Hd = lo.Hd, C4 = lo.C4, NCH = lo.NCH, NCG = lo.NCG, NCP = lo.NCP, K = lo.K, KPS = lo.KPS, DUS = lo.DUS;
-    const int NKG = (K + 7) / 8;
-    int NSPLIT = NW / NKG;
-    if (NSPLIT < 1) NSPLIT = 1;
-    const int CS = p.ring_kc;                          // column steps (of 32*NSPLIT columns) per phase-2 chunk
-    const int CC = 32 * NSPLIT * CS;                   // columns per phase-2 chunk
-    const int nchunks = (NCP + CC - 1) / CC;
+    const int Hd = lo.Hd, C4 = lo.C4, NCP = lo.NCP, DUS = lo.DUS, MTK = lo.MTK, NJC = lo.NJC;
+    const int CT = p.ring_kc;                          // tiles per ring slot = warps per group (NW = 2 * CT)
     const int NSLOT = p.ring_slots;
+    const int ntl = lo.n_wtiles;
+    const int nchunks = (ntl + CT - 1) / CT;
     const int HT = pad4(Hd * TS);
     const bool need_att = (lo.mode == ANCDE_MODE_TOP) && (p.grad_attention != nullptr);
-    const int64_t g_tile_f4 = (int64_t)TS * NCG;        // float4 per (stage, tile) block of saved tanh outputs
+    const int64_t g_tile = (int64_t)TS * NCP;           // floats per (stage, tile) block of saved tanh outputs
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -89,9 +92,8 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     float* smem = reinterpret_cast<float*>(smem_raw + 128);
     float* sHW = smem;                                   // hidden weights (packed, transposed)
     float* sp = sHW + pad4(lo.hidden_floats);
-    float* sWoT = sp;                                    // resident W_out[col][KPS], or the ring
-    sp += WO_SMEM ? (size_t)NCP * KPS : (size_t)NSLOT * CC * KPS;
-    float* sPre = sp;   sp += (size_t)NCP * TS;          // [q][col][VW]
+    uint4* sRing = reinterpret_cast<uint4*>(sp);         // [NSLOT][CT][MTK][64] W_out^T fragments
+    sp += (size_t)NSLOT * CT * MTK * 64 * 4;
     float* sActBuf = sp; sp += 2 * (size_t)lo.act_fwd_floats;   // saved activations, double buffered
     float* sG = sp;     sp += HT;                        // cotangent of the stage derivative
     float* sLam = sp;   sp += HT;                        // cotangent of z at the end of the step
@@ -101,40 +103,39 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     float* sV2 = sp;    sp += HT;
     float* sHb0 = sp;   sp += pad4(lo.Hmax * TS);
     float* sHb1 = sp;   sp += pad4(lo.Hmax * TS);
-    float* sHbPart = sp; sp += (size_t)NSPLIT * NKG * 8 * TS;
+    float* sHbP = sp;   sp += (size_t)NW * MTK * 128;    // per-warp partial sums of the hidden cotangent (fragment order)
+    float* sAttW = sp;  sp += need_att ? (size_t)NW * NJC * 64 : 0;   // per-warp partial sums of the dU cotangent [jc][b][8 j]
+    float* sMax = sp;   sp += 32;
     float* sTmp = sp;                                    // [C4][TS]
 
-    if (!WO_SMEM) {
-        if (tid == 0) {
-            for (int s = 0; s < NSLOT; ++s) {
-                mbar_init(bar_full + s, 1);
-                mbar_init(bar_empty + s, NKG * NSPLIT);  // the warps that take part in phase 2
-            }
-            mbar_fence_init();
+    if (tid == 0) {
+        for (int s = 0; s < NSLOT; ++s) {
+            mbar_init(bar_full + s, 1);
+            mbar_init(bar_empty + s, CT);                // one arrive per warp of the group that owns the slot's chunk
         }
-        __syncthreads();
-        if (tid >= NT) {
-            // ---- producer warp: W_out[col][KPS] chunks through the ring + L2 prefetch of the tanh outputs
-            if (lane == 0) {
-                const float* Wg = p.wpack + lo.off_wot;
-                int slot = 0;
-                uint32_t phase = 1;
-                for (int n = lo.n_stages - 1; n >= 0; --n) {
-                    if (n >= 1)
-                        bulk_prefetch_l2(reinterpret_cast<const float4*>(p.save_G) + ((int64_t)(n - 1) * lo.ntiles + tile) * g_tile_f4,
-                                         (uint32_t)(g_tile_f4 * 16));
-                    for (int c = 0; c < nchunks; ++c) {
-                        mbar_wait(bar_empty + slot, phase);
-                        const int cols = (NCP - c * CC < CC) ? NCP - c * CC : CC;
-                        const uint32_t bytes = (uint32_t)(cols * KPS * 4);
-                        mbar_arrive_expect_tx(bar_full + slot, bytes);
-                        bulk_g2s(sWoT + (size_t)slot * CC * KPS, Wg + (size_t)c * CC * KPS, bytes, bar_full + slot);
-                        if (++slot == NSLOT) { slot = 0; phase ^= 1; }
-                    }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid >= NT) {
+        // ---- producer warp: W_out^T tiles through the ring + L2 prefetch of the tanh outputs
+        if (lane == 0) {
+            const uint4* Wg = reinterpret_cast<const uint4*>(p.wpack + lo.off_wob);
+            int slot = 0;
+            uint32_t phase = 1;
+            for (int n = lo.n_stages - 1; n >= 0; --n) {
+                if (n >= 1)
+                    bulk_prefetch_l2(p.save_G + ((int64_t)(n - 1) * lo.ntiles + tile) * g_tile, (uint32_t)(g_tile * 4));
+                for (int c = 0; c < nchunks; ++c) {
+                    mbar_wait(bar_empty + slot, phase);
+                    const int tiles = (ntl - c * CT < CT) ? ntl - c * CT : CT;
+                    const uint32_t bytes = (uint32_t)(tiles * MTK * 64 * 16);
+                    mbar_arrive_expect_tx(bar_full + slot, bytes);
+                    bulk_g2s(sRing + (size_t)slot * CT * MTK * 64, Wg + (size_t)c * CT * MTK * 64, bytes, bar_full + slot);
+                    if (++slot == NSLOT) { slot = 0; phase ^= 1; }
                 }
             }
-            return;
         }
+        return;
     }
     auto cta_sync = [&]() { named_bar_sync(1, NT); };
     auto act_block = [&](int n) { return p.save_act + ((int64_t)n * lo.ntiles + tile) * lo.act_floats; };
@@ -148,21 +149,16 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
         const float4* src = reinterpret_cast<const float4*>(p.wpack);
         float4* dst = reinterpret_cast<float4*>(sHW);
         for (int i = tid; i < pad4(lo.hidden_floats) / 4; i += NT) dst[i] = __ldg(src + i);
-        if (WO_SMEM) {
-            const float4* s2 = reinterpret_cast<const float4*>(p.wpack + lo.off_wot);
-            float4* d2 = reinterpret_cast<float4*>(sWoT);
-            for (int i = tid; i < NCP * KPS / 4; i += NT) d2[i] = __ldg(s2 + i);
-        }
         for (int item = tid; item < Hd * TS; item += NT) { sLam[item] = 0.f; sMu[item] = 0.f; }
         issue_act(lo.n_stages - 1, sActBuf);
     }
     cta_sync();
 
     int jb = lo.n_out - 1;   // last output time whose cotangent has not been consumed yet
-    int rslot = 0;           // ring slot / phase parity of the next fill to consume
-    uint32_t rphase = 0;
     int abuf = 0;            // which half of sActBuf holds the current stage
     float gmax = 0.f;        // largest |stage cotangent| this thread wrote (scale of the FP16 weight-gradient operands)
+    const int grp = warp / CT, wl = warp - grp * CT;     // this warp's group and tile slot inside a chunk
+    int64_t gchunk = 0;      // chunks consumed so far (ring position), advanced by nchunks per stage
 
     for (int k = lo.n_steps - 1; k >= 0; --k) {
         const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step);
@@ -177,12 +173,12 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                 for (int j = jb; j >= 1; --j) {
                     const float tj = __ldg(p.t_out + j);
                     if (!(tj > t0)) break;
-                    const float g = (bg < lo.B) ? __ldg(p.grad_z_out + ((int64_t)j * lo.B + bg) * Hd + i) : 0.f;
-                    if (tj == t1) lam += g;
+                    const float gz = (bg < lo.B) ? __ldg(p.grad_z_out + ((int64_t)j * lo.B + bg) * Hd + i) : 0.f;
+                    if (tj == t1) lam += gz;
                     else {
                         const float th = (tj - t0) / (t1 - t0);
-                        lam += th * g;
-                        mu += (1.0f - th) * g;
+                        lam += th * gz;
+                        mu += (1.0f - th) * gz;
                     }
                 }
                 sLam[item] = lam;
@@ -199,115 +195,141 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
             float* sAct = sActBuf + (size_t)abuf * lo.act_fwd_floats;
             PHASE_T0();
             // ---- cotangent of the stage derivative k_{s+1}  (transpose of rk4_alt_step_func)
+            float lmax = 0.f;
             for (int item = tid; item < Hd * TS; item += NT) {
                 const float lam = sLam[item];
-                float g;
-                if (s == 3) g = dt * 0.125f * lam;
-                else if (s == 2) g = dt * (0.375f * lam + sV4[item]);
-                else if (s == 1) g = dt * (0.375f * lam - sV4[item] + sV3[item]);
-                else g = dt * (0.125f * lam + sV4[item] + (sV2[item] - sV3[item]) * (1.0f / 3.0f));
-                sG[item] = g;
+                float gv;
+                if (s == 3) gv = dt * 0.125f * lam;
+                else if (s == 2) gv = dt * (0.375f * lam + sV4[item]);
+                else if (s == 1) gv = dt * (0.375f * lam - sV4[item] + sV3[item]);
+                else gv = dt * (0.125f * lam + sV4[item] + (sV2[item] - sV3[item]) * (1.0f / 3.0f));
+                sG[item] = gv;
+                act[lo.act_off_gbar + item] = gv;        // the stage cotangent goes to HBM for the weight-gradient kernels
+                lmax = fmaxf(lmax, fabsf(gv));
+            }
+            gmax = fmaxf(gmax, lmax);
+            for (int o = 16; o >= 1; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+            if (lane == 0) sMax[warp] = lmax;
+            if (need_att) {
+                float2* z = reinterpret_cast<float2*>(sAttW + (size_t)warp * NJC * 64) + lane;
+                for (int jc = 0; jc < NJC; ++jc) z[jc * 32] = make_float2(0.f, 0.f);
             }
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");     // saved activations of this stage have landed
             cta_sync();
-            // prefetch the next stage's activations (this kernel walks n downwards); pull its tanh outputs into L2
+            // prefetch the next stage's activations (this kernel walks n downwards)
             if (n >= 1) issue_act(n - 1, sActBuf + (size_t)(abuf ^ 1) * lo.act_fwd_floats);
-            if (WO_SMEM && tid == 0 && n >= 1)
-                bulk_prefetch_l2(reinterpret_cast<const float4*>(p.save_G) + ((int64_t)(n - 1) * lo.ntiles + tile) * g_tile_f4,
-                                 (uint32_t)(g_tile_f4 * 16));
-            // the stage cotangent goes to HBM for the weight-gradient kernels
-            for (int item = tid; item < Hd * TS; item += NT) {
-                const float gv = sG[item];
-                act[lo.act_off_gbar + item] = gv;
-                gmax = fmaxf(gmax, fabsf(gv));
+            // power-of-two scale that brings the largest cotangent of this tile and stage to ~2^6
+            float scale = 1.0f;
+            {
+                float m = 0.f;
+                for (int w = 0; w < NW; ++w) m = fmaxf(m, sMax[w]);
+                if (m > 1e-30f && m < 1e30f) {
+                    const int e = (int)((__float_as_uint(m) >> 23) & 0xffu) - 126;     // m = f * 2^e, f in [0.5, 1)
+                    scale = __uint_as_float((uint32_t)(127 + 6 - e) << 23);
+                }
             }
-
             const float* sDU = sAct + lo.act_off_du;
             PHASE_MARK(8);    // stage cotangent + saved activations
-            // ---- phase 1: tanh outputs, pre-activation cotangent into shared memory
-            const float4* gbase = reinterpret_cast<const float4*>(p.save_G) + ((int64_t)n * lo.ntiles + tile) * g_tile_f4;
-            if (need_att) {
-                // cotangent of dU: dUbar[j][b] = sum_i gbar[i][b] * G[i][j][b]; the products go through
-                // shared memory (same layout as pre_bar) and are reduced over the rows i
-                for (int cg = tid; cg < NCG; cg += NT) {
-                    const int i = cg / NCH;
-                    float gb[TS];
+
+            // ---- phases 1+2: G -> pre_bar (registers, B fragments) -> hbar[k][b] += W_out^T pre_bar on the tensor cores
+            float acc[BW_MTK_MAX][4];
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) Vec<VW>::ld(sG + i * TS + q * VW, gb + q * VW);
-                    float g[TS][4];
+            for (int m = 0; m < BW_MTK_MAX; ++m)
 #pragma unroll
-                    for (int b = 0; b < TS; ++b) {
-                        const float4 t = __ldg(gbase + (int64_t)b * NCG + cg);
-                        g[b][0] = t.x; g[b][1] = t.y; g[b][2] = t.z; g[b][3] = t.w;
-                    }
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            float v[VW];
-#pragma unroll
-                            for (int e = 0; e < VW; ++e) v[e] = gb[q * VW + e] * g[q * VW + e][c];
-                            Vec<VW>::st(sPre + ((size_t)q * NCP + cg * 4 + c) * VW, v);
+                for (int e = 0; e < 4; ++e) acc[m][e] = 0.f;
+            {
+                const float* gbase = p.save_G + ((int64_t)n * lo.ntiles + tile) * g_tile + (int64_t)g * NCP;
+                const bool b_ok = g < TS;
+                auto tile_coords = [&](int tl, int& i0, int& j) {
+                    const int ip = (NJC == 1) ? tl : (int)__umulhi((unsigned)tl, lo.magicNJC);   // 2^32 / 1 does not fit the magic
+                    i0 = 2 * ip;
+                    j = 8 * (tl - ip * NJC) + 2 * t;
+                };
+                auto load_g = [&](int tl, float2& ga, float2& gb2) {
+                    ga = make_float2(0.f, 0.f);
+                    gb2 = make_float2(0.f, 0.f);
+                    if (tl < ntl && b_ok) {
+                        int i0, j;
+                        tile_coords(tl, i0, j);
+                        if (j < C4) {
+                            ga = __ldg(reinterpret_cast<const float2*>(gbase + i0 * C4 + j));
+                            if (i0 + 1 < Hd) gb2 = __ldg(reinterpret_cast<const float2*>(gbase + (i0 + 1) * C4 + j));
                         }
-                }
-                cta_sync();
-                for (int item = tid; item < C4 * NQ; item += NT) {
-                    const int q = item / C4, j = item - q * C4;
-                    float acc[VW];
-#pragma unroll
-                    for (int e = 0; e < VW; ++e) acc[e] = 0.f;
-                    for (int ii = 0; ii < Hd; ++ii) {
-                        float v[VW];
-                        Vec<VW>::ld(sPre + ((size_t)q * NCP + ii * C4 + j) * VW, v);
-#pragma unroll
-                        for (int e = 0; e < VW; ++e) acc[e] += v[e];
                     }
-                    float du[VW];
-                    Vec<VW>::ld(sAct + lo.act_off_duda + du_index(j, q * VW, TS, DUS), du);
-#pragma unroll
-                    for (int e = 0; e < VW; ++e) acc[e] *= du[e];
-                    Vec<VW>::st(sTmp + j * TS + q * VW, acc);
-                }
-                cta_sync();
-            }
-            for (int cg = tid; cg < NCG; cg += NT) {
-                const int i = cg / NCH, chunk = cg - i * NCH;
-                float gb[TS];
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) Vec<VW>::ld(sG + i * TS + q * VW, gb + q * VW);
-                float g[TS][4];
-#pragma unroll
-                for (int b = 0; b < TS; ++b) {
-                    const float4 t = __ldg(gbase + (int64_t)b * NCG + cg);
-                    g[b][0] = t.x; g[b][1] = t.y; g[b][2] = t.z; g[b][3] = t.w;
-                }
-#pragma unroll
-                for (int q = 0; q < NQ; ++q)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float du[VW], v[VW];
-                        Vec<VW>::ld(sDU + chunk * DUS + c * TS + q * VW, du);
-#pragma unroll
-                        for (int e = 0; e < VW; ++e) {
-                            const float gg = g[q * VW + e][c];
-                            v[e] = gb[q * VW + e] * du[e] * fmaf(-gg, gg, 1.0f);
+                };
+                float2 g0n, g1n;
+                load_g(grp * CT + wl, g0n, g1n);
+                for (int c = grp; c < nchunks; c += 2) {
+                    const int tl = c * CT + wl;
+                    const float2 g0 = g0n, g1 = g1n;
+                    load_g(tl + 2 * CT, g0n, g1n);
+                    const int64_t gc = gchunk + c;
+                    const int slot = (int)(gc % NSLOT);
+                    const uint32_t parity = (uint32_t)((gc / NSLOT) & 1);
+                    mbar_wait(bar_full + slot, parity);
+                    if (tl < ntl) {
+                        int i0, j;
+                        tile_coords(tl, i0, j);
+                        float p00 = 0.f, p01 = 0.f, p10 = 0.f, p11 = 0.f;
+                        if (b_ok && j < C4) {
+                            const float gb0 = sG[i0 * TS + g] * scale;
+                            const float gb1 = (i0 + 1 < Hd) ? sG[(i0 + 1) * TS + g] * scale : 0.f;
+                            const float du0 = sDU[du_index(j, g, TS, DUS)], du1 = sDU[du_index(j + 1, g, TS, DUS)];
+                            p00 = gb0 * du0 * fmaf(-g0.x, g0.x, 1.0f);
+                            p01 = gb0 * du1 * fmaf(-g0.y, g0.y, 1.0f);
+                            p10 = gb1 * du0 * fmaf(-g1.x, g1.x, 1.0f);
+                            p11 = gb1 * du1 * fmaf(-g1.y, g1.y, 1.0f);
+                            if (need_att) {
+                                // cotangent of dU: dUbar[j][b] = sum_i gbar[i][b] * G[i][j][b] (scaled like gbar)
+                                float2* q = reinterpret_cast<float2*>(sAttW + ((size_t)warp * NJC + (j >> 3)) * 64) + lane;
+                                float2 v = *q;
+                                v.x += gb0 * g0.x + gb1 * g1.x;
+                                v.y += gb0 * g0.y + gb1 * g1.y;
+                                *q = v;
+                            }
                         }
-                        Vec<VW>::st(sPre + ((size_t)q * NCP + cg * 4 + c) * VW, v);
+                        uint32_t bh0, bl0, bh1, bl1;
+                        split_pair(p00, p01, bh0, bl0);      // rows 2t, 2t+1   = (i0, j), (i0, j+1)
+                        split_pair(p10, p11, bh1, bl1);      // rows 2t+8, 2t+9 = (i0+1, j), (i0+1, j+1)
+                        const uint4* A = sRing + ((size_t)slot * CT + wl) * MTK * 64 + lane;
+#pragma unroll
+                        for (int m = 0; m < BW_MTK_MAX; ++m) {
+                            if (m < MTK) {
+                                const uint4 ah = A[m * 64], al = A[m * 64 + 32];
+                                mma16x3(acc[m], ah, al, bh0, bh1, bl0, bl1);
+                            }
+                        }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_empty + slot);
+                }
+                gchunk += nchunks;
+                float4* hp4 = reinterpret_cast<float4*>(sHbP) + (size_t)warp * MTK * 32 + lane;
+#pragma unroll
+                for (int m = 0; m < BW_MTK_MAX; ++m)
+                    if (m < MTK) hp4[m * 32] = make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]);
             }
             cta_sync();
-            PHASE_MARK(9);    // phase 1: G -> pre_bar (+ attention products)
+            PHASE_MARK(11);   // phases 1+2
             // ---- cotangent of the attention: a[q] += dUbar * dU/da   
             if (need_att) {
+                const float inv_s = 1.0f / scale;
+                for (int item = tid; item < lo.C * TS; item += NT) {
+                    const int j = item / TS, b = item - j * TS;
+                    float a = 0.f;
+                    for (int w = 0; w < NW; ++w) a += sAttW[(((size_t)w * NJC + (j >> 3)) * 8 + b) * 8 + (j & 7)];
+                    sTmp[j * TS + b] = a * inv_s * sAct[lo.act_off_duda + du_index(j, b, TS, DUS)];
+                }
+                cta_sync();
                 const float ts = stage_time(t0, dt, s);
                 int qa = (int)floorf(ts) - 1;
                 if (qa < 0) qa += lo.att_L;
                 qa = qa < 0 ? 0 : (qa >= lo.att_L ? lo.att_L - 1 : qa);
                 if (lo.att_C == 1) {
                     if (tid < TS && b0 + tid < lo.B) {
-                        float acc = 0.f;
-                        for (int j = 0; j < lo.C; ++j) acc += sTmp[j * TS + tid];
-                        atomicAdd(p.grad_attention + (int64_t)qa * lo.B + b0 + tid, acc);
+                        float a = 0.f;
+                        for (int j = 0; j < lo.C; ++j) a += sTmp[j * TS + tid];
+                        atomicAdd(p.grad_attention + (int64_t)qa * lo.B + b0 + tid, a);
                     }
                 } else {
                     for (int item = tid; item < lo.C * TS; item += NT) {
@@ -317,66 +339,9 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                     }
                 }
             }
-            PHASE_MARK(10);   // attention atomics
-            // ---- phase 2: hbar[k][b] = sum_col pre_bar[col][b] * W_out[col][k]; warp = (k group, column split)
-            if (warp < NKG * NSPLIT) {
-                const int kg = warp % NKG, split = warp / NKG;
-                float acc[8 * TS];
-#pragma unroll
-                for (int i = 0; i < 8 * TS; ++i) acc[i] = 0.f;
-                for (int c = 0; c < nchunks; ++c) {
-                    int slot = 0;
-                    const float* wbase;
-                    if (WO_SMEM) {
-                        wbase = sWoT + (size_t)c * CC * KPS;
-                    } else {
-                        slot = rslot;
-                        mbar_wait(bar_full + slot, rphase);
-                        wbase = sWoT + (size_t)slot * CC * KPS;
-                    }
-                    for (int cs = 0; cs < CS; ++cs) {
-                        const int lcol = (cs * NSPLIT + split) * 32 + lane;
-                        const int col = c * CC + lcol;
-                        if (col < NCP) {
-                            const float* wrow = wbase + (size_t)lcol * KPS + kg * 8;
-                            const float4 w0 = *reinterpret_cast<const float4*>(wrow);
-                            const float4 w1 = *reinterpret_cast<const float4*>(wrow + 4);
-                            float pv[TS];
-#pragma unroll
-                            for (int q = 0; q < NQ; ++q) Vec<VW>::ld(sPre + ((size_t)q * NCP + col) * VW, pv + q * VW);
-                            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-                            for (int kk = 0; kk < 8; ++kk)
-#pragma unroll
-                                for (int b = 0; b < TS; ++b) acc[kk * TS + b] = fmaf(wv[kk], pv[b], acc[kk * TS + b]);
-                        }
-                    }
-                    if (!WO_SMEM) {
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_empty + slot);
-                        if (++rslot == NSLOT) { rslot = 0; rphase ^= 1; }
-                    }
-                }
-                warp_reduce_scatter<8 * TS>(acc, lane);
-                constexpr int V = 8 * TS;
-                if constexpr (V >= 32) {
-#pragma unroll
-                    for (int r = 0; r < V / 32; ++r) {
-                        const int idx = lane * (V / 32) + r;
-                        sHbPart[((size_t)split * NKG + kg) * V + idx] = acc[r];
-                    }
-                } else {
-                    constexpr int per = 32 / V;
-                    if (lane % per == 0) sHbPart[((size_t)split * NKG + kg) * V + lane / per] = acc[0];
-                }
-            } else if (!WO_SMEM) {
-                // warps without a phase-2 role still track the ring position
-                for (int c = 0; c < nchunks; ++c)
-                    if (++rslot == NSLOT) { rslot = 0; rphase ^= 1; }
-            }
-            cta_sync();
-            PHASE_MARK(11);   // phase 2: pre_bar x W_out + reduce + barrier
+            PHASE_MARK(10);   // attention
             // ---- phase 3: hidden layers backwards
+            const float inv_hb = 1.0f / (64.0f * scale);
             float* hb = sHb0;
             float* hb_next = sHb1;
             for (int l = lo.n_hidden - 1; l >= 0; --l) {
@@ -386,10 +351,13 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                 for (int item = tid; item < N * TS; item += NT) {
                     float v;
                     if (l == lo.n_hidden - 1) {
+                        // hbar[o][b] from the warps' partial accumulator fragments: element (o, b) lives in m-tile o/16,
+                        // lane (o%8)*4 + b/2, register ((o%16)/8)*2 + b%2
                         const int o = item / TS, b = item - o * TS;
+                        const int idx = ((o >> 4) * 32 + (o & 7) * 4 + (b >> 1)) * 4 + ((o >> 3) & 1) * 2 + (b & 1);
                         v = 0.f;
-                        for (int sp2 = 0; sp2 < NSPLIT; ++sp2)
-                            v += sHbPart[((size_t)sp2 * NKG + o / 8) * (8 * TS) + (o % 8) * TS + b];
+                        for (int w = 0; w < NW; ++w) v += sHbP[(size_t)w * MTK * 128 + idx];
+                        v *= inv_hb;
                     } else {
                         v = hb[item];
                     }
@@ -416,9 +384,9 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                         const bool valid = item < nitems;
                         int q = 0, kk = valid ? item : 0;
                         if (NQ > 1 && kk >= Kin) { q = 1; kk -= Kin; }
-                        float acc[VW];
+                        float accv[VW];
 #pragma unroll
-                        for (int e = 0; e < VW; ++e) acc[e] = 0.f;
+                        for (int e = 0; e < VW; ++e) accv[e] = 0.f;
                         if (valid) {
                             const float* wp = Wt + kk * S + obeg;
                             const float* dp = hb + obeg * TS + q * VW;
@@ -430,17 +398,17 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                                 ++wp;
                                 dp += TS;
 #pragma unroll
-                                for (int e = 0; e < VW; ++e) acc[e] = fmaf(w, dv[e], acc[e]);
+                                for (int e = 0; e < VW; ++e) accv[e] = fmaf(w, dv[e], accv[e]);
                             }
                         }
                         for (int m = KS >> 1; m >= 1; m >>= 1)
 #pragma unroll
-                            for (int e = 0; e < VW; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], m);
-                        if (valid && ks == 0) Vec<VW>::st(hb_next + kk * TS + q * VW, acc);
+                            for (int e = 0; e < VW; ++e) accv[e] += __shfl_xor_sync(0xffffffffu, accv[e], m);
+                        if (valid && ks == 0) Vec<VW>::st(hb_next + kk * TS + q * VW, accv);
                     }
                 }
                 cta_sync();
-                float* t = hb; hb = hb_next; hb_next = t;
+                float* tsw = hb; hb = hb_next; hb_next = tsw;
             }
             PHASE_MARK(12);   // phase 3: hidden layers
             // hb now holds the cotangent of the stage input
@@ -470,90 +438,59 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     }
 }
 
-static int bwd_threads(const NcdeLayout& lo)
+// consumer warps of the backward: two groups of CT warps (CT tiles of the output layer per ring slot)
+static int bwd_ct(const NcdeLayout& lo)
 {
-    int per = (lo.NCG + 447) / 448;
-    int nt = round_up((lo.NCG + per - 1) / per, 32);
-    const int NKG = (lo.K + 7) / 8;
-    if (nt < NKG * 32) nt = NKG * 32;
-    if (nt < 64) nt = 64;
-    return nt;
+    int ct = (lo.n_wtiles + 1) / 2;
+    if (ct > 7) ct = 7;
+    if (ct < 1) ct = 1;
+    // phase 3 wants at least one thread per (input, sample-quad) item of the widest layer
+    return ct;
 }
 
-// shared memory (bytes) of the backward without the output-layer weights / ring
-static size_t bwd_smem_base(const NcdeLayout& lo, int nt)
+static size_t bwd_smem_bytes(const NcdeLayout& lo, int ct, int slots, bool att)
 {
-    const int NKG = (lo.K + 7) / 8;
-    int nsplit = (nt / 32) / NKG;
-    if (nsplit < 1) nsplit = 1;
+    const int nw = 2 * ct;
     size_t f = (size_t)pad4(lo.hidden_floats);
-    f += (size_t)lo.NCP * lo.TS + 2 * (size_t)lo.act_fwd_floats + 6 * (size_t)pad4(lo.Hd * lo.TS) +
-         2 * (size_t)pad4(lo.Hmax * lo.TS) + (size_t)nsplit * NKG * 8 * lo.TS + (size_t)lo.C4 * lo.TS;
+    f += (size_t)slots * ct * lo.MTK * 64 * 4;
+    f += 2 * (size_t)lo.act_fwd_floats + 6 * (size_t)pad4(lo.Hd * lo.TS) + 2 * (size_t)pad4(lo.Hmax * lo.TS);
+    f += (size_t)nw * lo.MTK * 128 + (att ? (size_t)nw * lo.NJC * 64 : 0) + 32 + (size_t)lo.C4 * lo.TS;
     return f * 4 + 128;
-}
-
-static size_t bwd_ring_bytes(const NcdeLayout& lo, int nt, int slots, int cs)
-{
-    const int NKG = (lo.K + 7) / 8;
-    int nsplit = (nt / 32) / NKG;
-    if (nsplit < 1) nsplit = 1;
-    return (size_t)slots * 32 * nsplit * cs * lo.KPS * 4;
 }
 
 // Used by make_layout's tile-size choice: does the backward fit with this many samples per CTA?
 bool bwd_fits(const NcdeLayout& lo)
 {
-    const int nt = bwd_threads(lo);
-    return nt <= 480 && bwd_smem_base(lo, nt) + bwd_ring_bytes(lo, nt, 2, 1) <= 227 * 1024;
+    return lo.MTK <= BW_MTK_MAX && bwd_smem_bytes(lo, bwd_ct(lo), 2, lo.mode == ANCDE_MODE_TOP) <= 227 * 1024;
 }
 
 template <int TS>
 static int launch_bwd(const ancde_ncde_desc* d, SolveArgs& a, cudaStream_t stream)
 {
     const NcdeLayout& lo = a.lo;
-    const int nt = bwd_threads(lo);
     const size_t max_smem = 227 * 1024;
-    if (nt > 480) {
-        set_error("ncde_backward: needs %d threads per CTA (max 480)", nt);
+    if (lo.MTK > BW_MTK_MAX) {
+        set_error("ncde_backward: last hidden width %d exceeds %d", lo.K, 16 * BW_MTK_MAX);
         return ANCDE_EUNSUPPORTED;
     }
-    const size_t base = bwd_smem_base(lo, nt);
-    const bool wo_smem = base + (size_t)lo.NCP * lo.KPS * 4 <= max_smem;
-    size_t smem;
-    int threads = nt;
+    const int ct = bwd_ct(lo);
+    const int nt = 2 * ct * 32;
+    const bool att = (lo.mode == ANCDE_MODE_TOP) && (a.grad_attention != nullptr);
+    int slots = 4;
+    while (slots > 2 && bwd_smem_bytes(lo, ct, slots, att) > max_smem) --slots;
+    const size_t smem = bwd_smem_bytes(lo, ct, slots, att);
+    if (smem > max_smem) {
+        set_error("ncde_backward: needs %zu bytes of shared memory per CTA (max %zu)", smem, max_smem);
+        return ANCDE_EUNSUPPORTED;
+    }
     a.ntc = nt;
-    a.ring_kc = 1; a.ring_pw = 0;
-    if (wo_smem) {
-        a.ring_slots = 1;
-        smem = base + (size_t)lo.NCP * lo.KPS * 4;
-    } else {
-        // the deepest ring that fits: prefer two column steps per slot (fewer barrier waits), at least 3 slots
-        int slots = 4, cs = 2;
-        while (base + bwd_ring_bytes(lo, nt, slots, cs) > max_smem) {
-            if (slots > 3) --slots;
-            else if (cs > 1) { cs = 1; slots = 4; }
-            else if (slots > 2) --slots;
-            else break;
-        }
-        smem = base + bwd_ring_bytes(lo, nt, slots, cs);
-        if (smem > max_smem) {
-            set_error("ncde_backward: needs %zu bytes of shared memory per CTA (max %zu)", smem, max_smem);
-            return ANCDE_EUNSUPPORTED;
-        }
-        a.ring_slots = slots;
-        a.ring_kc = cs;
-        threads = nt + 32;
-    }
+    a.ring_kc = ct;
+    a.ring_slots = slots;
+    a.ring_pw = 0;
     static const char* names[3] = {"ncde_bwd_plain", "ncde_bwd_bottom", "ncde_bwd_top"};
-    if (wo_smem) {
-        ANCDE_CUDA(cudaFuncSetAttribute(ncde_bwd_kernel<TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        prof_begin(names[lo.mode], stream);
-        ncde_bwd_kernel<TS, true><<<lo.ntiles, threads, smem, stream>>>(a);
-    } else {
-        ANCDE_CUDA(cudaFuncSetAttribute(ncde_bwd_kernel<TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        prof_begin(names[lo.mode], stream);
-        ncde_bwd_kernel<TS, false><<<lo.ntiles, threads, smem, stream>>>(a);
-    }
+    ANCDE_CUDA(cudaFuncSetAttribute(ncde_bwd_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin(names[lo.mode], stream);
+    ncde_bwd_kernel<TS><<<lo.ntiles, nt + 32, smem, stream>>>(a);
     prof_end(stream);
     count_launch();
     ANCDE_CUDA(cudaGetLastError());

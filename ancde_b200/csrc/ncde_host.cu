@@ -27,6 +27,31 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a)
         for (int o = gtid; o < pad4(out); o += gsz) a.wpack[lo.off_b[l] + o] = (o < out) ? a.bias[l][o] : 0.f;
     }
     if (gtid < 4) a.wpack[lo.off_gscale + gtid] = 0.f;
+    {
+        // W_out^T tiles as FP16 hi/lo A fragments (m16n8k16 row-major A: a0 = (m g, k 2t..2t+1), a1 = (m g+8, ..),
+        // a2 = (m g, k 2t+8..), a3 = (m g+8, k 2t+8..)); m = hidden index, k = tile row
+        uint4* dst = reinterpret_cast<uint4*>(a.wpack + lo.off_wob);
+        const float* Wo = a.W[lo.n_hidden];
+        const int total = lo.n_wtiles * lo.MTK * 32;
+        for (int idx = gtid; idx < total; idx += gsz) {
+            const int lane = idx & 31, mt = (idx >> 5) % lo.MTK, tile = (idx >> 5) / lo.MTK;
+            const int g = lane >> 2, t = lane & 3;
+            const int ip = tile / lo.NJC, jc = tile - ip * lo.NJC;
+            auto el = [&](int m, int r) -> float {
+                const int i = 2 * ip + (r >> 3), j = 8 * jc + (r & 7);
+                return (m < lo.K && i < lo.Hd && j < lo.C) ? 64.0f * Wo[((int64_t)i * lo.C + j) * lo.K + m] : 0.f;
+            };
+            const int m0 = mt * 16 + g, m1 = m0 + 8, r0 = 2 * t;
+            uint32_t h[4], l[4];
+            split_pair(el(m0, r0), el(m0, r0 + 1), h[0], l[0]);
+            split_pair(el(m1, r0), el(m1, r0 + 1), h[1], l[1]);
+            split_pair(el(m0, r0 + 8), el(m0, r0 + 9), h[2], l[2]);
+            split_pair(el(m1, r0 + 8), el(m1, r0 + 9), h[3], l[3]);
+            uint4* d = dst + ((int64_t)tile * lo.MTK + mt) * 64;
+            d[lane] = make_uint4(h[0], h[1], h[2], h[3]);
+            d[32 + lane] = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+    }
     const int K = lo.K, NCP = lo.NCP, C4 = lo.C4, C = lo.C;
     const float* Wout = a.W[lo.n_hidden];
     const float* bout = a.bias[lo.n_hidden];
@@ -79,6 +104,12 @@ static void fill_layout(const ancde_ncde_desc* d, int TS, NcdeLayout* lo)
     lo->off_bo = off; off += lo->NCP;
     lo->KPS = 8 * ((lo->K + 7) / 8) + 4;   // +4: 16-byte rows whose stride is bank-conflict free for LDS.128
     lo->off_wot = off; off += lo->NCP * lo->KPS;
+    lo->NIP = (d->Hd + 1) / 2;
+    lo->NJC = (d->C + 7) / 8;
+    lo->MTK = (lo->K + 15) / 16;
+    lo->n_wtiles = lo->NIP * lo->NJC;
+    lo->magicNJC = (unsigned)((((uint64_t)1 << 32) + lo->NJC - 1) / lo->NJC);
+    lo->off_wob = off; off += lo->n_wtiles * lo->MTK * 64 * 4;
     lo->off_gscale = off; off += 4;
     lo->wpack_floats = off;
     int a = d->Hd * TS;

@@ -25,6 +25,11 @@ struct NcdeLayout {
     int hidden_floats;  // all hidden layers (weights + biases)
     int off_wo, off_bo; // output layer Wt_out[k][NCP], bias_out[NCP]
     int off_wot, KPS;   // second copy for the backward: W_out[col][KPS] (k contiguous, KPS = 8*ceil(K/8) + 4)
+    // tensor-core copy for the backward: the output layer as FP16 hi/lo A fragments of W_out^T, per TILE of 16 rows
+    // (2 field rows x 8 control channels: row r < 8 -> (2*ip, 8*jc + r), r >= 8 -> (2*ip + 1, 8*jc + r - 8)); a tile holds
+    // MTK m-tiles (16 k each) of 64 uint4 (32 lanes hi, 32 lanes lo); values are scaled by 64
+    int NIP, NJC, MTK, n_wtiles, off_wob;
+    unsigned magicNJC;  // ceil(2^32 / NJC)
     int off_gscale;     // 4 floats of scratch: max |stage cotangent| of the running backward (bits, atomicMax)
     int64_t wpack_floats;
     // saved activations per (stage, tile): z_s | h_1 .. h_n | dU | dU/da   (each [feature][TS])
