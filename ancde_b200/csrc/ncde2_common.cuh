@@ -29,18 +29,6 @@ constexpr int V2_MAX_KSTEPS = 4;            // output-layer reduction size K <= 
 constexpr int V2_RK_ITEMS = 6;              // (state element, sample) items a thread keeps in registers
 constexpr int V2_MAX_CS = 8;
 
-// A-operand pack of a matrix A[M][K]: m-tiles of 16 rows; per m-tile `full` k16 steps (64 uint4 each: 32 lanes of hi
-// fragments then 32 lanes of lo fragments) and an optional k8 tail (32 uint4: {hi a0, hi a1, lo a0, lo a1} per lane)
-// or k16 tail.
-struct APack {
-    int M, K;           // logical sizes
-    int mtiles;         // ceil(M / 16)
-    int full;           // k16 steps (including a k16 tail)
-    int tail8;          // 1 if a final k8 step follows
-    int stride;         // uint4 per m-tile = full*64 + tail8*32
-    int off;            // offset in uint4 units from the start of wpack
-};
-
 struct V2Layout {
     // ---- problem ----
     int B, L, C, Hd, n_hidden, mode, att_C, att_L, n_hp, n_steps, n_out, n_stages;

@@ -4,19 +4,6 @@
 
 namespace ancde {
 
-static APack make_apack(int M, int K, int off)
-{
-    APack a;
-    a.M = M; a.K = K;
-    a.mtiles = (M + 15) / 16;
-    const int rem = K % 16;
-    a.full = K / 16 + (rem > 8 ? 1 : 0);
-    a.tail8 = (rem > 0 && rem <= 8) ? 1 : 0;
-    a.stride = a.full * 64 + a.tail8 * 32;
-    a.off = off;
-    return a;
-}
-
 int make_layout2(const ancde_ncde_desc* d, V2Layout* lo)
 {
     ANCDE_CHECK_ARG(d != nullptr, "ncde: null descriptor");

@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* bar_empty = bar_full + 8;
     float* smem = reinterpret_cast<float*>(smem_raw + 128);
-    float* sHW = smem;                                   // hidden weights (packed, transposed)
-    float* sp = sHW + pad4(lo.hidden_floats);
+    const uint4* sWhb = reinterpret_cast<const uint4*>(smem);   // hidden layers, W_l^T as FP16 hi/lo A fragments
+    float* sp = smem + (size_t)lo.hb_u4 * 4;
     uint4* sRing = reinterpret_cast<uint4*>(sp);         // [NSLOT][CT][MTK][64] W_out^T fragments
     sp += (size_t)NSLOT * CT * MTK * 64 * 4;
     float* sActBuf = sp; sp += 2 * (size_t)lo.act_fwd_floats;   // saved activations, double buffered
@@ -101,8 +101,10 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     float* sV4 = sp;    sp += HT;
     float* sV3 = sp;    sp += HT;
     float* sV2 = sp;    sp += HT;
-    float* sHb0 = sp;   sp += pad4(lo.Hmax * TS);
-    float* sHb1 = sp;   sp += pad4(lo.Hmax * TS);
+    float* sZb = sp;    sp += HT;                        // cotangent of the stage input
+    const int KP = 16 * lo.KSB + 8;                      // halfs per row of the cotangent operand matrices [sample][feature]
+    __half* sBd = reinterpret_cast<__half*>(sp);         // two buffers of {hi, lo} [8][KP]
+    sp += (size_t)(4 * 8 * KP) / 2;
     float* sHbP = sp;   sp += (size_t)NW * MTK * 128;    // per-warp partial sums of the hidden cotangent (fragment order)
     float* sAttW = sp;  sp += need_att ? (size_t)NW * NJC * 64 : 0;   // per-warp partial sums of the dU cotangent [jc][b][8 j]
     float* sMax = sp;   sp += 32;
@@ -146,9 +148,11 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     };
 
     {
-        const float4* src = reinterpret_cast<const float4*>(p.wpack);
-        float4* dst = reinterpret_cast<float4*>(sHW);
-        for (int i = tid; i < pad4(lo.hidden_floats) / 4; i += NT) dst[i] = __ldg(src + i);
+        const uint4* src = reinterpret_cast<const uint4*>(p.wpack + lo.off_whb);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (int i = tid; i < lo.hb_u4; i += NT) dst[i] = __ldg(src + i);
+        uint32_t* zb = reinterpret_cast<uint32_t*>(sBd);
+        for (int i = tid; i < 2 * 8 * KP; i += NT) zb[i] = 0u;      // 4 matrices of 8*KP halfs
         for (int item = tid; item < Hd * TS; item += NT) { sLam[item] = 0.f; sMu[item] = 0.f; }
         issue_act(lo.n_stages - 1, sActBuf);
     }
@@ -159,6 +163,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     float gmax = 0.f;        // largest |stage cotangent| this thread wrote (scale of the FP16 weight-gradient operands)
     const int grp = warp / CT, wl = warp - grp * CT;     // this warp's group and tile slot inside a chunk
     int64_t gchunk = 0;      // chunks consumed so far (ring position), advanced by nchunks per stage
+    PH2_DECL();
 
     for (int k = lo.n_steps - 1; k >= 0; --k) {
         const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step);
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
             const int n = 4 * k + s;
             float* act = act_block(n);
             float* sAct = sActBuf + (size_t)abuf * lo.act_fwd_floats;
-            PHASE_T0();
+            PH2_T0();
             // ---- cotangent of the stage derivative k_{s+1}  (transpose of rk4_alt_step_func)
             float lmax = 0.f;
             for (int item = tid; item < Hd * TS; item += NT) {
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                 }
             }
             const float* sDU = sAct + lo.act_off_du;
-            PHASE_MARK(8);    // stage cotangent + saved activations
+            PH2_MARK(0);      // stage cotangent + saved activations
 
             // ---- phases 1+2: G -> pre_bar (registers, B fragments) -> hbar[k][b] += W_out^T pre_bar on the tensor cores
             float acc[BW_MTK_MAX][4];
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                     if (m < MTK) hp4[m * 32] = make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]);
             }
             cta_sync();
-            PHASE_MARK(11);   // phases 1+2
+            PH2_MARK(1);      // phases 1+2
             // ---- cotangent of the attention: a[q] += dUbar * dU/da   
             if (need_att) {
                 const float inv_s = 1.0f / scale;
@@ -339,78 +344,87 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                     }
                 }
             }
-            PHASE_MARK(10);   // attention
-            // ---- phase 3: hidden layers backwards
-            const float inv_hb = 1.0f / (64.0f * scale);
-            float* hb = sHb0;
-            float* hb_next = sHb1;
-            for (int l = lo.n_hidden - 1; l >= 0; --l) {
-                const int N = lo.width[l], Kin = lo.in_dim[l], S = lo.stride[l];
+            PH2_MARK(2);      // attention
+            // ---- phase 3: hidden layers backwards on the tensor cores.  Cotangents stay multiplied by `scale` inside the
+            // chain (FP16 range); delta_l = (W_{l+1}^T delta_{l+1}) * relu'(h_l), the stage-input cotangent is W_0^T delta_0
+            const float inv_s = 1.0f / scale;
+            const uint32_t bd_base = smem_u32(sBd);
+            const uint32_t bd_mat = (uint32_t)(8 * KP * 2);          // bytes of one FP16 matrix
+            const uint32_t bd_lane = (uint32_t)(((lane & 7) * KP + ((lane >> 3) & 1) * 8) * 2) + ((lane >> 4) ? bd_mat : 0u);
+            {
+                // delta of the last hidden layer from the warps' partial accumulator fragments: element (o, b) lives in
+                // m-tile o/16, lane (o%8)*4 + b/2, register ((o%16)/8)*2 + b%2
+                const int l = lo.n_hidden - 1;
+                const int N = lo.width[l];
                 const float* hl = sAct + lo.act_off_h[l];
-                // delta = hbar * relu'(h)
                 for (int item = tid; item < N * TS; item += NT) {
-                    float v;
-                    if (l == lo.n_hidden - 1) {
-                        // hbar[o][b] from the warps' partial accumulator fragments: element (o, b) lives in m-tile o/16,
-                        // lane (o%8)*4 + b/2, register ((o%16)/8)*2 + b%2
-                        const int o = item / TS, b = item - o * TS;
-                        const int idx = ((o >> 4) * 32 + (o & 7) * 4 + (b >> 1)) * 4 + ((o >> 3) & 1) * 2 + (b & 1);
-                        v = 0.f;
-                        for (int w = 0; w < NW; ++w) v += sHbP[(size_t)w * MTK * 128 + idx];
-                        v *= inv_hb;
-                    } else {
-                        v = hb[item];
-                    }
-                    v = (hl[item] > 0.f) ? v : 0.f;
-                    hb[item] = v;
-                    act[lo.act_off_delta[l] + item] = v;     // for the hidden weight-gradient kernel
+                    const int o = item / TS, b = item - o * TS;
+                    const int idx = ((o >> 4) * 32 + (o & 7) * 4 + (b >> 1)) * 4 + ((o >> 3) & 1) * 2 + (b & 1);
+                    float v = 0.f;
+                    for (int w = 0; w < NW; ++w) v += sHbP[(size_t)w * MTK * 128 + idx];
+                    v = (hl[item] > 0.f) ? v * (1.0f / 64.0f) : 0.f;
+                    act[lo.act_off_delta[l] + item] = v * inv_s;     // for the hidden weight-gradient kernel
+                    const __half hi = __float2half_rn(v);
+                    sBd[b * KP + o] = hi;
+                    sBd[8 * KP + b * KP + o] = __float2half_rn(v - __half2float(hi));
                 }
-                cta_sync();
-                {
-                    // cotangent of the layer input: hb_next[k][b] = sum_o Wt[k][o] * delta[o][b]; KS adjacent lanes
-                    // split the sum over o and combine with shuffles
-                    const int nitems = Kin * NQ;
-                    int KS = 4;
-                    while (KS > 1 && nitems * KS > NT) KS >>= 1;
-                    const int ks = tid & (KS - 1);
-                    const int per = NT / KS;
-                    const int OL = (N + KS - 1) / KS;
-                    const int obeg = ks * OL;
-                    int ocnt = N - obeg;
-                    ocnt = ocnt > OL ? OL : ocnt;
-                    const float* Wt = sHW + lo.off_w[l];
-                    for (int base = 0; base < nitems; base += per) {
-                        const int item = base + tid / KS;
-                        const bool valid = item < nitems;
-                        int q = 0, kk = valid ? item : 0;
-                        if (NQ > 1 && kk >= Kin) { q = 1; kk -= Kin; }
-                        float accv[VW];
-#pragma unroll
-                        for (int e = 0; e < VW; ++e) accv[e] = 0.f;
-                        if (valid) {
-                            const float* wp = Wt + kk * S + obeg;
-                            const float* dp = hb + obeg * TS + q * VW;
-#pragma unroll 4
-                            for (int o = 0; o < ocnt; ++o) {
-                                const float w = *wp;
-                                float dv[VW];
-                                Vec<VW>::ld(dp, dv);
-                                ++wp;
-                                dp += TS;
-#pragma unroll
-                                for (int e = 0; e < VW; ++e) accv[e] = fmaf(w, dv[e], accv[e]);
-                            }
-                        }
-                        for (int m = KS >> 1; m >= 1; m >>= 1)
-#pragma unroll
-                            for (int e = 0; e < VW; ++e) accv[e] += __shfl_xor_sync(0xffffffffu, accv[e], m);
-                        if (valid && ks == 0) Vec<VW>::st(hb_next + kk * TS + q * VW, accv);
-                    }
-                }
-                cta_sync();
-                float* tsw = hb; hb = hb_next; hb_next = tsw;
             }
-            PHASE_MARK(12);   // phase 3: hidden layers
+            cta_sync();
+            int cur = 0;
+            for (int l = lo.n_hidden - 1; l >= 0; --l) {
+                const APack ap = lo.hbp[l];
+                if (warp < ap.mtiles) {
+                    const int mt = warp;
+                    const uint4* A = sWhb + ap.off + mt * ap.stride + lane;
+                    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+                    uint32_t baddr = bd_base + (uint32_t)cur * 2u * bd_mat + bd_lane;
+                    for (int ks = 0; ks < ap.full; ++ks) {
+                        const uint4 ah = A[ks * 64], al = A[ks * 64 + 32];
+                        uint32_t bh0, bh1, bl0, bl1;
+                        ldmatrix_x4(baddr, bh0, bh1, bl0, bl1);
+                        baddr += 32;
+                        mma16(a0, al.x, al.y, al.z, al.w, bh0, bh1);
+                        mma16(a1, ah.x, ah.y, ah.z, ah.w, bl0, bl1);
+                        mma16(a2, ah.x, ah.y, ah.z, ah.w, bh0, bh1);
+                    }
+                    if (ap.tail8) {
+                        const uint4 a = A[ap.full * 64];
+                        uint32_t bh0, bh1, bl0, bl1;
+                        ldmatrix_x4(baddr, bh0, bh1, bl0, bl1);
+                        mma8(a0, a.z, a.w, bh0);
+                        mma8(a1, a.x, a.y, bl0);
+                        mma8(a2, a.x, a.y, bh0);
+                    }
+                    // rows = inputs of layer l (16*mt + g, + 8), columns = samples 2t, 2t+1
+                    float dv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) dv[e] = (a0[e] + a1[e] + a2[e]) * (1.0f / 64.0f);
+                    const int bcol = 2 * t;
+                    if (l > 0) {
+                        const float* hl = sAct + lo.act_off_h[l - 1];
+                        float* dsave = act + lo.act_off_delta[l - 1];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int kin = mt * 16 + g + (e >> 1) * 8, b = bcol + (e & 1);
+                            const bool ok = kin < ap.M && b < TS;
+                            const float hv = ok ? hl[kin * TS + b] : 0.f;
+                            dv[e] = (hv > 0.f) ? dv[e] : 0.f;
+                            if (ok) dsave[kin * TS + b] = dv[e] * inv_s;
+                        }
+                        store_act_tile(bd_base + (uint32_t)(cur ^ 1) * 2u * bd_mat + bd_lane + (uint32_t)(mt * 16 * 2), dv);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int kin = mt * 16 + g + (e >> 1) * 8, b = bcol + (e & 1);
+                            if (kin < ap.M && b < TS) sZb[kin * TS + b] = dv[e] * inv_s;
+                        }
+                    }
+                }
+                cta_sync();
+                cur ^= 1;
+            }
+            const float* hb = sZb;
+            PH2_MARK(3);      // phase 3: hidden layers
             // hb now holds the cotangent of the stage input
             for (int item = tid; item < Hd * TS; item += NT) {
                 const float v = hb[item];
@@ -424,9 +438,10 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
             }
             abuf ^= 1;
             cta_sync();
-            PHASE_MARK(13);   // RK4 adjoint combine + barrier
+            PH2_MARK(4);      // RK4 adjoint combine + barrier
         }
     }
+    PH2_FLUSH(lo.mode == ANCDE_MODE_TOP ? 40 : 32);
     // ---- results
     for (int o = 16; o >= 1; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
     if (lane == 0 && gmax > 0.f && gmax < 3.0e38f)
@@ -444,16 +459,19 @@ static int bwd_ct(const NcdeLayout& lo)
     int ct = (lo.n_wtiles + 1) / 2;
     if (ct > 7) ct = 7;
     if (ct < 1) ct = 1;
-    // phase 3 wants at least one thread per (input, sample-quad) item of the widest layer
+    // phase 3 gives every m-tile (16 inputs) of a hidden layer its own warp
+    int maxmt = 1;
+    for (int l = 0; l < lo.n_hidden; ++l) maxmt = lo.hbp[l].mtiles > maxmt ? lo.hbp[l].mtiles : maxmt;
+    if (2 * ct < maxmt) ct = (maxmt + 1) / 2;
     return ct;
 }
 
 static size_t bwd_smem_bytes(const NcdeLayout& lo, int ct, int slots, bool att)
 {
     const int nw = 2 * ct;
-    size_t f = (size_t)pad4(lo.hidden_floats);
+    size_t f = (size_t)lo.hb_u4 * 4;
     f += (size_t)slots * ct * lo.MTK * 64 * 4;
-    f += 2 * (size_t)lo.act_fwd_floats + 6 * (size_t)pad4(lo.Hd * lo.TS) + 2 * (size_t)pad4(lo.Hmax * lo.TS);
+    f += 2 * (size_t)lo.act_fwd_floats + 7 * (size_t)pad4(lo.Hd * lo.TS) + (size_t)(4 * 8 * (16 * lo.KSB + 8)) / 2;
     f += (size_t)nw * lo.MTK * 128 + (att ? (size_t)nw * lo.NJC * 64 : 0) + 32 + (size_t)lo.C4 * lo.TS;
     return f * 4 + 128;
 }

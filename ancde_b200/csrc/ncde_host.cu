@@ -27,6 +27,45 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a)
         for (int o = gtid; o < pad4(out); o += gsz) a.wpack[lo.off_b[l] + o] = (o < out) ? a.bias[l][o] : 0.f;
     }
     if (gtid < 4) a.wpack[lo.off_gscale + gtid] = 0.f;
+    for (int which = 0; which < 2 * lo.n_hidden; ++which) {
+        // hidden layers as FP16 hi/lo A fragments: forward (which < L) A[m][k] = 64*W_l[m][k], backward A[m][k] = 64*W_l[k][m]
+        const bool fwd = which < lo.n_hidden;
+        const int l = fwd ? which : which - lo.n_hidden;
+        const APack ap = fwd ? lo.hfp[l] : lo.hbp[l];
+        uint4* base = reinterpret_cast<uint4*>(a.wpack + (fwd ? lo.off_whf : lo.off_whb)) + ap.off;
+        const float* Wl = a.W[l];
+        const int in = lo.in_dim[l], out = lo.width[l];
+        auto el = [&](int m, int k) -> float {
+            if (fwd) return (m < out && k < in) ? 64.0f * Wl[(int64_t)m * in + k] : 0.f;
+            return (m < in && k < out) ? 64.0f * Wl[(int64_t)k * in + m] : 0.f;
+        };
+        const int steps = ap.full + ap.tail8;
+        const int total = ap.mtiles * steps * 32;
+        for (int idx = gtid; idx < total; idx += gsz) {
+            const int lane = idx & 31, ks = (idx >> 5) % steps, mt = (idx >> 5) / steps;
+            const int g = lane >> 2, t = lane & 3;
+            const int m0 = mt * 16 + g, m1 = m0 + 8, k0 = ks * 16 + 2 * t;
+            uint4* dst = base + mt * ap.stride + ks * 64;
+            uint32_t h[4], lw[4];
+            split_pair(el(m0, k0), el(m0, k0 + 1), h[0], lw[0]);
+            split_pair(el(m1, k0), el(m1, k0 + 1), h[1], lw[1]);
+            if (ks < ap.full) {
+                split_pair(el(m0, k0 + 8), el(m0, k0 + 9), h[2], lw[2]);
+                split_pair(el(m1, k0 + 8), el(m1, k0 + 9), h[3], lw[3]);
+                dst[lane] = make_uint4(h[0], h[1], h[2], h[3]);
+                dst[32 + lane] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            } else {
+                dst[lane] = make_uint4(h[0], h[1], lw[0], lw[1]);
+            }
+        }
+    }
+    {
+        int o = lo.off_hbias64;
+        for (int l = 0; l < lo.n_hidden; ++l) {
+            for (int i = gtid; i < lo.hfp[l].mtiles * 16; i += gsz) a.wpack[o + i] = (i < lo.width[l]) ? 64.0f * a.bias[l][i] : 0.f;
+            o += lo.hfp[l].mtiles * 16;
+        }
+    }
     {
         // W_out^T tiles as FP16 hi/lo A fragments (m16n8k16 row-major A: a0 = (m g, k 2t..2t+1), a1 = (m g+8, ..),
         // a2 = (m g, k 2t+8..), a3 = (m g+8, k 2t+8..)); m = hidden index, k = tile row
@@ -110,6 +149,19 @@ static void fill_layout(const ancde_ncde_desc* d, int TS, NcdeLayout* lo)
     lo->n_wtiles = lo->NIP * lo->NJC;
     lo->magicNJC = (unsigned)((((uint64_t)1 << 32) + lo->NJC - 1) / lo->NJC);
     lo->off_wob = off; off += lo->n_wtiles * lo->MTK * 64 * 4;
+    {
+        int u = 0, kmax = d->Hd;
+        for (int l = 0; l < d->n_hidden; ++l) { lo->hfp[l] = make_apack(lo->width[l], lo->in_dim[l], u); u += lo->hfp[l].mtiles * lo->hfp[l].stride; }
+        lo->hf_u4 = u;
+        lo->off_whf = off; off += u * 4;
+        u = 0;
+        for (int l = 0; l < d->n_hidden; ++l) { lo->hbp[l] = make_apack(lo->in_dim[l], lo->width[l], u); u += lo->hbp[l].mtiles * lo->hbp[l].stride; }
+        lo->hb_u4 = u;
+        lo->off_whb = off; off += u * 4;
+        lo->off_hbias64 = off;
+        for (int l = 0; l < d->n_hidden; ++l) { off += lo->hfp[l].mtiles * 16; if (lo->width[l] > kmax) kmax = lo->width[l]; }
+        lo->KSB = (kmax + 15) / 16;
+    }
     lo->off_gscale = off; off += 4;
     lo->wpack_floats = off;
     int a = d->Hd * TS;

@@ -5,6 +5,31 @@
 
 namespace ancde {
 
+// A-operand pack of a matrix A[M][K]: m-tiles of 16 rows; per m-tile `full` k16 steps (64 uint4 each: 32 lanes of hi
+// fragments then 32 lanes of lo fragments) and an optional k8 tail (32 uint4: {hi a0, hi a1, lo a0, lo a1} per lane)
+// or k16 tail.
+struct APack {
+    int M, K;           // logical sizes
+    int mtiles;         // ceil(M / 16)
+    int full;           // k16 steps (including a k16 tail)
+    int tail8;          // 1 if a final k8 step follows
+    int stride;         // uint4 per m-tile = full*64 + tail8*32
+    int off;            // offset in uint4 units from the start of wpack
+};
+
+__host__ __device__ static inline APack make_apack(int M, int K, int off)
+{
+    APack a;
+    a.M = M; a.K = K;
+    a.mtiles = (M + 15) / 16;
+    const int rem = K % 16;
+    a.full = K / 16 + (rem > 8 ? 1 : 0);
+    a.tail8 = (rem > 0 && rem <= 8) ? 1 : 0;
+    a.stride = a.full * 64 + a.tail8 * 32;
+    a.off = off;
+    return a;
+}
+
 struct NcdeLayout {
     // ---- problem ----
     int B, L, C, Hd, n_hidden, mode, att_C, att_L, n_hp, n_steps, n_out;
@@ -29,6 +54,10 @@ struct NcdeLayout {
     // (2 field rows x 8 control channels: row r < 8 -> (2*ip, 8*jc + r), r >= 8 -> (2*ip + 1, 8*jc + r - 8)); a tile holds
     // MTK m-tiles (16 k each) of 64 uint4 (32 lanes hi, 32 lanes lo); values are scaled by 64
     int NIP, NJC, MTK, n_wtiles, off_wob;
+    // hidden layers as FP16 hi/lo A fragments (scaled by 64): forward A = W_l [width][in], backward A = W_l^T [in][width];
+    // APack::off is in uint4 units from off_whf / off_whb (float offsets into wpack)
+    APack hfp[ANCDE_MAX_LAYERS], hbp[ANCDE_MAX_LAYERS];
+    int off_whf, off_whb, hf_u4, hb_u4, off_hbias64, KSB;   // KSB: k16 steps of the widest activation
     unsigned magicNJC;  // ceil(2^32 / NJC)
     int off_gscale;     // 4 floats of scratch: max |stage cotangent| of the running backward (bits, atomicMax)
     int64_t wpack_floats;

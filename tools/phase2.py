@@ -28,10 +28,11 @@ L.ancde_debug_set_buffer(ctypes.c_void_p(dbg.data_ptr()))
 run(); torch.cuda.synchronize()
 d = dbg.cpu().tolist()
 stages = 4 * (cfg['L'] - 1)
+bnames = ['gbar + act wait', 'G -> pre_bar -> W^T mma', 'attention', 'hidden layers', 'combine', '', '', '']
 names = ['hidden layers', 'out layer + epilogue', 'sync', 'ctl issue + gather/scatter', 'cluster barrier', 'ctl finish', 'combine + sync', '-']
 for base, nm in ((16, 'fwd bottom'), (24, 'fwd top'), (32, 'bwd bottom'), (40, 'bwd top')):
     tot = sum(d[base:base + 8])
     if tot == 0: continue
     print('%s: cycles per stage (CTA 0), total %.0f' % (nm, tot / stages))
     for i in range(8):
-        if d[base + i]: print('  %d %-28s %9.0f' % (i, names[i] if base < 32 else '', d[base + i] / stages))
+        if d[base + i]: print('  %d %-28s %9.0f' % (i, names[i] if base < 32 else bnames[i], d[base + i] / stages))
