@@ -494,7 +494,7 @@ static int launch_bwd(const ancde_ncde_desc* d, SolveArgs& a, cudaStream_t strea
     const int ct = bwd_ct(lo);
     const int nt = 2 * ct * 32;
     const bool att = (lo.mode == ANCDE_MODE_TOP) && (a.grad_attention != nullptr);
-    int slots = 4;
+    int slots = 8;      // as deep a ring as fits: the fills are latency bound (~1.5 us each)
     while (slots > 2 && bwd_smem_bytes(lo, ct, slots, att) > max_smem) --slots;
     const size_t smem = bwd_smem_bytes(lo, ct, slots, att);
     if (smem > max_smem) {

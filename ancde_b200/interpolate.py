@@ -73,18 +73,23 @@ class NaturalCubicSpline:
     def _interpret_t(self, t):
         maxlen = self._b.size(-2) - 1
         index = (t > self._times).sum() - 1
-        index = index.clamp(0, maxlen)
-        fractional_part = t - self._times[index]
+        index = index.clamp(0, maxlen).view(1)
+        # index_select keeps the lookup on the device: indexing with a 0-dim tensor (the reference's form) reads the
+        # index back to the host, one synchronisation per coefficient tensor
+        fractional_part = t - self._times.index_select(0, index).squeeze(0)
         return fractional_part, index
+
+    def _piece(self, coeff, index):
+        return coeff.index_select(-2, index).squeeze(-2)
 
     def evaluate(self, t):
         fractional_part, index = self._interpret_t(t)
-        inner = 0.5 * self._two_c[..., index, :] + self._three_d[..., index, :] * fractional_part / 3
-        inner = self._b[..., index, :] + inner * fractional_part
-        return self._a[..., index, :] + inner * fractional_part
+        inner = 0.5 * self._piece(self._two_c, index) + self._piece(self._three_d, index) * fractional_part / 3
+        inner = self._piece(self._b, index) + inner * fractional_part
+        return self._piece(self._a, index) + inner * fractional_part
 
     def derivative(self, t):
         fractional_part, index = self._interpret_t(t)
-        inner = self._two_c[..., index, :] + self._three_d[..., index, :] * fractional_part
-        deriv = self._b[..., index, :] + inner * fractional_part
+        inner = self._piece(self._two_c, index) + self._piece(self._three_d, index) * fractional_part
+        deriv = self._piece(self._b, index) + inner * fractional_part
         return deriv

@@ -35,19 +35,14 @@ RoundST = RoundFunctionST.apply
 
 
 def _solve_times(times, final_index, stream):
-    """Which times the top solve must report (reference: metamodel.py:287-302)."""
-    if stream:
-        return times, final_index
-    sorted_final_index, inverse_final_index = final_index.unique(sorted=True, return_inverse=True)
-    if 0 in sorted_final_index:
-        sorted_final_index = sorted_final_index[1:]
-        final_index = inverse_final_index
-    else:
-        final_index = inverse_final_index + 1
-    if len(times) - 1 in sorted_final_index:
-        sorted_final_index = sorted_final_index[:-1]
-    t = torch.cat([times[0].unsqueeze(0), times[sorted_final_index], times[-1].unsqueeze(0)])
-    return t, final_index
+    """Which times the top solve must report.
+
+    The reference (metamodel.py:287-302) asks the solver for {t0} + unique(final times) + {t_end} and gathers each
+    sample's row; every requested time is a grid point, so the result equals the all-knots solution indexed at
+    final_index.  The fused solver therefore always reports every knot: `unique` (two sorts and three
+    host synchronisations per step in the reference's formulation) disappears, the gather below is unchanged.
+    """
+    return times, final_index
 
 
 def _default_rk4(times, kwargs):
@@ -58,8 +53,11 @@ def _default_rk4(times, kwargs):
             kwargs['options'] = {}
         options = kwargs['options']
         if 'step_size' not in options and 'grid_constructor' not in options:
-            time_diffs = times[1:] - times[:-1]
-            options['step_size'] = time_diffs.min().item()
+            # reference: time_diffs.min().item() every call (metamodel.py:311-313); cached per times tensor here so that
+            # a training step has no host synchronisation
+            from .solver import cached_host_scalar
+            step = cached_host_scalar(times, 'min_dt', lambda t: (t[1:] - t[:-1]).min().item())
+            options['step_size'] = step
     return kwargs
 
 

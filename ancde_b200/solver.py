@@ -6,6 +6,7 @@ only moves pointers around -- it contains no arithmetic of the path.
 """
 import ctypes
 import math
+import weakref
 
 import torch
 
@@ -42,26 +43,37 @@ def _f32(x, dev):
     return x.detach().to(device=dev, dtype=torch.float32).contiguous()
 
 
-def fixed_grid_meta(t_out, step_size):
-    """(t_start, t_end, step, n_steps) of torchdiffeq's _grid_constructor_from_step_size, float32."""
-    key = (t_out.data_ptr(), t_out._version, t_out.numel(), str(t_out.device), float(step_size))
+def cached_host_scalar(tensor, tag, fn):
+    """fn(tensor) -> host value, remembered per tensor OBJECT (weak reference + version counter).
+
+    The reference reads such scalars back with .item() on every call (a host synchronisation per step); keyed on object
+    identity rather than on the data pointer so that a recycled allocation can never return a stale value.
+    """
+    key = (id(tensor), tag)
     hit = _grid_cache.get(key)
-    if hit is not None:
-        return hit
-    th = t_out.detach().to('cpu', torch.float32)
-    if th.numel() < 2:
-        raise ValueError('t must contain at least two times')
-    if not bool((th[1:] > th[:-1]).all()):
-        if bool((th[1:] < th[:-1]).all()):
-            raise NotImplementedError('decreasing integration times are not supported by the fused solver')
-        raise AssertionError('t must be strictly increasing or decreasing')
-    step = torch.tensor(float(step_size), dtype=torch.float32)
-    niters = int(torch.ceil((th[-1] - th[0]) / step + 1).item())
-    meta = (float(th[0]), float(th[-1]), float(step), niters - 1)
+    if hit is not None and hit[0]() is tensor and hit[1] == tensor._version:
+        return hit[2]
+    value = fn(tensor)
     if len(_grid_cache) > 256:
         _grid_cache.clear()
-    _grid_cache[key] = meta
-    return meta
+    _grid_cache[key] = (weakref.ref(tensor), tensor._version, value)
+    return value
+
+
+def fixed_grid_meta(t_out, step_size):
+    """(t_start, t_end, step, n_steps) of torchdiffeq's _grid_constructor_from_step_size, float32."""
+    def compute(t):
+        th = t.detach().to('cpu', torch.float32)
+        if th.numel() < 2:
+            raise ValueError('t must contain at least two times')
+        if not bool((th[1:] > th[:-1]).all()):
+            if bool((th[1:] < th[:-1]).all()):
+                raise NotImplementedError('decreasing integration times are not supported by the fused solver')
+            raise AssertionError('t must be strictly increasing or decreasing')
+        step = torch.tensor(float(step_size), dtype=torch.float32)
+        niters = int(torch.ceil((th[-1] - th[0]) / step + 1).item())
+        return (float(th[0]), float(th[-1]), float(step), niters - 1)
+    return cached_host_scalar(t_out, ('grid', float(step_size)), compute)
 
 
 def mlp_params(func):

@@ -11,11 +11,16 @@ from . import metamodel, synthetic
 from .dp import FlatGradBucket
 
 
+_pos_weight = {}
+
+
 def task_loss(cfg, pred, y):
     if cfg['kind'] == 'ancde_forecasting':
         return torch.nn.functional.mse_loss(pred, y)                          # common.py:766
     if cfg['out'] == 1:                                                       # Sepsis: BCE, pos_weight 10
-        pw = torch.tensor(10.0, device=pred.device)
+        pw = _pos_weight.get(pred.device)
+        if pw is None:      # created once: torch.tensor(..., device=cuda) is a synchronising pageable copy
+            pw = _pos_weight[pred.device] = torch.tensor(10.0, device=pred.device)
         return torch.nn.functional.binary_cross_entropy_with_logits(pred.squeeze(-1), y, pos_weight=pw)
     return torch.nn.functional.cross_entropy(pred, y)
 

@@ -73,13 +73,22 @@ def test_spline_evaluate_and_derivative_match_reference_port():
 
 
 def test_solve_times_and_readout_follow_the_reference():
+    """The reference solves for {t0} + unique(final times) + {t_end} and gathers (metamodel.py:287-302, 364-371); the
+    fused solver reports every knot and gathers at final_index -- the two agree because every requested time is a
+    grid point.  Checked here against the reference's own index arithmetic."""
     times = torch.arange(6.) + 1
     fi = torch.tensor([5, 2, 2, 0, 3])
     t, idx = metamodel._solve_times(times, fi, stream=False)
-    assert t.tolist() == [1.0, 3.0, 4.0, 6.0] and idx.tolist() == [3, 1, 1, 0, 2]
-    z = torch.arange(4 * 5 * 2, dtype=torch.float32).view(4, 5, 2)
+    assert torch.equal(t, times) and torch.equal(idx, fi)
+    z = torch.arange(6 * 5 * 2, dtype=torch.float32).view(6, 5, 2)          # one row per knot
     out = metamodel._readout(z, idx, stream=False)
-    assert torch.equal(out, torch.stack([z[3, 0], z[1, 1], z[1, 2], z[0, 3], z[2, 4]]))
+    # reference formulation
+    sorted_fi, inverse = fi.unique(sorted=True, return_inverse=True)
+    ref_t = torch.cat([times[0].unsqueeze(0), times[sorted_fi[1:-1]], times[-1].unsqueeze(0)])
+    assert ref_t.tolist() == [1.0, 3.0, 4.0, 6.0] and inverse.tolist() == [3, 1, 1, 0, 2]
+    z_ref = z[(ref_t - 1).long()]                                            # the rows the reference's solve returns
+    ref = z_ref.gather(0, inverse.view(1, -1, 1).expand(1, 5, 2)).squeeze(0)
+    assert torch.equal(out, ref)
 
 
 def test_synthetic_batches_have_the_baseline_shapes():
