@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libancde_b200.so')
+LIB_PATH = os.environ.get('ANCDE_LIB') or os.path.join(_HERE, 'libancde_b200.so')   # ANCDE_LIB: development builds
 
 MAX_LAYERS = 8
 MODE_PLAIN, MODE_BOTTOM, MODE_TOP = 0, 1, 2

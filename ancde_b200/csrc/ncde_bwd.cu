@@ -262,12 +262,15 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                         }
                     }
                 };
-                float2 g0n, g1n;
+                // tanh outputs of the next two tiles of this warp are in flight while the current one is processed
+                float2 g0n, g1n, g0nn, g1nn;
                 load_g(grp * CT + wl, g0n, g1n);
+                load_g(grp * CT + wl + 2 * CT, g0nn, g1nn);
                 for (int c = grp; c < nchunks; c += 2) {
                     const int tl = c * CT + wl;
                     const float2 g0 = g0n, g1 = g1n;
-                    load_g(tl + 2 * CT, g0n, g1n);
+                    g0n = g0nn; g1n = g1nn;
+                    load_g(tl + 4 * CT, g0nn, g1nn);
                     const int64_t gc = gchunk + c;
                     const int slot = (int)(gc % NSLOT);
                     const uint32_t parity = (uint32_t)((gc / NSLOT) & 1);
@@ -331,10 +334,12 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                 if (qa < 0) qa += lo.att_L;
                 qa = qa < 0 ? 0 : (qa >= lo.att_L ? lo.att_L - 1 : qa);
                 if (lo.att_C == 1) {
-                    if (tid < TS && b0 + tid < lo.B) {
+                    // timewise attention: one cotangent per sample = sum over the channels; warp b sums sample b
+                    for (int b = warp; b < TS; b += NW) {
                         float a = 0.f;
-                        for (int j = 0; j < lo.C; ++j) a += sTmp[j * TS + tid];
-                        atomicAdd(p.grad_attention + (int64_t)qa * lo.B + b0 + tid, a);
+                        for (int j = lane; j < lo.C; j += 32) a += sTmp[j * TS + b];
+                        for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                        if (lane == 0 && b0 + b < lo.B) atomicAdd(p.grad_attention + (int64_t)qa * lo.B + b0 + b, a);
                     }
                 } else {
                     for (int item = tid; item < lo.C * TS; item += NT) {
