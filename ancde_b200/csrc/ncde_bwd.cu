@@ -22,6 +22,7 @@ namespace ancde {
 
 int fill_args(const ancde_ncde_desc* d, const NcdeLayout& lo, SolveArgs* a);
 int pack_weights(const ancde_ncde_desc* d, const NcdeLayout& lo, cudaStream_t stream);
+int engine_of(const ancde_ncde_desc* d);
 int launch_wgrad(const SolveArgs& a, float* gW, float* gB, cudaStream_t stream);   // ncde_wgrad.cu
 struct HiddenGradPtrs { float* gW[ANCDE_MAX_LAYERS]; float* gB[ANCDE_MAX_LAYERS]; };
 int launch_hidden_wgrad(const SolveArgs& a, const HiddenGradPtrs& hp, cudaStream_t stream);
@@ -538,6 +539,11 @@ extern "C" int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream_)
 {
     reset_launch_count();
     cudaStream_t stream = (cudaStream_t)stream_;
+    ANCDE_CHECK_ARG(d != nullptr, "ncde_backward: null descriptor");
+    if (engine_of(d) == ANCDE_ENGINE_CLUSTER) {
+        set_error("ncde_backward: the cluster engine is forward-only; solve with ANCDE_ENGINE_STREAMED to differentiate");
+        return ANCDE_EUNSUPPORTED;
+    }
     NcdeLayout lo;
     int rc = make_layout(d, &lo);
     if (rc != ANCDE_OK) return rc;

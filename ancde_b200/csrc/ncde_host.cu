@@ -250,14 +250,14 @@ int fill_args(const ancde_ncde_desc* d, const NcdeLayout& lo, SolveArgs* a)
 using namespace ancde;
 
 // Engine choice: the descriptor's `engine`, else the library default.
-static const int DEFAULT_ENGINE = ANCDE_ENGINE_FFMA;
+static const int DEFAULT_ENGINE = ANCDE_ENGINE_STREAMED;
 namespace ancde {
 int engine_of(const ancde_ncde_desc* d) { return (d && d->engine) ? d->engine : DEFAULT_ENGINE; }
 }
 
 extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
 {
-    if (engine_of(d) == ANCDE_ENGINE_MMA) {
+    if (engine_of(d) == ANCDE_ENGINE_CLUSTER) {
         V2Layout l2;
         return make_layout2(d, &l2) == ANCDE_OK ? l2.wpack_floats : -1;
     }
@@ -268,7 +268,7 @@ extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
 
 extern "C" int64_t ancde_ncde_save_act_floats(const ancde_ncde_desc* d)
 {
-    if (engine_of(d) == ANCDE_ENGINE_MMA) {
+    if (engine_of(d) == ANCDE_ENGINE_CLUSTER) {
         V2Layout l2;
         return make_layout2(d, &l2) == ANCDE_OK ? (int64_t)l2.n_stages * l2.nclusters * l2.act_block : -1;
     }
@@ -279,7 +279,7 @@ extern "C" int64_t ancde_ncde_save_act_floats(const ancde_ncde_desc* d)
 
 extern "C" int64_t ancde_ncde_save_G_floats(const ancde_ncde_desc* d)
 {
-    if (engine_of(d) == ANCDE_ENGINE_MMA) {
+    if (engine_of(d) == ANCDE_ENGINE_CLUSTER) {
         V2Layout l2;
         return make_layout2(d, &l2) == ANCDE_OK ? (int64_t)l2.n_stages * l2.nclusters * l2.ntiles * l2.NT * 128 : -1;
     }
@@ -294,7 +294,7 @@ extern "C" int ancde_ncde_forward(const ancde_ncde_desc* d, void* stream_)
     cudaStream_t stream = (cudaStream_t)stream_;
     ANCDE_CHECK_ARG(d != nullptr, "ncde_forward: null descriptor");
     ANCDE_CHECK_ARG((d->save_act == nullptr) == (d->save_G == nullptr), "ncde_forward: save_act and save_G go together");
-    if (engine_of(d) == ANCDE_ENGINE_MMA) {
+    if (engine_of(d) == ANCDE_ENGINE_CLUSTER) {
         V2Layout l2;
         int rc2 = make_layout2(d, &l2);
         if (rc2 != ANCDE_OK) return rc2;

@@ -15,7 +15,7 @@ from . import _lib
 _grid_cache = {}
 import os
 FORCE_SAMPLES_PER_CTA = int(os.environ.get('ANCDE_SAMPLES_PER_CTA', '0'))   # 0 = library default; tests set 1/2/4/8
-ENGINE = int(os.environ.get('ANCDE_ENGINE', '0'))                           # 0 = library default; 1 = FFMA, 2 = tensor-core
+ENGINE = int(os.environ.get('ANCDE_ENGINE', '0'))   # 0 = library default (streamed); 2 = forward-only cluster engine
 
 
 class SolvePlan:
@@ -157,7 +157,11 @@ class _NcdeSolve(torch.autograd.Function):
         d.k_out = k_out.data_ptr() if plan.want_k else None
         wpack = torch.empty(L_.ancde_ncde_wpack_floats(ctypes.byref(d)), dtype=torch.float32, device=dev)
         d.wpack = wpack.data_ptr()
-        need_grad = any(ctx.needs_input_grad)
+        # under torch.no_grad() nothing is saved (ctx.needs_input_grad still reports the inputs' requires_grad there, and
+        # grad mode is always off inside forward(), so solve() records it on the plan)
+        need_grad = plan.grad_mode and any(ctx.needs_input_grad)
+        if need_grad and ENGINE == _lib.ENGINE_CLUSTER:
+            raise NotImplementedError('the cluster engine (ANCDE_ENGINE=2) is forward-only: run it under torch.no_grad()')
         save_act = save_G = None
         if need_grad:
             save_act = torch.empty(L_.ancde_ncde_save_act_floats(ctypes.byref(d)), dtype=torch.float32, device=dev)
@@ -215,5 +219,6 @@ def solve(plan, func, z0, attention=None):
                          "returned batch shape (%d,), whilst z0 has shape %s." % (plan.B, tuple(z0.shape)))
     if attention is None:
         attention = z0.new_zeros(())
+    plan.grad_mode = torch.is_grad_enabled()
     z_out, k_out = _NcdeSolve.apply(plan, widths, z0, attention, *wb)
     return z_out, (k_out if plan.want_k else None)

@@ -70,11 +70,14 @@ int ancde_spline_coeffs_f64(const double* times, const double* X, double* a, dou
 
 /* Two implementations of the same operator (identical inputs/outputs; the workspace sizes differ, so query them with
  * the same `engine` value that the solve will use):
- *   ANCDE_ENGINE_FFMA  one CTA per 8 samples, FP32 FMA, output-layer weights streamed through a TMA ring
- *   ANCDE_ENGINE_MMA   one thread-block cluster per 8..32 samples, output-layer weights resident in shared memory as
- *                      FP16 hi/lo fragments, tensor-core products (3 per tile, FP32-grade accuracy)              */
-#define ANCDE_ENGINE_FFMA 1
-#define ANCDE_ENGINE_MMA  2
+ *   ANCDE_ENGINE_STREAMED  (default) one CTA per tile of 8 samples; the output-layer weights are streamed from L2 through
+ *                          a TMA ring every stage.  Forward: FP32 FMA.  Backward and weight gradients: tensor cores
+ *                          (mma.sync, FP16 hi/lo split, three products per tile = FP32-grade accuracy).
+ *   ANCDE_ENGINE_CLUSTER   forward only (inference): a thread-block cluster per 8..32 samples keeps the output layer
+ *                          RESIDENT in shared memory as FP16 hi/lo fragments and exchanges the stage derivative through
+ *                          distributed shared memory; ancde_ncde_backward returns ANCDE_EUNSUPPORTED for it.         */
+#define ANCDE_ENGINE_STREAMED 1
+#define ANCDE_ENGINE_CLUSTER  2
 
 typedef struct ancde_ncde_desc {
     /* ---- shapes ---- */
@@ -116,8 +119,8 @@ typedef struct ancde_ncde_desc {
     float* grad_W[ANCDE_MAX_LAYERS + 1];      /* accumulated into (caller zeroes), same layout as W */
     float* grad_bias[ANCDE_MAX_LAYERS + 1];
     float* grad_attention;     /* TOP, or NULL (adjoint-mode gradient flow): (att_L, B, att_C) accumulated into */
-    int32_t samples_per_cta;   /* FFMA engine only: 0 = let the library choose (8, 4, 2 or 1) */
-    int32_t engine;            /* 0 = library default; ANCDE_ENGINE_FFMA or ANCDE_ENGINE_MMA (see below) */
+    int32_t samples_per_cta;   /* streamed engine only: 0 = let the library choose (8, 4, 2 or 1) */
+    int32_t engine;            /* 0 = library default; ANCDE_ENGINE_STREAMED or ANCDE_ENGINE_CLUSTER (see above) */
 } ancde_ncde_desc;
 
 /* Workspace sizes (in floats) for a descriptor whose shape fields are filled in. */

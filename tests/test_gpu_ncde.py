@@ -203,3 +203,25 @@ def test_api_errors():
     with pytest.raises(ValueError):
         ancde_b200.cdeint(sp.derivative, torch.randn(3, 4).cuda(), func, times, method='rk4',
                           options=dict(step_size=1.0))
+
+
+@pytest.mark.parametrize('case', DUAL_CASES)
+def test_cluster_engine_forward_matches_reference_golden(case):
+    """ANCDE_ENGINE_CLUSTER (thread-block clusters, output layer resident in shared memory, tensor cores): inference
+    parity against the same golden vectors; it refuses to differentiate."""
+    import ancde_b200
+    from ancde_b200 import solver, _lib
+    g = dual_case(case)
+    model = _build(g['cfg'], g['sd'])
+    solver.ENGINE = _lib.ENGINE_CLUSTER
+    try:
+        with torch.no_grad():
+            pred = _forward(model, g)
+        torch.cuda.synchronize()
+        hp = ancde_b200.load_h_prime('test_h_prime')
+        assert rel_err(pred, g['pred']) < FWD_TOL, case
+        assert rel_err(hp, g['h_prime']) < FWD_TOL, case
+        with pytest.raises(NotImplementedError):
+            _forward(model, g)
+    finally:
+        solver.ENGINE = 0
