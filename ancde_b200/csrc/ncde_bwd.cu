@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     int abuf = 0;            // which half of sActBuf holds the current stage
     float gmax = 0.f;        // largest |stage cotangent| this thread wrote (scale of the FP16 weight-gradient operands)
     const int grp = warp / CT, wl = warp - grp * CT;     // this warp's group and tile slot inside a chunk
-    int64_t gchunk = 0;      // chunks consumed so far (ring position), advanced by nchunks per stage
+    int ring_base = 0;       // ring position of this stage's chunk 0, modulo 2*NSLOT (slot and phase parity in one number)
     PH2_DECL();
 
     for (int k = lo.n_steps - 1; k >= 0; --k) {
@@ -267,14 +267,16 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                 float2 g0n, g1n, g0nn, g1nn;
                 load_g(grp * CT + wl, g0n, g1n);
                 load_g(grp * CT + wl + 2 * CT, g0nn, g1nn);
+                int rpos = (ring_base + grp) % (2 * NSLOT);
                 for (int c = grp; c < nchunks; c += 2) {
                     const int tl = c * CT + wl;
                     const float2 g0 = g0n, g1 = g1n;
                     g0n = g0nn; g1n = g1nn;
                     load_g(tl + 4 * CT, g0nn, g1nn);
-                    const int64_t gc = gchunk + c;
-                    const int slot = (int)(gc % NSLOT);
-                    const uint32_t parity = (uint32_t)((gc / NSLOT) & 1);
+                    const int slot = (rpos >= NSLOT) ? rpos - NSLOT : rpos;
+                    const uint32_t parity = (rpos >= NSLOT) ? 1u : 0u;
+                    rpos += 2;
+                    if (rpos >= 2 * NSLOT) rpos -= 2 * NSLOT;
                     mbar_wait(bar_full + slot, parity);
                     if (tl < ntl) {
                         int i0, j;
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_empty + slot);
                 }
-                gchunk += nchunks;
+                ring_base = (ring_base + nchunks) % (2 * NSLOT);
                 float4* hp4 = reinterpret_cast<float4*>(sHbP) + (size_t)warp * MTK * 32 + lane;
 #pragma unroll
                 for (int m = 0; m < BW_MTK_MAX; ++m)

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(256) ncde_wgrad_mma_kernel(const __grid_consta
 
     // shared memory: two cp.async stages of { G [32][128] f32, gbar [BPC][Hd*TS], dU [BPC][du_floats], h [BPC][K*TS] },
     // then the FP16 operands { pre_bar hi, lo [32][WM_AS], h hi, lo [KP][WM_HS] }
+    __shared__ __align__(8) uint64_t ld_bar[2];        // TMA completion of the two load stages (TS >= 4)
     extern __shared__ __align__(16) float smem[];
     const int szP = WM_ROWS * WM_COLS, szG = BPC * pad4(Hd * TS), szD = BPC * lo.du_floats, szH = pad4(BPC * K * TS);
     const int stage_floats = szP + szG + szD + szH;
@@ -85,12 +86,43 @@ __global__ void __launch_bounds__(256) ncde_wgrad_mma_kernel(const __grid_consta
         const int sz = ok ? 4 : 0;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(sz) : "memory");
     };
+    // Loads of a chunk.  TS >= 4: every piece is a contiguous run of >= 16 bytes, so one warp hands them to the TMA
+    // engine (bulk copies that complete on the stage's mbarrier) and no thread spends issue slots on address
+    // arithmetic; smaller tiles fall back to per-thread cp.async.
     auto issue = [&](int64_t ch, int s) {
         const uint32_t sP = smem_base + (uint32_t)(s * stage_floats) * 4u;
         const uint32_t sG = sP + (uint32_t)szP * 4u;
         const uint32_t sD = sG + (uint32_t)szG * 4u;
         const uint32_t sH = sD + (uint32_t)szD * 4u;
         const int64_t blk0 = ch * BPC;
+        if (TS >= 4) {
+            if (warp != 0) return;
+            int64_t nvalid = nblocks - blk0;                      // (stage, tile) blocks of this chunk that exist
+            if (nvalid > BPC) nvalid = BPC;
+            const int ncg = (NCG - blockIdx.x * WM_CW < WM_CW) ? NCG - blockIdx.x * WM_CW : WM_CW;
+            const uint32_t bytes_g = (uint32_t)ncg * 16u;
+            const uint32_t bytes_o = (uint32_t)((Hd * TS + lo.du_floats + K * TS) * 4);
+            if (lane == 0) mbar_arrive_expect_tx(ld_bar + s, (uint32_t)nvalid * (TS * bytes_g + bytes_o));
+            __syncwarp();
+            {
+                const int r = lane, bl = r / TS;
+                if (bl < nvalid)
+                    bulk_g2s(smem + s * stage_floats + (size_t)r * WM_COLS,
+                             reinterpret_cast<const float4*>(p.save_G) + ((blk0 + bl) * TS + (r % TS)) * NCG + blockIdx.x * WM_CW, bytes_g,
+                             ld_bar + s);
+            }
+            if (lane < 3 * BPC) {
+                const int bl = lane / 3, what = lane - bl * 3;
+                if (bl < nvalid) {
+                    const float* act = p.save_act + (blk0 + bl) * lo.act_floats;
+                    float* base = smem + s * stage_floats + szP;
+                    if (what == 0) bulk_g2s(base + bl * pad4(Hd * TS), act + lo.act_off_gbar, (uint32_t)(Hd * TS * 4), ld_bar + s);
+                    else if (what == 1) bulk_g2s(base + szG + bl * lo.du_floats, act + lo.act_off_du, (uint32_t)(lo.du_floats * 4), ld_bar + s);
+                    else bulk_g2s(base + szG + szD + bl * K * TS, act + off_hl, (uint32_t)(K * TS * 4), ld_bar + s);
+                }
+            }
+            return;
+        }
         const float4* gsrc = reinterpret_cast<const float4*>(p.save_G) + (col_ok ? gcg0 : 0);
 #pragma unroll
         for (int r = r0; r < WM_ROWS; r += NWARP) {
@@ -102,17 +134,19 @@ __global__ void __launch_bounds__(256) ncde_wgrad_mma_kernel(const __grid_consta
             const int64_t blk = blk0 + bl;
             const bool ok = blk < nblocks;
             const float* act = p.save_act + (ok ? blk : 0) * lo.act_floats;
-            if (TS >= 4) {
-                for (int i = tid; i < Hd * TS / 4; i += NT) cp16(sG + (uint32_t)(bl * pad4(Hd * TS) + i * 4) * 4u, act + lo.act_off_gbar + i * 4, ok);
-                for (int i = tid; i < lo.du_floats / 4; i += NT) cp16(sD + (uint32_t)(bl * lo.du_floats + i * 4) * 4u, act + lo.act_off_du + i * 4, ok);
-                for (int i = tid; i < K * TS / 4; i += NT) cp16(sH + (uint32_t)(bl * K * TS + i * 4) * 4u, act + off_hl + i * 4, ok);
-            } else {
-                for (int i = tid; i < Hd * TS; i += NT) cp4(sG + (uint32_t)(bl * pad4(Hd * TS) + i) * 4u, act + lo.act_off_gbar + i, ok);
-                for (int i = tid; i < lo.du_floats; i += NT) cp4(sD + (uint32_t)(bl * lo.du_floats + i) * 4u, act + lo.act_off_du + i, ok);
-                for (int i = tid; i < K * TS; i += NT) cp4(sH + (uint32_t)(bl * K * TS + i) * 4u, act + off_hl + i, ok);
-            }
+            for (int i = tid; i < Hd * TS; i += NT) cp4(sG + (uint32_t)(bl * pad4(Hd * TS) + i) * 4u, act + lo.act_off_gbar + i, ok);
+            for (int i = tid; i < lo.du_floats; i += NT) cp4(sD + (uint32_t)(bl * lo.du_floats + i) * 4u, act + lo.act_off_du + i, ok);
+            for (int i = tid; i < K * TS; i += NT) cp4(sH + (uint32_t)(bl * K * TS + i) * 4u, act + off_hl + i, ok);
         }
     };
+    if (TS >= 4) {
+        if (tid == 0) {
+            mbar_init(ld_bar + 0, 1);
+            mbar_init(ld_bar + 1, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
 
     // rows k >= K of the h operand: k == K is the bias column (1.0), the rest is padding
     for (int idx = tid; idx < KP * WM_HS; idx += NT) {
@@ -146,20 +180,26 @@ __global__ void __launch_bounds__(256) ncde_wgrad_mma_kernel(const __grid_consta
         const float* sG = sP + szP;
         const float* sD = sG + szG;
         const float* sH = sD + szD;
-        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        if (TS >= 4) mbar_wait(ld_bar + s, (uint32_t)(((ch - c0) >> 1) & 1));
+        else asm volatile("cp.async.wait_group 1;\n" ::: "memory");
         __syncthreads();
+        const int64_t blk_left = nblocks - ch * BPC;            // rows of blocks beyond the end contribute nothing
         // ---- G -> scaled pre_bar, FP16 hi/lo: this lane's column group, rows warp, warp + NKT, ...
 #pragma unroll
         for (int rr = 0; rr < WM_ROWS / NWARP; ++rr) {
             const int r = warp + rr * NWARP;
             const int bl = r / TS, b = r - bl * TS;
             const float4 gq = *reinterpret_cast<const float4*>(sP + ((size_t)r * WM_CW + lane) * 4);
-            const float gb = sG[bl * pad4(Hd * TS) + i_row * TS + b] * scale;
+            const bool live = bl < blk_left;
+            const float gb = live ? sG[bl * pad4(Hd * TS) + i_row * TS + b] * scale : 0.f;
             const float* du = sD + bl * lo.du_floats + chunk * lo.DUS + b;
-            const float v0 = gb * du[0 * TS] * fmaf(-gq.x, gq.x, 1.0f);
-            const float v1 = gb * du[1 * TS] * fmaf(-gq.y, gq.y, 1.0f);
-            const float v2 = gb * du[2 * TS] * fmaf(-gq.z, gq.z, 1.0f);
-            const float v3 = gb * du[3 * TS] * fmaf(-gq.w, gq.w, 1.0f);
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+            if (live) {
+                v0 = gb * du[0 * TS] * fmaf(-gq.x, gq.x, 1.0f);
+                v1 = gb * du[1 * TS] * fmaf(-gq.y, gq.y, 1.0f);
+                v2 = gb * du[2 * TS] * fmaf(-gq.z, gq.z, 1.0f);
+                v3 = gb * du[3 * TS] * fmaf(-gq.w, gq.w, 1.0f);
+            }
             uint32_t h0, l0, h1, l1;
             split_pair(v0, v1, h0, l0);
             split_pair(v2, v3, h1, l1);
@@ -171,7 +211,7 @@ __global__ void __launch_bounds__(256) ncde_wgrad_mma_kernel(const __grid_consta
         for (int idx = tid; idx < K * WM_ROWS; idx += NT) {
             const int kk = idx / WM_ROWS, r = idx - kk * WM_ROWS;
             const int bl = r / TS, b = r - bl * TS;
-            const float v = sH[bl * K * TS + kk * TS + b];
+            const float v = (bl < blk_left) ? sH[bl * K * TS + kk * TS + b] : 0.f;
             const __half hi = __float2half_rn(v);
             sHh[kk * WM_HS + r] = hi;
             sHl[kk * WM_HS + r] = __float2half_rn(v - __half2float(hi));
