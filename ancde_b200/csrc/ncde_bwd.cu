@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     float* sHbP = sp;   sp += (size_t)NW * MTK * 128;    // per-warp partial sums of the hidden cotangent (fragment order)
     float* sAttW = sp;  sp += need_att ? (size_t)NW * NJC * 64 : 0;   // per-warp partial sums of the dU cotangent [jc][b][8 j]
     float* sMax = sp;   sp += 32;
+    int* sLp = reinterpret_cast<int*>(sp); sp += 8 * ANCDE_MAX_LAYERS;   // per-layer {mtiles, full, tail8, stride, off, M, act_off_h[l-1], act_off_delta[l-1]}
     float* sTmp = sp;                                    // [C4][TS]
 
     if (tid == 0) {
@@ -155,6 +156,15 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
         uint32_t* zb = reinterpret_cast<uint32_t*>(sBd);
         for (int i = tid; i < 2 * 8 * KP; i += NT) zb[i] = 0u;      // 4 matrices of 8*KP halfs
         for (int item = tid; item < Hd * TS; item += NT) { sLam[item] = 0.f; sMu[item] = 0.f; }
+        if (tid < lo.n_hidden) {
+            // the layer loop reads its parameters from shared memory: register-indexed loads from the kernel-parameter
+            // constant bank cost hundreds of cycles each on the critical path of every layer
+            const int l = tid;
+            int* q = sLp + 8 * l;
+            q[0] = lo.hbp[l].mtiles; q[1] = lo.hbp[l].full; q[2] = lo.hbp[l].tail8; q[3] = lo.hbp[l].stride;
+            q[4] = lo.hbp[l].off; q[5] = lo.hbp[l].M;
+            q[6] = l > 0 ? lo.act_off_h[l - 1] : 0; q[7] = l > 0 ? lo.act_off_delta[l - 1] : 0;
+        }
         issue_act(lo.n_stages - 1, sActBuf);
     }
     cta_sync();
@@ -380,13 +390,15 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
             cta_sync();
             int cur = 0;
             for (int l = lo.n_hidden - 1; l >= 0; --l) {
-                const APack ap = lo.hbp[l];
-                if (warp < ap.mtiles) {
+                const int4 lp0 = *reinterpret_cast<const int4*>(sLp + 8 * l), lp1 = *reinterpret_cast<const int4*>(sLp + 8 * l + 4);
+                const int l_mtiles = lp0.x, l_full = lp0.y, l_tail8 = lp0.z, l_stride = lp0.w, l_off = lp1.x, l_M = lp1.y;
+                if (warp < l_mtiles) {
                     const int mt = warp;
-                    const uint4* A = sWhb + ap.off + mt * ap.stride + lane;
+                    const uint4* A = sWhb + l_off + mt * l_stride + lane;
                     float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
                     uint32_t baddr = bd_base + (uint32_t)cur * 2u * bd_mat + bd_lane;
-                    for (int ks = 0; ks < ap.full; ++ks) {
+#pragma unroll 4
+                    for (int ks = 0; ks < l_full; ++ks) {
                         const uint4 ah = A[ks * 64], al = A[ks * 64 + 32];
                         uint32_t bh0, bh1, bl0, bl1;
                         ldmatrix_x4(baddr, bh0, bh1, bl0, bl1);
@@ -395,8 +407,8 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                         mma16(a1, ah.x, ah.y, ah.z, ah.w, bl0, bl1);
                         mma16(a2, ah.x, ah.y, ah.z, ah.w, bh0, bh1);
                     }
-                    if (ap.tail8) {
-                        const uint4 a = A[ap.full * 64];
+                    if (l_tail8) {
+                        const uint4 a = A[l_full * 64];
                         uint32_t bh0, bh1, bl0, bl1;
                         ldmatrix_x4(baddr, bh0, bh1, bl0, bl1);
                         mma8(a0, a.z, a.w, bh0);
@@ -409,12 +421,12 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                     for (int e = 0; e < 4; ++e) dv[e] = (a0[e] + a1[e] + a2[e]) * (1.0f / 64.0f);
                     const int bcol = 2 * t;
                     if (l > 0) {
-                        const float* hl = sAct + lo.act_off_h[l - 1];
-                        float* dsave = act + lo.act_off_delta[l - 1];
+                        const float* hl = sAct + lp1.z;
+                        float* dsave = act + lp1.w;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int kin = mt * 16 + g + (e >> 1) * 8, b = bcol + (e & 1);
-                            const bool ok = kin < ap.M && b < TS;
+                            const bool ok = kin < l_M && b < TS;
                             const float hv = ok ? hl[kin * TS + b] : 0.f;
                             dv[e] = (hv > 0.f) ? dv[e] : 0.f;
                             if (ok) dsave[kin * TS + b] = dv[e] * inv_s;
@@ -424,7 +436,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int kin = mt * 16 + g + (e >> 1) * 8, b = bcol + (e & 1);
-                            if (kin < ap.M && b < TS) sZb[kin * TS + b] = dv[e] * inv_s;
+                            if (kin < l_M && b < TS) sZb[kin * TS + b] = dv[e] * inv_s;
                         }
                     }
                 }
@@ -480,7 +492,7 @@ static size_t bwd_smem_bytes(const NcdeLayout& lo, int ct, int slots, bool att)
     size_t f = (size_t)lo.hb_u4 * 4;
     f += (size_t)slots * ct * lo.MTK * 64 * 4;
     f += 2 * (size_t)lo.act_fwd_floats + 7 * (size_t)pad4(lo.Hd * lo.TS) + (size_t)(4 * 8 * (16 * lo.KSB + 8)) / 2;
-    f += (size_t)nw * lo.MTK * 128 + (att ? (size_t)nw * lo.NJC * 64 : 0) + 32 + (size_t)lo.C4 * lo.TS;
+    f += (size_t)nw * lo.MTK * 128 + (att ? (size_t)nw * lo.NJC * 64 : 0) + 32 + 8 * ANCDE_MAX_LAYERS + (size_t)lo.C4 * lo.TS;
     return f * 4 + 128;
 }
 
