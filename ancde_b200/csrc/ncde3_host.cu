@@ -1,0 +1,155 @@
+// Host side of the UMMA (tcgen05) NCDE forward: cluster / row tiling, the packed FP16 hi/lo operand images and the
+// packing kernel.
+#include "ncde3_common.cuh"
+
+namespace ancde {
+
+static int pow2ceil(int x)
+{
+    int p = 1;
+    while (p < x) p *= 2;
+    return p;
+}
+static int ilog2(int x)
+{
+    int l = 0;
+    while ((1 << l) < x) ++l;
+    return l;
+}
+
+int make_layout3(const ancde_ncde_desc* d, const NcdeLayout* st, V3Layout* lo)
+{
+    *lo = V3Layout();
+    lo->B = d->B; lo->L = d->L; lo->C = d->C; lo->Hd = d->Hd; lo->n_hidden = d->n_hidden; lo->mode = d->mode;
+    lo->att_C = d->att_C; lo->att_L = d->att_L; lo->n_hp = d->n_hp; lo->n_steps = d->n_steps; lo->n_out = d->n_out;
+    lo->n_stages = 4 * d->n_steps;
+    if (d->Hd > 63 || d->C > 128 || d->C < 1) return ANCDE_EUNSUPPORTED;
+    if ((int64_t)d->B * (d->L - 1) * d->C >= ((int64_t)1 << 31)) return ANCDE_EUNSUPPORTED;
+    for (int l = 0; l < d->n_hidden; ++l) {
+        if (d->width[l] > 63) return ANCDE_EUNSUPPORTED;
+        lo->width[l] = d->width[l];
+        lo->in_dim[l] = (l == 0) ? d->Hd : d->width[l - 1];
+    }
+    lo->K = d->width[d->n_hidden - 1];
+    lo->nfull = d->C / 32;
+    lo->rem = d->C % 32;
+    lo->seg = lo->rem ? pow2ceil(lo->rem) : 1;
+    lo->seg_log2 = ilog2(lo->seg);
+    lo->ipb = lo->rem ? 32 / lo->seg : 0;
+    lo->nchunks = lo->nfull + (lo->rem ? 1 : 0);
+    lo->KPo = 16 * ((lo->K + 1 + 15) / 16);
+    lo->SBOo = lo->KPo / 8 * 128;
+    lo->KPa = lo->KPo;
+    int off = 0;
+    for (int l = 0; l < d->n_hidden; ++l) {
+        lo->KPh[l] = 16 * ((lo->in_dim[l] + 1 + 15) / 16);
+        lo->SBOh[l] = lo->KPh[l] / 8 * 128;
+        lo->rows_h[l] = 8 * ((lo->width[l] + 7) / 8);
+        if (lo->KPh[l] > lo->KPa) lo->KPa = lo->KPh[l];
+        lo->off_hhi[l] = off; off += lo->rows_h[l] / 8 * lo->SBOh[l];
+        lo->off_hlo[l] = off; off += lo->rows_h[l] / 8 * lo->SBOh[l];
+    }
+    lo->hidden_bytes = off;
+    lo->SBOa = lo->KPa / 8 * 128;
+    if (st) {
+        lo->sv_ntiles = st->ntiles; lo->sv_act_floats = st->act_floats; lo->sv_off_du = st->act_off_du;
+        lo->sv_off_duda = st->act_off_duda; lo->sv_DUS = st->DUS; lo->sv_NCP = st->NCP; lo->sv_C4 = st->C4;
+        for (int l = 0; l < d->n_hidden; ++l) lo->sv_off_h[l] = st->act_off_h[l];
+    }
+    static const int cand[3] = {2, 4, 8};
+    for (int c = 0; c < 3; ++c) {
+        const int CS = cand[c];
+        if (d->Hd < CS) continue;
+        lo->CS = CS;
+        lo->NS = 8 * CS;
+        lo->ns_log2 = ilog2(lo->NS);
+        lo->nclusters = (d->B + lo->NS - 1) / lo->NS;
+        const int base = d->Hd / CS, extra = d->Hd % CS;
+        lo->i_begin[0] = 0;
+        for (int r = 0; r < CS; ++r) lo->i_begin[r + 1] = lo->i_begin[r] + base + (r < extra ? 1 : 0);
+        for (int r = CS; r < V3_MAX_CS; ++r) lo->i_begin[r + 1] = lo->i_begin[CS];
+        lo->ni_max = base + (extra ? 1 : 0);
+        const int nblk = lo->ni_max * lo->nfull + (lo->rem ? (lo->ni_max + lo->ipb - 1) / lo->ipb : 0);
+        lo->mtiles = (nblk + 3) / 4;
+        if (lo->mtiles > V3_MAX_TILES || (lo->mtiles + 1) * 2 * lo->NS > 512) continue;     // TMEM columns (hi and lo halves per tile)
+        lo->wo_mat_bytes = 16 * lo->mtiles * lo->SBOo;
+        lo->img_bytes = (int64_t)lo->hidden_bytes + (int64_t)CS * 2 * lo->wo_mat_bytes;
+        lo->DUSTR = lo->NS + 4;
+        lo->du_floats = pad4(d->C * lo->DUSTR);
+        lo->tcol_h = lo->mtiles * 2 * lo->NS;
+        if (v3_smem(*lo).total > 227 * 1024) continue;
+        // a hidden layer's A descriptor spans 128 rows: what it reads past the stored rows must stay inside the image
+        bool ok = true;
+        const int img_cta = lo->hidden_bytes + 2 * lo->wo_mat_bytes;
+        for (int l = 0; l < d->n_hidden; ++l)
+            if (lo->off_hlo[l] + 16 * lo->SBOh[l] > img_cta) ok = false;
+        // the RK4 state lives in registers: one thread per (field row, chunk of 8 samples)
+        if (d->Hd * CS > V3_THREADS) ok = false;
+        if (ok) return ANCDE_OK;
+    }
+    return ANCDE_EUNSUPPORTED;
+}
+
+struct Pack3Args {
+    V3Layout lo;
+    const float* W[ANCDE_MAX_LAYERS + 1];
+    const float* bias[ANCDE_MAX_LAYERS + 1];
+    unsigned char* img;
+};
+
+__device__ __forceinline__ void put_hilo(unsigned char* hi_mat, unsigned char* lo_mat, int sbo, int r, int k, float v)
+{
+    const size_t o = (size_t)(r >> 3) * sbo + (size_t)(k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2;
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    *reinterpret_cast<__half*>(hi_mat + o) = h;
+    *reinterpret_cast<__half*>(lo_mat + o) = l;
+}
+
+__global__ void pack_weights3_kernel(const __grid_constant__ Pack3Args a)
+{
+    const V3Layout& lo = a.lo;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (int l = 0; l < lo.n_hidden; ++l) {
+        const int KP = lo.KPh[l], in = lo.in_dim[l], out = lo.width[l];
+        for (int idx = gtid; idx < lo.rows_h[l] * KP; idx += gsz) {
+            const int m = idx / KP, k = idx - m * KP;
+            float v = 0.f;
+            if (m < out) v = (k < in) ? a.W[l][(int64_t)m * in + k] : (k == in ? a.bias[l][m] : 0.f);
+            put_hilo(a.img + lo.off_hhi[l], a.img + lo.off_hlo[l], lo.SBOh[l], m, k, V3_WSCALE * v);
+        }
+    }
+    const int rows = 128 * lo.mtiles, KP = lo.KPo, K = lo.K;
+    const float* Wo = a.W[lo.n_hidden];
+    const float* bo = a.bias[lo.n_hidden];
+    for (int64_t idx = gtid; idx < (int64_t)lo.CS * rows * KP; idx += gsz) {
+        const int k = (int)(idx % KP);
+        const int r = (int)((idx / KP) % rows);
+        const int rank = (int)(idx / ((int64_t)KP * rows));
+        int i, j;
+        float v = 0.f;
+        if (v3_row(lo, rank, r, &i, &j)) v = (k < K) ? Wo[((int64_t)i * lo.C + j) * K + k] : (k == K ? bo[i * lo.C + j] : 0.f);
+        unsigned char* hi = a.img + lo.hidden_bytes + (size_t)rank * 2 * lo.wo_mat_bytes;
+        put_hilo(hi, hi + lo.wo_mat_bytes, lo.SBOo, r, k, V3_WSCALE * v);
+    }
+}
+
+int pack_weights3(const ancde_ncde_desc* d, const V3Layout& lo, unsigned char* img, cudaStream_t stream)
+{
+    Pack3Args pa;
+    pa.lo = lo;
+    for (int l = 0; l <= d->n_hidden; ++l) {
+        ANCDE_CHECK_ARG(d->W[l] && d->bias[l], "ncde: null weight/bias pointer for layer %d", l);
+        pa.W[l] = d->W[l];
+        pa.bias[l] = d->bias[l];
+    }
+    pa.img = img;
+    prof_begin("pack_weights", stream);
+    pack_weights3_kernel<<<148, 256, 0, stream>>>(pa);
+    prof_end(stream);
+    count_launch();
+    ANCDE_CUDA(cudaGetLastError());
+    return ANCDE_OK;
+}
+
+}  // namespace ancde

@@ -1,10 +1,12 @@
 // Host side of the fused NCDE solve: layout of packed weights / saved activations, weight packing,
 // argument marshalling and the C-ABI entry points for the forward.
 #include "ncde2_common.cuh"
+#include "ncde3_common.cuh"
 
 namespace ancde {
 
 int launch_fwd(const SolveArgs& a, cudaStream_t stream);   // ncde_fwd.cu
+int engine_of(const ancde_ncde_desc* d);
 
 // ---- weight packing: torch (out, in) row-major -> transposed, padded layout of NcdeLayout
 struct PackArgs {
@@ -195,6 +197,7 @@ int make_layout(const ancde_ncde_desc* d, NcdeLayout* lo)
     }
     for (int l = 0; l < d->n_hidden; ++l) ANCDE_CHECK_ARG(d->width[l] >= 1, "ncde: width[%d]=%d", l, d->width[l]);
     int TS = d->samples_per_cta;
+    if (TS == 0 && engine_of(d) == ANCDE_ENGINE_UMMA) TS = 8;    // the UMMA forward saves in tiles of 8 samples
     if (TS == 0) {
         // the largest tile that still gives every SM work (148 SMs); weight reuse grows with TS.
         // The backward's shared-memory footprint grows with TS too, so shrink until it fits.
@@ -249,10 +252,31 @@ int fill_args(const ancde_ncde_desc* d, const NcdeLayout& lo, SolveArgs* a)
 
 using namespace ancde;
 
-// Engine choice: the descriptor's `engine`, else the library default.
-static const int DEFAULT_ENGINE = ANCDE_ENGINE_STREAMED;
+// Engine choice: the descriptor's `engine`; 0 = the UMMA (tcgen05) forward where the shape supports it and the output
+// layer is large enough to fill 128-row tensor-core tiles, else the streamed engine.
 namespace ancde {
-int engine_of(const ancde_ncde_desc* d) { return (d && d->engine) ? d->engine : DEFAULT_ENGINE; }
+static bool umma_layouts(const ancde_ncde_desc* d, NcdeLayout* st, V3Layout* l3)
+{
+    if (d->B < 1 || d->L < 2 || d->C < 1 || d->Hd < 1 || d->n_hidden < 1 || d->n_hidden > ANCDE_MAX_LAYERS || d->n_steps < 1) return false;
+    for (int l = 0; l < d->n_hidden; ++l)
+        if (d->width[l] < 1) return false;
+    if (d->samples_per_cta != 0 && d->samples_per_cta != 8) return false;
+    fill_layout(d, 8, st);
+    if (!bwd_fits(*st)) return false;
+    return make_layout3(d, st, l3) == ANCDE_OK;
+}
+int engine_of(const ancde_ncde_desc* d)
+{
+    if (!d) return ANCDE_ENGINE_STREAMED;
+    if (d->engine == ANCDE_ENGINE_STREAMED || d->engine == ANCDE_ENGINE_CLUSTER) return d->engine;
+    NcdeLayout st;
+    V3Layout l3;
+    if (d->engine == ANCDE_ENGINE_UMMA) return umma_layouts(d, &st, &l3) ? ANCDE_ENGINE_UMMA : -1;
+    if (d->Hd * d->C >= 512 && umma_layouts(d, &st, &l3)) return ANCDE_ENGINE_UMMA;
+    return ANCDE_ENGINE_STREAMED;
+}
+// float offset of the UMMA operand image inside wpack (behind the streamed engine's packed weights, 16-byte aligned)
+static int64_t umma_img_offset(const NcdeLayout& st) { return (st.wpack_floats + 3) & ~(int64_t)3; }
 }
 
 extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
@@ -261,8 +285,14 @@ extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
         V2Layout l2;
         return make_layout2(d, &l2) == ANCDE_OK ? l2.wpack_floats : -1;
     }
+    if (engine_of(d) < 0) { set_error("ncde: this shape is not supported by the UMMA engine"); return -1; }
     NcdeLayout lo;
     if (make_layout(d, &lo) != ANCDE_OK) return -1;
+    if (engine_of(d) == ANCDE_ENGINE_UMMA) {
+        V3Layout l3;
+        if (make_layout3(d, &lo, &l3) != ANCDE_OK) return -1;
+        return umma_img_offset(lo) + (l3.img_bytes + 3) / 4;
+    }
     return lo.wpack_floats;
 }
 
@@ -305,9 +335,24 @@ extern "C" int ancde_ncde_forward(const ancde_ncde_desc* d, void* stream_)
         if (rc2 != ANCDE_OK) return rc2;
         return launch_fwd2(a2, stream);
     }
+    const int engine = engine_of(d);
+    if (engine < 0) {
+        set_error("ncde_forward: this shape is not supported by the UMMA engine (state / hidden widths <= 63, C <= 128, backward tile of 8)");
+        return ANCDE_EUNSUPPORTED;
+    }
     NcdeLayout lo;
     int rc = make_layout(d, &lo);
     if (rc != ANCDE_OK) return rc;
+    if (engine == ANCDE_ENGINE_UMMA) {
+        ANCDE_CHECK_ARG(d->wpack != nullptr, "ncde: null wpack");
+        V3Layout l3;
+        rc = make_layout3(d, &lo, &l3);
+        if (rc != ANCDE_OK) { set_error("ncde_forward: UMMA layout failed"); return rc; }
+        unsigned char* img = reinterpret_cast<unsigned char*>(d->wpack + umma_img_offset(lo));
+        rc = pack_weights3(d, l3, img, stream);     // (the backward packs the streamed engine's weights itself)
+        if (rc != ANCDE_OK) return rc;
+        return launch_fwd3(d, l3, img, stream);
+    }
     SolveArgs a;
     rc = fill_args(d, lo, &a);
     if (rc != ANCDE_OK) return rc;

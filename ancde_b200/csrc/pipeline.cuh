@@ -47,6 +47,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     }
 }
 
+// Busy-polls instead (mbarrier.test_wait never suspends the thread): for waits of a few hundred cycles, where the
+// wake-up latency of a suspended try_wait would be a large part of the wait itself.
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
 // 1-D bulk copy global -> shared through the TMA engine; completion is signalled on `bar` as transaction
 // bytes.  dst, src and bytes must be multiples of 16.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)

@@ -78,6 +78,12 @@ int ancde_spline_coeffs_f64(const double* times, const double* X, double* a, dou
  *                          distributed shared memory; ancde_ncde_backward returns ANCDE_EUNSUPPORTED for it.         */
 #define ANCDE_ENGINE_STREAMED 1
 #define ANCDE_ENGINE_CLUSTER  2
+/*   ANCDE_ENGINE_UMMA      forward on the tcgen05 tensor cores (accumulators in tensor memory): a cluster of 2/4/8 CTAs per
+ *                          16/32/64 samples keeps the output layer resident in shared memory as FP16 hi/lo operands; three
+ *                          products per k step = FP32-grade accuracy.  Saves the activations in the streamed engine's
+ *                          layout, so ancde_ncde_backward (streamed kernels) works on its output.  Chosen by default
+ *                          (engine = 0) when the shape is supported and Hd*C >= 512; state and hidden widths <= 63.   */
+#define ANCDE_ENGINE_UMMA     3
 
 typedef struct ancde_ncde_desc {
     /* ---- shapes ---- */
@@ -120,7 +126,7 @@ typedef struct ancde_ncde_desc {
     float* grad_bias[ANCDE_MAX_LAYERS + 1];
     float* grad_attention;     /* TOP, or NULL (adjoint-mode gradient flow): (att_L, B, att_C) accumulated into */
     int32_t samples_per_cta;   /* streamed engine only: 0 = let the library choose (8, 4, 2 or 1) */
-    int32_t engine;            /* 0 = library default; ANCDE_ENGINE_STREAMED or ANCDE_ENGINE_CLUSTER (see above) */
+    int32_t engine;            /* 0 = library default; ANCDE_ENGINE_STREAMED, _CLUSTER or _UMMA (see above) */
 } ancde_ncde_desc;
 
 /* Workspace sizes (in floats) for a descriptor whose shape fields are filled in. */
