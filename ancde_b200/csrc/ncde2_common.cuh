@@ -191,6 +191,15 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v)
 {
     asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory");
 }
+// Asynchronous remote store: writes `v` into a peer CTA's shared memory and counts 4 bytes on the peer's mbarrier.
+// Unlike st.shared::cluster + barrier.cluster (release/acquire over ALL prior writes of the thread, global stores
+// included), the completion is tracked per datum, so the consumer only waits for the data it needs.
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_mbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];\n" ::"r"(remote_addr), "r"(__float_as_uint(v)),
+                 "r"(remote_mbar)
+                 : "memory");
+}
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }

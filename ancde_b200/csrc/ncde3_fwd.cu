@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
     float* sTimes = reinterpret_cast<float*>(smem_raw + sm.times);
     uint64_t* bar_h = reinterpret_cast<uint64_t*>(smem_raw + sm.bars);          // hidden layers' accumulator ready
     uint64_t* bar_t = bar_h + 1;                                                // [V3_MAX_TILES] W_out tile t ready
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(bar_t + V3_MAX_TILES);
+    uint64_t* bar_k = bar_t + V3_MAX_TILES;                                     // [2] stage derivative of buffer b complete (transaction bytes)
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bar_k + 2);
     const int SBOa = lo.SBOa;
     const int KSTR = lo.NS + 4;                       // row stride of the stage-derivative buffers (conflict-free 128-bit reads)
     // activation operand (B of every product): MN-major, i.e. 8 consecutive SAMPLES of one feature k are contiguous, so
@@ -94,6 +95,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
         if (tid == 0) {
             mbar_init(bar_h, 1);
             for (int t = 0; t < V3_MAX_TILES; ++t) mbar_init(bar_t + t, 1);
+            mbar_init(bar_k + 0, 1);
+            mbar_init(bar_k + 1, 1);
             mbar_fence_init();
         }
         if (warp == 0) tmem_alloc(tslot, 512);
@@ -223,6 +226,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
     uint32_t sK_rank[V3_MAX_CS];
 #pragma unroll
     for (int r = 0; r < V3_MAX_CS; ++r) sK_rank[r] = map_to_rank(smem_u32(sK), (uint32_t)(r < CS ? r : 0));
+    // the peers' copies of bar_k sit at the same distance from their sK
+    const uint32_t bark_delta = smem_u32(bar_k) - smem_u32(sK);
 
     fence_async_smem();
     cluster_arrive();     // every CTA of the cluster has initialised its shared memory before anyone writes into it
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
     int jout = 1;                     // next requested output time
     PH2_DECL();
 #ifdef ANCDE_PHASE_TIMING
-    long long phx_acc[4] = {0, 0, 0, 0}, phx_t = 0;
+    long long phx_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, phx_t = 0;
 #define PHX_T0() phx_t = clock64()
 #define PHX_MARK(i) do { const long long now__ = clock64(); phx_acc[i] += now__ - phx_t; phx_t = now__; } while (0)
 #else
@@ -273,10 +278,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
 #pragma unroll 1
             for (int l = 0; l < lo.n_hidden; ++l) {
                 if (!hidden_warp) break;                  // the other warps: control of the next stage, below
-                PHX_T0();
                 if (warp_u == 0) {
                     if (elect_one()) {
-                        PHX_MARK(0);
                         tc_fence_after();
                         const uint32_t d = tbase + lo.tcol_h;
                         // W_hi x [act_hi ; act_lo] (the two activation matrices are adjacent: one B operand of 2*NS rows) fills
@@ -286,9 +289,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                         for (int ks = 0; ks < hk; ++ks) umma_f16(d, hHi + (uint64_t)(ks * 16), dBhi + (uint64_t)(ks * 16), idesc2, ks != 0);
 #pragma unroll 4
                         for (int ks = 0; ks < hk; ++ks) umma_f16(d, hLo + (uint64_t)(ks * 16), dBhi + (uint64_t)(ks * 16), idesc, true);
-                        PHX_MARK(1);
                         umma_commit(bar_h);
-                        PHX_MARK(2);
                     }
                     // the descriptors of the next product (next layer, or layer 0 of the next stage) while this one runs
                     const int ln = (l + 1 < lo.n_hidden) ? l + 1 : 0;
@@ -297,7 +298,6 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                     hLo = umma_smem_desc(smem_u32(sImg) + lo.off_hlo[ln], 128, (uint32_t)lo.SBOh[ln]);
                 }
                 __syncwarp();
-                PHX_MARK(3);
                 PH2_MARK(0);
                 const int KPn = (l + 1 < lo.n_hidden) ? lo.KPh[l + 1] : lo.KPo;      // k extent the consumer reads
                 if (32 * wq < KPn) {
@@ -339,8 +339,14 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                 PH2_MARK(3);
             }
             if (!hidden_warp && (lo.n_hidden & 1)) ph_h ^= 1;      // (keeps the parity in step; these warps never wait on bar_h)
+#ifdef ANCDE_PHASE_TIMING
+            const long long ctl_t0 = clock64();
+#endif
             if (!hidden_warp && wq >= 2 && have_next)     // meanwhile: control of the next stage
                 control(s == 3 ? k + 1 : k, s == 3 ? 0 : s + 1, du_next, ((wg << 1) + (wq - 2)) * 32 + lane, NTHR / 2);
+#ifdef ANCDE_PHASE_TIMING
+            if (tid == 64 && blockIdx.x == 0 && p.dbg) p.dbg[top ? 1 : 0] += clock64() - ctl_t0;
+#endif
             __syncthreads();
 
             // ---- (2) output layer slice x all samples (one commit per 128-row tile), tanh, contraction with dU
@@ -379,12 +385,15 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                     R = lo.seg_log2;
                 }
                 const int jc = valid ? j : 0;
+                const bool vec_g = blk < ni * lo.nfull || lo.seg >= 4;      // 4 consecutive lanes = 4 consecutive channels of one field row
                 const int nb = nbase4 & ~((16 >> (R < 4 ? R : 4)) - 1);       // bits fixed by the rounds actually run
                 float* kp = sKpart + ((il < ni ? il : 0) * lo.nchunks + chunk) * NS;
                 const bool writer = il < ni && (R < 5 || lane < 16);
                 const int cntv = R >= 4 ? 1 : (16 >> R);
+                PHX_T0();
                 mbar_spin(bar_t + t, ph_t);
                 tc_fence_after();
+                PHX_MARK(0);
                 for (int sl = 0; sl < nslab; ++sl) {
                     const int n0 = 16 * sl;
                     float v[16];
@@ -394,6 +403,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
 #pragma unroll
                         for (int e = 0; e < 16; ++e) v[e] += v2[e];
                     }
+                    PHX_MARK(1);
                     const float4* dup = reinterpret_cast<const float4*>(du_cur + jc * lo.DUSTR + n0);
                     float du[16];
 #pragma unroll
@@ -407,18 +417,51 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                         g[e] = tanh_scaled3(v[e], tanh_c);
                         v[e] = valid ? g[e] * du[e] : 0.f;
                     }
-                    if (training && valid) {
-                        // tanh outputs in the streamed engine's layout: [stage][sample][i*C4 + j]
+                    PHX_MARK(2);
+                    if (training && vec_g) {
+                        // tanh outputs in the streamed engine's layout [stage][sample][i*C4 + j]: 4x4 transposes over the 4 lanes
+                        // that own 4 consecutive channels, so that a lane stores 4 channels of one sample (128-bit stores, 4
+                        // samples x 128 contiguous bytes per warp instruction; scalar stores cost ~4x the store-issue time)
+                        const int r4 = lane & 3;
+                        const int64_t rows = (int64_t)lo.sv_ntiles * 8;
+                        const int j0 = j & ~3;
+                        const bool st_ok = il < ni && j0 < lo.sv_C4;
+                        float* gp = p.save_G + ((int64_t)stage * rows + b0 + n0 + r4) * lo.sv_NCP + (i0 + il) * lo.sv_C4 + j0;
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            float a0 = valid ? g[4 * q4] : 0.f, a1 = valid ? g[4 * q4 + 1] : 0.f, a2 = valid ? g[4 * q4 + 2] : 0.f,
+                                  a3 = valid ? g[4 * q4 + 3] : 0.f;
+                            {
+                                const bool up = r4 & 1;
+                                float t0 = up ? a0 : a1, t1 = up ? a2 : a3;
+                                t0 = __shfl_xor_sync(0xffffffffu, t0, 1);
+                                t1 = __shfl_xor_sync(0xffffffffu, t1, 1);
+                                if (up) { a0 = t0; a2 = t1; } else { a1 = t0; a3 = t1; }
+                            }
+                            {
+                                const bool up = r4 & 2;
+                                float t0 = up ? a0 : a2, t1 = up ? a1 : a3;
+                                t0 = __shfl_xor_sync(0xffffffffu, t0, 2);
+                                t1 = __shfl_xor_sync(0xffffffffu, t1, 2);
+                                if (up) { a0 = t0; a1 = t1; } else { a2 = t0; a3 = t1; }
+                            }
+                            if (st_ok && b0 + n0 + 4 * q4 + r4 < rows)
+                                *reinterpret_cast<float4*>(gp + (int64_t)(4 * q4) * lo.sv_NCP) = make_float4(a0, a1, a2, a3);
+                        }
+                    } else if (training && valid) {
+                        // (partial chunks narrower than 4 lanes: scalar stores)
                         const int64_t rows = (int64_t)lo.sv_ntiles * 8;
                         float* gp = p.save_G + ((int64_t)stage * rows + b0 + n0) * lo.sv_NCP + (i0 + il) * lo.sv_C4 + j;
+                        const int nrow = (int)((rows - b0 - n0 < 16) ? rows - b0 - n0 : 16);
 #pragma unroll
-                        for (int e = 0; e < 16; ++e)
-                            if (b0 + n0 + e < rows) {
-                                gp[(int64_t)e * lo.sv_NCP] = g[e];
-                                if (j == C - 1)
-                                    for (int jp = C; jp < lo.sv_C4; ++jp) gp[(int64_t)e * lo.sv_NCP + (jp - j)] = 0.f;
-                            }
+                        for (int e = 0; e < 16; ++e) { if (e < nrow) *gp = g[e]; gp += lo.sv_NCP; }
+                        if (j == C - 1 && lo.sv_C4 > C) {          // the padding channels of the row: zeros
+                            gp -= (int64_t)16 * lo.sv_NCP;
+                            for (int e = 0; e < nrow; ++e)
+                                for (int jp = 1; jp <= lo.sv_C4 - C; ++jp) gp[(int64_t)e * lo.sv_NCP + jp] = 0.f;
+                        }
                     }
+                    PHX_MARK(3);
                     // reduce over the lanes of a segment, halving the live values each round
                     if (R >= 1) {
                         const bool up = lane & 1;
@@ -450,11 +493,13 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                         v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
                     }
                     if (R >= 5) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+                    PHX_MARK(4);
                     if (writer) {
 #pragma unroll
                         for (int e = 0; e < 16; ++e)
                             if (e < cntv) kp[n0 + nb + e] = v[e];
                     }
+                    PHX_MARK(5);
                 }
             }
             ph_t ^= 1;
@@ -473,12 +518,15 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                 const uint32_t off = (uint32_t)(((buf * Hd + i) * KSTR + n) * 4);
 #pragma unroll
                 for (int r = 0; r < V3_MAX_CS; ++r)
-                    if (r < CS) st_cluster_f32(sK_rank[r] + off, o);
+                    if (r < CS) st_async_f32(sK_rank[r] + off, o, sK_rank[r] + bark_delta + buf * 8);
                 const int bg = b0 + n;
                 if (p.k_out && bg < B) p.k_out[((int64_t)stage * B + bg) * Hd + i] = o;
             }
-            cluster_arrive();
-            cluster_wait();
+            // Every CTA of the cluster sends its rows to everybody: buffer `buf` is complete when Hd*NS floats have landed.
+            // No cluster barrier: a peer can only overwrite this buffer two stages later, after it has received OUR rows of
+            // the next stage, which we send after the reads below.
+            if (tid == 0) mbar_arrive_expect_tx(bar_k + buf, (uint32_t)(Hd * NS * 4));
+            if (state_thr) mbar_wait(bar_k + buf, (uint32_t)((stage >> 1) & 1));
             PH2_MARK(6);
 
             // ---- (4) RK4 recurrence (rk4_alt_step_func); next stage input -> B operand of the first hidden layer
@@ -541,7 +589,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
     PH2_FLUSH(16 + (top ? 8 : 0));
 #ifdef ANCDE_PHASE_TIMING
     if (threadIdx.x == 0 && blockIdx.x == 0 && p.dbg)
-        for (int i = 0; i < 4; ++i) p.dbg[40 + (top ? 8 : 0) + i] += phx_acc[i];
+        for (int i = 0; i < 8; ++i) p.dbg[40 + (top ? 8 : 0) + i] += phx_acc[i];
 #endif
     tc_fence_before();
     cluster_arrive();     // nobody leaves while a peer may still address its shared memory

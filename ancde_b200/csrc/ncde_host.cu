@@ -272,7 +272,10 @@ int engine_of(const ancde_ncde_desc* d)
     NcdeLayout st;
     V3Layout l3;
     if (d->engine == ANCDE_ENGINE_UMMA) return umma_layouts(d, &st, &l3) ? ANCDE_ENGINE_UMMA : -1;
-    if (d->Hd * d->C >= 512 && umma_layouts(d, &st, &l3)) return ANCDE_ENGINE_UMMA;
+    // measured on B200 (Sepsis shapes, B = 1024): the UMMA forward wins once the output layer has >= ~50 k weights
+    // (top network 49*35*49: 2.1 ms against 3.3 ms); below that the per-layer latency of the tensor-core round trip
+    // (commit -> mbarrier -> tcgen05.ld, ~1.2 k cycles) outweighs it (bottom network 35*35*20: 2.2 ms against 1.8 ms)
+    if ((int64_t)d->Hd * d->C * d->width[d->n_hidden - 1] >= 50000 && umma_layouts(d, &st, &l3)) return ANCDE_ENGINE_UMMA;
     return ANCDE_ENGINE_STREAMED;
 }
 // float offset of the UMMA operand image inside wpack (behind the streamed engine's packed weights, 16-byte aligned)

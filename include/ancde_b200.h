@@ -82,7 +82,7 @@ int ancde_spline_coeffs_f64(const double* times, const double* X, double* a, dou
  *                          16/32/64 samples keeps the output layer resident in shared memory as FP16 hi/lo operands; three
  *                          products per k step = FP32-grade accuracy.  Saves the activations in the streamed engine's
  *                          layout, so ancde_ncde_backward (streamed kernels) works on its output.  Chosen by default
- *                          (engine = 0) when the shape is supported and Hd*C >= 512; state and hidden widths <= 63.   */
+ *                          (engine = 0) when the shape is supported and the output layer has >= 50 000 weights; state and hidden widths <= 63.   */
 #define ANCDE_ENGINE_UMMA     3
 
 typedef struct ancde_ncde_desc {

@@ -36,7 +36,7 @@ for base, nm in ((16, 'fwd bottom'), (24, 'fwd top')):
     print('%s: cycles per stage (CTA 0 thread 0), total %.0f' % (nm, tot / stages))
     for i in range(8):
         print('  %d %-34s %9.0f' % (i, names[i], d[base + i] / stages))
-    x = d[base + 24:base + 28]
-    print('  hidden issue detail: to elect %.0f, fence + descriptors + mma %.0f, commit %.0f, syncwarp %.0f' % (x[0] / stages, x[1] / stages, x[2] / stages, x[3] / stages))
+    x = d[base + 24:base + 32]
+    print('  out epilogue detail (warp 0): wait tile %.0f, tmem ld %.0f, dU + tanh %.0f, G store %.0f, butterfly %.0f, write %.0f' % tuple(v / stages for v in x[:6]))
 nl = cfg['nl'] if 'nl' in cfg else 4
-print('top: per-warp busy cycles per hidden layer (l >= 1):', ' '.join('%d' % (d[w] / stages / 3) for w in range(16)))
+print('control (warp 2) cycles per stage: bottom %.0f top %.0f' % (d[0] / stages, d[1] / stages))
