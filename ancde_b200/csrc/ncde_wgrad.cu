@@ -186,8 +186,20 @@ int launch_hidden_wgrad(const SolveArgs& a, const HiddenGradPtrs& hp, cudaStream
 
 int launch_wgrad_mma(const SolveArgs& a, float* gW, float* gB, cudaStream_t stream);   // ncde_wgrad_mma.cu
 
+int launch_wgrad_umma(const SolveArgs& a, float* gW, float* gB, cudaStream_t stream);  // ncde_wgrad_umma.cu
+
+// tcgen05 kernel for tiles of 8 samples (ANCDE_WGRAD_MMA_SYNC=1 forces the mma.sync kernel: A/B timing, tests)
 int launch_wgrad(const SolveArgs& a, float* gW, float* gB, cudaStream_t stream)
 {
+    static int force_sync = -1;
+    if (force_sync < 0) {
+        const char* e = getenv("ANCDE_WGRAD_MMA_SYNC");
+        force_sync = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!force_sync) {
+        const int rc = launch_wgrad_umma(a, gW, gB, stream);
+        if (rc != ANCDE_EUNSUPPORTED) return rc;
+    }
     return launch_wgrad_mma(a, gW, gB, stream);
 }
 

@@ -10,7 +10,7 @@
 using namespace ancde;
 
 // A: [rowsA][K] halfs, B: [N][K] halfs (global, row-major); D out: [128][N] floats
-__global__ void probe(const __half* A, const __half* B, float* D, int rowsA, int N, int K, int lbo, int ntiles, int passes, int bmn)
+__global__ void probe(const __half* A, const __half* B, float* D, int rowsA, int N, int K, int lbo, int ntiles, int passes, int bmn, int amn)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
@@ -22,7 +22,8 @@ __global__ void probe(const __half* A, const __half* B, float* D, int rowsA, int
     unsigned char* sB = smem + (size_t)(rowsA / 8) * sboA;
     for (int idx = tid; idx < rowsA * K; idx += blockDim.x) {
         int r = idx / K, k = idx % K;
-        *reinterpret_cast<__half*>(sA + (r / 8) * sboA + (k / 8) * lbo + (r % 8) * 16 + (k % 8) * 2) = A[idx];
+        if (amn) *reinterpret_cast<__half*>(sA + (r / 8) * sboA + (k / 8) * lbo + (k % 8) * 16 + (r % 8) * 2) = A[idx];   // MN-major
+        else *reinterpret_cast<__half*>(sA + (r / 8) * sboA + (k / 8) * lbo + (r % 8) * 16 + (k % 8) * 2) = A[idx];
     }
     for (int idx = tid; idx < N * K; idx += blockDim.x) {
         int r = idx / K, k = idx % K;
@@ -36,7 +37,7 @@ __global__ void probe(const __half* A, const __half* B, float* D, int rowsA, int
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = tslot;
-    const uint32_t idesc = umma_idesc_f16(128, N) | (bmn ? (1u << 16) : 0u);
+    const uint32_t idesc = umma_idesc_f16(128, N) | (bmn ? (1u << 16) : 0u) | (amn ? (1u << 15) : 0u);
     if (tid == 0) {
         for (int t = 0; t < ntiles; ++t)
             for (int ps = 0; ps < passes; ++ps)
@@ -60,7 +61,7 @@ __global__ void probe(const __half* A, const __half* B, float* D, int rowsA, int
     if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
-int run(int rowsA, int N, int K, int lbo, int ntiles, int passes, int bmn = 0)
+int run(int rowsA, int N, int K, int lbo, int ntiles, int passes, int bmn = 0, int amn = 0, int sbo_extra = 0)
 {
     std::vector<__half> hA((size_t)rowsA * K), hB((size_t)N * K);
     std::vector<float> fA(hA.size()), fB(hB.size());
@@ -73,7 +74,7 @@ int run(int rowsA, int N, int K, int lbo, int ntiles, int passes, int bmn = 0)
     cudaMemset(dD, 0, (size_t)ntiles * 128 * N * 4);
     size_t smem = (size_t)(rowsA / 8 + N / 8) * (K / 8) * lbo + 1024;
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    probe<<<1, 128, smem>>>(dA, dB, dD, rowsA, N, K, lbo, ntiles, passes, bmn);
+    probe<<<1, 128, smem>>>(dA, dB, dD, rowsA, N, K, lbo, ntiles, passes, bmn, amn);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("rows %d N %d K %d lbo %d: CUDA error %s\n", rowsA, N, K, lbo, cudaGetErrorString(e)); return 1; }
     std::vector<float> hD((size_t)ntiles * 128 * N);
@@ -90,7 +91,7 @@ int run(int rowsA, int N, int K, int lbo, int ntiles, int passes, int bmn = 0)
                 maxerr = fmax(maxerr, fabs(s - hD[((size_t)t * 128 + m) * N + n]));
             }
         }
-    printf("bmn %d rows %d N %d K %d lbo %d tiles %d passes %d: max abs err %.3g %s\n", bmn, rowsA, N, K, lbo, ntiles, passes, maxerr, maxerr < 1e-3 ? "OK" : "MISMATCH");
+    printf("amn %d bmn %d rows %d N %d K %d lbo %d tiles %d passes %d: max abs err %.3g %s\n", amn, bmn, rowsA, N, K, lbo, ntiles, passes, maxerr, maxerr < 1e-3 ? "OK" : "MISMATCH");
     cudaFree(dA); cudaFree(dB); cudaFree(dD);
     return maxerr < 1e-3 ? 0 : 1;
 }
@@ -106,6 +107,8 @@ int main()
     bad += run(128, 32, 64, 128, 1, 1, 1);   // B operand MN-major
     bad += run(256, 64, 48, 128, 2, 2, 1);
     bad += run(128, 16, 32, 128, 1, 1, 1);
+    bad += run(128, 64, 32, 128, 1, 1, 0, 1);   // A operand MN-major (the weight-gradient kernel)
+    bad += run(128, 128, 32, 128, 1, 2, 0, 1);
     printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
     return bad;
 }
