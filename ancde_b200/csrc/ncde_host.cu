@@ -282,6 +282,14 @@ int engine_of(const ancde_ncde_desc* d)
 static int64_t umma_img_offset(const NcdeLayout& st) { return (st.wpack_floats + 3) & ~(int64_t)3; }
 }
 
+extern "C" int ancde_ncde_engine(const ancde_ncde_desc* d)
+{
+    ANCDE_CHECK_ARG(d != nullptr, "ncde_engine: null descriptor");
+    NcdeLayout lo;
+    if (make_layout(d, &lo) != ANCDE_OK) return -1;
+    return engine_of(d);
+}
+
 extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
 {
     if (engine_of(d) == ANCDE_ENGINE_CLUSTER) {

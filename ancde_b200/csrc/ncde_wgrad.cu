@@ -188,15 +188,16 @@ int launch_wgrad_mma(const SolveArgs& a, float* gW, float* gB, cudaStream_t stre
 
 int launch_wgrad_umma(const SolveArgs& a, float* gW, float* gB, cudaStream_t stream);  // ncde_wgrad_umma.cu
 
-// tcgen05 kernel for tiles of 8 samples (ANCDE_WGRAD_MMA_SYNC=1 forces the mma.sync kernel: A/B timing, tests)
+// tcgen05 kernel for tiles of 8 samples; the mma.sync kernel otherwise, or when forced (ANCDE_WGRAD_MMA_SYNC=1 in the
+// environment or ancde_debug_force_wgrad_mma_sync(): A/B timing and tests)
+static int g_force_sync = -1;
 int launch_wgrad(const SolveArgs& a, float* gW, float* gB, cudaStream_t stream)
 {
-    static int force_sync = -1;
-    if (force_sync < 0) {
+    if (g_force_sync < 0) {
         const char* e = getenv("ANCDE_WGRAD_MMA_SYNC");
-        force_sync = (e && e[0] == '1') ? 1 : 0;
+        g_force_sync = (e && e[0] == '1') ? 1 : 0;
     }
-    if (!force_sync) {
+    if (!g_force_sync) {
         const int rc = launch_wgrad_umma(a, gW, gB, stream);
         if (rc != ANCDE_EUNSUPPORTED) return rc;
     }
@@ -204,3 +205,10 @@ int launch_wgrad(const SolveArgs& a, float* gW, float* gB, cudaStream_t stream)
 }
 
 }  // namespace ancde
+
+extern "C" int ancde_debug_force_wgrad_mma_sync(int on)
+{
+    const int old = ancde::g_force_sync > 0 ? 1 : 0;
+    ancde::g_force_sync = on ? 1 : 0;
+    return old;
+}

@@ -132,6 +132,17 @@ def _desc(plan, z0, attention, wb, widths, Hd):
     return d
 
 
+def _ws(query, d):
+    """Workspace size in floats; the library answers -1 (with a message) for a descriptor it cannot run."""
+    n = query(ctypes.byref(d))
+    if n < 0:
+        msg = _lib.last_error()
+        if 'not supported' in msg:
+            raise NotImplementedError(msg)
+        raise ValueError(msg)
+    return n
+
+
 class _NcdeSolve(torch.autograd.Function):
     """z_out, k_out = solve(plan, widths, z0, attention, W0, b0, ..., W_out, b_out)."""
 
@@ -155,7 +166,7 @@ class _NcdeSolve(torch.autograd.Function):
         k_out = torch.empty(4 * n_steps if plan.want_k else 0, plan.B, Hd, dtype=torch.float32, device=dev)
         d.z_out = z_out.data_ptr()
         d.k_out = k_out.data_ptr() if plan.want_k else None
-        wpack = torch.empty(L_.ancde_ncde_wpack_floats(ctypes.byref(d)), dtype=torch.float32, device=dev)
+        wpack = torch.empty(_ws(L_.ancde_ncde_wpack_floats, d), dtype=torch.float32, device=dev)
         d.wpack = wpack.data_ptr()
         # under torch.no_grad() nothing is saved (ctx.needs_input_grad still reports the inputs' requires_grad there, and
         # grad mode is always off inside forward(), so solve() records it on the plan)
@@ -164,8 +175,8 @@ class _NcdeSolve(torch.autograd.Function):
             raise NotImplementedError('the cluster engine (ANCDE_ENGINE=2) is forward-only: run it under torch.no_grad()')
         save_act = save_G = None
         if need_grad:
-            save_act = torch.empty(L_.ancde_ncde_save_act_floats(ctypes.byref(d)), dtype=torch.float32, device=dev)
-            save_G = torch.empty(L_.ancde_ncde_save_G_floats(ctypes.byref(d)), dtype=torch.float32, device=dev)
+            save_act = torch.empty(_ws(L_.ancde_ncde_save_act_floats, d), dtype=torch.float32, device=dev)
+            save_G = torch.empty(_ws(L_.ancde_ncde_save_G_floats, d), dtype=torch.float32, device=dev)
             d.save_act, d.save_G = save_act.data_ptr(), save_G.data_ptr()
         with torch.cuda.device(dev):
             rc = L_.ancde_ncde_forward(ctypes.byref(d), _lib.stream_ptr(dev))

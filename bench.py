@@ -327,6 +327,22 @@ def run_ours(args):
                     'step_frac': round(total_flops * args.steps / (ms * 1e-3) / 1e12 / fp32_peak, 4),
                     'step_algorithmic_gflop': round(total_flops / 1e9, 2)}
 
+    # ---- HBM roofline of the output-layer weight-gradient kernel (tcgen05; reads the saved tanh outputs exactly once)
+    roofline_wgrad = None
+    wg = next((k for k in kernels if k['name'] == 'ncde_wgrad_top'), None)
+    if wg is not None:
+        stages = 4 * (cfg['L'] - 1)
+        c4 = (cfg['C'] + 3) // 4 * 4
+        g_bytes = stages * B * cfg['H'] * c4 * 4                                  # tanh outputs, read once
+        small = stages * B * (cfg['HH'] + cfg['H'] + c4) * 4                      # last hidden activation, cotangent, dU
+        nbytes = g_bytes + small
+        peak, src = hbm_peak()
+        ach = nbytes / (wg['avg_ms'] * 1e-3) / 1e9
+        roofline_wgrad = {'bound': 'hbm', 'kernel': 'ncde_wgrad_top', 'achieved': round(ach, 1), 'peak': peak, 'unit': 'GB/s',
+                          'frac': round(ach / peak, 4), 'traffic': None, 'peak_source': src, 'avg_ms': wg['avg_ms'],
+                          'algorithmic_bytes_per_launch': nbytes,
+                          'tensor_pipe': 'tcgen05.mma kind::f16, FP16 hi/lo x3 = FP32-grade; accumulator in tensor memory'}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         v, sec, cores = cpu_reference_samples_per_sec(args.workload, args.cpu_sample, 3, 1)
@@ -349,6 +365,7 @@ def run_ours(args):
         'gpu_launches': launches,
         'roofline': roofline,
         'roofline_spline': spline_roofline(device, cfg) if world == 1 else None,
+        'roofline_wgrad': roofline_wgrad,
         'kernels': kernels,
         'cpu_baseline': cpu,
     }
@@ -356,6 +373,16 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def hbm_peak():
+    peak, src = 6650.0, 'fallback 6.65 TB/s (B200_PROFILING.md)'
+    try:
+        mp = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        peak, src = float(mp['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs'
+    except (OSError, KeyError, ValueError):
+        pass
+    return peak, src
 
 
 def spline_roofline(device, cfg, n_paths_target=2 ** 20):
@@ -381,12 +408,7 @@ def spline_roofline(device, cfg, n_paths_target=2 ** 20):
     _lib.profile_enable(False)
     ms = sum(ts) / len(ts)
     nbytes = N * C * (L + 4 * (L - 1)) * 4           # algorithmic: read X once, write a, b, two_c, three_d once
-    peak, src = 6650.0, 'fallback 6.65 TB/s (B200_PROFILING.md)'
-    try:
-        mp = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-        peak, src = float(mp['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs'
-    except (OSError, KeyError, ValueError):
-        pass
+    peak, src = hbm_peak()
     achieved = nbytes / (ms * 1e-3) / 1e9
     return {'bound': 'hbm', 'kernel': 'spline_coeffs_f32', 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s',
             'frac': round(achieved / peak, 4), 'traffic': None, 'peak_source': src, 'avg_ms': round(ms, 4),

@@ -134,6 +134,10 @@ int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d);
 int64_t ancde_ncde_save_act_floats(const ancde_ncde_desc* d);
 int64_t ancde_ncde_save_G_floats(const ancde_ncde_desc* d);
 
+/* The engine a descriptor resolves to (ANCDE_ENGINE_*; shape fields and `engine` filled in), or -1 when the requested
+ * engine does not support the shape.  With engine = 0 this is the library's automatic choice. */
+int ancde_ncde_engine(const ancde_ncde_desc* d);
+
 /* Forward solve.  Writes z_out (and k_out, save_act, save_G when non-NULL). */
 int ancde_ncde_forward(const ancde_ncde_desc* d, void* stream);
 
@@ -151,6 +155,10 @@ int ancde_last_launch_count(void);
 int ancde_profile_enable(int on);
 int ancde_profile_count(void);
 int ancde_profile_get(int i, char* name, size_t len, float* ms);
+
+/* Development / test aid: 1 = compute the output-layer weight gradient with the mma.sync kernel (ncde_wgrad_mma.cu)
+ * instead of the tcgen05 kernel (ncde_wgrad_umma.cu), which is the default for tiles of 8 samples.  Returns the old value. */
+int ancde_debug_force_wgrad_mma_sync(int on);
 
 /* Development aid: 64 int64 counters in device memory that kernels built with -DANCDE_PHASE_TIMING
  * fill with per-phase clock64() totals (normal builds never touch the buffer). NULL disables. */

@@ -56,6 +56,33 @@ def test_workspace_queries_run_without_a_gpu():
     assert 'n_hidden' in _lib.last_error()
 
 
+def test_engine_resolution_runs_without_a_gpu():
+    """ancde_ncde_engine: the automatic choice (UMMA for a large output layer, streamed otherwise) and the refusal of
+    shapes the forced engine cannot run."""
+    from ancde_b200 import _lib
+    L = _lib.lib()
+
+    def desc(C, Hd, widths, engine=0):
+        d = _lib.NcdeDesc()
+        d.B, d.L, d.C, d.Hd, d.n_hidden = 1024, 72, C, Hd, len(widths)
+        for i, w in enumerate(widths):
+            d.width[i] = w
+        d.mode, d.att_C, d.att_L, d.n_hp = _lib.MODE_TOP, 1, 72, 284
+        d.t_start, d.t_end, d.step, d.n_steps, d.n_out = 1.0, 72.0, 1.0, 71, 72
+        d.engine = engine
+        return d
+
+    assert L.ancde_ncde_engine(ctypes.byref(desc(35, 49, [49] * 4))) == _lib.ENGINE_UMMA
+    assert L.ancde_ncde_engine(ctypes.byref(desc(6, 12, [12, 12]))) == _lib.ENGINE_STREAMED
+    assert L.ancde_ncde_engine(ctypes.byref(desc(6, 12, [12, 12], _lib.ENGINE_UMMA))) == _lib.ENGINE_UMMA
+    assert L.ancde_ncde_engine(ctypes.byref(desc(69, 69, [20] * 5, _lib.ENGINE_UMMA))) == -1      # state wider than 63
+    assert L.ancde_ncde_engine(ctypes.byref(desc(35, 49, [49] * 4, _lib.ENGINE_CLUSTER))) == _lib.ENGINE_CLUSTER
+    # the UMMA engine appends its operand image to the streamed engine's packed weights
+    a = L.ancde_ncde_wpack_floats(ctypes.byref(desc(35, 49, [49] * 4, _lib.ENGINE_STREAMED)))
+    b = L.ancde_ncde_wpack_floats(ctypes.byref(desc(35, 49, [49] * 4, _lib.ENGINE_UMMA)))
+    assert b > a > 0
+
+
 def test_no_cpu_fallback():
     import torch
     import ancde_b200
