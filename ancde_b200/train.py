@@ -38,7 +38,8 @@ class DualNcdeTrainer:
         self.model = self.model.to(self.device)
         self.bucket = FlatGradBucket(self.model.parameters())
         fused = self.device.type == 'cuda'
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, weight_decay=1e-4, fused=fused)
+        # capturable: the step counter lives on the device, so a whole step can be captured in a CUDA graph
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, weight_decay=1e-4, fused=fused, capturable=fused)
         self.reg_params = [p for p in self.func_g.parameters()]
 
     def forward(self, batch, slope=1.0):
@@ -60,3 +61,46 @@ class DualNcdeTrainer:
         self.bucket.all_reduce_mean()
         self.opt.step()
         return loss.detach()
+
+    def capture(self, batch, slope=1.0, warmup=2):
+        """Captures one whole training step on `batch` (forward, loss, backward through the solver, gradient all-reduce,
+        Adam) in a CUDA graph: the ~230 launches of a step -- 10 of them the library's kernels, the rest small torch
+        kernels of the heads, the loss and the optimizer -- replay without per-launch host overhead.  `batch`'s tensors
+        are the graph's static inputs (copy new data into them before a replay); returns a GraphedStep.
+        The step has no host synchronisation (cached grid metadata, device-side spline lookup), which capture requires."""
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                   # allocator warm-up, cached host scalars, lazy CUDA initialisation
+                self.step(batch, slope)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self.step(batch, slope)
+        return GraphedStep(graph, batch, loss)
+
+
+class GraphedStep:
+    """A captured training step: replay() runs it on whatever the static batch tensors hold now."""
+
+    def __init__(self, graph, batch, loss):
+        self.graph, self.batch, self.loss = graph, batch, loss
+
+    def load(self, host_batch):
+        """Asynchronous host -> device copy of a (pinned) batch into the static input tensors; returns the bytes copied."""
+        n = 0
+        for k, v in host_batch.items():
+            dst = self.batch[k]
+            if k == 'coeffs':
+                for d, c in zip(dst, v):
+                    d.copy_(c, non_blocking=True)
+                    n += c.numel() * c.element_size()
+            else:
+                dst.copy_(v, non_blocking=True)
+                n += v.numel() * v.element_size()
+        return n
+
+    def replay(self):
+        self.graph.replay()
+        return self.loss
