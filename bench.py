@@ -319,10 +319,19 @@ def run_ours(args):
     ms_e2e, _, _ = timed(e2e_step, e2e_steps, 2)
     e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
 
-    if rank != 0:
+    def finish():
+        """Multi-rank runs leave with a hard exit once every rank is done with its collectives: tearing down an NCCL
+        communicator whose kernels sit inside captured CUDA graphs can block forever in destroy_process_group / at
+        interpreter exit (seen on 2 x B200), and nothing is left to clean up that the driver would miss."""
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            os._exit(0)
         return 0
+
+    barrier()                       # the last collective of every rank
+    if rank != 0:
+        return finish()
 
     # ---- per-kernel roofline from the CUDA-event timings taken inside the timed region
     flops = kernel_flops(cfg, B)
@@ -398,9 +407,7 @@ def run_ours(args):
         'cpu_baseline': cpu,
     }
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    return finish()
 
 
 def hbm_peak():
