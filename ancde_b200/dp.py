@@ -19,12 +19,31 @@ class FlatGradBucket:
         dev = self.params[0].device
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        # the parameter VALUES live in one buffer too (p.data become views): whole-model elementwise work -- the weight
+        # regulariser of the training step -- is a handful of kernels instead of a handful per parameter
+        self.flat_param = torch.empty(self.numel, dtype=torch.float32, device=dev)
+        self.offset = {}
         off = 0
         for p in self.params:
             if p.dtype != torch.float32:
                 raise ValueError('FlatGradBucket expects float32 parameters')
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            n = p.numel()
+            self.flat_param[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = self.flat_param[off:off + n].view_as(p)
+            p.grad = self.flat[off:off + n].view_as(p)
+            self.offset[id(p)] = (off, n)
+            off += n
+
+    def segments(self, params):
+        """(start, end, seg) of a run of parameters that sit next to each other in the flat buffers: seg[i] is the index
+        (within `params`) of the parameter that element start + i belongs to."""
+        spans = sorted(self.offset[id(p)] for p in params)
+        for (o0, n0), (o1, _) in zip(spans, spans[1:]):
+            if o0 + n0 != o1:
+                raise ValueError('the parameters are not contiguous in the flat buffer')
+        start, end = spans[0][0], spans[-1][0] + spans[-1][1]
+        seg = torch.cat([torch.full((n,), i, dtype=torch.int64) for i, (_, n) in enumerate(spans)])
+        return start, end, seg.to(self.flat.device)
 
     def zero(self):
         """Zeroes every gradient in one fill (the views stay attached to the parameters)."""

@@ -197,7 +197,11 @@ class _NcdeSolve(torch.autograd.Function):
         d.wpack, d.save_act, d.save_G = wpack.data_ptr(), save_act.data_ptr(), save_G.data_ptr()
         g = g_z_out.detach().float().contiguous()
         grad_z0 = torch.empty_like(z0c)
-        grads = [torch.zeros_like(w) for w in wbc]
+        gflat = torch.zeros(sum(w.numel() for w in wbc), dtype=torch.float32, device=dev)    # one fill for every gradient
+        grads, off = [], 0
+        for w in wbc:
+            grads.append(gflat[off:off + w.numel()].view_as(w))
+            off += w.numel()
         d.grad_z_out, d.grad_z0 = g.data_ptr(), grad_z0.data_ptr()
         for i in range(len(widths) + 1):
             d.grad_W[i] = grads[2 * i].data_ptr()

@@ -40,7 +40,9 @@ class DualNcdeTrainer:
         fused = self.device.type == 'cuda'
         # capturable: the step counter lives on the device, so a whole step can be captured in a CUDA graph
         self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, weight_decay=1e-4, fused=fused, capturable=fused)
-        self.reg_params = [p for p in self.func_g.parameters()]
+        self.reg_params = [p for p in self.func_g.parameters() if p.requires_grad]
+        self.reg_scaling = 0.03
+        self._reg = self.bucket.segments(self.reg_params) if self.reg_params else None
 
     def forward(self, batch, slope=1.0):
         cfg = self.cfg
@@ -55,12 +57,25 @@ class DualNcdeTrainer:
         self.bucket.zero()
         pred = self.forward(batch, slope)
         loss = task_loss(self.cfg, pred, batch['y'])
-        for p in self.reg_params:
-            loss = loss + 0.03 * p.norm()
         loss.backward()
+        loss = loss.detach() + self.add_weight_regularisation()
         self.bucket.all_reduce_mean()
         self.opt.step()
-        return loss.detach()
+        return loss
+
+    def add_weight_regularisation(self):
+        """The reference's `loss + 0.03 * sum_p ||p||_2` over func_g (common.py:47-58), value AND gradient, computed on
+        the flat parameter / gradient buffers: d||p|| = p / ||p|| (0 for a zero parameter, like torch.norm's backward) is
+        added to the gradients after loss.backward().  ~10 kernels instead of ~9 per parameter through autograd."""
+        if self._reg is None:
+            return 0.0
+        a, b, seg = self._reg
+        w = self.bucket.flat_param[a:b]
+        sq = torch.zeros(len(self.reg_params), dtype=torch.float32, device=w.device).index_add_(0, seg, w * w)
+        norms = sq.sqrt()
+        coef = torch.where(norms > 0, self.reg_scaling / norms, torch.zeros_like(norms))
+        self.bucket.flat[a:b].addcmul_(w, coef[seg])
+        return self.reg_scaling * norms.sum()
 
     def capture(self, batch, slope=1.0, warmup=2):
         """Captures one whole training step on `batch` (forward, loss, backward through the solver, gradient all-reduce,

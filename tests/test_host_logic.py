@@ -98,3 +98,30 @@ def test_synthetic_batches_have_the_baseline_shapes():
         assert bt['times'].shape == (cfg['L'],) and float(bt['times'][0]) == cfg['t0']
         assert torch.isnan(bt['X']).any()
         assert (bt['static'] is None) == (cfg['static'] == 0)
+
+
+def test_fused_weight_regularisation_matches_autograd():
+    """train.DualNcdeTrainer.add_weight_regularisation: value and gradient of the reference's
+    `0.03 * sum_p ||p||` over func_g (experiments/common.py:47-58), computed on the flat parameter / gradient buffers,
+    against autograd through torch.norm -- including a parameter that is exactly zero (gradient 0, not NaN)."""
+    import torch
+    from ancde_b200.train import DualNcdeTrainer
+    tr = DualNcdeTrainer('mujoco', 'cpu')
+    with torch.no_grad():
+        tr.reg_params[1].zero_()
+    ref_params = [p.detach().clone().requires_grad_(True) for p in tr.reg_params]
+    ref = sum(0.03 * p.norm() for p in ref_params)
+    ref.backward()
+    tr.bucket.zero()
+    val = tr.add_weight_regularisation()
+    assert abs(float(val) - float(ref.detach())) <= 1e-6 * abs(float(ref.detach()))
+    for p, r in zip(tr.reg_params, ref_params):
+        assert torch.isfinite(p.grad).all()
+        assert (p.grad - r.grad).abs().max() <= 1e-6 * max(1.0, float(r.grad.abs().max()))
+    # parameters outside func_g get nothing
+    reg_ids = {id(p) for p in tr.reg_params}
+    for p in tr.model.parameters():
+        if id(p) not in reg_ids:
+            assert float(p.grad.abs().max()) == 0.0
+    # the parameters are views of one buffer and still what the model computes with
+    assert all(p.data_ptr() >= tr.bucket.flat_param.data_ptr() for p in tr.model.parameters())
