@@ -302,11 +302,28 @@ def run_ours(args):
     h2d_bytes = [0]
     d2h_bytes = [0]
 
+    # Double-buffered input pipeline: while the captured step i runs on batch buffer i % 2, the copy stream moves the
+    # pinned host batch of step i + 1 into the other buffer (after the replay that last read that buffer has finished).
+    # Every step's host -> device copy and its device -> host loss read happen inside the timed region.
+    copy_stream = torch.cuda.Stream(device)
+    ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        sl = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_consumed[sl])
+            h2d_bytes[0] = graphed[sl].load(host_batches[sl])
+            ev_copied[sl].record(copy_stream)
+
     def e2e_step(i):
         if graphed is not None:                   # pinned host batch -> the graph's static inputs -> replay
-            gs = graphed[i % len(host_batches)]
-            h2d_bytes[0] = gs.load(host_batches[i % len(host_batches)])
-            loss = gs.replay()
+            sl = i % 2
+            cur = torch.cuda.current_stream(device)
+            prefetch(i + 1)
+            cur.wait_event(ev_copied[sl])
+            loss = graphed[sl].replay()
+            ev_consumed[sl].record(cur)
         else:
             dev_batch, nb = h2d(host_batches[i % len(host_batches)], device)
             h2d_bytes[0] = nb
@@ -315,6 +332,9 @@ def run_ours(args):
         d2h_bytes[0] = loss_host.numel() * loss_host.element_size()
         return loss_host
 
+    if graphed is not None:
+        torch.cuda.synchronize(device)
+        prefetch(0)
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e, _, _ = timed(e2e_step, e2e_steps, 2)
     e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
@@ -397,7 +417,8 @@ def run_ours(args):
                          'through HBM (>> 126 MB L2)' % (n_res, saved_gb(cfg, B))},
         'clocks': clk,
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes[0],
-                'd2h_bytes_per_step': d2h_bytes[0], 'ms_per_step': ms_e2e / e2e_steps, 'steps': e2e_steps},
+                'd2h_bytes_per_step': d2h_bytes[0], 'ms_per_step': ms_e2e / e2e_steps, 'steps': e2e_steps,
+                'input_pipeline': 'double-buffered: the copy of step i+1 overlaps the compute of step i' if graphed is not None else 'serial'},
         'gpu_launches': launches,
         'kernel_profile_steps': prof_steps,
         'roofline': roofline,
