@@ -103,7 +103,7 @@ struct SolveArgs {
     do {                                                                   \
         if (threadIdx.x == 0 && blockIdx.x == 0 && p.dbg) {                \
             const long long now__ = clock64();                             \
-            p.dbg[i] += now__ - pt__;                                      \
+            p.dbg[8 + (i)] += now__ - pt__;                                      \
             pt__ = now__;                                                  \
         }                                                                  \
     } while (0)

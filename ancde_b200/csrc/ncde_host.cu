@@ -21,10 +21,14 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a)
     const NcdeLayout& lo = a.lo;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     for (int l = 0; l < lo.n_hidden; ++l) {
-        const int in = lo.in_dim[l], out = lo.width[l], S = lo.stride[l];
-        for (int idx = gtid; idx < in * S; idx += gsz) {
-            const int k = idx / S, o = idx - k * S;
-            a.wpack[lo.off_w[l] + idx] = (o < out) ? a.W[l][(int64_t)o * in + k] : 0.f;
+        const int in = lo.in_dim[l], out = lo.width[l], S = lo.stride[l], T = lo.tstride[l];
+        for (int idx = gtid; idx < out * S; idx += gsz) {
+            const int o = idx / S, k = idx - o * S;
+            a.wpack[lo.off_w[l] + idx] = (k < in) ? a.W[l][(int64_t)o * in + k] : 0.f;
+        }
+        for (int idx = gtid; idx < in * T; idx += gsz) {
+            const int k = idx / T, o = idx - k * T;
+            a.wpack[lo.off_wt[l] + idx] = (o < out) ? a.W[l][(int64_t)o * in + k] : 0.f;
         }
         for (int o = gtid; o < pad4(out); o += gsz) a.wpack[lo.off_b[l] + o] = (o < out) ? a.bias[l][o] : 0.f;
     }
@@ -125,7 +129,8 @@ static void fill_layout(const ancde_ncde_desc* d, int TS, NcdeLayout* lo)
     for (int l = 0; l < d->n_hidden; ++l) {
         lo->width[l] = d->width[l];
         lo->in_dim[l] = (l == 0) ? d->Hd : d->width[l - 1];
-        lo->stride[l] = d->width[l] | 1;
+        lo->stride[l] = pad4odd(lo->in_dim[l]);
+        lo->tstride[l] = pad4odd(d->width[l]);
         if (d->width[l] > lo->Hmax) lo->Hmax = d->width[l];
     }
     lo->TS = TS;
@@ -137,10 +142,13 @@ static void fill_layout(const ancde_ncde_desc* d, int TS, NcdeLayout* lo)
     lo->K = d->width[d->n_hidden - 1];
     int off = 0;
     for (int l = 0; l < d->n_hidden; ++l) {
-        lo->off_w[l] = off; off += pad4(lo->in_dim[l] * lo->stride[l]);
+        lo->off_w[l] = off; off += lo->width[l] * lo->stride[l];
         lo->off_b[l] = off; off += pad4(lo->width[l]);
     }
     lo->hidden_floats = off;
+    lo->off_hiddenb = off;
+    for (int l = 0; l < d->n_hidden; ++l) { lo->off_wt[l] = off; off += lo->in_dim[l] * lo->tstride[l]; }
+    lo->hiddenb_floats = off - lo->off_hiddenb;
     lo->off_wo = off; off += lo->K * lo->NCP;
     lo->off_bo = off; off += lo->NCP;
     lo->KPS = 8 * ((lo->K + 7) / 8) + 4;   // +4: 16-byte rows whose stride is bank-conflict free for LDS.128

@@ -43,11 +43,14 @@ struct NcdeLayout {
     int NCP;           // Hd * C4 padded columns
     int K;             // width of the last hidden layer = reduction size of the output layer
     int Hmax;          // widest activation
-    // packed weights (floats from the start of wpack); hidden layer l is stored transposed
-    // Wt[k][o] with an odd row stride so that both o-major and k-major walks are conflict free.
-    int in_dim[ANCDE_MAX_LAYERS], stride[ANCDE_MAX_LAYERS];
-    int off_w[ANCDE_MAX_LAYERS], off_b[ANCDE_MAX_LAYERS];
-    int hidden_floats;  // all hidden layers (weights + biases)
+    // packed weights (floats from the start of wpack).  Hidden layer l for the forward chain: rows W[o][stride] (k
+    // contiguous, zero padded) + bias; for the backward chain a second block holds the transpose Wt[k][tstride] (o
+    // contiguous).  Both strides are 4 * (odd number): 16-byte rows that a warp reads with conflict-free LDS.128
+    // when lane = row.
+    int in_dim[ANCDE_MAX_LAYERS], stride[ANCDE_MAX_LAYERS], tstride[ANCDE_MAX_LAYERS];
+    int off_w[ANCDE_MAX_LAYERS], off_b[ANCDE_MAX_LAYERS], off_wt[ANCDE_MAX_LAYERS];
+    int hidden_floats;  // forward block: all hidden layers (row-major weights + biases), starts at wpack[0]
+    int off_hiddenb, hiddenb_floats;   // backward block: the transposed weights of all hidden layers
     int off_wo, off_bo; // output layer Wt_out[k][NCP], bias_out[NCP]
     int off_wot, KPS;   // second copy for the backward: W_out[col][KPS] (k contiguous, KPS = 8*ceil(K/8) + 4)
     // tensor-core copy for the backward: the output layer as FP16 hi/lo A fragments of W_out^T, per TILE of 16 rows
@@ -73,6 +76,9 @@ struct NcdeLayout {
 };
 
 __host__ __device__ static inline int pad4(int x) { return (x + 3) & ~3; }
+// smallest 4 * (odd number) >= x: a row stride in floats whose 16-byte chunks of 8 consecutive rows fall in 8 distinct
+// bank groups
+__host__ __device__ static inline int pad4odd(int x) { int q = (x + 3) >> 2; if ((q & 1) == 0) ++q; return 4 * q; }
 
 // Fills the layout from a descriptor; returns 0 or an ANCDE_E* code (message set).
 int make_layout(const ancde_ncde_desc* d, NcdeLayout* lo);
