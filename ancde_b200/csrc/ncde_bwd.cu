@@ -58,6 +58,92 @@ __device__ __forceinline__ void cp_async16_b(void* smem_dst, const void* gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 
+// The hidden ReLU layers backwards as ONE warp-synchronous chain (the mirror image of hidden_chain in ncde_fwd.cu):
+// a warp owns SPW samples for all layers, lane = input unit k of layer l, and per 4 outputs reads one 128-bit piece of
+// the transposed weight row Wt_l[k][o..o+3] plus one 128-bit broadcast per sample of the layer's cotangent
+// [sample][unit]; delta_{l-1} = (W_l^T delta_l) * relu'(h_{l-1}) goes to the next layer through shared memory behind a
+// __syncwarp.  FP32 FMA: these layers are far too small for the tensor cores (measured: 1.0-1.2 k cycles per layer
+// with mma.sync, one CTA barrier per layer and FP16 hi/lo operand conversions, 5.1 k cycles per stage for the Sepsis
+// bottom network).
+//   sLp[8*l ..] = {ceil(width / 4), in_dim, row stride, off_wt, act_off_h[l-1], act_off_delta[l-1], -, -}
+template <int TS>
+__device__ __forceinline__ void hidden_chain_bwd(const int* __restrict__ sLp, int n_hidden, const float* __restrict__ sW,
+                                                 float* __restrict__ sD0, float* __restrict__ sD1,
+                                                 const float* __restrict__ sAct, float* __restrict__ act,
+                                                 float* __restrict__ sZb, int HP, int warp, int NW, int lane)
+{
+    constexpr int SPW = (TS >= 2) ? 2 : 1;
+    constexpr int NCW = TS / SPW;
+    for (int cw = warp; cw < NCW; cw += NW) {
+        const int s0 = cw * SPW;
+        const float* in = sD0 + s0 * HP;
+        int pp = 1;
+        for (int l = n_hidden - 1; l >= 0; --l) {
+            const int4 q0 = *reinterpret_cast<const int4*>(sLp + 8 * l);
+            const int2 q1 = *reinterpret_cast<const int2*>(sLp + 8 * l + 4);
+            const int nk4 = q0.x, N = q0.y;
+            float* out = (pp ? sD1 : sD0) + s0 * HP;
+            const int N4 = pad4(N);
+            for (int k0 = 0; k0 < N4; k0 += 32) {
+                const int k = k0 + lane;
+                const bool valid = k < N;
+                const int kc = valid ? k : N - 1;
+                const float4* wr = reinterpret_cast<const float4*>(sW + q0.w + kc * q0.z);
+                const float4* x0 = reinterpret_cast<const float4*>(in);
+                const float4* x1 = reinterpret_cast<const float4*>(in + (SPW - 1) * HP);
+                float h[SPW];
+#pragma unroll
+                for (int e = 0; e < SPW; ++e) h[e] = 1.0f;
+                if (l > 0) Vec<SPW>::ld(sAct + q1.x + kc * TS + s0, h);
+                float accA[SPW], accB[SPW];
+#pragma unroll
+                for (int e = 0; e < SPW; ++e) { accA[e] = 0.f; accB[e] = 0.f; }
+                float4 w = wr[0], xa = x0[0], xb = x1[0];
+#pragma unroll 2
+                for (int q = 1; q < nk4; ++q) {
+                    const float4 wn = wr[q], xan = x0[q], xbn = x1[q];
+                    accA[0] = fmaf(w.x, xa.x, accA[0]);
+                    accB[0] = fmaf(w.y, xa.y, accB[0]);
+                    accA[0] = fmaf(w.z, xa.z, accA[0]);
+                    accB[0] = fmaf(w.w, xa.w, accB[0]);
+                    if (SPW == 2) {
+                        accA[SPW - 1] = fmaf(w.x, xb.x, accA[SPW - 1]);
+                        accB[SPW - 1] = fmaf(w.y, xb.y, accB[SPW - 1]);
+                        accA[SPW - 1] = fmaf(w.z, xb.z, accA[SPW - 1]);
+                        accB[SPW - 1] = fmaf(w.w, xb.w, accB[SPW - 1]);
+                    }
+                    w = wn; xa = xan; xb = xbn;
+                }
+                accA[0] = fmaf(w.x, xa.x, accA[0]);
+                accB[0] = fmaf(w.y, xa.y, accB[0]);
+                accA[0] = fmaf(w.z, xa.z, accA[0]);
+                accB[0] = fmaf(w.w, xa.w, accB[0]);
+                if (SPW == 2) {
+                    accA[SPW - 1] = fmaf(w.x, xb.x, accA[SPW - 1]);
+                    accB[SPW - 1] = fmaf(w.y, xb.y, accB[SPW - 1]);
+                    accA[SPW - 1] = fmaf(w.z, xb.z, accA[SPW - 1]);
+                    accB[SPW - 1] = fmaf(w.w, xb.w, accB[SPW - 1]);
+                }
+                float v[SPW];
+#pragma unroll
+                for (int e = 0; e < SPW; ++e) v[e] = (valid && h[e] > 0.f) ? accA[e] + accB[e] : 0.f;
+                if (l > 0) {
+                    if (k < N4) {
+#pragma unroll
+                        for (int e = 0; e < SPW; ++e) out[e * HP + k] = v[e];
+                    }
+                    if (valid) Vec<SPW>::st(act + q1.y + k * TS + s0, v);     // for the hidden weight-gradient kernel
+                } else if (valid) {
+                    Vec<SPW>::st(sZb + k * TS + s0, v);                       // cotangent of the stage input
+                }
+            }
+            __syncwarp();
+            in = out;
+            pp ^= 1;
+        }
+    }
+}
+
 constexpr int BW_MTK_MAX = 4;      // output-layer reduction size K <= 64
 
 // The output layer's vector-Jacobian product runs on the tensor cores: per TILE of 16 output rows (2 field rows x 8
@@ -66,7 +152,9 @@ constexpr int BW_MTK_MAX = 4;      // output-layer reduction size K <= 64
 // from the largest stage cotangent of the tile) and multiplies it with the W_out^T fragments that a producer warp
 // streams from L2 through a ring of shared-memory slots (TMA bulk copies).  CT tiles per slot, one per warp of a
 // group of CT warps; two groups work on alternate slots.
-template <int TS>
+// CHAIN: every hidden layer has at most 32 units -> FP32 warp-synchronous hidden_chain_bwd; wider layers go through
+// the tensor cores (mma.sync, FP16 hi/lo x3), one CTA barrier per layer.
+template <int TS, bool CHAIN>
 __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant__ SolveArgs p)
 {
     constexpr int VW = (TS >= 4) ? 4 : TS;
@@ -91,8 +179,9 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* bar_empty = bar_full + 8;
     float* smem = reinterpret_cast<float*>(smem_raw + 128);
-    const uint4* sWhb = reinterpret_cast<const uint4*>(smem);   // hidden layers, W_l^T as FP16 hi/lo A fragments
-    float* sp = smem + (size_t)lo.hb_u4 * 4;
+    const uint4* sWhb = reinterpret_cast<const uint4*>(smem);   // !CHAIN: hidden layers, W_l^T as FP16 hi/lo A fragments
+    const float* sWtb = smem;                            // CHAIN: transposed weights Wt_l[k][o] (FP32)
+    float* sp = smem + (CHAIN ? (size_t)pad4(lo.hiddenb_floats) : (size_t)lo.hb_u4 * 4);
     uint4* sRing = reinterpret_cast<uint4*>(sp);         // [NSLOT][CT][MTK][64] W_out^T fragments
     sp += (size_t)NSLOT * CT * MTK * 64 * 4;
     float* sActBuf = sp; sp += 2 * (size_t)lo.act_fwd_floats;   // saved activations, double buffered
@@ -104,8 +193,11 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     float* sV2 = sp;    sp += HT;
     float* sZb = sp;    sp += HT;                        // cotangent of the stage input
     const int KP = 16 * lo.KSB + 8;                      // halfs per row of the cotangent operand matrices [sample][feature]
-    __half* sBd = reinterpret_cast<__half*>(sp);         // two buffers of {hi, lo} [8][KP]
-    sp += (size_t)(4 * 8 * KP) / 2;
+    __half* sBd = reinterpret_cast<__half*>(sp);         // !CHAIN: two buffers of {hi, lo} [8][KP]
+    const int HP = pad4(lo.Hmax);                        // CHAIN: floats per sample row of the chain's buffers
+    float* sD0 = sp;                                     // CHAIN: hidden-layer cotangents ping [sample][unit]
+    float* sD1 = sp + TS * HP;                           //        pong
+    sp += CHAIN ? (size_t)2 * TS * HP : (size_t)(4 * 8 * KP) / 2;
     float* sHbP = sp;   sp += (size_t)NW * MTK * 128;    // per-warp partial sums of the hidden cotangent (fragment order)
     float* sAttW = sp;  sp += need_att ? (size_t)NW * NJC * 64 : 0;   // per-warp partial sums of the dU cotangent [jc][b][8 j]
     float* sMax = sp;   sp += 32;
@@ -150,20 +242,32 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     };
 
     {
-        const uint4* src = reinterpret_cast<const uint4*>(p.wpack + lo.off_whb);
-        uint4* dst = reinterpret_cast<uint4*>(smem);
-        for (int i = tid; i < lo.hb_u4; i += NT) dst[i] = __ldg(src + i);
-        uint32_t* zb = reinterpret_cast<uint32_t*>(sBd);
-        for (int i = tid; i < 2 * 8 * KP; i += NT) zb[i] = 0u;      // 4 matrices of 8*KP halfs
+        if constexpr (CHAIN) {
+            const float4* src = reinterpret_cast<const float4*>(p.wpack + lo.off_hiddenb);
+            float4* dst = reinterpret_cast<float4*>(smem);
+            for (int i = tid; i < lo.hiddenb_floats / 4; i += NT) dst[i] = __ldg(src + i);
+            for (int i = tid; i < 2 * TS * HP; i += NT) sD0[i] = 0.f;    // sD0, sD1 (contiguous)
+        } else {
+            const uint4* src = reinterpret_cast<const uint4*>(p.wpack + lo.off_whb);
+            uint4* dst = reinterpret_cast<uint4*>(smem);
+            for (int i = tid; i < lo.hb_u4; i += NT) dst[i] = __ldg(src + i);
+            uint32_t* zb = reinterpret_cast<uint32_t*>(sBd);
+            for (int i = tid; i < 2 * 8 * KP; i += NT) zb[i] = 0u;      // 4 matrices of 8*KP halfs
+        }
         for (int item = tid; item < Hd * TS; item += NT) { sLam[item] = 0.f; sMu[item] = 0.f; }
         if (tid < lo.n_hidden) {
             // the layer loop reads its parameters from shared memory: register-indexed loads from the kernel-parameter
             // constant bank cost hundreds of cycles each on the critical path of every layer
             const int l = tid;
             int* q = sLp + 8 * l;
-            q[0] = lo.hbp[l].mtiles; q[1] = lo.hbp[l].full; q[2] = lo.hbp[l].tail8; q[3] = lo.hbp[l].stride;
-            q[4] = lo.hbp[l].off; q[5] = lo.hbp[l].M;
-            q[6] = l > 0 ? lo.act_off_h[l - 1] : 0; q[7] = l > 0 ? lo.act_off_delta[l - 1] : 0;
+            if (CHAIN) {
+                q[0] = (lo.width[l] + 3) / 4; q[1] = lo.in_dim[l]; q[2] = lo.tstride[l]; q[3] = lo.off_wt[l] - lo.off_hiddenb;
+                q[4] = l > 0 ? lo.act_off_h[l - 1] : 0; q[5] = l > 0 ? lo.act_off_delta[l - 1] : 0; q[6] = 0; q[7] = 0;
+            } else {
+                q[0] = lo.hbp[l].mtiles; q[1] = lo.hbp[l].full; q[2] = lo.hbp[l].tail8; q[3] = lo.hbp[l].stride;
+                q[4] = lo.hbp[l].off; q[5] = lo.hbp[l].M;
+                q[6] = l > 0 ? lo.act_off_h[l - 1] : 0; q[7] = l > 0 ? lo.act_off_delta[l - 1] : 0;
+            }
         }
         issue_act(lo.n_stages - 1, sActBuf);
     }
@@ -363,85 +467,111 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                 }
             }
             PH2_MARK(2);      // attention
-            // ---- phase 3: hidden layers backwards on the tensor cores.  Cotangents stay multiplied by `scale` inside the
-            // chain (FP16 range); delta_l = (W_{l+1}^T delta_{l+1}) * relu'(h_l), the stage-input cotangent is W_0^T delta_0
-            const float inv_s = 1.0f / scale;
-            const uint32_t bd_base = smem_u32(sBd);
-            const uint32_t bd_mat = (uint32_t)(8 * KP * 2);          // bytes of one FP16 matrix
-            const uint32_t bd_lane = (uint32_t)(((lane & 7) * KP + ((lane >> 3) & 1) * 8) * 2) + ((lane >> 4) ? bd_mat : 0u);
-            {
-                // delta of the last hidden layer from the warps' partial accumulator fragments: element (o, b) lives in
-                // m-tile o/16, lane (o%8)*4 + b/2, register ((o%16)/8)*2 + b%2
-                const int l = lo.n_hidden - 1;
-                const int N = lo.width[l];
-                const float* hl = sAct + lo.act_off_h[l];
-                for (int item = tid; item < N * TS; item += NT) {
-                    const int o = item / TS, b = item - o * TS;
-                    const int idx = ((o >> 4) * 32 + (o & 7) * 4 + (b >> 1)) * 4 + ((o >> 3) & 1) * 2 + (b & 1);
-                    float v = 0.f;
-                    for (int w = 0; w < NW; ++w) v += sHbP[(size_t)w * MTK * 128 + idx];
-                    v = (hl[item] > 0.f) ? v * (1.0f / 64.0f) : 0.f;
-                    act[lo.act_off_delta[l] + item] = v * inv_s;     // for the hidden weight-gradient kernel
-                    const __half hi = __float2half_rn(v);
-                    sBd[b * KP + o] = hi;
-                    sBd[8 * KP + b * KP + o] = __float2half_rn(v - __half2float(hi));
-                }
-            }
-            cta_sync();
-            int cur = 0;
-            for (int l = lo.n_hidden - 1; l >= 0; --l) {
-                const int4 lp0 = *reinterpret_cast<const int4*>(sLp + 8 * l), lp1 = *reinterpret_cast<const int4*>(sLp + 8 * l + 4);
-                const int l_mtiles = lp0.x, l_full = lp0.y, l_tail8 = lp0.z, l_stride = lp0.w, l_off = lp1.x, l_M = lp1.y;
-                if (warp < l_mtiles) {
-                    const int mt = warp;
-                    const uint4* A = sWhb + l_off + mt * l_stride + lane;
-                    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
-                    uint32_t baddr = bd_base + (uint32_t)cur * 2u * bd_mat + bd_lane;
-#pragma unroll 4
-                    for (int ks = 0; ks < l_full; ++ks) {
-                        const uint4 ah = A[ks * 64], al = A[ks * 64 + 32];
-                        uint32_t bh0, bh1, bl0, bl1;
-                        ldmatrix_x4(baddr, bh0, bh1, bl0, bl1);
-                        baddr += 32;
-                        mma16(a0, al.x, al.y, al.z, al.w, bh0, bh1);
-                        mma16(a1, ah.x, ah.y, ah.z, ah.w, bl0, bl1);
-                        mma16(a2, ah.x, ah.y, ah.z, ah.w, bh0, bh1);
-                    }
-                    if (l_tail8) {
-                        const uint4 a = A[l_full * 64];
-                        uint32_t bh0, bh1, bl0, bl1;
-                        ldmatrix_x4(baddr, bh0, bh1, bl0, bl1);
-                        mma8(a0, a.z, a.w, bh0);
-                        mma8(a1, a.x, a.y, bl0);
-                        mma8(a2, a.x, a.y, bh0);
-                    }
-                    // rows = inputs of layer l (16*mt + g, + 8), columns = samples 2t, 2t+1
-                    float dv[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) dv[e] = (a0[e] + a1[e] + a2[e]) * (1.0f / 64.0f);
-                    const int bcol = 2 * t;
-                    if (l > 0) {
-                        const float* hl = sAct + lp1.z;
-                        float* dsave = act + lp1.w;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int kin = mt * 16 + g + (e >> 1) * 8, b = bcol + (e & 1);
-                            const bool ok = kin < l_M && b < TS;
-                            const float hv = ok ? hl[kin * TS + b] : 0.f;
-                            dv[e] = (hv > 0.f) ? dv[e] : 0.f;
-                            if (ok) dsave[kin * TS + b] = dv[e] * inv_s;
-                        }
-                        store_act_tile(bd_base + (uint32_t)(cur ^ 1) * 2u * bd_mat + bd_lane + (uint32_t)(mt * 16 * 2), dv);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int kin = mt * 16 + g + (e >> 1) * 8, b = bcol + (e & 1);
-                            if (kin < l_M && b < TS) sZb[kin * TS + b] = dv[e] * inv_s;
-                        }
+            if constexpr (CHAIN) {
+                // ---- phase 3: hidden layers backwards (FP32, warp-synchronous chain):
+                // delta_l = (W_{l+1}^T delta_{l+1}) * relu'(h_l), the stage-input cotangent is W_0^T delta_0
+                {
+                    // delta of the last hidden layer from the warps' partial accumulator fragments: element (o, b) lives in
+                    // m-tile o/16, lane (o%8)*4 + b/2, register ((o%16)/8)*2 + b%2; the tensor-core operands carried the
+                    // factors 64 (weights) and `scale` (cotangent)
+                    const float unscale = (1.0f / 64.0f) / scale;
+                    const int l = lo.n_hidden - 1;
+                    const int N = lo.width[l];
+                    const float* hl = sAct + lo.act_off_h[l];
+                    for (int item = tid; item < N * TS; item += NT) {
+                        const int o = item / TS, b = item - o * TS;
+                        const int idx = ((o >> 4) * 32 + (o & 7) * 4 + (b >> 1)) * 4 + ((o >> 3) & 1) * 2 + (b & 1);
+                        float v = 0.f;
+                        for (int w = 0; w < NW; ++w) v += sHbP[(size_t)w * MTK * 128 + idx];
+                        v = (hl[item] > 0.f) ? v * unscale : 0.f;
+                        act[lo.act_off_delta[l] + item] = v;     // for the hidden weight-gradient kernel
+                        sD0[b * HP + o] = v;
                     }
                 }
                 cta_sync();
-                cur ^= 1;
+                hidden_chain_bwd<TS>(sLp, lo.n_hidden, sWtb, sD0, sD1, sAct, act, sZb, HP, warp, NW, lane);
+                cta_sync();
+            } else {
+                // ---- phase 3: hidden layers backwards on the tensor cores.  Cotangents stay multiplied by `scale` inside the
+                // chain (FP16 range); delta_l = (W_{l+1}^T delta_{l+1}) * relu'(h_l), the stage-input cotangent is W_0^T delta_0
+                const float inv_s = 1.0f / scale;
+                const uint32_t bd_base = smem_u32(sBd);
+                const uint32_t bd_mat = (uint32_t)(8 * KP * 2);          // bytes of one FP16 matrix
+                const uint32_t bd_lane = (uint32_t)(((lane & 7) * KP + ((lane >> 3) & 1) * 8) * 2) + ((lane >> 4) ? bd_mat : 0u);
+                {
+                    // delta of the last hidden layer from the warps' partial accumulator fragments: element (o, b) lives in
+                    // m-tile o/16, lane (o%8)*4 + b/2, register ((o%16)/8)*2 + b%2
+                    const int l = lo.n_hidden - 1;
+                    const int N = lo.width[l];
+                    const float* hl = sAct + lo.act_off_h[l];
+                    for (int item = tid; item < N * TS; item += NT) {
+                        const int o = item / TS, b = item - o * TS;
+                        const int idx = ((o >> 4) * 32 + (o & 7) * 4 + (b >> 1)) * 4 + ((o >> 3) & 1) * 2 + (b & 1);
+                        float v = 0.f;
+                        for (int w = 0; w < NW; ++w) v += sHbP[(size_t)w * MTK * 128 + idx];
+                        v = (hl[item] > 0.f) ? v * (1.0f / 64.0f) : 0.f;
+                        act[lo.act_off_delta[l] + item] = v * inv_s;     // for the hidden weight-gradient kernel
+                        const __half hi = __float2half_rn(v);
+                        sBd[b * KP + o] = hi;
+                        sBd[8 * KP + b * KP + o] = __float2half_rn(v - __half2float(hi));
+                    }
+                }
+                cta_sync();
+                int cur = 0;
+                for (int l = lo.n_hidden - 1; l >= 0; --l) {
+                    const int4 lp0 = *reinterpret_cast<const int4*>(sLp + 8 * l), lp1 = *reinterpret_cast<const int4*>(sLp + 8 * l + 4);
+                    const int l_mtiles = lp0.x, l_full = lp0.y, l_tail8 = lp0.z, l_stride = lp0.w, l_off = lp1.x, l_M = lp1.y;
+                    if (warp < l_mtiles) {
+                        const int mt = warp;
+                        const uint4* A = sWhb + l_off + mt * l_stride + lane;
+                        float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+                        uint32_t baddr = bd_base + (uint32_t)cur * 2u * bd_mat + bd_lane;
+    #pragma unroll 4
+                        for (int ks = 0; ks < l_full; ++ks) {
+                            const uint4 ah = A[ks * 64], al = A[ks * 64 + 32];
+                            uint32_t bh0, bh1, bl0, bl1;
+                            ldmatrix_x4(baddr, bh0, bh1, bl0, bl1);
+                            baddr += 32;
+                            mma16(a0, al.x, al.y, al.z, al.w, bh0, bh1);
+                            mma16(a1, ah.x, ah.y, ah.z, ah.w, bl0, bl1);
+                            mma16(a2, ah.x, ah.y, ah.z, ah.w, bh0, bh1);
+                        }
+                        if (l_tail8) {
+                            const uint4 a = A[l_full * 64];
+                            uint32_t bh0, bh1, bl0, bl1;
+                            ldmatrix_x4(baddr, bh0, bh1, bl0, bl1);
+                            mma8(a0, a.z, a.w, bh0);
+                            mma8(a1, a.x, a.y, bl0);
+                            mma8(a2, a.x, a.y, bh0);
+                        }
+                        // rows = inputs of layer l (16*mt + g, + 8), columns = samples 2t, 2t+1
+                        float dv[4];
+    #pragma unroll
+                        for (int e = 0; e < 4; ++e) dv[e] = (a0[e] + a1[e] + a2[e]) * (1.0f / 64.0f);
+                        const int bcol = 2 * t;
+                        if (l > 0) {
+                            const float* hl = sAct + lp1.z;
+                            float* dsave = act + lp1.w;
+    #pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int kin = mt * 16 + g + (e >> 1) * 8, b = bcol + (e & 1);
+                                const bool ok = kin < l_M && b < TS;
+                                const float hv = ok ? hl[kin * TS + b] : 0.f;
+                                dv[e] = (hv > 0.f) ? dv[e] : 0.f;
+                                if (ok) dsave[kin * TS + b] = dv[e] * inv_s;
+                            }
+                            store_act_tile(bd_base + (uint32_t)(cur ^ 1) * 2u * bd_mat + bd_lane + (uint32_t)(mt * 16 * 2), dv);
+                        } else {
+    #pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int kin = mt * 16 + g + (e >> 1) * 8, b = bcol + (e & 1);
+                                if (kin < l_M && b < TS) sZb[kin * TS + b] = dv[e] * inv_s;
+                            }
+                        }
+                    }
+                    cta_sync();
+                    cur ^= 1;
+                }
             }
             const float* hb = sZb;
             PH2_MARK(3);      // phase 3: hidden layers
@@ -486,12 +616,21 @@ static int bwd_ct(const NcdeLayout& lo)
     return ct;
 }
 
+static bool bwd_chain(const NcdeLayout& lo)
+{
+    for (int l = 0; l < lo.n_hidden; ++l)
+        if (lo.width[l] > 32) return false;
+    return true;
+}
+
 static size_t bwd_smem_bytes(const NcdeLayout& lo, int ct, int slots, bool att)
 {
     const int nw = 2 * ct;
-    size_t f = (size_t)lo.hb_u4 * 4;
+    const bool chain = bwd_chain(lo);
+    size_t f = chain ? (size_t)pad4(lo.hiddenb_floats) : (size_t)lo.hb_u4 * 4;
     f += (size_t)slots * ct * lo.MTK * 64 * 4;
-    f += 2 * (size_t)lo.act_fwd_floats + 7 * (size_t)pad4(lo.Hd * lo.TS) + (size_t)(4 * 8 * (16 * lo.KSB + 8)) / 2;
+    f += 2 * (size_t)lo.act_fwd_floats + 7 * (size_t)pad4(lo.Hd * lo.TS) +
+         (chain ? 2 * (size_t)lo.TS * pad4(lo.Hmax) : (size_t)(4 * 8 * (16 * lo.KSB + 8)) / 2);
     f += (size_t)nw * lo.MTK * 128 + (att ? (size_t)nw * lo.NJC * 64 : 0) + 32 + 8 * ANCDE_MAX_LAYERS + (size_t)lo.C4 * lo.TS;
     return f * 4 + 128;
 }
@@ -526,9 +665,10 @@ static int launch_bwd(const ancde_ncde_desc* d, SolveArgs& a, cudaStream_t strea
     a.ring_slots = slots;
     a.ring_pw = 0;
     static const char* names[3] = {"ncde_bwd_plain", "ncde_bwd_bottom", "ncde_bwd_top"};
-    ANCDE_CUDA(cudaFuncSetAttribute(ncde_bwd_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*kern)(SolveArgs) = bwd_chain(lo) ? ncde_bwd_kernel<TS, true> : ncde_bwd_kernel<TS, false>;
+    ANCDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(names[lo.mode], stream);
-    ncde_bwd_kernel<TS><<<lo.ntiles, nt + 32, smem, stream>>>(a);
+    kern<<<lo.ntiles, nt + 32, smem, stream>>>(a);
     prof_end(stream);
     count_launch();
     ANCDE_CUDA(cudaGetLastError());

@@ -184,8 +184,65 @@ __device__ __forceinline__ void hidden_chain(const int* __restrict__ sLp, int n_
     }
 }
 
+// Hidden layers wider than 32 units (one CTA barrier per layer): out[o][.] = relu(bias[o] + sum_k W[o][k] * in[k][.])
+// for all TS samples, activations [unit][TS].  One (output, group of VW samples) item per thread pair -- the two lanes
+// of a pair split k and add with one shuffle; the weight row is read in 128-bit pieces.
+template <int TS>
+__device__ __forceinline__ void dense_relu(const float* __restrict__ Wr, const float* __restrict__ bias, int nk4,
+                                           int N, int S, const float* __restrict__ in, float* __restrict__ out,
+                                           float* __restrict__ gsave, int tid, int NT)
+{
+    constexpr int VW = (TS >= 4) ? 4 : TS;
+    constexpr int NQ = TS / VW;
+    const int ks = tid & 1, slot = tid >> 1, nslots = NT >> 1;
+    const int h4 = (nk4 + 1) >> 1;
+    const int qbeg = ks * h4;
+    const int qcnt = ks ? nk4 - h4 : h4;
+    const int nitems = N * NQ;
+    for (int base = 0; base < nitems; base += nslots) {
+        const int item = base + slot;
+        const bool valid = item < nitems;
+        int q = 0, o = valid ? item : 0;
+        if (NQ > 1 && o >= N) { q = 1; o -= N; }
+        float acc[VW];
+#pragma unroll
+        for (int e = 0; e < VW; ++e) acc[e] = 0.f;
+        if (valid) {
+            const float4* wp = reinterpret_cast<const float4*>(Wr + o * S) + qbeg;
+            const float* ip = in + (qbeg * 4) * TS + q * VW;
+#pragma unroll 2
+            for (int j = 0; j < qcnt; ++j) {
+                const float4 w = wp[j];
+                float v0[VW], v1[VW], v2[VW], v3[VW];
+                Vec<VW>::ld(ip, v0);
+                Vec<VW>::ld(ip + TS, v1);
+                Vec<VW>::ld(ip + 2 * TS, v2);
+                Vec<VW>::ld(ip + 3 * TS, v3);
+                ip += 4 * TS;
+#pragma unroll
+                for (int e = 0; e < VW; ++e) {
+                    acc[e] = fmaf(w.x, v0[e], acc[e]);
+                    acc[e] = fmaf(w.y, v1[e], acc[e]);
+                    acc[e] = fmaf(w.z, v2[e], acc[e]);
+                    acc[e] = fmaf(w.w, v3[e], acc[e]);
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < VW; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 1);
+        if (valid && ks == 0) {
+            const float bv = bias[o];
+#pragma unroll
+            for (int e = 0; e < VW; ++e) acc[e] = fmaxf(acc[e] + bv, 0.f);
+            Vec<VW>::st(out + o * TS + q * VW, acc);
+            if (gsave) Vec<VW>::st(gsave + o * TS + q * VW, acc);
+        }
+    }
+}
+
 // WO_SMEM: output-layer weights resident in shared memory; otherwise streamed through the TMA ring.
-template <int TS, bool WO_SMEM>
+// CHAIN: every hidden layer has at most 32 units -> warp-synchronous hidden_chain; otherwise dense_relu per layer.
+template <int TS, bool WO_SMEM, bool CHAIN>
 __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant__ SolveArgs p)
 {
     constexpr int VW = (TS >= 4) ? 4 : TS;
@@ -211,8 +268,9 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
     sp += WO_SMEM ? (size_t)K * NCP : (size_t)NSLOT * KC * PW;
     float* sTimes = sp; sp += pad4(lo.L);
     const int HP = pad4(lo.Hmax);                        // floats per sample row of the hidden chain's buffers
-    float* sInT = sp;   sp += TS * HP;                   // stage input z_s      [sample][i] (padding stays zero)
-    float* sT0 = sp;    sp += TS * HP;                   // hidden activations ping [sample][unit]
+    // CHAIN: rows per sample [sample][unit]; otherwise rows per unit [unit][TS] (both TS * HP floats, padding stays finite)
+    float* sInT = sp;   sp += TS * HP;                   // stage input z_s
+    float* sT0 = sp;    sp += TS * HP;                   // hidden activations ping
     float* sT1 = sp;    sp += TS * HP;                   // hidden activations pong
     float* sLast = sp;  sp += pad4(lo.Hmax * TS);        // last hidden layer    [unit][TS]
     int* sLp = reinterpret_cast<int*>(sp); sp += 8 * ANCDE_MAX_LAYERS;   // per-layer parameters of hidden_chain
@@ -288,7 +346,7 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
             const int i = item / TS, b = item - i * TS;
             const int bg = b0 + b;
             const float v = (bg < lo.B) ? p.z0[(int64_t)bg * Hd + i] : 0.f;
-            sInT[b * HP + i] = v;
+            sInT[CHAIN ? b * HP + i : item] = v;
             sY[item] = v;
             if (bg < lo.B) p.z_out[(int64_t)bg * Hd + i] = v;          // solution[0] = y0
             if (p.save_act) p.save_act[(int64_t)tile * lo.act_floats + item] = v;
@@ -328,9 +386,22 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
             PHASE_MARK(5);   // control issue
 
             // (2) hidden layers: warp-synchronous chain, one CTA barrier at the end
-            hidden_chain<TS>(sLp, lo.n_hidden, sHW, sInT, sT0, sT1, sLast, act, HP, tid >> 5, NT >> 5, lane);
-            cta_sync();
             const float* in = sLast;
+            if constexpr (CHAIN) {
+                hidden_chain<TS>(sLp, lo.n_hidden, sHW, sInT, sT0, sT1, sLast, act, HP, tid >> 5, NT >> 5, lane);
+                cta_sync();
+            } else {
+                in = sInT;
+                float* outb = sT0;
+                for (int l = 0; l < lo.n_hidden; ++l) {
+                    const int4 q0 = *reinterpret_cast<const int4*>(sLp + 8 * l);
+                    const int2 q1 = *reinterpret_cast<const int2*>(sLp + 8 * l + 4);
+                    dense_relu<TS>(sHW + q0.w, sHW + q1.x, q0.x, q0.y, q0.z, in, outb, act ? act + q1.y : nullptr, tid, NT);
+                    cta_sync();
+                    in = outb;
+                    outb = (outb == sT0) ? sT1 : sT0;
+                }
+            }
             PHASE_MARK(0);   // ctl issue + hidden layers
 
             // (3) output layer, tanh, contraction with dU: thread = 4 columns x TS samples
@@ -455,7 +526,7 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
                     sY[item] = y1;
                     zin = y1;
                 }
-                sInT[b * HP + i] = zin;
+                sInT[CHAIN ? b * HP + i : item] = zin;
                 if (act_next) act_next[item] = zin;
             }
             if (s == 3) {
@@ -527,15 +598,13 @@ static int launch_fwd_ts(SolveArgs a, cudaStream_t stream)
         threads = nt + 32;
     }
     static const char* names[3] = {"ncde_fwd_plain", "ncde_fwd_bottom", "ncde_fwd_top"};
-    if (wo_smem) {
-        ANCDE_CUDA(cudaFuncSetAttribute(ncde_fwd_kernel<TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        prof_begin(names[lo.mode], stream);
-        ncde_fwd_kernel<TS, true><<<lo.ntiles, threads, smem, stream>>>(a);
-    } else {
-        ANCDE_CUDA(cudaFuncSetAttribute(ncde_fwd_kernel<TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        prof_begin(names[lo.mode], stream);
-        ncde_fwd_kernel<TS, false><<<lo.ntiles, threads, smem, stream>>>(a);
-    }
+    bool chain = true;
+    for (int l = 0; l < lo.n_hidden; ++l) chain = chain && lo.width[l] <= 32;
+    void (*kern)(SolveArgs) = wo_smem ? (chain ? ncde_fwd_kernel<TS, true, true> : ncde_fwd_kernel<TS, true, false>)
+                                      : (chain ? ncde_fwd_kernel<TS, false, true> : ncde_fwd_kernel<TS, false, false>);
+    ANCDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin(names[lo.mode], stream);
+    kern<<<lo.ntiles, threads, smem, stream>>>(a);
     prof_end(stream);
     count_launch();
     ANCDE_CUDA(cudaGetLastError());
