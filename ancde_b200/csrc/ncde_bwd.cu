@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     float* sAttW = sp;  sp += need_att ? (size_t)NW * NJC * 64 : 0;   // per-warp partial sums of the dU cotangent [jc][b][8 j]
     float* sMax = sp;   sp += 32;
     int* sLp = reinterpret_cast<int*>(sp); sp += 8 * ANCDE_MAX_LAYERS;   // per-layer {mtiles, full, tail8, stride, off, M, act_off_h[l-1], act_off_delta[l-1]}
-    float* sTmp = sp;                                    // [C4][TS]
+    float* sTmp = sp;   sp += (size_t)C4 * TS;           // [C4][TS]
+    int4* sTile = reinterpret_cast<int4*>(sp);           // per output-layer tile: {G offset, stage-cotangent offset, dU offset, flags}
 
     if (tid == 0) {
         for (int s = 0; s < NSLOT; ++s) {
@@ -269,10 +270,26 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                 q[6] = l > 0 ? lo.act_off_h[l - 1] : 0; q[7] = l > 0 ? lo.act_off_delta[l - 1] : 0;
             }
         }
+        // Coordinates of the output-layer tiles, worked out once: tile tl = (ip, jc) covers field rows 2*ip, 2*ip + 1 and
+        // control channels 8*jc .. 8*jc + 7; lane (g, t) owns sample g and channels 8*jc + 2t, + 1.
+        //   x = offset of (row 2*ip, channel 8*jc) in a sample's saved tanh outputs,  y = offset of row 2*ip in [Hd][TS],
+        //   z = dU offset of channel 8*jc,  w = bit t: channel 8*jc + 2t exists, bit 4: row 2*ip + 1 exists, bits 8..: jc
+        for (int tl = tid; tl < ntl; tl += NT) {
+            const int ip = tl / NJC, jc = tl - ip * NJC;
+            int flags = jc << 8;
+            for (int tt = 0; tt < 4; ++tt)
+                if (8 * jc + 2 * tt < C4) flags |= 1 << tt;
+            if (2 * ip + 1 < Hd) flags |= 16;
+            sTile[tl] = make_int4(2 * ip * C4 + 8 * jc, 2 * ip * TS, 2 * jc * DUS, flags);
+        }
         issue_act(lo.n_stages - 1, sActBuf);
     }
     cta_sync();
 
+    const int lane_g = g * NCP + 2 * t;                                   // this lane's offset inside a tile's tanh outputs
+    const int lane_du = (t >> 1) * DUS + 2 * (t & 1) * TS + g;            // ... and inside a dU chunk pair (du_index of channel 2t)
+    const bool b_ok = g < TS;
+    const uint32_t bar_full_a = smem_u32(bar_full), bar_empty_a = smem_u32(bar_empty);
     int jb = lo.n_out - 1;   // last output time whose cotangent has not been consumed yet
     int abuf = 0;            // which half of sActBuf holds the current stage
     float gmax = 0.f;        // largest |stage cotangent| this thread wrote (scale of the FP16 weight-gradient operands)
@@ -358,22 +375,16 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[m][e] = 0.f;
             {
-                const float* gbase = p.save_G + ((int64_t)n * lo.ntiles + tile) * g_tile + (int64_t)g * NCP;
-                const bool b_ok = g < TS;
-                auto tile_coords = [&](int tl, int& i0, int& j) {
-                    const int ip = (NJC == 1) ? tl : (int)__umulhi((unsigned)tl, lo.magicNJC);   // 2^32 / 1 does not fit the magic
-                    i0 = 2 * ip;
-                    j = 8 * (tl - ip * NJC) + 2 * t;
-                };
+                const float* gbase = p.save_G + ((int64_t)n * lo.ntiles + tile) * g_tile + lane_g;
                 auto load_g = [&](int tl, float2& ga, float2& gb2) {
                     ga = make_float2(0.f, 0.f);
                     gb2 = make_float2(0.f, 0.f);
                     if (tl < ntl && b_ok) {
-                        int i0, j;
-                        tile_coords(tl, i0, j);
-                        if (j < C4) {
-                            ga = __ldg(reinterpret_cast<const float2*>(gbase + i0 * C4 + j));
-                            if (i0 + 1 < Hd) gb2 = __ldg(reinterpret_cast<const float2*>(gbase + (i0 + 1) * C4 + j));
+                        const int4 e = sTile[tl];
+                        if ((e.w >> t) & 1) {
+                            const float* gp = gbase + e.x;
+                            ga = __ldg(reinterpret_cast<const float2*>(gp));
+                            if (e.w & 16) gb2 = __ldg(reinterpret_cast<const float2*>(gp + C4));
                         }
                     }
                 };
@@ -382,6 +393,10 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                 load_g(grp * CT + wl, g0n, g1n);
                 load_g(grp * CT + wl + 2 * CT, g0nn, g1nn);
                 int rpos = (ring_base + grp) % (2 * NSLOT);
+                float2* const attw = reinterpret_cast<float2*>(sAttW + (size_t)warp * NJC * 64) + lane;
+                const float* const sGl = sG + g;
+                const float* const sDUl = sDU + lane_du;
+                const uint4* const ringl = sRing + (size_t)wl * MTK * 64 + lane;
                 for (int c = grp; c < nchunks; c += 2) {
                     const int tl = c * CT + wl;
                     const float2 g0 = g0n, g1 = g1n;
@@ -391,22 +406,21 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                     const uint32_t parity = (rpos >= NSLOT) ? 1u : 0u;
                     rpos += 2;
                     if (rpos >= 2 * NSLOT) rpos -= 2 * NSLOT;
-                    mbar_wait(bar_full + slot, parity);
+                    mbar_wait_a(bar_full_a + 8u * (uint32_t)slot, parity);
                     if (tl < ntl) {
-                        int i0, j;
-                        tile_coords(tl, i0, j);
                         float p00 = 0.f, p01 = 0.f, p10 = 0.f, p11 = 0.f;
-                        if (b_ok && j < C4) {
-                            const float gb0 = sG[i0 * TS + g] * scale;
-                            const float gb1 = (i0 + 1 < Hd) ? sG[(i0 + 1) * TS + g] * scale : 0.f;
-                            const float du0 = sDU[du_index(j, g, TS, DUS)], du1 = sDU[du_index(j + 1, g, TS, DUS)];
+                        const int4 e = sTile[tl];
+                        if (b_ok && ((e.w >> t) & 1)) {
+                            const float gb0 = sGl[e.y] * scale;
+                            const float gb1 = (e.w & 16) ? sGl[e.y + TS] * scale : 0.f;
+                            const float du0 = sDUl[e.z], du1 = sDUl[e.z + TS];
                             p00 = gb0 * du0 * fmaf(-g0.x, g0.x, 1.0f);
                             p01 = gb0 * du1 * fmaf(-g0.y, g0.y, 1.0f);
                             p10 = gb1 * du0 * fmaf(-g1.x, g1.x, 1.0f);
                             p11 = gb1 * du1 * fmaf(-g1.y, g1.y, 1.0f);
                             if (need_att) {
                                 // cotangent of dU: dUbar[j][b] = sum_i gbar[i][b] * G[i][j][b] (scaled like gbar)
-                                float2* q = reinterpret_cast<float2*>(sAttW + ((size_t)warp * NJC + (j >> 3)) * 64) + lane;
+                                float2* q = attw + (e.w >> 8) * 32;
                                 float2 v = *q;
                                 v.x += gb0 * g0.x + gb1 * g1.x;
                                 v.y += gb0 * g0.y + gb1 * g1.y;
@@ -416,7 +430,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                         uint32_t bh0, bl0, bh1, bl1;
                         split_pair(p00, p01, bh0, bl0);      // rows 2t, 2t+1   = (i0, j), (i0, j+1)
                         split_pair(p10, p11, bh1, bl1);      // rows 2t+8, 2t+9 = (i0+1, j), (i0+1, j+1)
-                        const uint4* A = sRing + ((size_t)slot * CT + wl) * MTK * 64 + lane;
+                        const uint4* A = ringl + (size_t)slot * CT * MTK * 64;
 #pragma unroll
                         for (int m = 0; m < BW_MTK_MAX; ++m) {
                             if (m < MTK) {
@@ -426,7 +440,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_empty + slot);
+                    if (lane == 0) mbar_arrive_a(bar_empty_a + 8u * (uint32_t)slot);
                 }
                 ring_base = (ring_base + nchunks) % (2 * NSLOT);
                 float4* hp4 = reinterpret_cast<float4*>(sHbP) + (size_t)warp * MTK * 32 + lane;
@@ -631,7 +645,7 @@ static size_t bwd_smem_bytes(const NcdeLayout& lo, int ct, int slots, bool att)
     f += (size_t)slots * ct * lo.MTK * 64 * 4;
     f += 2 * (size_t)lo.act_fwd_floats + 7 * (size_t)pad4(lo.Hd * lo.TS) +
          (chain ? 2 * (size_t)lo.TS * pad4(lo.Hmax) : (size_t)(4 * 8 * (16 * lo.KSB + 8)) / 2);
-    f += (size_t)nw * lo.MTK * 128 + (att ? (size_t)nw * lo.NJC * 64 : 0) + 32 + 8 * ANCDE_MAX_LAYERS + (size_t)lo.C4 * lo.TS;
+    f += (size_t)nw * lo.MTK * 128 + (att ? (size_t)nw * lo.NJC * 64 : 0) + 32 + 8 * ANCDE_MAX_LAYERS + (size_t)lo.C4 * lo.TS + 4 * (size_t)lo.n_wtiles;
     return f * 4 + 128;
 }
 

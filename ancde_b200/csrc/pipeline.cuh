@@ -47,6 +47,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     }
 }
 
+// The same on a precomputed 32-bit shared-memory address (saves the generic -> shared conversion in inner loops).
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(bar_addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar_addr) : "memory");
+}
+
 // Busy-polls instead (mbarrier.test_wait never suspends the thread): for waits of a few hundred cycles, where the
 // wake-up latency of a suspended try_wait would be a large part of the wait itself.
 __device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity)
