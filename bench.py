@@ -355,6 +355,14 @@ def run_ours(args):
 
     # ---- per-kernel roofline from the CUDA-event timings taken inside the timed region
     flops = kernel_flops(cfg, B)
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of one `ncu --set full` capture of this
+    # workload at this batch (profiles/r01c_ncu_set_full.txt); a measured constant, only valid for the captured shape
+    NCU_TRAFFIC = {('sepsis', 1024): {'ncde_bwd_top': 2.450118e9 + 0.280220e9, 'ncde_fwd_top': 0.094415e9 + 2.388326e9,
+                                      'ncde_bwd_bottom': 1.684576e9 + 0.154525e9, 'ncde_fwd_bottom': 0.041351e9 + 1.660350e9,
+                                      'ncde_wgrad_top': 2.279596e9 + 0.003482e9, 'ncde_wgrad_bottom': 1.586187e9 + 0.004195e9,
+                                      'ncde_hidden_wgrad_top': 0.459724e9 + 0.003799e9,
+                                      'ncde_hidden_wgrad_bottom': 0.254357e9 + 0.006072e9}}
+    traffic = NCU_TRAFFIC.get((args.workload, B), {})
     agg = {}
     for name, t in prof:
         a = agg.setdefault(name, [0.0, 0])
@@ -369,6 +377,8 @@ def run_ours(args):
             k['algorithmic_gflop_per_launch'] = round(flops[name] / 1e9, 3)
             k['achieved_tflops'] = round(flops[name] / (avg * 1e-3) / 1e12, 3)
             k['frac_of_fp32_peak'] = round(flops[name] / (avg * 1e-3) / 1e12 / fp32_peak, 4)
+        if name in traffic:
+            k['dram_bytes_per_launch'] = traffic[name]
         kernels.append(k)
     dom = next((k for k in kernels if 'achieved_tflops' in k), None)
     total_flops = sum(flops.values())
@@ -378,7 +388,8 @@ def run_ours(args):
                     'peak': round(fp32_peak, 2), 'unit': 'TFLOP/s', 'frac': dom['frac_of_fp32_peak'],
                     'peak_source': 'FFMA microbenchmark (ancde_fp32_peak_kernel) measured in this run; '
                                    'MEASURED_PEAKS.json holds no FP32 figure',
-                    'traffic': None,
+                    'traffic': traffic.get(dom['name']),
+                    'traffic_source': 'profiles/r01c_ncu_set_full.txt (bytes per launch)' if dom['name'] in traffic else None,
                     'step_frac': round(total_flops * args.steps / (ms * 1e-3) / 1e12 / fp32_peak, 4),
                     'step_algorithmic_gflop': round(total_flops / 1e9, 2)}
 
@@ -394,7 +405,8 @@ def run_ours(args):
         peak, src = hbm_peak()
         ach = nbytes / (wg['avg_ms'] * 1e-3) / 1e9
         roofline_wgrad = {'bound': 'hbm', 'kernel': 'ncde_wgrad_top', 'achieved': round(ach, 1), 'peak': peak, 'unit': 'GB/s',
-                          'frac': round(ach / peak, 4), 'traffic': None, 'peak_source': src, 'avg_ms': wg['avg_ms'],
+                          'frac': round(ach / peak, 4), 'traffic': traffic.get('ncde_wgrad_top'), 'peak_source': src,
+                          'avg_ms': wg['avg_ms'],
                           'algorithmic_bytes_per_launch': nbytes,
                           'tensor_pipe': 'tcgen05.mma kind::f16, FP16 hi/lo x3 = FP32-grade; accumulator in tensor memory'}
 

@@ -225,3 +225,42 @@ def test_cluster_engine_forward_matches_reference_golden(case):
             _forward(model, g)
     finally:
         solver.ENGINE = 0
+
+
+@pytest.mark.parametrize('workload,B', [('mujoco', 11), ('stock', 3), ('uea', 5), ('sepsis', 19), ('sepsis_oi', 9)])
+def test_ragged_batches_against_oracle(workload, B):
+    """Batches that do not fill the last tile of 8 samples (and, for Sepsis, the last cluster of the UMMA engine):
+    prediction and every gradient against the CPU oracle, the same check smoke() runs."""
+    import __graft_entry__ as entry
+    err, worst = entry._smoke_case(workload, B)
+    assert err < FWD_TOL and worst < GRAD_TOL
+
+
+def test_minimal_grid_two_knots_single_sample():
+    """L = 2 (one linear spline piece, the reference's `length == 2` branch, interpolate.py:18-24), B = 1."""
+    import ancde_b200
+    from oracle import port
+    torch.manual_seed(5)
+    C, H, HH, nl = 3, 4, 6, 1
+    func = ancde_b200.FinalTanh(C, H, HH, nl)
+    times = torch.tensor([0.0, 1.0])
+    X = torch.randn(1, 2, C)
+    coeffs = port.natural_cubic_spline_coeffs(times, X)
+    z0 = torch.randn(1, H)
+    sd = {'func.' + k: v.detach().clone().requires_grad_(True) for k, v in func.state_dict().items()}
+    z0r = z0.clone().requires_grad_(True)
+    ref = port.cdeint_port(sd, times, coeffs, z0r, times, 1.0, H, C, prefix='func')
+    ref.square().sum().backward()
+    func = func.cuda()
+    got_coeffs = ancde_b200.natural_cubic_spline_coeffs(times.cuda(), X.cuda())
+    for a, b in zip(got_coeffs, coeffs):
+        assert torch.equal(a.cpu(), b)
+    sp = ancde_b200.NaturalCubicSpline(times.cuda(), got_coeffs)
+    z0g = z0.cuda().requires_grad_(True)
+    got = ancde_b200.cdeint(sp.derivative, z0g, func, times.cuda(), adjoint=False, method='rk4', options=dict(step_size=1.0))
+    got.square().sum().backward()
+    assert got.shape == (2, 1, H)
+    assert rel_err(got, ref) < FWD_TOL
+    assert rel_err(z0g.grad, z0r.grad) < GRAD_TOL
+    for k, p in func.named_parameters():
+        assert rel_err(p.grad, sd['func.' + k].grad) < GRAD_TOL, k
