@@ -173,6 +173,9 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     const int nchunks = (ntl + CT - 1) / CT;
     const int HT = pad4(Hd * TS);
     const bool need_att = (lo.mode == ANCDE_MODE_TOP) && (p.grad_attention != nullptr);
+    // timewise attention (one value per sample and knot): its cotangent is ONE number per sample and stage, so every lane
+    // sums its share in a register while it walks the output-layer tiles -- no per-channel partial sums in shared memory
+    const bool att_tw = need_att && lo.att_C == 1;
     const int64_t g_tile = (int64_t)TS * NCP;           // floats per (stage, tile) block of saved tanh outputs
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
             gmax = fmaxf(gmax, lmax);
             for (int o = 16; o >= 1; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
             if (lane == 0) sMax[warp] = lmax;
-            if (need_att) {
+            if (need_att && !att_tw) {
                 float2* z = reinterpret_cast<float2*>(sAttW + (size_t)warp * NJC * 64) + lane;
                 for (int jc = 0; jc < NJC; ++jc) z[jc * 32] = make_float2(0.f, 0.f);
             }
@@ -396,6 +399,8 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                 float2* const attw = reinterpret_cast<float2*>(sAttW + (size_t)warp * NJC * 64) + lane;
                 const float* const sGl = sG + g;
                 const float* const sDUl = sDU + lane_du;
+                const float* const sDAl = sAct + lo.act_off_duda + lane_du;      // dU/da of this lane's channels
+                float att_acc = 0.f;
                 const uint4* const ringl = sRing + (size_t)wl * MTK * 64 + lane;
                 for (int c = grp; c < nchunks; c += 2) {
                     const int tl = c * CT + wl;
@@ -418,7 +423,11 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                             p01 = gb0 * du1 * fmaf(-g0.y, g0.y, 1.0f);
                             p10 = gb1 * du0 * fmaf(-g1.x, g1.x, 1.0f);
                             p11 = gb1 * du1 * fmaf(-g1.y, g1.y, 1.0f);
-                            if (need_att) {
+                            if (att_tw) {
+                                // sum_j dUbar[j][b] * dU/da[j][b] with dUbar[j][b] = sum_i gbar[i][b] * G[i][j][b]
+                                att_acc = fmaf(gb0 * g0.x + gb1 * g1.x, sDAl[e.z], att_acc);
+                                att_acc = fmaf(gb0 * g0.y + gb1 * g1.y, sDAl[e.z + TS], att_acc);
+                            } else if (need_att) {
                                 // cotangent of dU: dUbar[j][b] = sum_i gbar[i][b] * G[i][j][b] (scaled like gbar)
                                 float2* q = attw + (e.w >> 8) * 32;
                                 float2 v = *q;
@@ -442,6 +451,11 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                     __syncwarp();
                     if (lane == 0) mbar_arrive_a(bar_empty_a + 8u * (uint32_t)slot);
                 }
+                if (att_tw) {
+                    att_acc += __shfl_xor_sync(0xffffffffu, att_acc, 1);
+                    att_acc += __shfl_xor_sync(0xffffffffu, att_acc, 2);
+                    if (t == 0) sAttW[warp * 8 + g] = att_acc;              // this warp's share for sample g
+                }
                 ring_base = (ring_base + nchunks) % (2 * NSLOT);
                 float4* hp4 = reinterpret_cast<float4*>(sHbP) + (size_t)warp * MTK * 32 + lane;
 #pragma unroll
@@ -451,7 +465,24 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
             cta_sync();
             PH2_MARK(1);      // phases 1+2
             // ---- cotangent of the attention: a[q] += dUbar * dU/da   
-            if (need_att) {
+            if (att_tw) {
+                if (warp == 0) {
+                    // lane = (quarter of the warps' partial sums, sample); two shuffles finish the sum
+                    const int smp = lane & 7;
+                    float a = 0.f;
+                    for (int w = lane >> 3; w < NW; w += 4) a += sAttW[w * 8 + smp];
+                    a += __shfl_xor_sync(0xffffffffu, a, 8);
+                    a += __shfl_xor_sync(0xffffffffu, a, 16);
+                    const float ts = stage_time(t0, dt, s);
+                    int qa = (int)floorf(ts) - 1;
+                    if (qa < 0) qa += lo.att_L;
+                    qa = qa < 0 ? 0 : (qa >= lo.att_L ? lo.att_L - 1 : qa);
+                    // scale is a power of two: its reciprocal is an exponent flip
+                    const float inv_scale = __uint_as_float((254u << 23) - __float_as_uint(scale));
+                    if (lane < TS && b0 + lane < lo.B)
+                        atomicAdd(p.grad_attention + (int64_t)qa * lo.B + b0 + lane, a * inv_scale);
+                }
+            } else if (need_att) {
                 const float inv_s = 1.0f / scale;
                 for (int item = tid; item < lo.C * TS; item += NT) {
                     const int j = item / TS, b = item - j * TS;

@@ -18,6 +18,26 @@ FORCE_SAMPLES_PER_CTA = int(os.environ.get('ANCDE_SAMPLES_PER_CTA', '0'))   # 0 
 ENGINE = int(os.environ.get('ANCDE_ENGINE', '0'))   # 0 = library default (streamed); 2 = forward-only cluster engine
 
 
+import contextlib
+
+_ACCUMULATE_INTO_PARAM_GRADS = False
+
+
+@contextlib.contextmanager
+def accumulate_into_param_grads():
+    """Inside this context the backward kernels add the weight gradients STRAIGHT into `param.grad` (they accumulate with
+    atomicAdd, the C ABI's contract: "flat_grad is accumulated into, caller zeroes") instead of into a scratch buffer that
+    autograd then adds to `param.grad` with one small kernel per parameter.  For callers that own pre-allocated,
+    zeroed, contiguous FP32 gradients -- the flat gradient bucket of the training step (dp.FlatGradBucket)."""
+    global _ACCUMULATE_INTO_PARAM_GRADS
+    old = _ACCUMULATE_INTO_PARAM_GRADS
+    _ACCUMULATE_INTO_PARAM_GRADS = True
+    try:
+        yield
+    finally:
+        _ACCUMULATE_INTO_PARAM_GRADS = old
+
+
 class SolvePlan:
     """Everything about one solve that is not a differentiable tensor."""
 
@@ -184,6 +204,7 @@ class _NcdeSolve(torch.autograd.Function):
         _lib.note_launches()
         ctx.plan, ctx.widths, ctx.Hd = plan, widths, Hd
         ctx.keep = (z0c, attc, wbc, wpack, save_act, save_G)
+        ctx.params = wb
         ctx.mark_non_differentiable(k_out)
         return z_out, k_out
 
@@ -197,11 +218,18 @@ class _NcdeSolve(torch.autograd.Function):
         d.wpack, d.save_act, d.save_G = wpack.data_ptr(), save_act.data_ptr(), save_G.data_ptr()
         g = g_z_out.detach().float().contiguous()
         grad_z0 = torch.empty_like(z0c)
-        gflat = torch.zeros(sum(w.numel() for w in wbc), dtype=torch.float32, device=dev)    # one fill for every gradient
-        grads, off = [], 0
-        for w in wbc:
-            grads.append(gflat[off:off + w.numel()].view_as(w))
-            off += w.numel()
+        direct = _ACCUMULATE_INTO_PARAM_GRADS and all(
+            isinstance(q, torch.nn.Parameter) and q.grad is not None and q.grad.dtype == torch.float32 and
+            q.grad.is_contiguous() and q.grad.device == dev and q.grad.shape == w.shape
+            for q, w in zip(ctx.params, wbc))
+        if direct:
+            grads = [q.grad for q in ctx.params]
+        else:
+            gflat = torch.zeros(sum(w.numel() for w in wbc), dtype=torch.float32, device=dev)    # one fill for every gradient
+            grads, off = [], 0
+            for w in wbc:
+                grads.append(gflat[off:off + w.numel()].view_as(w))
+                off += w.numel()
         d.grad_z_out, d.grad_z0 = g.data_ptr(), grad_z0.data_ptr()
         for i in range(len(widths) + 1):
             d.grad_W[i] = grads[2 * i].data_ptr()
@@ -217,6 +245,9 @@ class _NcdeSolve(torch.autograd.Function):
         _lib.check(rc, 'ancde_ncde_backward')
         _lib.note_launches()
         ctx.keep = None
+        ctx.params = None
+        if direct:
+            return (None, None, grad_z0, grad_att) + (None,) * len(grads)
         return (None, None, grad_z0, grad_att) + tuple(grads)
 
 

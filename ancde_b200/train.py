@@ -7,7 +7,7 @@ add one flat-gradient all-reduce between backward and the optimizer step (ancde_
 """
 import torch
 
-from . import metamodel, synthetic
+from . import metamodel, solver, synthetic
 from .dp import FlatGradBucket
 
 
@@ -60,7 +60,8 @@ class DualNcdeTrainer:
         self.bucket.zero()
         pred = self.forward(batch, slope)
         loss = task_loss(self.cfg, pred, batch['y'])
-        loss.backward()
+        with solver.accumulate_into_param_grads():      # the solver's weight gradients go straight into the flat bucket
+            loss.backward()
         loss = loss.detach() + self.add_weight_regularisation()
         self.bucket.all_reduce_mean()
         self.opt.step()
