@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
             for (int i = tid; i < 2 * 8 * KP; i += NT) zb[i] = 0u;      // 4 matrices of 8*KP halfs
         }
         for (int item = tid; item < Hd * TS; item += NT) { sLam[item] = 0.f; sMu[item] = 0.f; }
+        if (tid < 32) sMax[tid] = 0.f;
         if (tid < lo.n_hidden) {
             // the layer loop reads its parameters from shared memory: register-indexed loads from the kernel-parameter
             // constant bank cost hundreds of cycles each on the critical path of every layer
@@ -361,8 +362,11 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
             // power-of-two scale that brings the largest cotangent of this tile and stage to ~2^6
             float scale = 1.0f;
             {
-                float m = 0.f;
-                for (int w = 0; w < NW; ++w) m = fmaxf(m, sMax[w]);
+                // 16 slots (NW <= 14, the rest stay zero): four independent 128-bit loads instead of a dependent loop
+                const float4 m0 = *reinterpret_cast<const float4*>(sMax), m1 = *reinterpret_cast<const float4*>(sMax + 4);
+                const float4 m2 = *reinterpret_cast<const float4*>(sMax + 8), m3 = *reinterpret_cast<const float4*>(sMax + 12);
+                const float m = fmaxf(fmaxf(fmaxf(fmaxf(m0.x, m0.y), fmaxf(m0.z, m0.w)), fmaxf(fmaxf(m1.x, m1.y), fmaxf(m1.z, m1.w))),
+                                      fmaxf(fmaxf(fmaxf(m2.x, m2.y), fmaxf(m2.z, m2.w)), fmaxf(fmaxf(m3.x, m3.y), fmaxf(m3.z, m3.w))));
                 if (m > 1e-30f && m < 1e30f) {
                     const int e = (int)((__float_as_uint(m) >> 23) & 0xffu) - 126;     // m = f * 2^e, f in [0.5, 1)
                     scale = __uint_as_float((uint32_t)(127 + 6 - e) << 23);
@@ -696,6 +700,10 @@ static int launch_bwd(const ancde_ncde_desc* d, SolveArgs& a, cudaStream_t strea
         return ANCDE_EUNSUPPORTED;
     }
     const int ct = bwd_ct(lo);
+    if (2 * ct > 16) {
+        set_error("ncde_backward: %d consumer warps (hidden layers wider than 256 units are not supported)", 2 * ct);
+        return ANCDE_EUNSUPPORTED;
+    }
     const int nt = 2 * ct * 32;
     const bool att = (lo.mode == ANCDE_MODE_TOP) && (a.grad_attention != nullptr);
     int slots = 8;      // as deep a ring as fits: the fills are latency bound (~1.5 us each)
