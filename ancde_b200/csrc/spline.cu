@@ -15,8 +15,19 @@
 // SIMT efficiency: with 90 % of the entries missing (Sepsis) nearly every knot is observed by SOME
 // lane of a warp, so loops over knots with a per-lane "observed?" branch run at ~10 % lane
 // utilisation.  Instead pass 0 compacts the observed knot indices of each path into shared memory
-// ([ordinal][thread], 16 bit), the two Thomas sweeps iterate over ORDINALS (all lanes busy until
+// ([ordinal][thread], 16 bit; the values are re-read from X), the two Thomas sweeps iterate over ORDINALS (all lanes busy until
 // the shortest path ends) and the expansion pass walks the L-1 intervals in lock step.
+//
+// Measured alternatives (B200, 29 959 x 72 x 35 floats, 90 % missing; this kernel: 0.825 ms = 28 % of the HBM roofline,
+// 16.5 of 32 threads active per instruction, issue slots 47 % busy):
+//  * piece coefficients computed in the ordinal loop of pass 2 and parked in the output slots (saves ~45 divergent
+//    instructions per interval, costs three stores and three L2 loads per ordinal): 0.916 ms;
+//  * a tile kernel -- one CTA per sample, X block and every scratch value in shared memory, thread = channel for the
+//    compaction and the Thomas sweeps, thread = (interval, channel) element for the expansion, fully coalesced 128-bit
+//    loads and 128-byte stores, bit-identical results: 0.951 ms (the per-channel phases keep 35 of 128 threads busy and
+//    serialise ~15 k cycles per sample).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ancde {
@@ -32,8 +43,7 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
     const int tid = threadIdx.x;
     T* sT = reinterpret_cast<T*>(smem_raw);
     const int Lp = (L + 3) & ~3;
-    T* sxv = sT + Lp;                                                     // [L+2][NT] observed value per ordinal
-    unsigned short* sidx = reinterpret_cast<unsigned short*>(sxv + (size_t)(L + 2) * NT);   // [L+2][NT] knot index per ordinal
+    unsigned short* sidx = reinterpret_cast<unsigned short*>(sT + Lp);   // [L+2][NT] knot index per ordinal
 
     for (int i = tid; i < L; i += NT) sT[i] = times[i];
     __syncthreads();
@@ -56,7 +66,6 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
             last = i;
             xlast = v;
             sidx[pos * NT + tid] = (unsigned short)i;
-            sxv[pos * NT + tid] = v;
             ++pos;
         }
     }
@@ -70,12 +79,21 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
     // end-point imputation (interpolate.py:104-114): knot 0 takes the first observed value, knot L-1 the last
     const bool imp_first = first != 0, imp_last = last != L - 1;
     int base = 1;
-    if (imp_first) { sidx[tid] = 0; sxv[tid] = xfirst; base = 0; }
-    if (imp_last) { sidx[pos * NT + tid] = (unsigned short)(L - 1); sxv[pos * NT + tid] = xlast; ++pos; }
+    if (imp_first) { sidx[tid] = 0; base = 0; }
+    if (imp_last) { sidx[pos * NT + tid] = (unsigned short)(L - 1); ++pos; }
     const int m = pos - base;                        // observed knots after imputation, >= 2
     const unsigned short* jx = sidx + base * NT + tid;     // jx[j*NT] = knot index of ordinal j
-    const T* jv = sxv + base * NT + tid;                    // jv[j*NT] = value of ordinal j (imputed ends included)
-    auto xval = [&](int j, int) -> T { return jv[j * NT]; };
+    // value of ordinal j (knot i): read again from X (L1/L2 resident after pass 0) instead of a shared-memory copy --
+    // shared memory per thread drops from 6 to 2 bytes per knot, which doubles the resident warps of this
+    // latency-bound kernel (measured: 0.883 -> 0.825 ms on the Sepsis-size split); the two imputed ends come from
+    // registers.  (Also measured, and rejected: computing the piece coefficients in the ordinal loop of pass 2 and
+    // parking them in the output slots saves ~45 instructions per interval but adds three stores and three L2 loads
+    // per ordinal: 0.916 ms.)
+    auto xval = [&](int j, int i) -> T {
+        if (j == 0 && imp_first) return xfirst;
+        if (j == m - 1 && imp_last) return xlast;
+        return __ldg(xp + (int64_t)i * C);
+    };
 
     // reciprocal of a time difference in the dtype of `times` (float32 for the Stock fixtures)
     auto recip = [&](int i1, int i0, T& r, T& r2) {
@@ -205,7 +223,7 @@ static int launch_spline(const T* times, const T* X, T* a, T* b, T* c2, T* d3, i
     int nt = 128;
     size_t smem = 0;
     for (;; nt /= 2) {
-        smem = (size_t)Lp * sizeof(T) + (size_t)(L + 2) * nt * (sizeof(unsigned short) + sizeof(T));
+        smem = (size_t)Lp * sizeof(T) + (size_t)(L + 2) * nt * sizeof(unsigned short);
         if (smem <= 56 * 1024 || nt == 32) break;
     }
     if (smem > 227 * 1024) {
