@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get('ANCDE_LIB') or os.path.join(_HERE, 'libancde_b200.so'
 MAX_LAYERS = 8
 MODE_PLAIN, MODE_BOTTOM, MODE_TOP = 0, 1, 2
 ENGINE_STREAMED, ENGINE_CLUSTER, ENGINE_UMMA = 1, 2, 3
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _f32p = ctypes.POINTER(ctypes.c_float)
 
@@ -36,7 +36,7 @@ class NcdeDesc(ctypes.Structure):
         ('grad_z_out', ctypes.c_void_p), ('grad_z0', ctypes.c_void_p),
         ('grad_W', ctypes.c_void_p * (MAX_LAYERS + 1)), ('grad_bias', ctypes.c_void_p * (MAX_LAYERS + 1)),
         ('grad_attention', ctypes.c_void_p),
-        ('samples_per_cta', ctypes.c_int32), ('engine', ctypes.c_int32),
+        ('samples_per_cta', ctypes.c_int32), ('engine', ctypes.c_int32), ('async_wgrad', ctypes.c_int32),
     ]
 
 
@@ -44,7 +44,7 @@ _lib = None
 
 EXPORTS = ['ancde_abi_version', 'ancde_last_error', 'ancde_spline_coeffs_f32', 'ancde_spline_coeffs_f64',
            'ancde_ncde_wpack_floats', 'ancde_ncde_save_act_floats', 'ancde_ncde_save_G_floats',
-           'ancde_ncde_engine', 'ancde_ncde_forward', 'ancde_ncde_backward', 'ancde_debug_force_wgrad_mma_sync', 'ancde_last_launch_count', 'ancde_fp32_peak_kernel',
+           'ancde_ncde_engine', 'ancde_ncde_forward', 'ancde_ncde_backward', 'ancde_ncde_join', 'ancde_debug_force_wgrad_mma_sync', 'ancde_last_launch_count', 'ancde_fp32_peak_kernel',
            'ancde_profile_enable', 'ancde_profile_count', 'ancde_profile_get']
 
 
@@ -74,6 +74,7 @@ def lib():
     L.ancde_ncde_engine.argtypes = [ctypes.POINTER(NcdeDesc)]
     L.ancde_ncde_forward.argtypes = [ctypes.POINTER(NcdeDesc), vp]
     L.ancde_ncde_backward.argtypes = [ctypes.POINTER(NcdeDesc), vp]
+    L.ancde_ncde_join.argtypes = [vp]
     L.ancde_fp32_peak_kernel.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double), vp]
     L.ancde_profile_get.argtypes = [ci, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_float)]
     _lib = L

@@ -690,6 +690,32 @@ bool bwd_fits(const NcdeLayout& lo)
     return lo.MTK <= BW_MTK_MAX && bwd_smem_bytes(lo, bwd_ct(lo), 2, lo.mode == ANCDE_MODE_TOP) <= 227 * 1024;
 }
 
+// Side stream of the asynchronous weight gradients (ancde_ncde_desc::async_wgrad), one per device.
+// (Measured alternative: deferring the launches until the NEXT recurrent kernel has been enqueued, so that it gets its
+// SMs first, stretches the persistent tcgen05 weight-gradient kernel over the whole recurrent kernel on the 20 free SMs
+// and its last wave then runs alone: 11.49 ms per step against 11.40 ms with the immediate launch below.)
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, done = nullptr;
+    bool pending = false;
+};
+static SideStream g_side[64];
+
+static int side_stream(SideStream** out)
+{
+    int dev = 0;
+    ANCDE_CUDA(cudaGetDevice(&dev));
+    ANCDE_CHECK_ARG(dev >= 0 && dev < 64, "ncde_backward: device index %d", dev);
+    SideStream* ss = &g_side[dev];
+    if (!ss->s) {
+        ANCDE_CUDA(cudaStreamCreateWithFlags(&ss->s, cudaStreamNonBlocking));
+        ANCDE_CUDA(cudaEventCreateWithFlags(&ss->fork, cudaEventDisableTiming));
+        ANCDE_CUDA(cudaEventCreateWithFlags(&ss->done, cudaEventDisableTiming));
+    }
+    *out = ss;
+    return ANCDE_OK;
+}
+
 template <int TS>
 static int launch_bwd(const ancde_ncde_desc* d, SolveArgs& a, cudaStream_t stream)
 {
@@ -726,14 +752,29 @@ static int launch_bwd(const ancde_ncde_desc* d, SolveArgs& a, cudaStream_t strea
     count_launch();
     ANCDE_CUDA(cudaGetLastError());
 
-    // weight gradients (read the stage / layer cotangents the kernel above left in save_act)
+    // weight gradients (read the stage / layer cotangents the kernel above left in save_act).  They depend on nothing
+    // but that kernel: with async_wgrad they go to the side stream and run next to whatever the caller enqueues after
+    // this call -- in a training step the recurrent backward of the OTHER network, which leaves 20 of the 148 SMs idle
     {
-        int rc = launch_wgrad(a, d->grad_W[lo.n_hidden], d->grad_bias[lo.n_hidden], stream);
+        cudaStream_t ws = stream;
+        SideStream* ss = nullptr;
+        if (d->async_wgrad) {
+            int rc = side_stream(&ss);
+            if (rc != ANCDE_OK) return rc;
+            ANCDE_CUDA(cudaEventRecord(ss->fork, stream));
+            ANCDE_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+            ws = ss->s;
+        }
+        int rc = launch_wgrad(a, d->grad_W[lo.n_hidden], d->grad_bias[lo.n_hidden], ws);
         if (rc != ANCDE_OK) return rc;
         HiddenGradPtrs hp;
         for (int l = 0; l < lo.n_hidden; ++l) { hp.gW[l] = d->grad_W[l]; hp.gB[l] = d->grad_bias[l]; }
-        rc = launch_hidden_wgrad(a, hp, stream);
+        rc = launch_hidden_wgrad(a, hp, ws);
         if (rc != ANCDE_OK) return rc;
+        if (ss) {
+            ANCDE_CUDA(cudaEventRecord(ss->done, ss->s));
+            ss->pending = true;
+        }
     }
     return ANCDE_OK;
 }
@@ -741,6 +782,19 @@ static int launch_bwd(const ancde_ncde_desc* d, SolveArgs& a, cudaStream_t strea
 }  // namespace ancde
 
 using namespace ancde;
+
+extern "C" int ancde_ncde_join(void* stream_)
+{
+    int dev = 0;
+    ANCDE_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return ANCDE_OK;
+    ancde::SideStream* ss = &ancde::g_side[dev];
+    if (ss->s && ss->pending) {
+        ANCDE_CUDA(cudaStreamWaitEvent((cudaStream_t)stream_, ss->done, 0));
+        ss->pending = false;
+    }
+    return ANCDE_OK;
+}
 
 extern "C" int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream_)
 {

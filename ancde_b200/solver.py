@@ -21,21 +21,40 @@ ENGINE = int(os.environ.get('ANCDE_ENGINE', '0'))   # 0 = library default (strea
 import contextlib
 
 _ACCUMULATE_INTO_PARAM_GRADS = False
+_ASYNC_WGRAD = False
+_pending = []        # buffers of backward calls whose weight-gradient kernels may still run on the side stream
 
 
 @contextlib.contextmanager
-def accumulate_into_param_grads():
+def accumulate_into_param_grads(async_wgrad=True):
     """Inside this context the backward kernels add the weight gradients STRAIGHT into `param.grad` (they accumulate with
     atomicAdd, the C ABI's contract: "flat_grad is accumulated into, caller zeroes") instead of into a scratch buffer that
     autograd then adds to `param.grad` with one small kernel per parameter.  For callers that own pre-allocated,
-    zeroed, contiguous FP32 gradients -- the flat gradient bucket of the training step (dp.FlatGradBucket)."""
-    global _ACCUMULATE_INTO_PARAM_GRADS
-    old = _ACCUMULATE_INTO_PARAM_GRADS
-    _ACCUMULATE_INTO_PARAM_GRADS = True
+    zeroed, contiguous FP32 gradients -- the flat gradient bucket of the training step (dp.FlatGradBucket).
+
+    Nothing reads those gradients before the context ends, so (async_wgrad) the weight-gradient kernels of a solve are
+    put on the library's side stream, where they overlap the recurrent backward of the other network; leaving the
+    context joins the side stream into the current one (ancde_ncde_join: an event wait, capturable in a CUDA graph).
+    The buffers those kernels read are kept alive until then."""
+    global _ACCUMULATE_INTO_PARAM_GRADS, _ASYNC_WGRAD
+    old = (_ACCUMULATE_INTO_PARAM_GRADS, _ASYNC_WGRAD)
+    _ACCUMULATE_INTO_PARAM_GRADS, _ASYNC_WGRAD = True, bool(async_wgrad)
     try:
         yield
     finally:
-        _ACCUMULATE_INTO_PARAM_GRADS = old
+        _ACCUMULATE_INTO_PARAM_GRADS, _ASYNC_WGRAD = old
+        join()
+
+
+def join():
+    """Makes the current stream of every device with pending asynchronous weight gradients wait for them."""
+    if not _pending:
+        return
+    L_ = _lib.lib()
+    for dev in {k[0] for k in _pending}:
+        with torch.cuda.device(dev):
+            _lib.check(L_.ancde_ncde_join(_lib.stream_ptr(dev)), 'ancde_ncde_join')
+    _pending.clear()
 
 
 class SolvePlan:
@@ -238,12 +257,16 @@ class _NcdeSolve(torch.autograd.Function):
         if plan.mode == _lib.MODE_TOP and plan.att_grad and ctx.needs_input_grad[3]:
             grad_att = torch.zeros_like(attc)
             d.grad_attention = grad_att.data_ptr()
+        use_async = direct and _ASYNC_WGRAD
+        d.async_wgrad = 1 if use_async else 0
         # z_out / k_out are not needed by the backward kernels
         d.z_out = save_act.data_ptr()
         with torch.cuda.device(dev):
             rc = L_.ancde_ncde_backward(ctypes.byref(d), _lib.stream_ptr(dev))
         _lib.check(rc, 'ancde_ncde_backward')
         _lib.note_launches()
+        if use_async:
+            _pending.append((dev, ctx.keep, g, grads))     # alive until join(): the side stream still reads them
         ctx.keep = None
         ctx.params = None
         if direct:

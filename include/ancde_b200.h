@@ -127,6 +127,10 @@ typedef struct ancde_ncde_desc {
     float* grad_attention;     /* TOP, or NULL (adjoint-mode gradient flow): (att_L, B, att_C) accumulated into */
     int32_t samples_per_cta;   /* streamed engine only: 0 = let the library choose (8, 4, 2 or 1) */
     int32_t engine;            /* 0 = library default; ANCDE_ENGINE_STREAMED, _CLUSTER or _UMMA (see above) */
+    int32_t async_wgrad;       /* backward only: 1 = launch the weight-gradient kernels on the library's side stream (they only
+                                * depend on the recurrent kernel of the same call) so that they overlap whatever the caller
+                                * enqueues next; the caller must call ancde_ncde_join() on its stream before it reads the
+                                * gradients, and keep every buffer of the descriptor alive until then.  0 = same stream. */
 } ancde_ncde_desc;
 
 /* Workspace sizes (in floats) for a descriptor whose shape fields are filled in. */
@@ -145,6 +149,10 @@ int ancde_ncde_forward(const ancde_ncde_desc* d, void* stream);
  * written by ancde_ncde_forward with the same descriptor.  Overwrites the stage-input slots of save_act
  * with the stage cotangents (consumed by the weight-gradient kernel launched from the same call). */
 int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream);
+
+/* Makes `stream` wait for every weight-gradient kernel that backward calls with async_wgrad = 1 put on the side stream
+ * of the current device (an event wait: no host synchronisation, capturable in a CUDA graph).  No-op when none is pending. */
+int ancde_ncde_join(void* stream);
 
 /* Number of kernel launches the last forward / backward call of this thread issued. */
 int ancde_last_launch_count(void);
