@@ -157,8 +157,6 @@ constexpr int BW_MTK_MAX = 4;      // output-layer reduction size K <= 64
 template <int TS, bool CHAIN>
 __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant__ SolveArgs p)
 {
-    constexpr int VW = (TS >= 4) ? 4 : TS;
-    constexpr int NQ = TS / VW;
     const NcdeLayout& lo = p.lo;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;

@@ -25,11 +25,40 @@ struct CtlRegs {
     float frac;
 };
 
+// What does not change from stage to stage for the control elements (j, b) a thread owns: worked out once per kernel
+// (an integer division and 64-bit index arithmetic per element and stage otherwise).
+struct CtlItems {
+    int obase[CTL_ITEMS];   // (bg * (L-1)) * C + j: coefficient offset of piece 0, or -1 when the element does not exist
+    int abase[CTL_ITEMS];   // bg * att_C + (elementwise attention: j)
+    int hbase[CTL_ITEMS];   // bg * C + j
+    int di[CTL_ITEMS];      // du_index(j, b), or -1 past the C4 * TS elements
+};
+
+template <int TS>
+__device__ __forceinline__ void ctl_setup(const NcdeLayout& lo, int b0, int tid, int NT, CtlItems& ci)
+{
+#pragma unroll
+    for (int it = 0; it < CTL_ITEMS; ++it) {
+        const int item = tid + it * NT;
+        ci.obase[it] = -1; ci.abase[it] = 0; ci.hbase[it] = 0; ci.di[it] = -1;
+        if (item < lo.C4 * TS) {
+            const int b = item / lo.C4, j = item - b * lo.C4;
+            const int bg = b0 + b;
+            ci.di[it] = du_index(j, b, TS, lo.DUS);
+            if (j < lo.C && bg < lo.B) {
+                ci.obase[it] = bg * (lo.L - 1) * lo.C + j;
+                ci.abase[it] = bg * lo.att_C + (lo.att_C == 1 ? 0 : j);
+                ci.hbase[it] = bg * lo.C + j;
+            }
+        }
+    }
+}
+
 // Issues the global loads of the control of stage (k, s); nothing is consumed here so the
 // latency overlaps with the MLP of the current stage.
 template <int TS>
 __device__ __forceinline__ void ctl_issue(const SolveArgs& p, const float* sTimes, int& cnt, int k, int s,
-                                          int b0, int tid, int NT, CtlRegs& r)
+                                          const CtlItems& ci, CtlRegs& r)
 {
     const NcdeLayout& lo = p.lo;
     const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step);
@@ -44,24 +73,25 @@ __device__ __forceinline__ void ctl_issue(const SolveArgs& p, const float* sTime
     int q = (int)floorf(ts) - 1;                      // attention[int(floor(t)) - 1], python wrap
     if (q < 0) q += lo.att_L;
     q = q < 0 ? 0 : (q >= lo.att_L ? lo.att_L - 1 : q);
-    const int m = (lo.mode == ANCDE_MODE_TOP) ? n % (lo.n_hp - 1) : 0;   // call counter + reset rule (:134-137)
+    const bool top = lo.mode == ANCDE_MODE_TOP;
+    const int m = top ? n % (lo.n_hp - 1) : 0;        // call counter + reset rule (:134-137)
+    const float* cb = p.cb + (int64_t)idx * lo.C;
+    const float* cc2 = p.cc2 + (int64_t)idx * lo.C;
+    const float* cd3 = p.cd3 + (int64_t)idx * lo.C;
+    const float* att = top ? p.attention + (int64_t)q * lo.B * lo.att_C : nullptr;
+    const float* hpr = top ? p.h_prime + (int64_t)m * lo.B * lo.C : nullptr;
 #pragma unroll
     for (int it = 0; it < CTL_ITEMS; ++it) {
-        const int item = tid + it * NT;
         r.b[it] = r.c2[it] = r.d3[it] = 0.f;
         r.a[it] = r.hp[it] = 0.f;
-        if (item < lo.C4 * TS) {
-            const int b = item / lo.C4, j = item - b * lo.C4;
-            const int bg = b0 + b;
-            if (j < lo.C && bg < lo.B) {
-                const int64_t o = ((int64_t)bg * (lo.L - 1) + idx) * lo.C + j;
-                r.b[it] = __ldg(p.cb + o);
-                r.c2[it] = __ldg(p.cc2 + o);
-                r.d3[it] = __ldg(p.cd3 + o);
-                if (lo.mode == ANCDE_MODE_TOP) {
-                    r.a[it] = __ldg(p.attention + ((int64_t)q * lo.B + bg) * lo.att_C + (lo.att_C == 1 ? 0 : j));
-                    r.hp[it] = __ldg(p.h_prime + ((int64_t)m * lo.B + bg) * lo.C + j);
-                }
+        const int o = ci.obase[it];
+        if (o >= 0) {
+            r.b[it] = __ldg(cb + o);
+            r.c2[it] = __ldg(cc2 + o);
+            r.d3[it] = __ldg(cd3 + o);
+            if (top) {
+                r.a[it] = __ldg(att + ci.abase[it]);
+                r.hp[it] = __ldg(hpr + ci.hbase[it]);
             }
         }
     }
@@ -69,15 +99,13 @@ __device__ __forceinline__ void ctl_issue(const SolveArgs& p, const float* sTime
 
 // Turns the loaded coefficients into dU (and dU/da for the backward) and stores them [j][TS].
 template <int TS>
-__device__ __forceinline__ void ctl_finish(const SolveArgs& p, const CtlRegs& r, float* sDU, float* act,
-                                           int tid, int NT)
+__device__ __forceinline__ void ctl_finish(const SolveArgs& p, const CtlRegs& r, const CtlItems& ci, float* sDU, float* act)
 {
     const NcdeLayout& lo = p.lo;
 #pragma unroll
     for (int it = 0; it < CTL_ITEMS; ++it) {
-        const int item = tid + it * NT;
-        if (item < lo.C4 * TS) {
-            const int b = item / lo.C4, j = item - b * lo.C4;
+        const int di = ci.di[it];
+        if (di >= 0) {
             // derivative = b + (two_c + three_d * frac) * frac   (interpolate.py:298-303)
             float dX = __fadd_rn(r.b[it], __fmul_rn(__fadd_rn(r.c2[it], __fmul_rn(r.d3[it], r.frac)), r.frac));
             float dU = dX, duda = 0.f;
@@ -88,7 +116,6 @@ __device__ __forceinline__ void ctl_finish(const SolveArgs& p, const CtlRegs& r,
                                __fmul_rn(__fmul_rn(__fmul_rn(a, __fsub_rn(1.0f, a)), dX), hp));
                 duda = dX * (1.0f + (1.0f - 2.0f * a) * hp);
             }
-            const int di = du_index(j, b, TS, lo.DUS);
             sDU[di] = dU;
             if (act) {
                 act[lo.act_off_du + di] = dU;
@@ -252,7 +279,7 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
     const int NT = p.ntc;                         // consumer threads (the producer warp, if any, sits behind them)
     const int tile = blockIdx.x;
     const int b0 = tile * TS;
-    const int Hd = lo.Hd, C4 = lo.C4, NCH = lo.NCH, NCG = lo.NCG, NCP = lo.NCP, K = lo.K;
+    const int Hd = lo.Hd, NCH = lo.NCH, NCG = lo.NCG, NCP = lo.NCP, K = lo.K;
     const int KC = p.ring_kc, NSLOT = p.ring_slots, PW = p.ring_pw;
     const int npass = (NCG + NT - 1) / NT;        // column groups are walked NT at a time
     const int nchunks = (K + KC - 1) / KC;
@@ -358,10 +385,12 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
     int jout = 1;       // next requested output time
     int rslot = 0;      // ring slot / phase parity of the next fill to consume
     uint32_t rphase = 0;
+    CtlItems ci;
+    ctl_setup<TS>(lo, b0, tid, NT, ci);
     {
         CtlRegs r;
-        ctl_issue<TS>(p, sTimes, cnt, 0, 0, b0, tid, NT, r);
-        ctl_finish<TS>(p, r, sDU, p.save_act ? p.save_act + (int64_t)tile * lo.act_floats : nullptr, tid, NT);
+        ctl_issue<TS>(p, sTimes, cnt, 0, 0, ci, r);
+        ctl_finish<TS>(p, r, ci, sDU, p.save_act ? p.save_act + (int64_t)tile * lo.act_floats : nullptr);
     }
     cta_sync();
 
@@ -382,7 +411,7 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
             // (1) control of the NEXT stage: loads in flight while this stage's MLP runs
             CtlRegs ctl;
             const bool have_next = (n + 1 < lo.n_stages);
-            if (have_next) ctl_issue<TS>(p, sTimes, cnt, s == 3 ? k + 1 : k, s == 3 ? 0 : s + 1, b0, tid, NT, ctl);
+            if (have_next) ctl_issue<TS>(p, sTimes, cnt, s == 3 ? k + 1 : k, s == 3 ? 0 : s + 1, ci, ctl);
             PHASE_MARK(5);   // control issue
 
             // (2) hidden layers: warp-synchronous chain, one CTA barrier at the end
@@ -485,7 +514,7 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
                 }
             }
             PHASE_MARK(2);   // tanh, contraction, G store
-            if (have_next) ctl_finish<TS>(p, ctl, sDUnext, act_next, tid, NT);
+            if (have_next) ctl_finish<TS>(p, ctl, ci, sDUnext, act_next);
             cta_sync();
             PHASE_MARK(3);   // control finish + barrier
 
@@ -562,6 +591,11 @@ template <int TS>
 static int launch_fwd_ts(SolveArgs a, cudaStream_t stream)
 {
     const NcdeLayout& lo = a.lo;
+    if ((int64_t)lo.B * (lo.L - 1) * lo.C >= ((int64_t)1 << 31) - lo.C) {
+        set_error("ncde_forward: B * (L-1) * C = %lld does not fit the 32-bit coefficient offsets of the control lookup",
+                  (long long)lo.B * (lo.L - 1) * lo.C);
+        return ANCDE_EUNSUPPORTED;
+    }
     const int nt = fwd_threads(lo);
     if (nt > 480) {
         set_error("ncde_forward: C=%d with %d samples per CTA needs %d threads (max 480)", lo.C, lo.TS, nt);
