@@ -39,7 +39,11 @@ class DualNcdeTrainer:
         self.bucket = FlatGradBucket(self.model.parameters())
         fused = self.device.type == 'cuda'
         # capturable: the step counter lives on the device, so a whole step can be captured in a CUDA graph
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, weight_decay=1e-4, fused=fused, capturable=fused)
+        # Adam over the ONE flat parameter buffer (every parameter is a view of it, same lr / weight decay for all, like
+        # common.py:690,784): one elementwise kernel instead of a multi-tensor launch over ~40 small tensors
+        self.flat_parameter = torch.nn.Parameter(self.bucket.flat_param, requires_grad=True)
+        self.flat_parameter.grad = self.bucket.flat
+        self.opt = torch.optim.Adam([self.flat_parameter], lr=lr, weight_decay=1e-4, fused=fused, capturable=fused)
         self.reg_params = [p for p in self.func_g.parameters() if p.requires_grad]
         self.reg_scaling = 0.03
         self._reg = self.bucket.segments(self.reg_params) if self.reg_params else None

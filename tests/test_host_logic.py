@@ -125,3 +125,29 @@ def test_fused_weight_regularisation_matches_autograd():
             assert float(p.grad.abs().max()) == 0.0
     # the parameters are views of one buffer and still what the model computes with
     assert all(p.data_ptr() >= tr.bucket.flat_param.data_ptr() for p in tr.model.parameters())
+
+
+def test_flat_buffer_adam_equals_per_parameter_adam():
+    """The training step runs Adam over ONE flat parameter (every model parameter is a view of it); with one lr and one
+    weight decay for all parameters (common.py:690,784) that is the per-parameter update, bit for bit."""
+    import copy
+    from ancde_b200 import metamodel, synthetic
+    from ancde_b200.dp import FlatGradBucket
+    torch.manual_seed(0)
+    m1, _, _ = metamodel.model_from_config(synthetic.CONFIGS['mujoco'])
+    m2 = copy.deepcopy(m1)
+    o1 = torch.optim.Adam(m1.parameters(), lr=1e-3, weight_decay=1e-4)
+    b = FlatGradBucket(m2.parameters())
+    flat = torch.nn.Parameter(b.flat_param)
+    flat.grad = b.flat
+    o2 = torch.optim.Adam([flat], lr=1e-3, weight_decay=1e-4)
+    for it in range(3):
+        g = torch.Generator().manual_seed(it)
+        for p1, p2 in zip(m1.parameters(), m2.parameters()):
+            gr = torch.randn(p1.shape, generator=g)
+            p1.grad = gr.clone()
+            p2.grad.copy_(gr)
+        o1.step()
+        o2.step()
+    for p1, p2 in zip(m1.parameters(), m2.parameters()):
+        assert torch.equal(p1, p2)
