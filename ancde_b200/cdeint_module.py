@@ -110,10 +110,45 @@ def cdeint(dX_dt, z0, func, t, adjoint=True, **kwargs):
     the solver's O(h^4)), see DESIGN.md.
     """
     sp = _spline_of(dX_dt)
+    if kwargs.get('method', None) in (None, 'dopri5'):
+        # torchdiffeq's default solver (cdeint_module.py:146,149 forward **kwargs untouched): adaptive Dormand-Prince
+        return _cdeint_dopri5(sp, z0, func, t, adjoint, kwargs)
     step = _rk4_step(kwargs, None)
     plan = SolvePlan(_lib.MODE_PLAIN, sp._times, (sp._b, sp._two_c, sp._three_d), t, step)
     z_out, _ = solve(plan, func, z0)
     return z_out
+
+
+def _cdeint_dopri5(sp, z0, func, t, adjoint, kwargs):
+    """`cdeint(..., method='dopri5')`: host-driven adaptive steps, every field evaluation one fused kernel launch
+    (ancde_b200/dopri5.py).  rtol / atol default to torchdiffeq 0.0.1's (odeint: 1e-7 / 1e-9, odeint_adjoint: 1e-6 / 1e-12);
+    both `adjoint` settings differentiate through the solver's operations."""
+    from . import dopri5
+    from .solver import FieldPlan, field, mlp_params
+    kwargs = dict(kwargs)
+    kwargs.pop('method', None)
+    options = dict(kwargs.pop('options', None) or {})
+    rtol = kwargs.pop('rtol', 1e-6 if adjoint else 1e-7)
+    atol = kwargs.pop('atol', 1e-12 if adjoint else 1e-9)
+    if kwargs:
+        raise TypeError('unexpected solver arguments: %s' % sorted(kwargs))
+    allowed = {'first_step', 'safety', 'ifactor', 'dfactor', 'max_num_steps'}
+    if set(options) - allowed:
+        raise NotImplementedError('dopri5 options %s are not supported' % sorted(set(options) - allowed))
+    _, _, Hd, C = mlp_params(func)
+    if z0.dim() != 2 or z0.shape[-1] != Hd or C != sp._b.shape[-1]:
+        raise ValueError("func did not return a tensor with the same number of hidden / input channels as z0 / dX_dt. "
+                         "func has %d x %d channels, z0 has shape %s, dX_dt returned %d channels."
+                         % (Hd, C, tuple(z0.shape), sp._b.shape[-1]))
+    base = FieldPlan(sp._times, (sp._b, sp._two_c, sp._three_d), 0.0)
+    times = solver_times(t)
+    return dopri5.odeint(lambda tt, z: field(base.at(tt), func, z), z0.float(), times, rtol=rtol, atol=atol, **options)
+
+
+def solver_times(t):
+    """The requested times as python floats (one device read-back per distinct tensor, cached like the grid metadata)."""
+    from .solver import cached_host_scalar
+    return cached_host_scalar(t, 'times', lambda x: [float(v) for v in x.detach().to('cpu', torch.float64)])
 
 
 def ancde_bottom(dX_dt, z0, func, t, file, adjoint=True, **kwargs):

@@ -256,7 +256,10 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
             uint32_t* zb = reinterpret_cast<uint32_t*>(sBd);
             for (int i = tid; i < 2 * 8 * KP; i += NT) zb[i] = 0u;      // 4 matrices of 8*KP halfs
         }
-        for (int item = tid; item < Hd * TS; item += NT) { sLam[item] = 0.f; sMu[item] = 0.f; }
+        for (int item = tid; item < Hd * TS; item += NT) {
+            sLam[item] = 0.f; sMu[item] = 0.f;
+            sV4[item] = 0.f; sV3[item] = 0.f; sV2[item] = 0.f;       // read by stage 0 of the single-stage mode
+        }
         if (tid < 32) sMax[tid] = 0.f;
         if (tid < lo.n_hidden) {
             // the layer loop reads its parameters from shared memory: register-indexed loads from the kernel-parameter
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
         const float t1 = grid_time(k + 1, lo.n_steps, p.t_start, p.t_end, p.step);
         const float dt = __fsub_rn(t1, t0);
         // ---- cotangents of the outputs emitted during this step: t_out[j] in (t0, t1]
-        {
+        if (lo.n_stages > 1) {
             for (int item = tid; item < Hd * TS; item += NT) {
                 const int i = item / TS, b = item - i * TS;
                 const int bg = b0 + b;
@@ -330,6 +333,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
 #pragma unroll 1
         for (int s = 3; s >= 0; --s) {
             const int n = 4 * k + s;
+            if (n >= lo.n_stages) continue;          // single-stage mode: stage 0 only
             float* act = act_block(n);
             float* sAct = sActBuf + (size_t)abuf * lo.act_fwd_floats;
             PH2_T0();
@@ -342,6 +346,10 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                 else if (s == 2) gv = dt * (0.375f * lam + sV4[item]);
                 else if (s == 1) gv = dt * (0.375f * lam - sV4[item] + sV3[item]);
                 else gv = dt * (0.125f * lam + sV4[item] + (sV2[item] - sV3[item]) * (1.0f / 3.0f));
+                if (lo.n_stages == 1) {              // the cotangent of the one stage derivative comes from the caller
+                    const int i = item / TS, b = item - i * TS;
+                    gv = (b0 + b < lo.B) ? __ldg(p.grad_k_out + (int64_t)(b0 + b) * Hd + i) : 0.f;
+                }
                 sG[item] = gv;
                 act[lo.act_off_gbar + item] = gv;        // the stage cotangent goes to HBM for the weight-gradient kernels
                 lmax = fmaxf(lmax, fabsf(gv));
@@ -646,7 +654,8 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     for (int item = tid; item < Hd * TS; item += NT) {
         const int i = item / TS, b = item - i * TS;
         const int bg = b0 + b;
-        if (bg < lo.B) p.grad_z0[(int64_t)bg * Hd + i] = sLam[item] + __ldg(p.grad_z_out + (int64_t)bg * Hd + i);
+        if (bg < lo.B)
+            p.grad_z0[(int64_t)bg * Hd + i] = sLam[item] + (lo.n_stages > 1 ? __ldg(p.grad_z_out + (int64_t)bg * Hd + i) : 0.f);
     }
 }
 
@@ -807,7 +816,8 @@ extern "C" int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream_)
     int rc = make_layout(d, &lo);
     if (rc != ANCDE_OK) return rc;
     ANCDE_CHECK_ARG(d->save_act && d->save_G, "ncde_backward: needs the save_act / save_G buffers of the forward");
-    ANCDE_CHECK_ARG(d->grad_z_out && d->grad_z0, "ncde_backward: null grad_z_out / grad_z0");
+    ANCDE_CHECK_ARG((d->single_stage ? d->grad_k_out : d->grad_z_out) && d->grad_z0,
+                    "ncde_backward: null grad_z_out (grad_k_out in single-stage mode) / grad_z0");
     for (int l = 0; l <= d->n_hidden; ++l)
         ANCDE_CHECK_ARG(d->grad_W[l] && d->grad_bias[l], "ncde_backward: null gradient buffer for layer %d", l);
     SolveArgs a;

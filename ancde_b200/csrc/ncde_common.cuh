@@ -85,6 +85,7 @@ struct SolveArgs {
     float* save_G;
     // backward
     const float* grad_z_out;
+    const float* grad_k_out;   // single-stage mode: cotangent of the one stage derivative
     float* grad_z0;
     float* grad_attention;
     float* grad_hidden;     // packed like the hidden part of wpack (Wt layout), accumulated with atomics

@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
 #pragma unroll 1
         for (int s = 0; s < 4; ++s) {
             const int n = 4 * k + s;
+            if (n >= lo.n_stages) break;             // single-stage mode: the field at (t_start, z0) only
             float* act = p.save_act ? p.save_act + ((int64_t)n * lo.ntiles + tile) * lo.act_floats : nullptr;
             float* act_next = (p.save_act && n + 1 < lo.n_stages)
                                   ? p.save_act + ((int64_t)(n + 1) * lo.ntiles + tile) * lo.act_floats : nullptr;

@@ -124,7 +124,7 @@ static void fill_layout(const ancde_ncde_desc* d, int TS, NcdeLayout* lo)
     *lo = NcdeLayout();
     lo->B = d->B; lo->L = d->L; lo->C = d->C; lo->Hd = d->Hd; lo->n_hidden = d->n_hidden; lo->mode = d->mode;
     lo->att_C = d->att_C; lo->att_L = d->att_L; lo->n_hp = d->n_hp; lo->n_steps = d->n_steps; lo->n_out = d->n_out;
-    lo->n_stages = 4 * d->n_steps;
+    lo->n_stages = d->single_stage ? 1 : 4 * d->n_steps;      // single stage: the vector field at (t_start, z0) only
     lo->Hmax = d->Hd;
     for (int l = 0; l < d->n_hidden; ++l) {
         lo->width[l] = d->width[l];
@@ -204,6 +204,10 @@ int make_layout(const ancde_ncde_desc* d, NcdeLayout* lo)
         ANCDE_CHECK_ARG(d->att_L >= 1 && d->n_hp >= 2, "ncde: att_L=%d n_hp=%d", d->att_L, d->n_hp);
     }
     for (int l = 0; l < d->n_hidden; ++l) ANCDE_CHECK_ARG(d->width[l] >= 1, "ncde: width[%d]=%d", l, d->width[l]);
+    if (d->single_stage)
+        ANCDE_CHECK_ARG(d->n_steps == 1 && d->n_out == 1 && d->mode != ANCDE_MODE_TOP,
+                        "ncde: single_stage needs n_steps = n_out = 1 and a plain / bottom field (n_steps=%d n_out=%d mode=%d)",
+                        d->n_steps, d->n_out, d->mode);
     int TS = d->samples_per_cta;
     if (TS == 0 && engine_of(d) == ANCDE_ENGINE_UMMA) TS = 8;    // the UMMA forward saves in tiles of 8 samples
     if (TS == 0) {
@@ -252,6 +256,7 @@ int fill_args(const ancde_ncde_desc* d, const NcdeLayout& lo, SolveArgs* a)
     a->z0 = d->z0; a->attention = d->attention; a->h_prime = d->h_prime; a->wpack = d->wpack;
     a->z_out = d->z_out; a->k_out = d->k_out; a->save_act = d->save_act; a->save_G = d->save_G;
     a->grad_z_out = d->grad_z_out; a->grad_z0 = d->grad_z0; a->grad_attention = d->grad_attention;
+    a->grad_k_out = d->grad_k_out;
     a->dbg = debug_buffer();
     return ANCDE_OK;
 }
@@ -276,6 +281,7 @@ static bool umma_layouts(const ancde_ncde_desc* d, NcdeLayout* st, V3Layout* l3)
 int engine_of(const ancde_ncde_desc* d)
 {
     if (!d) return ANCDE_ENGINE_STREAMED;
+    if (d->single_stage) return (d->engine == 0 || d->engine == ANCDE_ENGINE_STREAMED) ? ANCDE_ENGINE_STREAMED : -1;
     if (d->engine == ANCDE_ENGINE_STREAMED || d->engine == ANCDE_ENGINE_CLUSTER) return d->engine;
     NcdeLayout st;
     V3Layout l3;

@@ -73,9 +73,40 @@ class SolvePlan:
         self.h_prime = None if h_prime is None else _f32(h_prime, dev)
         self.want_k = want_k
         self.att_grad = att_grad
+        self.single = False
         self.grid = fixed_grid_meta(t_out, step_size)
         if self.times.numel() != self.Lm1 + 1:
             raise ValueError('times has %d entries but the coefficients have %d pieces' % (self.times.numel(), self.Lm1))
+
+
+class FieldPlan(SolvePlan):
+    """Single-stage plan: the solver kernels evaluate only the vector field f(z) dX/dt(t) at one time (the C ABI's
+    `single_stage`), the building block of the host-driven adaptive solver (ancde_b200/dopri5.py)."""
+
+    def __init__(self, times, coeffs, t):
+        b, c2, d3 = coeffs
+        _lib.require_cuda(b, 'spline coefficients')
+        dev = b.device
+        self.mode = _lib.MODE_PLAIN
+        self.device = dev
+        self.B, self.Lm1, self.C = b.shape[0], b.shape[1], b.shape[2]
+        self.times = _f32(times, dev)
+        self.t_out = self.times[:1]          # one entry; never read in single-stage mode
+        self.b, self.c2, self.d3 = (_f32(x, dev) for x in (b, c2, d3))
+        self.h_prime = None
+        self.want_k = True
+        self.att_grad = False
+        self.single = True
+        self.grid = (float(t), float(t) + 1.0, 1.0, 1)
+        if self.times.numel() != self.Lm1 + 1:
+            raise ValueError('times has %d entries but the coefficients have %d pieces' % (self.times.numel(), self.Lm1))
+
+    def at(self, t):
+        """The same plan at another time (shares every tensor)."""
+        import copy
+        q = copy.copy(self)
+        q.grid = (float(t), float(t) + 1.0, 1.0, 1)
+        return q
 
 
 def _f32(x, dev):
@@ -168,6 +199,9 @@ def _desc(plan, z0, attention, wb, widths, Hd):
         d.h_prime = plan.h_prime.data_ptr()
     d.samples_per_cta = FORCE_SAMPLES_PER_CTA
     d.engine = ENGINE
+    if plan.single:
+        d.single_stage = 1
+        d.engine = 0
     return d
 
 
@@ -202,7 +236,8 @@ class _NcdeSolve(torch.autograd.Function):
         n_out = plan.t_out.numel()
         n_steps = plan.grid[3]
         z_out = torch.empty(n_out, plan.B, Hd, dtype=torch.float32, device=dev)
-        k_out = torch.empty(4 * n_steps if plan.want_k else 0, plan.B, Hd, dtype=torch.float32, device=dev)
+        k_rows = 1 if plan.single else (4 * n_steps if plan.want_k else 0)
+        k_out = torch.empty(k_rows, plan.B, Hd, dtype=torch.float32, device=dev)
         d.z_out = z_out.data_ptr()
         d.k_out = k_out.data_ptr() if plan.want_k else None
         wpack = torch.empty(_ws(L_.ancde_ncde_wpack_floats, d), dtype=torch.float32, device=dev)
@@ -224,7 +259,7 @@ class _NcdeSolve(torch.autograd.Function):
         ctx.plan, ctx.widths, ctx.Hd = plan, widths, Hd
         ctx.keep = (z0c, attc, wbc, wpack, save_act, save_G)
         ctx.params = wb
-        ctx.mark_non_differentiable(k_out)
+        ctx.mark_non_differentiable(z_out if plan.single else k_out)
         return z_out, k_out
 
     @staticmethod
@@ -235,7 +270,7 @@ class _NcdeSolve(torch.autograd.Function):
         dev = plan.device
         d = _desc(plan, z0c, attc, wbc, widths, Hd)
         d.wpack, d.save_act, d.save_G = wpack.data_ptr(), save_act.data_ptr(), save_G.data_ptr()
-        g = g_z_out.detach().float().contiguous()
+        g = (g_k_out if plan.single else g_z_out).detach().float().contiguous()
         grad_z0 = torch.empty_like(z0c)
         direct = _ACCUMULATE_INTO_PARAM_GRADS and all(
             isinstance(q, torch.nn.Parameter) and q.grad is not None and q.grad.dtype == torch.float32 and
@@ -249,7 +284,10 @@ class _NcdeSolve(torch.autograd.Function):
             for w in wbc:
                 grads.append(gflat[off:off + w.numel()].view_as(w))
                 off += w.numel()
-        d.grad_z_out, d.grad_z0 = g.data_ptr(), grad_z0.data_ptr()
+        if plan.single:
+            d.grad_k_out, d.grad_z0 = g.data_ptr(), grad_z0.data_ptr()
+        else:
+            d.grad_z_out, d.grad_z0 = g.data_ptr(), grad_z0.data_ptr()
         for i in range(len(widths) + 1):
             d.grad_W[i] = grads[2 * i].data_ptr()
             d.grad_bias[i] = grads[2 * i + 1].data_ptr()
@@ -272,6 +310,17 @@ class _NcdeSolve(torch.autograd.Function):
         if direct:
             return (None, None, grad_z0, grad_att) + (None,) * len(grads)
         return (None, None, grad_z0, grad_att) + tuple(grads)
+
+
+def field(plan, func, z):
+    """f(z) dX/dt at the time of a FieldPlan: (B, Hd), differentiable in z and the weights of `func`."""
+    wb, widths, Hd, C = mlp_params(func)
+    if C != plan.C or z.shape[-1] != Hd or z.dim() != 2 or z.shape[0] != plan.B:
+        raise ValueError('field: z has shape %s, expected (%d, %d) for a control with %d channels (func has %d)'
+                         % (tuple(z.shape), plan.B, Hd, plan.C, C))
+    plan.grad_mode = torch.is_grad_enabled()
+    _, k_out = _NcdeSolve.apply(plan, widths, z, z.new_zeros(()), *wb)
+    return k_out[0]
 
 
 def solve(plan, func, z0, attention=None):

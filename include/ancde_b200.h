@@ -127,6 +127,10 @@ typedef struct ancde_ncde_desc {
     float* grad_attention;     /* TOP, or NULL (adjoint-mode gradient flow): (att_L, B, att_C) accumulated into */
     int32_t samples_per_cta;   /* streamed engine only: 0 = let the library choose (8, 4, 2 or 1) */
     int32_t engine;            /* 0 = library default; ANCDE_ENGINE_STREAMED, _CLUSTER or _UMMA (see above) */
+    int32_t single_stage;      /* 1 = evaluate only the vector field at (t_start, z0): k_out (1, B, Hd) = f(z0) dX/dt(t_start), the
+                                * building block of adaptive solvers driven from the host (dopri5).  n_steps = n_out = 1; streamed
+                                * engine.  Backward: grad_k_out (B, Hd) is the cotangent of k_out, grad_z_out is not read. */
+    const float* grad_k_out;   /* single_stage backward only */
     int32_t async_wgrad;       /* backward only: 1 = launch the weight-gradient kernels on the library's side stream (they only
                                 * depend on the recurrent kernel of the same call) so that they overlap whatever the caller
                                 * enqueues next; the caller must call ancde_ncde_join() on its stream before it reads the

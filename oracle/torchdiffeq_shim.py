@@ -200,7 +200,11 @@ def _rms(x):
 
 class _Dopri5:
     def __init__(self, func, y0, rtol, atol, first_step=None, safety=0.9, ifactor=10.0, dfactor=0.2,
-                 max_num_steps=2 ** 31 - 1, **unused):
+                 max_num_steps=2 ** 31 - 1, detach_controller=False, **unused):
+        # detach_controller (NOT a torchdiffeq option; test infrastructure): the step sizes carry no autograd history,
+        # i.e. the gradient is that of the accepted steps' arithmetic alone.  torchdiffeq 0.0.1 itself differentiates
+        # through its controller (powers of a vanishing error ratio -- ill conditioned); the fused GPU path does not.
+        self.detach_controller = detach_controller
         self.func, self.y0 = func, y0
         self.rtol = rtol if isinstance(rtol, (tuple, list)) else [rtol] * len(y0)
         self.atol = atol if isinstance(atol, (tuple, list)) else [atol] * len(y0)
@@ -242,6 +246,8 @@ class _Dopri5:
         tol = tuple(a + r * torch.max(torch.abs(u), torch.abs(v))
                     for a, r, u, v in zip(self.atol, self.rtol, y0, y1))
         ratio = tuple(torch.mean((e / tl) ** 2) for e, tl in zip(err, tol))
+        if self.detach_controller:
+            ratio = tuple(r.detach() for r in ratio)
         accept = all(bool(r <= 1) for r in ratio)
         if accept:
             dt_ = dt.type_as(y0[0])
@@ -282,7 +288,11 @@ class _Dopri5:
         t = t.to(torch.float64)
         f0 = self.func(t[0].type_as(self.y0[0]), self.y0)
         if self.first_step is None:
-            first = self._initial_step(t[0], f0).to(t)
+            if self.detach_controller:
+                with torch.no_grad():
+                    first = self._initial_step(t[0], f0).to(t)
+            else:
+                first = self._initial_step(t[0], f0).to(t)
         else:
             first = torch.as_tensor(self.first_step, dtype=t.dtype)
         state = (self.y0, f0, t[0], t[0], first, [self.y0] * 5)

@@ -194,7 +194,7 @@ def test_api_errors():
     with pytest.raises(NotImplementedError):
         ancde_b200.cdeint(lambda t: None, z0, func, times, method='rk4', options=dict(step_size=1.0))
     with pytest.raises(NotImplementedError):
-        ancde_b200.cdeint(sp.derivative, z0, func, times, method='dopri5')
+        ancde_b200.cdeint(sp.derivative, z0, func, times, method='midpoint')
     with pytest.raises(ValueError):
         ancde_b200.cdeint(sp.derivative, z0, lambda z: z, times, method='rk4', options=dict(step_size=1.0))
     with pytest.raises(ValueError):
@@ -292,3 +292,106 @@ def test_training_step_accumulates_weight_gradients_in_place(workload):
         flats.append(tr.bucket.flat.clone())
     assert flats[0].abs().max().item() > 0
     assert rel_err(flats[1], flats[0]) < 1e-5
+
+
+def _oracle_field(sd, times, coeffs, H, C):
+    """The plain CDE vector field of the oracle as a module whose parameters are the tensors of `sd`."""
+    from oracle import port
+
+    class Field(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.names = list(sd)
+            self.params = torch.nn.ParameterList([torch.nn.Parameter(sd[k].detach().clone()) for k in self.names])
+
+        def grads(self):
+            return {k: p.grad for k, p in zip(self.names, self.params)}
+
+        def forward(self, t, z):
+            cur = dict(zip(self.names, self.params))
+            dX = port.spline_derivative(times, coeffs, t.to(times.dtype))
+            return (port.field_g(cur, z, H, C, 'func') @ dX.unsqueeze(-1)).squeeze(-1)
+    return Field()
+
+
+def test_single_stage_field_and_its_gradients_against_oracle():
+    """The kernels' single-stage mode (C ABI `single_stage`): f(z) dX/dt at one time, with gradients."""
+    import ancde_b200
+    from ancde_b200 import solver
+    from oracle import port
+    torch.manual_seed(11)
+    C, H, HH, nl, L, B = 5, 7, 9, 2, 9, 13
+    func = ancde_b200.FinalTanh(C, H, HH, nl)
+    times = torch.linspace(0.0, 4.0, L)
+    coeffs = port.natural_cubic_spline_coeffs(times, 0.3 * torch.randn(B, L, C).cumsum(1))
+    z = torch.randn(B, H)
+    sd = {'func.' + k: v.detach().clone() for k, v in func.state_dict().items()}
+    zr = z.clone().requires_grad_(True)
+    w = loss_weights((B, H))
+    func = func.cuda()
+    cg = tuple(c.cuda() for c in coeffs)
+    for t in (0.0, 1.3, 2.5, 4.0):
+        zr.grad = None
+        oracle = _oracle_field(sd, times, coeffs, H, C)
+        ref = oracle(torch.tensor(t), zr)
+        (ref * w).sum().backward()
+        func.zero_grad()
+        zg = z.cuda().requires_grad_(True)
+        got = solver.field(solver.FieldPlan(times.cuda(), cg[1:], t), func, zg)
+        (got * w.cuda()).sum().backward()
+        assert got.shape == (B, H)
+        assert rel_err(got, ref) < FWD_TOL, t
+        assert rel_err(zg.grad, zr.grad) < GRAD_TOL, t
+        for k, p in func.named_parameters():
+            assert rel_err(p.grad, oracle.grads()['func.' + k]) < GRAD_TOL, (t, k)
+
+
+@pytest.mark.parametrize('adjoint', [False, True])
+def test_cdeint_dopri5_against_the_torchdiffeq_restatement(adjoint):
+    """method='dopri5' (torchdiffeq's default): adaptive steps on the host around the fused field kernel, against the
+    oracle's restatement of torchdiffeq 0.0.1 on the CPU.  Parity to the solver tolerance, not bitwise."""
+    import ancde_b200
+    from oracle import port, torchdiffeq_shim
+    torch.manual_seed(4)
+    C, H, HH, nl, L, B = 4, 6, 8, 2, 7, 10
+    func = ancde_b200.FinalTanh(C, H, HH, nl)
+    times = torch.linspace(0.0, 3.0, L)
+    coeffs = port.natural_cubic_spline_coeffs(times, 0.4 * torch.randn(B, L, C).cumsum(1))
+    z0 = torch.randn(B, H)
+    t = torch.tensor([0.0, 0.4, 1.7, 3.0])
+    rtol, atol = (1e-6, 1e-12) if adjoint else (1e-7, 1e-9)
+    sd = {'func.' + k: v.detach().clone() for k, v in func.state_dict().items()}
+    oracle = _oracle_field(sd, times, coeffs, H, C)
+    with torch.no_grad():
+        ref = torchdiffeq_shim.odeint(oracle, z0, t, rtol=rtol, atol=atol, method='dopri5')
+    # Gradients: torchdiffeq's adjoint=False route also differentiates through its step-size controller (powers of a
+    # vanishing error ratio: ill conditioned, 1e7-size garbage on this case); the fused path treats the accepted step
+    # sizes as constants.  The gradients are pinned against the restatement with the controller detached from autograd
+    # (same steps, same arithmetic), and -- loosely -- against its continuous adjoint.
+    z0r = z0.clone().requires_grad_(True)
+    w = loss_weights(ref.shape)
+    ref_d = torchdiffeq_shim.odeint(oracle, z0r, t, rtol=rtol, atol=atol, method='dopri5',
+                                    options=dict(detach_controller=True))
+    assert torch.equal(ref_d.detach(), ref)
+    (ref_d * w).sum().backward()
+    z0a = z0.clone().requires_grad_(True)
+    oracle_a = _oracle_field(sd, times, coeffs, H, C)
+    ref_a = torchdiffeq_shim.odeint_adjoint(oracle_a, z0a, t, rtol=1e-7, atol=1e-9, method='dopri5')
+    (ref_a * w).sum().backward()
+    assert rel_err(z0r.grad, z0a.grad) < 1e-2            # discrete vs continuous adjoint of the same solve
+    func = func.cuda()
+    sp = ancde_b200.NaturalCubicSpline(times.cuda(), tuple(c.cuda() for c in coeffs))
+    z0g = z0.cuda().requires_grad_(True)
+    got = ancde_b200.cdeint(sp.derivative, z0g, func, t.cuda(), adjoint=adjoint)       # no method: dopri5
+    (got * w.cuda()).sum().backward()
+    assert got.shape == ref.shape
+    assert torch.equal(got[0].cpu(), z0)
+    assert rel_err(got, ref) < FWD_TOL
+    # Gradient bar 1e-2: differentiating the accepted steps of an adaptive solve is itself only that accurate on this
+    # piecewise-linear (ReLU) field -- measured on the CPU: the float64 restatement at rtol 1e-7 is 2.4e-3 away from its
+    # own rtol 1e-10 gradient, the float32 one 3.4e-3, while the forward values agree to 1e-6.
+    DOPRI_GRAD_TOL = 1e-2
+    assert rel_err(z0g.grad, z0r.grad) < DOPRI_GRAD_TOL
+    assert rel_err(z0g.grad, z0a.grad) < DOPRI_GRAD_TOL
+    for k, p in func.named_parameters():
+        assert rel_err(p.grad, oracle.grads()['func.' + k]) < DOPRI_GRAD_TOL, k

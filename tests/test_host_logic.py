@@ -51,9 +51,13 @@ def test_entry_points_reject_opaque_callables_and_other_solvers():
     with pytest.raises(NotImplementedError):
         ancde_b200.cdeint(sp.evaluate, z0, func, times, method='rk4', options=dict(step_size=1.0))
     with pytest.raises(NotImplementedError):
+        ancde_b200.cdeint(sp.derivative, z0, func, times, method='euler')
+    with pytest.raises(RuntimeError, match='no CPU path'):      # dopri5 (torchdiffeq's default) exists, but only on the GPU
         ancde_b200.cdeint(sp.derivative, z0, func, times, method='dopri5')
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        ancde_b200.cdeint(sp.derivative, z0, func, times)
     with pytest.raises(NotImplementedError):
-        ancde_b200.cdeint(sp.derivative, z0, func, times)     # torchdiffeq's default is dopri5
+        ancde_b200.cdeint(sp.derivative, z0, func, times, method='dopri5', options=dict(grid_constructor=None))
     with pytest.raises(ValueError):                            # adjoint + control that requires grad (cdeint_module.py:218-220)
         c2 = tuple(c.clone().requires_grad_(True) for c in coeffs)
         ancde_b200.ancde_bottom(ancde_b200.NaturalCubicSpline(times, c2).derivative, torch.randn(2, 3),
