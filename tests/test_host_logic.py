@@ -155,3 +155,43 @@ def test_flat_buffer_adam_equals_per_parameter_adam():
         o2.step()
     for p1, p2 in zip(m1.parameters(), m2.parameters()):
         assert torch.equal(p1, p2)
+
+
+def test_dopri5_driver_matches_the_torchdiffeq_restatement_on_cpu():
+    """ancde_b200/dopri5.py is host logic around a field callable: with the same (CPU) field it must walk the same steps as
+    the oracle's restatement of torchdiffeq 0.0.1 -- values, dense output, and the gradient of the accepted steps."""
+    from ancde_b200 import dopri5
+    from oracle import torchdiffeq_shim
+    torch.manual_seed(1)
+    A = torch.randn(5, 5) * 0.7
+    w = torch.randn(5)
+
+    class Field(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.A = torch.nn.Parameter(A.clone())
+
+        def forward(self, t, y):
+            tt = t if torch.is_tensor(t) else torch.tensor(t)
+            return torch.tanh(y @ self.A.t()) * torch.cos(tt.to(y.dtype)) + 0.1 * w
+
+    t = torch.tensor([0.0, 0.3, 1.1, 2.5, 4.0])
+    # (rtol, atol, bar on the values, bar on the gradients): at the loose setting round-off flips accept / reject
+    # decisions, so the two walks agree to the solver tolerance only
+    for rtol, atol, vtol, gtol in ((1e-7, 1e-9, 2e-5, 1e-3), (1e-4, 1e-6, 5e-3, 5e-2)):
+        f_ref, f_got = Field(), Field()
+        y0r = torch.randn(3, 5, generator=torch.Generator().manual_seed(2)).requires_grad_(True)
+        y0g = y0r.detach().clone().requires_grad_(True)
+        ref = torchdiffeq_shim.odeint(f_ref, y0r, t, rtol=rtol, atol=atol, method='dopri5',
+                                      options=dict(detach_controller=True))
+        got = dopri5.odeint(f_got, y0g, t.tolist(), rtol=rtol, atol=atol)
+        assert got.shape == ref.shape
+        assert (got - ref).abs().max().item() < vtol          # tight: float32 round-off of a different (Horner) evaluation order
+        ref.square().sum().backward()
+        got.square().sum().backward()
+        assert (y0g.grad - y0r.grad).abs().max().item() < gtol * y0r.grad.abs().max().item()
+        assert (f_got.A.grad - f_ref.A.grad).abs().max().item() < gtol * f_ref.A.grad.abs().max().item()
+    with pytest.raises(NotImplementedError):
+        dopri5.odeint(Field(), torch.zeros(1, 5), [1.0, 0.0])
+    with pytest.raises(AssertionError):
+        dopri5.odeint(Field(), torch.zeros(1, 5), [0.0, 1.0, 0.5])
