@@ -2,6 +2,7 @@
 #include <stdlib.h>
 
 #include "ncde_common.cuh"
+#include "pipeline.cuh"
 
 namespace ancde {
 
@@ -177,6 +178,17 @@ __global__ void __launch_bounds__(256, (NT8 <= 8) ? 4 : 2) ncde_hidden_wgrad_mma
     const int blk_floats = szD + szI;
     const int stage_floats = HW_BPC * blk_floats;
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+    // TS = 8: a block's delta_l and in_l are two contiguous, 16-byte aligned runs of the saved activations -- one thread
+    // stages a chunk with 2 TMA bulk copies per block on an mbarrier per pipeline stage instead of ~200 cp.async spread
+    // over the CTA (the staging loop was a fifth of this kernel's instructions)
+    constexpr bool BULK = (TS == 8);
+    __shared__ __align__(8) uint64_t bar_full[2];
+    if (BULK && tid == 0) {
+        mbar_init(bar_full + 0, 1);
+        mbar_init(bar_full + 1, 1);
+        mbar_fence_init();
+    }
+    if (BULK) __syncthreads();
 
     const int64_t nblocks = (int64_t)lo.n_stages * lo.ntiles;
     const int64_t nchunks = (nblocks + HW_BPC - 1) / HW_BPC;
@@ -185,6 +197,20 @@ __global__ void __launch_bounds__(256, (NT8 <= 8) ? 4 : 2) ncde_hidden_wgrad_mma
     if (c1 > nchunks) c1 = nchunks;
 
     auto issue = [&](int64_t ch, int s) {
+        if (BULK) {
+            if (tid == 0) {
+                int nb = 0;
+                for (int bl = 0; bl < HW_BPC; ++bl) nb += (ch * HW_BPC + bl < nblocks) ? 1 : 0;
+                mbar_arrive_expect_tx(bar_full + s, (uint32_t)(nb * (N + Kin) * TS * 4));
+                for (int bl = 0; bl < nb; ++bl) {
+                    const float* act = p.save_act + (ch * HW_BPC + bl) * lo.act_floats;
+                    float* dD = smem + s * stage_floats + bl * blk_floats;
+                    bulk_g2s(dD, act + off_delta, (uint32_t)(N * TS * 4), bar_full + s);
+                    bulk_g2s(dD + szD, act + off_in, (uint32_t)(Kin * TS * 4), bar_full + s);
+                }
+            }
+            return;
+        }
         for (int bl = 0; bl < HW_BPC; ++bl) {
             const int64_t blk = ch * HW_BPC + bl;
             const bool ok = blk < nblocks;
@@ -226,11 +252,16 @@ __global__ void __launch_bounds__(256, (NT8 <= 8) ? 4 : 2) ncde_hidden_wgrad_mma
     cp_async_commit();
     for (int64_t ch = c0; ch < c1; ++ch) {
         const int s = (int)((ch - c0) & 1);
-        cp_async_wait<1>();
-        __syncthreads();
+        if (BULK) {
+            mbar_wait(bar_full + s, (uint32_t)(((ch - c0) >> 1) & 1));
+        } else {
+            cp_async_wait<1>();
+            __syncthreads();
+        }
         if (active) {
 #pragma unroll 1
             for (int bl = grp; bl < HW_BPC; bl += 2) {
+                if (BULK && ch * HW_BPC + bl >= nblocks) break;      // past the last block: nothing was copied
                 const float* sD = smem + s * stage_floats + bl * blk_floats;
                 const float* sI = sD + szD;
                 const float d0 = (a_row0 && s_lo) ? sD[o0 * TS + t] : 0.f;
