@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* bar_empty = bar_full + 8;
-    float* smem = reinterpret_cast<float*>(smem_raw + 128);
+    uint64_t* bar_act = bar_full + 16;                   // [2] saved activations of a stage have landed (TMA bulk copy)
+    float* smem = reinterpret_cast<float*>(smem_raw + 160);
     const uint4* sWhb = reinterpret_cast<const uint4*>(smem);   // !CHAIN: hidden layers, W_l^T as FP16 hi/lo A fragments
     const float* sWtb = smem;                            // CHAIN: transposed weights Wt_l[k][o] (FP32)
     float* sp = smem + (CHAIN ? (size_t)pad4(lo.hiddenb_floats) : (size_t)lo.hb_u4 * 4);
@@ -211,6 +212,8 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
             mbar_init(bar_full + s, 1);
             mbar_init(bar_empty + s, CT);                // one arrive per warp of the group that owns the slot's chunk
         }
+        mbar_init(bar_act + 0, 1);
+        mbar_init(bar_act + 1, 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -237,11 +240,16 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     }
     auto cta_sync = [&]() { named_bar_sync(1, NT); };
     auto act_block = [&](int n) { return p.save_act + ((int64_t)n * lo.ntiles + tile) * lo.act_floats; };
-    auto issue_act = [&](int n, float* dst) {
-        const float* src = act_block(n);
-        for (int i = tid; i < lo.act_fwd_floats / 4; i += NT) cp_async16_b(dst + i * 4, src + i * 4);
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    // The block of saved activations of a stage is one contiguous, 16-byte aligned run: ONE thread stages it with a TMA
+    // bulk copy on the buffer's mbarrier (was: ~800 cp.async spread over the CTA plus a wait_group per stage).
+    auto issue_act = [&](int n, int buf) {
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(lo.act_fwd_floats * 4);
+            mbar_arrive_expect_tx(bar_act + buf, bytes);
+            bulk_g2s(sActBuf + (size_t)buf * lo.act_fwd_floats, act_block(n), bytes, bar_act + buf);
+        }
     };
+    uint32_t act_parity = 0u;                            // bit b: parity of the next completion of bar_act[b]
 
     {
         if constexpr (CHAIN) {
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
             if (2 * ip + 1 < Hd) flags |= 16;
             sTile[tl] = make_int4(2 * ip * C4 + 8 * jc, 2 * ip * TS, 2 * jc * DUS, flags);
         }
-        issue_act(lo.n_stages - 1, sActBuf);
+        issue_act(lo.n_stages - 1, 0);
     }
     cta_sync();
 
@@ -361,10 +369,11 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
                 float2* z = reinterpret_cast<float2*>(sAttW + (size_t)warp * NJC * 64) + lane;
                 for (int jc = 0; jc < NJC; ++jc) z[jc * 32] = make_float2(0.f, 0.f);
             }
-            asm volatile("cp.async.wait_group 0;\n" ::: "memory");     // saved activations of this stage have landed
+            mbar_wait(bar_act + abuf, (act_parity >> abuf) & 1u);      // saved activations of this stage have landed
+            act_parity ^= 1u << abuf;
             cta_sync();
             // prefetch the next stage's activations (this kernel walks n downwards)
-            if (n >= 1) issue_act(n - 1, sActBuf + (size_t)(abuf ^ 1) * lo.act_fwd_floats);
+            if (n >= 1) issue_act(n - 1, abuf ^ 1);
             // power-of-two scale that brings the largest cotangent of this tile and stage to ~2^6
             float scale = 1.0f;
             {
@@ -688,7 +697,7 @@ static size_t bwd_smem_bytes(const NcdeLayout& lo, int ct, int slots, bool att)
     f += 2 * (size_t)lo.act_fwd_floats + 7 * (size_t)pad4(lo.Hd * lo.TS) +
          (chain ? 2 * (size_t)lo.TS * pad4(lo.Hmax) : (size_t)(4 * 8 * (16 * lo.KSB + 8)) / 2);
     f += (size_t)nw * lo.MTK * 128 + (att ? (size_t)nw * lo.NJC * 64 : 0) + 32 + 8 * ANCDE_MAX_LAYERS + (size_t)lo.C4 * lo.TS + 4 * (size_t)lo.n_wtiles;
-    return f * 4 + 128;
+    return f * 4 + 160;
 }
 
 // Used by make_layout's tile-size choice: does the backward fit with this many samples per CTA?
