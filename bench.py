@@ -356,12 +356,8 @@ def run_ours(args):
     # ---- per-kernel roofline from the CUDA-event timings taken inside the timed region
     flops = kernel_flops(cfg, B)
     # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of one `ncu --set full` capture of this
-    # workload at this batch (profiles/r01e_ncu_set_full.txt); a measured constant, only valid for the captured shape
-    NCU_TRAFFIC = {('sepsis', 1024): {'ncde_bwd_top': 2.450176e9 + 0.280280e9, 'ncde_fwd_top': 0.094125e9 + 2.386195e9,
-                                      'ncde_bwd_bottom': 1.684512e9 + 0.154728e9, 'ncde_fwd_bottom': 0.041401e9 + 1.659457e9,
-                                      'ncde_wgrad_top': 2.271036e9 + 0.004141e9, 'ncde_wgrad_bottom': 1.583449e9 + 0.003670e9,
-                                      'ncde_hidden_wgrad_top': 0.459705e9 + 0.004302e9,
-                                      'ncde_hidden_wgrad_bottom': 0.254237e9 + 0.003826e9}}
+    # workload at this batch (profiles/r01f_ncu_set_full.txt); a measured constant, only valid for the captured shape
+    NCU_TRAFFIC = {('sepsis', 1024): {'ncde_fwd_bottom': 0.041357e9 + 1.659941e9, 'ncde_fwd_top': 0.094120e9 + 2.386643e9, 'ncde_bwd_top': 2.450084e9 + 0.280650e9, 'ncde_wgrad_top': 2.275437e9 + 0.005132e9, 'ncde_hidden_wgrad_top': 0.459675e9 + 0.003783e9, 'ncde_bwd_bottom': 1.684613e9 + 0.155929e9, 'ncde_wgrad_bottom': 1.583921e9 + 0.004289e9, 'ncde_hidden_wgrad_bottom': 0.254225e9 + 0.003811e9}}
     traffic = NCU_TRAFFIC.get((args.workload, B), {})
     agg = {}
     for name, t in prof:
@@ -389,7 +385,7 @@ def run_ours(args):
                     'peak_source': 'FFMA microbenchmark (ancde_fp32_peak_kernel) measured in this run; '
                                    'MEASURED_PEAKS.json holds no FP32 figure',
                     'traffic': traffic.get(dom['name']),
-                    'traffic_source': 'profiles/r01e_ncu_set_full.txt (bytes per launch)' if dom['name'] in traffic else None,
+                    'traffic_source': 'profiles/r01f_ncu_set_full.txt (bytes per launch)' if dom['name'] in traffic else None,
                     'step_frac': round(total_flops * args.steps / (ms * 1e-3) / 1e12 / fp32_peak, 4),
                     'step_algorithmic_gflop': round(total_flops / 1e9, 2)}
 
