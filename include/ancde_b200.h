@@ -28,7 +28,8 @@ extern "C" {
 
 #define ANCDE_MAX_LAYERS 8      /* hidden (ReLU) layers in a vector-field MLP */
 
-/* ABI version; bumped when a struct below changes. */
+/* ABI version; bumped when a struct below changes.  5: ancde_ncde_desc gained single_stage, grad_k_out (ABI 5) and
+ * async_wgrad (ABI 4, with ancde_ncde_join). */
 int ancde_abi_version(void);
 
 /* Copies the calling thread's last error message into buf (NUL terminated). Returns its length. */
