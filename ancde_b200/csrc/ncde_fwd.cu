@@ -634,7 +634,8 @@ static int launch_fwd_ts(SolveArgs a, cudaStream_t stream)
     }
     static const char* names[3] = {"ncde_fwd_plain", "ncde_fwd_bottom", "ncde_fwd_top"};
     bool chain = true;
-    for (int l = 0; l < lo.n_hidden; ++l) chain = chain && lo.width[l] <= 32;
+    // one or two samples per CTA (small batches): the chain's single warp beats a CTA barrier per layer up to 64 units
+    for (int l = 0; l < lo.n_hidden; ++l) chain = chain && lo.width[l] <= (TS <= 2 ? 64 : 32);
     void (*kern)(SolveArgs) = wo_smem ? (chain ? ncde_fwd_kernel<TS, true, true> : ncde_fwd_kernel<TS, true, false>)
                                       : (chain ? ncde_fwd_kernel<TS, false, true> : ncde_fwd_kernel<TS, false, false>);
     ANCDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
