@@ -12,8 +12,8 @@ LIB_PATH = os.environ.get('ANCDE_LIB') or os.path.join(_HERE, 'libancde_b200.so'
 
 MAX_LAYERS = 8
 MODE_PLAIN, MODE_BOTTOM, MODE_TOP = 0, 1, 2
-ENGINE_STREAMED, ENGINE_CLUSTER, ENGINE_UMMA = 1, 2, 3
-ABI_VERSION = 5
+ENGINE_STREAMED, ENGINE_UMMA = 1, 3
+ABI_VERSION = 6
 
 _f32p = ctypes.POINTER(ctypes.c_float)
 
@@ -37,7 +37,7 @@ class NcdeDesc(ctypes.Structure):
         ('grad_W', ctypes.c_void_p * (MAX_LAYERS + 1)), ('grad_bias', ctypes.c_void_p * (MAX_LAYERS + 1)),
         ('grad_attention', ctypes.c_void_p),
         ('samples_per_cta', ctypes.c_int32), ('engine', ctypes.c_int32), ('single_stage', ctypes.c_int32),
-        ('grad_k_out', ctypes.c_void_p), ('async_wgrad', ctypes.c_int32),
+        ('grad_k_out', ctypes.c_void_p), ('async_wgrad', ctypes.c_int32), ('grid', ctypes.c_void_p),
     ]
 
 

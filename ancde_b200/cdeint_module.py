@@ -12,22 +12,27 @@ python, so the opaque callables of the reference API are recognised structurally
 
 Anything else raises NotImplementedError -- there is no eager fallback.
 """
+import os
+import weakref
+
 import numpy as np
 import torch
 
 from . import _lib
 from .solver import SolvePlan, solve
 
-# h' of the latest bottom solve, keyed by the `file` argument.  The reference round-trips h'
-# through that .npy file on disk (cdeint_module.py:69-70, metamodel.py:326); here it stays in HBM.
-_H_PRIME = {}
+# The reference round-trips h' through a .npy file on disk (cdeint_module.py:69-70, metamodel.py:326); here it stays in
+# HBM and belongs to the forward pass that made it: `ancde_bottom` hangs it on its result and on the spline object.  This
+# table only maps the `file` argument to that tensor WEAKLY (nothing is kept alive, entries vanish with the tensors).
+_H_PRIME = weakref.WeakValueDictionary()
 
 
 def load_h_prime(file):
-    """Device tensor (4*steps, B, C) written by the latest `ancde_bottom(..., file=file)`."""
-    if file not in _H_PRIME:
-        raise FileNotFoundError("no bottom solve has produced h' for %r yet" % (file,))
-    return _H_PRIME[file]
+    """Device tensor (4*steps, B, C) of the latest `ancde_bottom(..., file=file)` whose result is still alive."""
+    hp = _H_PRIME.get(file)
+    if hp is None:
+        raise FileNotFoundError("no live bottom solve has produced h' for %r" % (file,))
+    return hp
 
 
 def _spline_of(dX_dt):
@@ -43,7 +48,9 @@ def _spline_of(dX_dt):
 
 
 def _rk4_step(kwargs, default_step):
-    """Resolves (method, step_size) the way the reference entry points do."""
+    """Resolves the solver arguments the way the reference entry points and torchdiffeq's FixedGridODESolver do.
+    Returns (step_size or None, grid_constructor or None): a step size makes the arithmetic grid t[0] + k * step, a
+    grid constructor is called as constructor(func, y0, t), and neither means the grid is `t` itself."""
     kwargs = dict(kwargs)
     method = kwargs.pop('method', None)
     options = dict(kwargs.pop('options', None) or {})
@@ -57,12 +64,21 @@ def _rk4_step(kwargs, default_step):
     if method != 'rk4':
         raise NotImplementedError("method=%r: the fused B200 solver implements the fixed-grid 'rk4' (3/8 rule) "
                                   "path the ANCDE experiments use" % (method,))
-    if 'grid_constructor' in options:
-        raise NotImplementedError("options['grid_constructor'] is not supported; pass options['step_size']")
-    step = options.get('step_size', default_step)
+    constructor = options.get('grid_constructor', None)
+    step = options.get('step_size', default_step if constructor is None else None)
+    if step is not None and constructor is not None:
+        step = None                     # torchdiffeq: an explicit grid constructor wins over step_size
+    return (None if step is None else float(step)), constructor
+
+
+def _plan(mode, sp, t, func, z0, step, constructor, **kw):
+    """SolvePlan on the arithmetic grid (step), on constructor(func, z0, t), or on `t` itself."""
+    grid = None
     if step is None:
-        raise NotImplementedError("rk4 needs options['step_size'] (a grid equal to `t` is not implemented)")
-    return float(step)
+        grid = t if constructor is None else constructor(func, z0, t)
+        if not torch.is_tensor(grid):
+            grid = torch.as_tensor(grid, dtype=torch.float32)
+    return SolvePlan(mode, sp._times, (sp._b, sp._two_c, sp._three_d), t, step, grid=grid, **kw)
 
 
 class VectorField(torch.nn.Module):
@@ -113,8 +129,8 @@ def cdeint(dX_dt, z0, func, t, adjoint=True, **kwargs):
     if kwargs.get('method', None) in (None, 'dopri5'):
         # torchdiffeq's default solver (cdeint_module.py:146,149 forward **kwargs untouched): adaptive Dormand-Prince
         return _cdeint_dopri5(sp, z0, func, t, adjoint, kwargs)
-    step = _rk4_step(kwargs, None)
-    plan = SolvePlan(_lib.MODE_PLAIN, sp._times, (sp._b, sp._two_c, sp._three_d), t, step)
+    step, constructor = _rk4_step(kwargs, None)
+    plan = _plan(_lib.MODE_PLAIN, sp, t, func, z0, step, constructor)
     z_out, _ = solve(plan, func, z0)
     return z_out
 
@@ -152,47 +168,56 @@ def solver_times(t):
 
 
 def ancde_bottom(dX_dt, z0, func, t, file, adjoint=True, **kwargs):
-    """Bottom (attention) NCDE over all of `t`; returns (len(t), batch, C) and keeps h' for `file`.
+    """Bottom (attention) NCDE over all of `t`; returns (len(t), batch, C).
 
-    Reference: cdeint_module.py:168-243.
+    Reference: cdeint_module.py:168-243.  h' (every stage derivative in call order, what the reference np.save()s to
+    `file`, :63-70) stays in HBM: it is attached to the returned tensor (`.h_prime`) and to the spline object of this
+    forward pass, and `load_h_prime(file)` finds it while either is alive.  With the environment variable
+    ANCDE_WRITE_H_PRIME=1 the `.npy` file is written as well (a device -> host copy per call), so that the unmodified
+    reference models (`np.load(self.file)`, metamodel.py:326,648) run on this package.
     """
     sp = _spline_of(dX_dt)
     if 'method' not in kwargs:
         kwargs['method'] = 'rk4'
-    step = _rk4_step(kwargs, 1.0)
+    step, constructor = _rk4_step(kwargs, 1.0)
     if adjoint and any(c.requires_grad for c in (sp._b, sp._two_c, sp._three_d)):
         raise ValueError("Gradients do not backpropagate through the control with adjoint=True. (This is a limitation "
                          "of the underlying torchdiffeq library.)")
-    plan = SolvePlan(_lib.MODE_BOTTOM, sp._times, (sp._b, sp._two_c, sp._three_d), t, step, want_k=True)
+    plan = _plan(_lib.MODE_BOTTOM, sp, t, func, z0, step, constructor, want_k=True)
     z_out, k_out = solve(plan, func, z0)
-    _H_PRIME[file] = k_out
+    z_out.h_prime = k_out               # per-call handle: lives exactly as long as the result (or the spline) does
+    sp._ancde_h_prime = k_out
+    _H_PRIME[file] = k_out              # weak: no device memory is kept alive by this table
+    if os.environ.get('ANCDE_WRITE_H_PRIME', '0') not in ('', '0'):
+        np.save(file, k_out.detach().cpu().numpy())
     return z_out
 
 
 def ancde(dX_dt, attention, z0, X_s, func_g, h_prime, t, timewise, adjoint=True, **kwargs):
     """Top NCDE driven by dY = dX*a + a(1-a)*dX*h'; returns (len(t), batch, hidden).
 
-    Reference: cdeint_module.py:247-254 + AttentiveVectorField (:103-138).  `h_prime` may be the device
-    tensor from `load_h_prime`, a numpy array (as np.load returns in the reference) or -- the reference's
-    timewise ANCDE passes `time_attention.weight` here and crashes -- a 2-D tensor, in which
-    case the h' of the latest bottom solve is used (what ANCDE_forecasting does).
+    Reference: cdeint_module.py:247-254 + AttentiveVectorField (:103-138).  `h_prime` may be the device tensor of the
+    bottom solve (`attention_raw.h_prime`), a numpy array (as np.load returns in the reference) or -- the reference's
+    timewise ANCDE passes `time_attention.weight` here and crashes -- a 2-D tensor, in which case the h' of
+    the bottom solve of THIS forward pass is used (the one made on the same spline object; what ANCDE_forecasting does).
     With adjoint=True the attention receives no gradient through this solve (torchdiffeq's adjoint
     only differentiates func parameters and z0).
     """
     sp = _spline_of(dX_dt)
-    step = _rk4_step(kwargs, None)
+    step, constructor = _rk4_step(kwargs, None)
     if isinstance(h_prime, np.ndarray):
         h_prime = torch.from_numpy(h_prime).to(z0.device)
     if torch.is_tensor(h_prime) and h_prime.dim() == 2:
-        if not _H_PRIME:
+        h_prime = getattr(sp, '_ancde_h_prime', None)
+        if h_prime is None:
             raise IndexError('too many indices for tensor of dimension 2')   # what the reference raises
-        h_prime = next(reversed(_H_PRIME.values()))
-    if h_prime.dim() != 3:
-        raise ValueError("h_prime must have shape (calls, batch, channels)")
+    B, C = sp._b.shape[0], sp._b.shape[2]
+    if h_prime.dim() != 3 or h_prime.shape[0] < 2 or tuple(h_prime.shape[1:]) != (B, C):
+        raise ValueError("h_prime must have shape (calls >= 2, batch, channels) = (4 * steps, %d, %d) like the bottom "
+                         "solve of this batch produced it; got %s" % (B, C, tuple(h_prime.shape)))
     att = attention
     if att.dim() == 2:
         att = att.unsqueeze(-1)
-    plan = SolvePlan(_lib.MODE_TOP, sp._times, (sp._b, sp._two_c, sp._three_d), t, step,
-                     h_prime=h_prime.detach(), att_grad=not adjoint)
+    plan = _plan(_lib.MODE_TOP, sp, t, func_g, z0, step, constructor, h_prime=h_prime.detach(), att_grad=not adjoint)
     z_out, _ = solve(plan, func_g, z0, att)
     return z_out

@@ -1,20 +1,6 @@
-// Tensor-core ("v2") fused NCDE solve: shared definitions.
-//
-// Design: the vector field's output layer  G = tanh(W_out h + b).view(Hd, C)  is 88 % of the
-// path's FLOPs.  With the batch spread over all SMs an SM only owns ~8 samples, so a plain FFMA or UMMA formulation
-// re-reads all of W_out (84 k floats at the Sepsis shape) from shared memory for every 8 samples and is bound by
-// shared-memory bandwidth.  Here a thread-block CLUSTER of CS CTAs integrates NS = 8*NT samples together: every CTA
-// keeps a 1/CS slice of W_out's rows resident in shared memory for the whole solve (pre-split into FP16 hi/lo
-// fragments, 4 bytes per weight), multiplies it with the activations of all NS samples on the tensor cores
-// (mma.sync m16n8k16, 3 products per tile = FP32-grade accuracy: hi*hi + lo*hi + hi*lo), applies tanh and the
-// contraction with dU in the accumulator registers, and the CTAs exchange the 1/CS slices of the stage derivative
-// through distributed shared memory.  The small hidden layers are evaluated redundantly by every CTA of the cluster.
-//
-// Output-layer rows are grouped into TILES of 16 = 2 field rows (i-pair) x 8 control channels (j-chunk):
-//   tile (ip, jc), row r < 8  -> (i = 2*ip,     j = 8*jc + r)
-//                  row r >= 8 -> (i = 2*ip + 1, j = 8*jc + r - 8)
-// so that in the m16n8 accumulator fragment a thread holds the same j for both field rows and the contraction over
-// j is a reduction over the 8 lanes that share lane%4.
+// Warp-level tensor-core (mma.sync) and thread-block-cluster helpers shared by the solver kernels:
+// FP16 hi/lo operand splitting, ldmatrix / stmatrix wrappers, cluster rank / DSMEM addressing, asynchronous remote
+// stores, and the register-resident phase timers used during kernel development.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -22,76 +8,6 @@
 #include "pipeline.cuh"
 
 namespace ancde {
-
-constexpr float V2_WSCALE = 64.0f;          // weights are stored as fp16(64*W): keeps the lo halves out of the subnormals
-constexpr float V2_WSCALE_INV = 1.0f / 64.0f;
-constexpr int V2_MAX_KSTEPS = 4;            // output-layer reduction size K <= 64
-constexpr int V2_RK_ITEMS = 6;              // (state element, sample) items a thread keeps in registers
-constexpr int V2_MAX_CS = 8;
-
-struct V2Layout {
-    // ---- problem ----
-    int B, L, C, Hd, n_hidden, mode, att_C, att_L, n_hp, n_steps, n_out, n_stages;
-    int width[ANCDE_MAX_LAYERS], in_dim[ANCDE_MAX_LAYERS];
-    int K;                      // width of the last hidden layer
-    // ---- output-layer tiling ----
-    int NIP, NJC, C8, ntiles;   // i-pairs, j-chunks, 8*NJC, NIP*NJC
-    // ---- packed weights (wpack, 16-byte units) ----
-    APack hf[ANCDE_MAX_LAYERS];     // hidden layer l forward:   A = 64*W_l      [width_l][in_l]
-    APack hb[ANCDE_MAX_LAYERS];     // hidden layer l backward:  A = 64*W_l^T    [in_l][width_l]
-    APack of;                       // output layer forward:     A = 64*W_out tiles, M = ntiles*16, K
-    APack ob;                       // output layer backward:    per tile A = 64*W_out^T [K][16 rows]; M = K, K = 16, `off` per tile = ob.off + tile*ob_tile
-    int ob_tile;                    // uint4 per tile of the backward pack = mtiles(K)*64
-    int off_hbias[ANCDE_MAX_LAYERS];    // float offsets (from wpack as float*): 64*bias_l padded to 16*mtiles
-    int off_obias;                      // 64*bias_out per tile row [ntiles][16]
-    int hidden_u4, hidden_b_u4;     // total uint4 of all hf / hb packs (contiguous from hf[0].off / hb[0].off)
-    int64_t wpack_floats;
-    int KSB;                        // k16 steps of the widest B-operand (activations) buffer
-    int MTz;                        // m-tiles of the state (ceil(Hd / 16))
-    // ---- tiling of the batch (fixed per shape so that forward and backward agree on the saved layouts) ----
-    int NT, NS, nclusters;          // n-tiles (8 samples each) and samples per cluster, clusters
-    unsigned magicC;                // ceil(2^32 / C): item / C == __umulhi(item, magicC) for item * C < 2^32
-    // ---- saved activations, per (stage, cluster) a block of act_block floats; matrices [rows][NS] are stored in
-    // accumulator-FRAGMENT order: m-tile mt, n-tile nt, lane -> float4 {(g, 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1)}
-    int fo_z, fo_h[ANCDE_MAX_LAYERS], fo_du, fo_duda, fo_gbar, fo_delta[ANCDE_MAX_LAYERS], act_block;
-    // dU / dU/da blocks are [item = n*C + j]
-    // tanh outputs: [stage][cluster][tile][nt][lane] float4 in the same fragment order (rows = tile rows)
-};
-
-struct V2Launch {
-    int CS, threads;
-    int ip_begin[V2_MAX_CS + 1];    // i-pair range of every cluster rank
-    size_t smem;
-};
-
-struct V2Args {
-    V2Layout lo;
-    V2Launch la;
-    float t_start, t_end, step;
-    const float* times;
-    const float* t_out;
-    const float* cb;
-    const float* cc2;
-    const float* cd3;
-    const float* z0;
-    const float* attention;
-    const float* h_prime;
-    const uint4* wpack;
-    float* z_out;
-    float* k_out;
-    float* save_act;
-    float* save_G;
-    const float* grad_z_out;
-    float* grad_z0;
-    float* grad_attention;
-    long long* dbg;
-};
-
-int make_layout2(const ancde_ncde_desc* d, V2Layout* lo);
-int pack_weights2(const ancde_ncde_desc* d, const V2Layout& lo, cudaStream_t stream);
-int fill_args2(const ancde_ncde_desc* d, const V2Layout& lo, V2Args* a);
-int launch_fwd2(V2Args& a, cudaStream_t stream);
-int choose_launch2_fwd(V2Layout* lo, V2Launch* la);
 
 // Phase timing for kernel development (-DANCDE_PHASE_TIMING): clock64() deltas are accumulated in registers and
 // written once at the end, so that the probe itself does not stall the warp on a global round trip per phase.
@@ -108,8 +24,8 @@ int choose_launch2_fwd(V2Layout* lo, V2Launch* la);
 #endif
 
 #ifdef __CUDACC__
-// ---- tensor-core primitives (legacy mma.sync path: the operands live in registers, M = 16 rows of weights,
-// N = 8 samples -- the shape of this problem; see DESIGN.md for why not tcgen05) ------------------------------
+// ---- warp-level tensor-core primitives (mma.sync: operands in registers, M = 16, N = 8): used where a CTA owns only
+// 8 samples (hidden layers of the backward, hidden weight gradients) ------------------------------------------
 __device__ __forceinline__ void mma16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
 {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"

@@ -80,6 +80,7 @@ __host__ __device__ static inline V3Smem v3_smem(const V3Layout& lo)
 struct V3Args {
     V3Layout lo;
     float t_start, t_end, step;
+    const float* grid;         // explicit grid points (n_steps + 1) or NULL
     const float* times;
     const float* t_out;
     const float* cb;

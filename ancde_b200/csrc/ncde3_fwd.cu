@@ -17,7 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
-#include "ncde2_common.cuh"
+#include "mma_common.cuh"
 #include "ncde3_common.cuh"
 #include "umma.cuh"
 
@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
     const int n_ctl = C4 << NSL;
     const unsigned magicC4 = (unsigned)((((uint64_t)1 << 32) + C4 - 1) / C4);      // item / C4 == umulhi(item, magicC4) for item < 2^16
     auto control = [&](int k, int s, float* du, int ctid, int cthreads) {
-        const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step);
-        const float t1 = grid_time(k + 1, lo.n_steps, p.t_start, p.t_end, p.step);
+        const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step, p.grid);
+        const float t1 = grid_time(k + 1, lo.n_steps, p.t_start, p.t_end, p.step, p.grid);
         const float ts = stage_time(t0, __fsub_rn(t1, t0), s);
         // index = clamp(#(times < t) - 1, 0, L-2): the LEFT piece at a knot (interpolate.py:261-267)
         while (cnt < lo.L && sTimes[cnt] < ts) ++cnt;
@@ -262,8 +262,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
 #endif
 
     for (int k = 0; k < lo.n_steps; ++k) {
-        const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step);
-        const float t1 = grid_time(k + 1, lo.n_steps, p.t_start, p.t_end, p.step);
+        const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step, p.grid);
+        const float t1 = grid_time(k + 1, lo.n_steps, p.t_start, p.t_end, p.step, p.grid);
         const float dt = __fsub_rn(t1, t0);
 #pragma unroll 1
         for (int s = 0; s < 4; ++s) {
@@ -634,7 +634,7 @@ int launch_fwd3(const ancde_ncde_desc* d, const V3Layout& lo, const unsigned cha
     if (d->mode == ANCDE_MODE_TOP) ANCDE_CHECK_ARG(d->attention && d->h_prime, "ncde: TOP mode needs attention and h_prime");
     V3Args a = V3Args();
     a.lo = lo;
-    a.t_start = d->t_start; a.t_end = d->t_end; a.step = d->step;
+    a.t_start = d->t_start; a.t_end = d->t_end; a.step = d->step; a.grid = d->grid;
     a.times = d->times; a.t_out = d->t_out; a.cb = d->coeff_b; a.cc2 = d->coeff_c2; a.cd3 = d->coeff_d3;
     a.z0 = d->z0; a.attention = d->attention; a.h_prime = d->h_prime;
     a.img = img;

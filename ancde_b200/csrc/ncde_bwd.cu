@@ -16,7 +16,7 @@
 //
 // Matches autograd through torchdiffeq's rk4_alt_step_func + the reference vector fields
 // (cdeint_module.py:25-32,56-72,103-138; vector_fields.py:205-218,237-250) to FP32 round-off.
-#include "ncde2_common.cuh"
+#include "mma_common.cuh"
 
 namespace ancde {
 
@@ -311,8 +311,8 @@ __global__ void __launch_bounds__(512, 1) ncde_bwd_kernel(const __grid_constant_
     PH2_DECL();
 
     for (int k = lo.n_steps - 1; k >= 0; --k) {
-        const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step);
-        const float t1 = grid_time(k + 1, lo.n_steps, p.t_start, p.t_end, p.step);
+        const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step, p.grid);
+        const float t1 = grid_time(k + 1, lo.n_steps, p.t_start, p.t_end, p.step, p.grid);
         const float dt = __fsub_rn(t1, t0);
         // ---- cotangents of the outputs emitted during this step: t_out[j] in (t0, t1]
         if (lo.n_stages > 1) {
@@ -817,10 +817,6 @@ extern "C" int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream_)
     reset_launch_count();
     cudaStream_t stream = (cudaStream_t)stream_;
     ANCDE_CHECK_ARG(d != nullptr, "ncde_backward: null descriptor");
-    if (engine_of(d) == ANCDE_ENGINE_CLUSTER) {
-        set_error("ncde_backward: the cluster engine is forward-only; solve with ANCDE_ENGINE_STREAMED to differentiate");
-        return ANCDE_EUNSUPPORTED;
-    }
     NcdeLayout lo;
     int rc = make_layout(d, &lo);
     if (rc != ANCDE_OK) return rc;

@@ -48,8 +48,10 @@ __device__ __forceinline__ float tanh_mufu(float x)
 
 // Time of grid point k: arange(k) * step + t_start, last point clipped (torchdiffeq
 // _grid_constructor_from_step_size), in float32 without contraction.
-__device__ __forceinline__ float grid_time(int k, int n_steps, float t_start, float t_end, float step)
+// An explicit grid (options['grid_constructor'], or rk4 without a step size: the grid is `t` itself) is read from memory.
+__device__ __forceinline__ float grid_time(int k, int n_steps, float t_start, float t_end, float step, const float* grid)
 {
+    if (grid) return __ldg(grid + k);
     float t = __fadd_rn(__fmul_rn((float)k, step), t_start);
     if (k == n_steps && t > t_end) t = t_end;
     return t;
@@ -70,6 +72,7 @@ __device__ __forceinline__ int du_index(int j, int b, int TS, int DUS) { return 
 struct SolveArgs {
     NcdeLayout lo;
     float t_start, t_end, step;
+    const float* grid;         // explicit grid points (n_steps + 1) or NULL
     const float* times;
     const float* t_out;
     const float* cb;

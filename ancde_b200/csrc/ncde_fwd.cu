@@ -61,8 +61,8 @@ __device__ __forceinline__ void ctl_issue(const SolveArgs& p, const float* sTime
                                           const CtlItems& ci, CtlRegs& r)
 {
     const NcdeLayout& lo = p.lo;
-    const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step);
-    const float t1 = grid_time(k + 1, lo.n_steps, p.t_start, p.t_end, p.step);
+    const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step, p.grid);
+    const float t1 = grid_time(k + 1, lo.n_steps, p.t_start, p.t_end, p.step, p.grid);
     const float ts = stage_time(t0, __fsub_rn(t1, t0), s);
     // index = clamp(#(times < t) - 1, 0, L-2): the LEFT piece at a knot (interpolate.py:261-267)
     while (cnt < lo.L && sTimes[cnt] < ts) ++cnt;
@@ -395,8 +395,8 @@ __global__ void __launch_bounds__(512, 1) ncde_fwd_kernel(const __grid_constant_
     cta_sync();
 
     for (int k = 0; k < lo.n_steps; ++k) {
-        const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step);
-        const float t1 = grid_time(k + 1, lo.n_steps, p.t_start, p.t_end, p.step);
+        const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step, p.grid);
+        const float t1 = grid_time(k + 1, lo.n_steps, p.t_start, p.t_end, p.step, p.grid);
         const float dt = __fsub_rn(t1, t0);
 #pragma unroll 1
         for (int s = 0; s < 4; ++s) {

@@ -1,6 +1,6 @@
 // Host side of the fused NCDE solve: layout of packed weights / saved activations, weight packing,
 // argument marshalling and the C-ABI entry points for the forward.
-#include "ncde2_common.cuh"
+#include "mma_common.cuh"
 #include "ncde3_common.cuh"
 
 namespace ancde {
@@ -198,7 +198,7 @@ int make_layout(const ancde_ncde_desc* d, NcdeLayout* lo)
                     d->n_hidden);
     ANCDE_CHECK_ARG(d->mode >= ANCDE_MODE_PLAIN && d->mode <= ANCDE_MODE_TOP, "ncde: bad mode %d", d->mode);
     ANCDE_CHECK_ARG(d->n_steps >= 1 && d->n_out >= 1, "ncde: n_steps=%d n_out=%d", d->n_steps, d->n_out);
-    ANCDE_CHECK_ARG(d->step > 0.f, "ncde: step must be positive");
+    ANCDE_CHECK_ARG(d->grid != nullptr || d->step > 0.f, "ncde: step must be positive");
     if (d->mode == ANCDE_MODE_TOP) {
         ANCDE_CHECK_ARG(d->att_C == 1 || d->att_C == d->C, "ncde: attention channels %d (need 1 or C=%d)", d->att_C, d->C);
         ANCDE_CHECK_ARG(d->att_L >= 1 && d->n_hp >= 2, "ncde: att_L=%d n_hp=%d", d->att_L, d->n_hp);
@@ -251,7 +251,7 @@ int fill_args(const ancde_ncde_desc* d, const NcdeLayout& lo, SolveArgs* a)
     if (d->mode == ANCDE_MODE_TOP) ANCDE_CHECK_ARG(d->attention && d->h_prime, "ncde: TOP mode needs attention and h_prime");
     *a = SolveArgs();
     a->lo = lo;
-    a->t_start = d->t_start; a->t_end = d->t_end; a->step = d->step;
+    a->t_start = d->t_start; a->t_end = d->t_end; a->step = d->step; a->grid = d->grid;
     a->times = d->times; a->t_out = d->t_out; a->cb = d->coeff_b; a->cc2 = d->coeff_c2; a->cd3 = d->coeff_d3;
     a->z0 = d->z0; a->attention = d->attention; a->h_prime = d->h_prime; a->wpack = d->wpack;
     a->z_out = d->z_out; a->k_out = d->k_out; a->save_act = d->save_act; a->save_G = d->save_G;
@@ -282,7 +282,8 @@ int engine_of(const ancde_ncde_desc* d)
 {
     if (!d) return ANCDE_ENGINE_STREAMED;
     if (d->single_stage) return (d->engine == 0 || d->engine == ANCDE_ENGINE_STREAMED) ? ANCDE_ENGINE_STREAMED : -1;
-    if (d->engine == ANCDE_ENGINE_STREAMED || d->engine == ANCDE_ENGINE_CLUSTER) return d->engine;
+    if (d->engine == ANCDE_ENGINE_STREAMED) return d->engine;
+    if (d->engine != 0 && d->engine != ANCDE_ENGINE_UMMA) return -1;
     NcdeLayout st;
     V3Layout l3;
     if (d->engine == ANCDE_ENGINE_UMMA) return umma_layouts(d, &st, &l3) ? ANCDE_ENGINE_UMMA : -1;
@@ -306,10 +307,6 @@ extern "C" int ancde_ncde_engine(const ancde_ncde_desc* d)
 
 extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
 {
-    if (engine_of(d) == ANCDE_ENGINE_CLUSTER) {
-        V2Layout l2;
-        return make_layout2(d, &l2) == ANCDE_OK ? l2.wpack_floats : -1;
-    }
     if (engine_of(d) < 0) { set_error("ncde: this shape is not supported by the UMMA engine"); return -1; }
     NcdeLayout lo;
     if (make_layout(d, &lo) != ANCDE_OK) return -1;
@@ -323,10 +320,6 @@ extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
 
 extern "C" int64_t ancde_ncde_save_act_floats(const ancde_ncde_desc* d)
 {
-    if (engine_of(d) == ANCDE_ENGINE_CLUSTER) {
-        V2Layout l2;
-        return make_layout2(d, &l2) == ANCDE_OK ? (int64_t)l2.n_stages * l2.nclusters * l2.act_block : -1;
-    }
     NcdeLayout lo;
     if (make_layout(d, &lo) != ANCDE_OK) return -1;
     return (int64_t)lo.n_stages * lo.ntiles * lo.act_floats;
@@ -334,10 +327,6 @@ extern "C" int64_t ancde_ncde_save_act_floats(const ancde_ncde_desc* d)
 
 extern "C" int64_t ancde_ncde_save_G_floats(const ancde_ncde_desc* d)
 {
-    if (engine_of(d) == ANCDE_ENGINE_CLUSTER) {
-        V2Layout l2;
-        return make_layout2(d, &l2) == ANCDE_OK ? (int64_t)l2.n_stages * l2.nclusters * l2.ntiles * l2.NT * 128 : -1;
-    }
     NcdeLayout lo;
     if (make_layout(d, &lo) != ANCDE_OK) return -1;
     return (int64_t)lo.n_stages * lo.ntiles * lo.TS * lo.NCP;
@@ -349,17 +338,6 @@ extern "C" int ancde_ncde_forward(const ancde_ncde_desc* d, void* stream_)
     cudaStream_t stream = (cudaStream_t)stream_;
     ANCDE_CHECK_ARG(d != nullptr, "ncde_forward: null descriptor");
     ANCDE_CHECK_ARG((d->save_act == nullptr) == (d->save_G == nullptr), "ncde_forward: save_act and save_G go together");
-    if (engine_of(d) == ANCDE_ENGINE_CLUSTER) {
-        V2Layout l2;
-        int rc2 = make_layout2(d, &l2);
-        if (rc2 != ANCDE_OK) return rc2;
-        V2Args a2;
-        rc2 = fill_args2(d, l2, &a2);
-        if (rc2 != ANCDE_OK) return rc2;
-        rc2 = pack_weights2(d, l2, stream);
-        if (rc2 != ANCDE_OK) return rc2;
-        return launch_fwd2(a2, stream);
-    }
     const int engine = engine_of(d);
     if (engine < 0) {
         set_error("ncde_forward: this shape is not supported by the UMMA engine (state / hidden widths <= 63, C <= 128, backward tile of 8)");

@@ -13,7 +13,7 @@
 //   3. accumulates  D[16 cols per warp][all k] += pre_bar^T h  with mma.sync m16n8k16, three products per tile
 //      (hi*hi + lo*hi + hi*lo), FP32 accumulators in registers for the whole kernel (8 warps = 128 columns).
 // The bias gradient is the extra k column h = 1.
-#include "ncde2_common.cuh"
+#include "mma_common.cuh"
 
 namespace ancde {
 

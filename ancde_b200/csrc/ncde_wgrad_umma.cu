@@ -22,7 +22,7 @@
 //      2 x 2 instructions per chunk; tcgen05.commit frees the operand buffer.
 // The bias gradient is the extra k column h = 1.  At the end D is read back (tcgen05.ld) and added to the gradient
 // with atomics (a column tile is shared by the CTAs of the row slices).
-#include "ncde2_common.cuh"
+#include "mma_common.cuh"
 #include "umma.cuh"
 
 namespace ancde {

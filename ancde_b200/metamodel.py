@@ -93,6 +93,7 @@ class _AttentiveBase(torch.nn.Module):
         self.linear = torch.nn.Linear(hidden_channels, out_features)
         self.time_attention = torch.nn.Linear(input_channels, 1)
         self.timewise = timewise
+        self._h_prime = None             # h' of the latest forward pass (device tensor)
 
     def extra_repr(self):
         return "input_channels={}, hidden_channels={}, output_channels={}, initial={}" \
@@ -128,7 +129,9 @@ class _AttentiveBase(torch.nn.Module):
 
         attention = _cde.ancde_bottom(dX_dt=cubic_spline.derivative, z0=z0, func=self.func_f, t=times,
                                       file=self.file, adjoint=adjoint, **kwargs)
-        h_prime = _cde.load_h_prime(self.file)
+        # the bottom solve's stage derivatives, still in HBM (reference: np.load(self.file)); the model keeps the latest one
+        # alive (controldiffeq.load_h_prime(self.file) finds it), the previous one is released
+        h_prime = self._h_prime = attention.h_prime
         attention = self._attention_head(attention, slope)
         y0 = self.feature_extractor(x0 * attention[0, :, :])
         z_t = _cde.ancde(dX_dt=cubic_spline.derivative, attention=attention, z0=y0, X_s=cubic_spline,

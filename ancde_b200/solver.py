@@ -15,7 +15,7 @@ from . import _lib
 _grid_cache = {}
 import os
 FORCE_SAMPLES_PER_CTA = int(os.environ.get('ANCDE_SAMPLES_PER_CTA', '0'))   # 0 = library default; tests set 1/2/4/8
-ENGINE = int(os.environ.get('ANCDE_ENGINE', '0'))   # 0 = library default (streamed); 2 = forward-only cluster engine
+ENGINE = int(os.environ.get('ANCDE_ENGINE', '0'))   # 0 = library default; 1 = streamed FP32 engine; 3 = UMMA (tcgen05) engine
 
 
 import contextlib
@@ -60,7 +60,7 @@ def join():
 class SolvePlan:
     """Everything about one solve that is not a differentiable tensor."""
 
-    def __init__(self, mode, times, coeffs, t_out, step_size, h_prime=None, want_k=False, att_grad=True):
+    def __init__(self, mode, times, coeffs, t_out, step_size, h_prime=None, want_k=False, att_grad=True, grid=None):
         b, c2, d3 = coeffs
         _lib.require_cuda(b, 'spline coefficients')
         dev = b.device
@@ -74,7 +74,12 @@ class SolvePlan:
         self.want_k = want_k
         self.att_grad = att_grad
         self.single = False
-        self.grid = fixed_grid_meta(t_out, step_size)
+        self.grid_points = None                     # explicit grid (device, float32) or None = arange(n) * step + t[0]
+        if grid is not None:
+            self.grid_points = _f32(grid, dev)
+            self.grid = explicit_grid_meta(t_out, grid)
+        else:
+            self.grid = fixed_grid_meta(t_out, step_size)
         if self.times.numel() != self.Lm1 + 1:
             raise ValueError('times has %d entries but the coefficients have %d pieces' % (self.times.numel(), self.Lm1))
 
@@ -97,6 +102,7 @@ class FieldPlan(SolvePlan):
         self.want_k = True
         self.att_grad = False
         self.single = True
+        self.grid_points = None
         self.grid = (float(t), float(t) + 1.0, 1.0, 1)
         if self.times.numel() != self.Lm1 + 1:
             raise ValueError('times has %d entries but the coefficients have %d pieces' % (self.times.numel(), self.Lm1))
@@ -131,19 +137,46 @@ def cached_host_scalar(tensor, tag, fn):
 
 
 def fixed_grid_meta(t_out, step_size):
-    """(t_start, t_end, step, n_steps) of torchdiffeq's _grid_constructor_from_step_size, float32."""
+    """(t_start, t_end, step, n_steps) of torchdiffeq's _grid_constructor_from_step_size, float32.
+
+    torchdiffeq's FixedGridODESolver.integrate asserts `time_grid[0] == t[0] and time_grid[-1] == t[-1]`: in float32
+    `arange(n) * step + t[0]` can end one ulp short of t[-1] (e.g. t = linspace(0, 10, 4), step = min dt), and the solve
+    then raises.  The same assertion is made here, on the same float32 arithmetic -- a kernel launched on such a grid would
+    never reach the last requested time."""
     def compute(t):
         th = t.detach().to('cpu', torch.float32)
-        if th.numel() < 2:
-            raise ValueError('t must contain at least two times')
-        if not bool((th[1:] > th[:-1]).all()):
-            if bool((th[1:] < th[:-1]).all()):
-                raise NotImplementedError('decreasing integration times are not supported by the fused solver')
-            raise AssertionError('t must be strictly increasing or decreasing')
+        _check_times(th)
         step = torch.tensor(float(step_size), dtype=torch.float32)
         niters = int(torch.ceil((th[-1] - th[0]) / step + 1).item())
+        last = torch.tensor(float(niters - 1), dtype=torch.float32) * step + th[0]
+        if last > th[-1]:
+            last = th[-1]
+        assert niters >= 2 and bool(last == th[-1]), \
+            'the fixed grid (step %r) ends at %r, not at t[-1] = %r' % (float(step), float(last), float(th[-1]))
         return (float(th[0]), float(th[-1]), float(step), niters - 1)
     return cached_host_scalar(t_out, ('grid', float(step_size)), compute)
+
+
+def _check_times(th):
+    if th.numel() < 2:
+        raise ValueError('t must contain at least two times')
+    if not bool((th[1:] > th[:-1]).all()):
+        if bool((th[1:] < th[:-1]).all()):
+            raise NotImplementedError('decreasing integration times are not supported by the fused solver')
+        raise AssertionError('t must be strictly increasing or decreasing')
+
+
+def explicit_grid_meta(t_out, grid):
+    """Grid metadata for an explicit time grid (torchdiffeq: `options['grid_constructor']`, or rk4 without a step size,
+    where the grid is `t` itself): (t_start, t_end, step=0, n_steps) after the checks of FixedGridODESolver.integrate."""
+    def compute(g):
+        gh = g.detach().to('cpu', torch.float32)
+        th = t_out.detach().to('cpu', torch.float32)
+        _check_times(th)
+        _check_times(gh)
+        assert bool(gh[0] == th[0]) and bool(gh[-1] == th[-1]), 'the time grid must start at t[0] and end at t[-1]'
+        return (float(gh[0]), float(gh[-1]), 0.0, gh.numel() - 1)
+    return cached_host_scalar(grid, ('explicit', id(t_out), t_out._version), compute)
 
 
 def mlp_params(func):
@@ -186,6 +219,7 @@ def _desc(plan, z0, attention, wb, widths, Hd):
     t_start, t_end, step, n_steps = plan.grid
     d.t_start, d.t_end, d.step, d.n_steps = t_start, t_end, step, n_steps
     d.n_out = plan.t_out.numel()
+    d.grid = plan.grid_points.data_ptr() if plan.grid_points is not None else None
     d.times, d.t_out = plan.times.data_ptr(), plan.t_out.data_ptr()
     d.coeff_b, d.coeff_c2, d.coeff_d3 = plan.b.data_ptr(), plan.c2.data_ptr(), plan.d3.data_ptr()
     d.z0 = z0.data_ptr()
@@ -245,8 +279,6 @@ class _NcdeSolve(torch.autograd.Function):
         # under torch.no_grad() nothing is saved (ctx.needs_input_grad still reports the inputs' requires_grad there, and
         # grad mode is always off inside forward(), so solve() records it on the plan)
         need_grad = plan.grad_mode and any(ctx.needs_input_grad)
-        if need_grad and ENGINE == _lib.ENGINE_CLUSTER:
-            raise NotImplementedError('the cluster engine (ANCDE_ENGINE=2) is forward-only: run it under torch.no_grad()')
         save_act = save_G = None
         if need_grad:
             save_act = torch.empty(_ws(L_.ancde_ncde_save_act_floats, d), dtype=torch.float32, device=dev)

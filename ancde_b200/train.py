@@ -53,7 +53,13 @@ class DualNcdeTrainer:
 
     def forward(self, batch, slope=1.0):
         cfg = self.cfg
-        coeffs = batch['coeffs']
+        if 'coeffs' in batch:
+            coeffs = batch['coeffs']
+        else:
+            # raw paths: the spline coefficients of the batch are built on the GPU inside the step (one kernel launch,
+            # datasets_common.coefficients_on_the_fly) instead of being read from a 4x larger precomputed cache
+            from .datasets_common import coefficients_on_the_fly
+            coeffs = coefficients_on_the_fly(batch['times'], batch['X'])
         kw = dict(stream=cfg['stream'], adjoint=self.adjoint)
         if cfg['static']:
             return self.model(batch['times'], tuple(coeffs) + (batch['static'],), batch['final_index'], slope, **kw)
@@ -113,6 +119,9 @@ class GraphedStep:
 
     def load(self, host_batch):
         """Asynchronous host -> device copy of a (pinned) batch into the static input tensors; returns the bytes copied."""
+        if 'times' in host_batch:
+            # the captured kernels hold the grid (t0, t_end, step, knot count) of the captured `times` as launch parameters
+            raise ValueError("a captured step integrates on the `times` it was captured with; capture a new step for another grid")
         n = 0
         for k, v in host_batch.items():
             dst = self.batch[k]

@@ -6,8 +6,9 @@
 A step = one pass of the hot path over one batch: dual-NCDE forward, loss, backward through the solver,
 (N>1: flat-gradient all-reduce over NCCL) and the Adam update.  Default workload: PhysioNet-Sepsis (no OI)
 shape, 1024 samples per GPU (weak scaling), synthetic data, random-init weights.
-Prints ONE JSON line on rank 0 (see the keys below).  `--impl reference` times the CPU restatement of the
-reference (oracle/port.py; /root/reference itself does not exist on the GPU box) on the host cores.
+Prints ONE JSON line on rank 0 (see the keys below).  `--impl reference` times the reference's own CPU path on the
+host cores: the unmodified reference from oracle/_ref (a copy made by oracle/make_ref.py; /root/reference itself does not
+exist on the GPU box), or the restatement oracle/port.py when that copy is absent.
 """
 import argparse
 import json
@@ -130,6 +131,17 @@ def make_device_batch(workload, B, seed, device):
     return out
 
 
+def make_raw_device_batch(workload, B, seed, device):
+    """The batch as the dataset holds it BEFORE the spline: raw X with NaNs (coefficients are made inside the step)."""
+    from ancde_b200 import synthetic
+    bt = synthetic.make_batch(workload, B=B, seed=seed)
+    out = dict(times=bt['times'].to(device), X=bt['X'].to(device), final_index=bt['final_index'].to(device),
+               y=bt['y'].to(device))
+    if bt['static'] is not None:
+        out['static'] = bt['static'].to(device)
+    return out
+
+
 def to_pinned_host(batch):
     host = {}
     for k, v in batch.items():
@@ -154,17 +166,63 @@ def h2d(host, device):
 
 
 # ------------------------------------------------------------------------------------------ CPU reference
-def cpu_reference_samples_per_sec(workload, sample_B, steps, warmup):
-    """fwd+bwd of the CPU restatement of the reference (oracle/port.py) with every host thread."""
-    from oracle import port
-    from ancde_b200 import synthetic, metamodel
+class _ReferenceIVN(torch.nn.Module):
+    """z0 = MLP(static) in front of the reference model, as experiments/sepsis_attentive.py:15-30 (that script itself
+    cannot be imported: it pulls in the dataset code)."""
+
+    def __init__(self, n_static, C, model):
+        super().__init__()
+        self.linear1 = torch.nn.Linear(n_static, 256)
+        self.linear2 = torch.nn.Linear(256, C)
+        self.model = model
+
+    def forward(self, times, coeffs, final_index, slope, static, **kwargs):
+        z0 = self.linear2(self.linear1(static).relu())
+        return self.model(times, coeffs, final_index, slope, z0=z0, **kwargs)
+
+
+def _h_prime_path():
+    d = '/dev/shm' if os.path.isdir('/dev/shm') and os.access('/dev/shm', os.W_OK) else tempfile.gettempdir()
+    return os.path.join(d, 'ancde_ref_h_prime_%d.npy' % os.getpid())
+
+
+def cpu_reference_step_fn(workload, sample_B, adjoint=False):
+    """Returns (one_step, kind, cores): one_step() runs forward + loss + backward of the reference on the host cores.
+
+    kind "reference": the UNMODIFIED reference (`controldiffeq` + `experiments/models` from oracle/_ref, a byte-for-byte
+    copy made by oracle/make_ref.py) on the restated torchdiffeq (oracle/torchdiffeq_shim.py), including its np.save /
+    np.load of h' (to tmpfs) and its python-level stage loop.  kind "port": oracle/port.py, when no copy is present."""
+    from ancde_b200 import synthetic
+    from ancde_b200.train import task_loss
     cfg = synthetic.CONFIGS[workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(2021)
-    model, _, _ = metamodel.model_from_config(cfg, file='cpu')
     bt = synthetic.make_batch(workload, B=sample_B, seed=2021)
+    from oracle import port
     coeffs = port.natural_cubic_spline_coeffs(bt['times'], bt['X'])
+    from oracle import reference_loader
+    if reference_loader.available():
+        path = _h_prime_path()
+        model = reference_loader.make_reference_model(cfg, path)
+        if cfg['static']:
+            model = _ReferenceIVN(cfg['static'], cfg['C'], model)
+        coeffs32 = tuple(c.float() for c in coeffs) if cfg['dtype'] == 'float32' else tuple(coeffs)
+
+        def one():
+            model.zero_grad(set_to_none=True)
+            kw = dict(stream=cfg['stream'], adjoint=adjoint)
+            if cfg['static']:
+                pred = model(bt['times'], coeffs32, bt['final_index'], 1.0, bt['static'], **kw)
+            else:
+                pred = model(bt['times'], coeffs32, bt['final_index'], 1.0, **kw)
+            loss = task_loss(cfg, pred, bt['y'])
+            loss.backward()
+            return float(loss.detach())
+        return one, 'reference', cores
+
+    from ancde_b200 import metamodel
+    model, _, _ = metamodel.model_from_config(cfg, file='cpu')
     sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
     sdm = {k[len('model.'):]: v for k, v in sd.items() if k.startswith('model.')} if cfg['static'] else sd
 
@@ -173,12 +231,16 @@ def cpu_reference_samples_per_sec(workload, sample_B, steps, warmup):
             v.grad = None
         z0 = port.ivn_z0(sd, bt['static']) if cfg['static'] else None
         res = port.dual_ncde_forward(sdm, cfg, bt['times'], coeffs, bt['final_index'], 1.0, stream=cfg['stream'],
-                                     z0=z0, adjoint=False)
-        from ancde_b200.train import task_loss
+                                     z0=z0, adjoint=adjoint)
         loss = task_loss(cfg, res['pred'], bt['y'])
         loss.backward()
         return float(loss.detach())
+    return one, 'port', cores
 
+
+def cpu_reference_samples_per_sec(workload, sample_B, steps, warmup, adjoint=False):
+    """fwd+bwd of the reference's CPU path with every host thread: (samples/s, seconds per step, cores, kind)."""
+    one, kind, cores = cpu_reference_step_fn(workload, sample_B, adjoint)
     for _ in range(warmup):
         one()
     ts = []
@@ -187,29 +249,58 @@ def cpu_reference_samples_per_sec(workload, sample_B, steps, warmup):
         one()
         ts.append(time.perf_counter() - t0)
     sec = statistics.median(ts)
-    return sample_B / sec, sec, cores
+    return sample_B / sec, sec, cores, kind
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path, same workload, same batch, same steps.
+    A step is the full batch unless one step is so slow that `steps + warmup` of them would take more than ~4 minutes;
+    then every step is a bounded sample (a power-of-two fraction of the batch), and the line says so."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
-    sample_B = args.cpu_sample
-    steps = max(1, min(args.steps, 5))
-    warmup = max(1, min(args.warmup, 2))
-    value, sec, cores = cpu_reference_samples_per_sec(args.workload, sample_B, steps, warmup)
-    sample = '%d samples of the %s workload per step (bounded sample of the %d-sample batch), fwd+bwd, ' \
-             'median of %d steps after %d warm-up' % (sample_B, args.workload, args.batch, steps, warmup)
+    B = args.batch
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    one, kind, cores = cpu_reference_step_fn(args.workload, B, args.adjoint)
+    t0 = time.perf_counter()
+    one()                                            # first warm-up step, timed to size the run
+    first = time.perf_counter() - t0
+    budget = 240.0
+    sample_B = B
+    while first * (sample_B / B) * (steps + warmup) > budget and sample_B > 64:
+        sample_B //= 2
+    if sample_B != B:
+        one, kind, cores = cpu_reference_step_fn(args.workload, sample_B, args.adjoint)
+        one()
+    for _ in range(warmup - 1):
+        one()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one()
+        ts.append(time.perf_counter() - t0)
+    sec = statistics.median(ts)
+    value = sample_B / sec
+    what = 'the unmodified reference (oracle/_ref: controldiffeq + experiments/models, incl. its np.save/np.load of h\') ' \
+           'on the restated torchdiffeq' if kind == 'reference' else 'the CPU restatement oracle/port.py'
+    sample = '%s; %d samples of the %s workload per step (%s), fwd+bwd, median of %d steps after %d warm-up' % (
+        what, sample_B, args.workload, 'the full batch' if sample_B == B else 'bounded sample of the %d-sample batch' % B,
+        steps, warmup)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': args.gpus,
         'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD_TEXT[args.workload], 'name': args.workload, 'batch_per_step': sample_B},
-        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'config': {'workload': WORKLOAD_TEXT[args.workload], 'name': args.workload, 'batch_per_gpu': B,
+                   'batch_per_step': sample_B, 'adjoint': bool(args.adjoint)},
+        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line))
+    try:
+        os.unlink(_h_prime_path())
+    except OSError:
+        pass
     return 0
 
 
@@ -244,7 +335,10 @@ def run_ours(args):
     # several distinct resident batches, cycled, so no step re-reads inputs the previous one left in L2
     n_res = 4
     batches = [make_device_batch(args.workload, B, 2021 + 1000 * rank + i, device) for i in range(n_res)]
-    host_batches = [to_pinned_host(b) for b in batches[:2]]
+    # e2e leg: the step starts from the raw paths X (NaN = missing) and builds the spline coefficients on the GPU
+    # (datasets_common.coefficients_on_the_fly): 1/4 of the host -> device bytes of precomputed coefficients
+    raw_batches = [make_raw_device_batch(args.workload, B, 2021 + 1000 * rank + i, device) for i in range(2)]
+    host_batches = [{k: v for k, v in to_pinned_host(b).items() if k != 'times'} for b in raw_batches]
     fp32_peak = _lib.fp32_peak_tflops(device)
 
     def timed(fn, steps, warmup, profile=False):
@@ -309,11 +403,15 @@ def run_ours(args):
     ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
     ev_consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
+    graphed_raw = None
+    if graphed is not None:
+        graphed_raw = [trainer.capture(b) for b in raw_batches]
+
     def prefetch(i):
         sl = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_consumed[sl])
-            h2d_bytes[0] = graphed[sl].load(host_batches[sl])
+            h2d_bytes[0] = graphed_raw[sl].load(host_batches[sl])
             ev_copied[sl].record(copy_stream)
 
     def e2e_step(i):
@@ -322,10 +420,11 @@ def run_ours(args):
             cur = torch.cuda.current_stream(device)
             prefetch(i + 1)
             cur.wait_event(ev_copied[sl])
-            loss = graphed[sl].replay()
+            loss = graphed_raw[sl].replay()
             ev_consumed[sl].record(cur)
         else:
             dev_batch, nb = h2d(host_batches[i % len(host_batches)], device)
+            dev_batch['times'] = raw_batches[0]['times']
             h2d_bytes[0] = nb
             loss = trainer.step(dev_batch)
         loss_host = loss.to('cpu')                # device -> host read of the step's result
@@ -340,14 +439,62 @@ def run_ours(args):
     e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
 
     def finish():
-        """Multi-rank runs leave with a hard exit once every rank is done with its collectives: tearing down an NCCL
-        communicator whose kernels sit inside captured CUDA graphs can block forever in destroy_process_group / at
-        interpreter exit (seen on 2 x B200), and nothing is left to clean up that the driver would miss."""
+        """Orderly teardown: the captured graphs (they hold NCCL kernels) are destroyed before the process group.  In
+        round 1 destroy_process_group / interpreter exit could block forever with live graphs on 2 x B200, so a watchdog
+        thread ends the process if the teardown has not finished after 20 s -- every result is printed by then."""
         sys.stdout.flush()
         sys.stderr.flush()
         if world > 1:
-            os._exit(0)
+            import threading
+            dog = threading.Timer(20.0, lambda: os._exit(0))
+            dog.daemon = True
+            dog.start()
+            graphed_all = [g for g in (graphed or []) + (graphed_raw or [])]
+            for g in graphed_all:
+                g.graph.reset()
+            torch.cuda.synchronize(device)
+            dist.destroy_process_group()
+            dog.cancel()
         return 0
+
+    # ---- the other BASELINE.json configs, short runs in the same process on every rank (whole steps from a CUDA graph,
+    # inputs resident): Sepsis OI weak (1024 / GPU) and strong (1024 in total), Sepsis with the adjoint gradient flow,
+    # UEA, Mujoco, Stock.  `value` = samples of all ranks / max-over-ranks device time, like the headline.
+    def measure_other(workload, B_gpu, adjoint, steps=5, warmup=3):
+        out = {'workload': workload, 'batch_per_gpu': B_gpu, 'global_batch': B_gpu * world, 'adjoint': bool(adjoint)}
+        try:
+            tr = DualNcdeTrainer(workload, device, seed=2021, adjoint=adjoint)
+            bs = [make_device_batch(workload, B_gpu, 4021 + 1000 * rank + i, device) for i in range(2)]
+            gs = [tr.capture(b) for b in bs]
+            ms_o, _, _ = timed(lambda i: gs[i % 2].replay(), steps, warmup)
+            fl = sum(kernel_flops(synthetic.CONFIGS[workload], B_gpu).values())
+            out.update(value=round(world * B_gpu * steps / (ms_o * 1e-3), 1), unit='samples/s',
+                       ms_per_step=round(ms_o / steps, 4), steps=steps, warmup=warmup,
+                       step_frac=round(fl * steps / (ms_o * 1e-3) / 1e12 / fp32_peak, 4))
+            for g_ in gs:
+                g_.graph.reset()
+            del gs, bs, tr
+        except Exception as e:                                   # noqa: BLE001 -- one config must not take the line down
+            out['error'] = '%s: %s' % (type(e).__name__, str(e)[:200])
+        torch.cuda.synchronize(device)
+        torch.cuda.empty_cache()
+        return out
+
+    other_configs = []
+    if not args.no_other_configs:
+        full = synthetic.CONFIGS
+        todo = [('sepsis_oi', full['sepsis_oi']['B'], False, 'weak')]
+        if world > 1:
+            todo.append(('sepsis_oi', max(1, full['sepsis_oi']['B'] // world), False, 'strong'))
+            todo.append(('sepsis', max(1, full['sepsis']['B'] // world), False, 'strong'))
+        todo += [('sepsis', full['sepsis']['B'], True, 'weak'), ('uea', full['uea']['B'], False, 'weak'),
+                 ('mujoco', full['mujoco']['B'], False, 'weak'), ('stock', full['stock']['B'], False, 'weak')]
+        for wl, bg, adj, scaling in todo:
+            if wl == args.workload and bg == B and adj == bool(args.adjoint):
+                continue
+            r = measure_other(wl, bg, adj)
+            r['scaling'] = scaling
+            other_configs.append(r)
 
     barrier()                       # the last collective of every rank
     if rank != 0:
@@ -408,8 +555,8 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, sec, cores = cpu_reference_samples_per_sec(args.workload, args.cpu_sample, 3, 1)
-        cpu = {'value': round(v, 2), 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+        v, sec, cores, kind = cpu_reference_samples_per_sec(args.workload, args.cpu_sample, 3, 1, args.adjoint)
+        cpu = {'value': round(v, 2), 'unit': 'samples/s', 'cores': cores, 'kind': kind,
                'sample': '%d samples of the same workload, fwd+bwd, median of 3 after 1 warm-up (%.2f s each)'
                          % (args.cpu_sample, sec)}
 
@@ -434,6 +581,7 @@ def run_ours(args):
         'roofline_wgrad': roofline_wgrad,
         'kernels': kernels,
         'cpu_baseline': cpu,
+        'other_configs': other_configs,
     }
     print(json.dumps(line))
     return finish()
@@ -497,6 +645,7 @@ def main():
     ap.add_argument('--adjoint', action='store_true', help="reference's adjoint=True gradient flow")
     ap.add_argument('--cpu-sample', type=int, default=512, help='samples per CPU-baseline step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-other-configs', action='store_true', help='skip the short runs of the other BASELINE configs')
     ap.add_argument('--no-graph', action='store_true', help='launch every step eagerly instead of replaying CUDA graphs')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':

@@ -28,7 +28,7 @@ extern "C" {
 
 #define ANCDE_MAX_LAYERS 8      /* hidden (ReLU) layers in a vector-field MLP */
 
-/* ABI version; bumped when a struct below changes.  5: ancde_ncde_desc gained single_stage, grad_k_out (ABI 5) and
+/* ABI version; bumped when a struct below changes.  6: ancde_ncde_desc gained `grid`.  5: ancde_ncde_desc gained single_stage, grad_k_out (ABI 5) and
  * async_wgrad (ABI 4, with ancde_ncde_join). */
 int ancde_abi_version(void);
 
@@ -74,11 +74,8 @@ int ancde_spline_coeffs_f64(const double* times, const double* X, double* a, dou
  *   ANCDE_ENGINE_STREAMED  (default) one CTA per tile of 8 samples; the output-layer weights are streamed from L2 through
  *                          a TMA ring every stage.  Forward: FP32 FMA.  Backward and weight gradients: tensor cores
  *                          (mma.sync, FP16 hi/lo split, three products per tile = FP32-grade accuracy).
- *   ANCDE_ENGINE_CLUSTER   forward only (inference): a thread-block cluster per 8..32 samples keeps the output layer
- *                          RESIDENT in shared memory as FP16 hi/lo fragments and exchanges the stage derivative through
- *                          distributed shared memory; ancde_ncde_backward returns ANCDE_EUNSUPPORTED for it.         */
+ *   (value 2 was the round-1 mma.sync cluster engine; it was superseded by ANCDE_ENGINE_UMMA and removed)            */
 #define ANCDE_ENGINE_STREAMED 1
-#define ANCDE_ENGINE_CLUSTER  2
 /*   ANCDE_ENGINE_UMMA      forward on the tcgen05 tensor cores (accumulators in tensor memory): a cluster of 2/4/8 CTAs per
  *                          16/32/64 samples keeps the output layer resident in shared memory as FP16 hi/lo operands; three
  *                          products per k step = FP32-grade accuracy.  Saves the activations in the streamed engine's
@@ -127,7 +124,7 @@ typedef struct ancde_ncde_desc {
     float* grad_bias[ANCDE_MAX_LAYERS + 1];
     float* grad_attention;     /* TOP, or NULL (adjoint-mode gradient flow): (att_L, B, att_C) accumulated into */
     int32_t samples_per_cta;   /* streamed engine only: 0 = let the library choose (8, 4, 2 or 1) */
-    int32_t engine;            /* 0 = library default; ANCDE_ENGINE_STREAMED, _CLUSTER or _UMMA (see above) */
+    int32_t engine;            /* 0 = library default; ANCDE_ENGINE_STREAMED or _UMMA (see above) */
     int32_t single_stage;      /* 1 = evaluate only the vector field at (t_start, z0): k_out (1, B, Hd) = f(z0) dX/dt(t_start), the
                                 * building block of adaptive solvers driven from the host (dopri5).  n_steps = n_out = 1; streamed
                                 * engine.  Backward: grad_k_out (B, Hd) is the cotangent of k_out, grad_z_out is not read. */
@@ -136,6 +133,9 @@ typedef struct ancde_ncde_desc {
                                 * depend on the recurrent kernel of the same call) so that they overlap whatever the caller
                                 * enqueues next; the caller must call ancde_ncde_join() on its stream before it reads the
                                 * gradients, and keep every buffer of the descriptor alive until then.  0 = same stream. */
+    const float* grid;         /* NULL: the arithmetic grid above.  Else n_steps + 1 increasing grid points (device), grid[0] = t_start,
+                                * grid[n_steps] = t_end: torchdiffeq's `options['grid_constructor']`, or rk4 without a step size
+                                * (the grid is `t` itself; FixedGridODESolver.__init__).  `step` is not read then. */
 } ancde_ncde_desc;
 
 /* Workspace sizes (in floats) for a descriptor whose shape fields are filled in. */

@@ -218,11 +218,17 @@ def fixed_grid(t, step_size):
     return grid
 
 
-def rk4_38(func, y0, t, step_size):
+def rk4_38(func, y0, t, step_size, grid=None):
     """torchdiffeq FixedGridODESolver.integrate + rk4_alt_step_func.
 
-    func(t, y, n) -> dy, where n is the running call counter (0-based)."""
-    grid = fixed_grid(t, step_size)
+    func(t, y, n) -> dy, where n is the running call counter (0-based).  The grid is t[0] + k * step_size; with
+    step_size None it is `grid` (options['grid_constructor']) or, with neither, `t` itself (FixedGridODESolver.__init__:
+    grid_constructor = lambda f, y0, t: t)."""
+    if step_size is not None:
+        grid = fixed_grid(t, step_size)
+    elif grid is None:
+        grid = t
+    assert grid[0] == t[0] and grid[-1] == t[-1]
     sol = [y0]
     j = 1
     y = y0
@@ -250,7 +256,7 @@ def rk4_38(func, y0, t, step_size):
 # =============================================================================
 # plain NCDE: controldiffeq.cdeint with FinalTanh (a6, VectorField)
 # =============================================================================
-def cdeint_port(sd, times, coeffs, z0, t, step_size, H, C, prefix='func'):
+def cdeint_port(sd, times, coeffs, z0, t, step_size, H, C, prefix='func', grid=None):
     """controldiffeq/cdeint_module.py:25-32,141-151 with func = FinalTanh."""
     cf = tuple(c.to(z0.dtype) for c in coeffs)
 
@@ -258,7 +264,7 @@ def cdeint_port(sd, times, coeffs, z0, t, step_size, H, C, prefix='func'):
         dX = spline_derivative(times, cf, tt)
         return (field_g(sd, z, H, C, prefix) @ dX.unsqueeze(-1)).squeeze(-1)
 
-    return rk4_38(field, z0, t, step_size)
+    return rk4_38(field, z0, t, step_size, grid)
 
 
 # =============================================================================

@@ -1,9 +1,12 @@
-"""Import the UNMODIFIED reference python packages (TEST INFRASTRUCTURE, build container only).
+"""Import the UNMODIFIED reference python packages (TEST INFRASTRUCTURE).
 
-``/root/reference`` exists only in the build container, never on the GPU box, so
-this module is used by ``oracle/gen_golden.py`` (to make ``tests/golden``) and by
-the CPU tests that pin ``oracle/port.py`` against the reference itself.  Those
-tests skip when the directory is absent.
+``/root/reference`` exists only in the build container, never on the GPU box; there
+the byte-for-byte copy ``oracle/_ref`` (made by ``oracle/make_ref.py``, git-ignored,
+shipped with the snapshot) takes its place.  This module is used by
+``oracle/gen_golden.py`` (to make ``tests/golden``), by the CPU tests that pin
+``oracle/port.py`` against the reference itself, by ``bench.py --impl reference`` and by
+the GPU test that runs the reference's own model classes on this repo's drop-in
+``controldiffeq`` (``load_models_on_dropin``).  Tests skip when neither tree is present.
 
 What is done to make the reference importable, none of which
 edits a reference file:
@@ -30,7 +33,19 @@ import torch
 
 from . import torchdiffeq_shim
 
-REFERENCE_ROOT = os.environ.get('ANCDE_REFERENCE_ROOT', '/root/reference')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _default_root():
+    env = os.environ.get('ANCDE_REFERENCE_ROOT')
+    if env:
+        return env
+    if os.path.isdir('/root/reference/controldiffeq'):
+        return '/root/reference'
+    return os.path.join(_HERE, '_ref')
+
+
+REFERENCE_ROOT = _default_root()
 
 _cache = {}
 
@@ -71,10 +86,45 @@ def load():
         sys.path[:] = old_path
         _purge(prefixes)
         sys.modules.update(saved)
-    assert ref_cde.__file__.startswith(REFERENCE_ROOT), ref_cde.__file__
+    assert os.path.abspath(ref_cde.__file__).startswith(os.path.abspath(REFERENCE_ROOT)), ref_cde.__file__
     _install_q7_repair(ref_cde)
     _cache['mods'] = (ref_cde, ref_models)
     return _cache['mods']
+
+
+def load_models_on_dropin():
+    """The reference's own ``experiments/models`` package (unmodified) imported on top of THIS repository's drop-in
+    ``controldiffeq`` package instead of the reference's: what a user gets who puts this repo first on ``sys.path``
+    (metamodel.py:5-8 *appends* the reference root).  No torchdiffeq shim, no Q7 wrapper: the drop-in solves on the GPU
+    and repairs the 2-D ``h_prime`` itself.  Returns the ``models`` module."""
+    if 'dropin' in _cache:
+        return _cache['dropin']
+    if not available():
+        raise RuntimeError('reference tree not present at %s' % REFERENCE_ROOT)
+    repo_root = os.path.dirname(_HERE)
+    prefixes = ('controldiffeq', 'models', 'torchdiffeq')
+    saved = _purge(prefixes)
+    old_path = list(sys.path)
+    # models/other.py (the ODE-RNN baselines, not on this path) imports torchdiffeq at module level; the ANCDE classes
+    # themselves only call `controldiffeq`, which is the drop-in here
+    torchdiffeq_shim.install()
+    sys.path.insert(0, os.path.join(REFERENCE_ROOT, 'experiments'))
+    sys.path.insert(0, repo_root)                   # the drop-in shadows the reference's controldiffeq
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            dropin = importlib.import_module('controldiffeq')
+            ref_models = importlib.import_module('models')
+    finally:
+        sys.path[:] = old_path
+        mods = _purge(prefixes)
+        sys.modules.update(saved)
+    assert os.path.abspath(dropin.__file__).startswith(repo_root + os.sep + 'controldiffeq'), dropin.__file__
+    assert ref_models.metamodel.controldiffeq is dropin
+    assert os.path.abspath(ref_models.__file__).startswith(os.path.abspath(REFERENCE_ROOT))
+    _cache['dropin'] = ref_models
+    return ref_models
 
 
 def _install_q7_repair(ref_cde):

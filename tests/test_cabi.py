@@ -76,7 +76,7 @@ def test_engine_resolution_runs_without_a_gpu():
     assert L.ancde_ncde_engine(ctypes.byref(desc(6, 12, [12, 12]))) == _lib.ENGINE_STREAMED
     assert L.ancde_ncde_engine(ctypes.byref(desc(6, 12, [12, 12], _lib.ENGINE_UMMA))) == _lib.ENGINE_UMMA
     assert L.ancde_ncde_engine(ctypes.byref(desc(69, 69, [20] * 5, _lib.ENGINE_UMMA))) == -1      # state wider than 63
-    assert L.ancde_ncde_engine(ctypes.byref(desc(35, 49, [49] * 4, _lib.ENGINE_CLUSTER))) == _lib.ENGINE_CLUSTER
+    assert L.ancde_ncde_engine(ctypes.byref(desc(35, 49, [49] * 4, 2))) == -1      # the removed round-1 cluster engine
     # the UMMA engine appends its operand image to the streamed engine's packed weights
     a = L.ancde_ncde_wpack_floats(ctypes.byref(desc(35, 49, [49] * 4, _lib.ENGINE_STREAMED)))
     b = L.ancde_ncde_wpack_floats(ctypes.byref(desc(35, 49, [49] * 4, _lib.ENGINE_UMMA)))

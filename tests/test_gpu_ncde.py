@@ -205,28 +205,6 @@ def test_api_errors():
                           options=dict(step_size=1.0))
 
 
-@pytest.mark.parametrize('case', DUAL_CASES)
-def test_cluster_engine_forward_matches_reference_golden(case):
-    """ANCDE_ENGINE_CLUSTER (thread-block clusters, output layer resident in shared memory, tensor cores): inference
-    parity against the same golden vectors; it refuses to differentiate."""
-    import ancde_b200
-    from ancde_b200 import solver, _lib
-    g = dual_case(case)
-    model = _build(g['cfg'], g['sd'])
-    solver.ENGINE = _lib.ENGINE_CLUSTER
-    try:
-        with torch.no_grad():
-            pred = _forward(model, g)
-        torch.cuda.synchronize()
-        hp = ancde_b200.load_h_prime('test_h_prime')
-        assert rel_err(pred, g['pred']) < FWD_TOL, case
-        assert rel_err(hp, g['h_prime']) < FWD_TOL, case
-        with pytest.raises(NotImplementedError):
-            _forward(model, g)
-    finally:
-        solver.ENGINE = 0
-
-
 @pytest.mark.parametrize('workload,B', [('mujoco', 11), ('stock', 3), ('uea', 5), ('sepsis', 19), ('sepsis_oi', 9)])
 def test_ragged_batches_against_oracle(workload, B):
     """Batches that do not fill the last tile of 8 samples (and, for Sepsis, the last cluster of the UMMA engine):
@@ -389,3 +367,163 @@ def test_cdeint_dopri5_against_the_torchdiffeq_restatement(adjoint):
     assert rel_err(z0g.grad, z0r.grad) < DOPRI_GRAD_TOL
     for k, p in func.named_parameters():
         assert rel_err(p.grad, oracle.grads()['func.' + k]) < DOPRI_GRAD_TOL, k
+
+
+def test_full_size_sepsis_batch_against_oracle():
+    """BASELINE size (B=1024, Sepsis shape): predictions of the whole batch against the CPU oracle (1e-4 relative)."""
+    from ancde_b200 import synthetic, metamodel
+    import ancde_b200
+    from oracle import port
+    cfg = synthetic.CONFIGS['sepsis']
+    torch.manual_seed(2021)
+    model, _, _ = metamodel.model_from_config(cfg, file='full_oracle')
+    bt = synthetic.make_batch('sepsis', B=1024)
+    coeffs_ref = port.natural_cubic_spline_coeffs(bt['times'], bt['X'])
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    sdm = {k[len('model.'):]: v for k, v in sd.items() if k.startswith('model.')}
+    with torch.no_grad():
+        ref = port.dual_ncde_forward(sdm, cfg, bt['times'], coeffs_ref, bt['final_index'], 1.0, stream=cfg['stream'],
+                                     z0=port.ivn_z0(sd, bt['static']))
+        model = model.cuda()
+        times = bt['times'].cuda()
+        coeffs = ancde_b200.natural_cubic_spline_coeffs(times, bt['X'].cuda())
+        pred = model(times, coeffs + (bt['static'].cuda(),), bt['final_index'].cuda(), 1.0)
+    for a, b in zip(coeffs, coeffs_ref):
+        assert rel_err(a, b) < 1e-5
+    assert pred.shape == ref['pred'].shape == (1024, 1)
+    assert rel_err(pred, ref['pred']) < FWD_TOL
+    assert rel_err(model.model._h_prime, ref['h_prime']) < FWD_TOL
+
+
+def test_rk4_on_an_explicit_grid_against_oracle():
+    """torchdiffeq semantics the reference forwards verbatim (cdeint_module.py:149): rk4 WITHOUT a step size integrates on
+    the grid `t` itself, and options['grid_constructor'](func, y0, t) supplies any other grid (FixedGridODESolver.__init__).
+    Values and gradients against the restated solver (oracle/torchdiffeq_shim.py) driving the ported vector field."""
+    import ancde_b200
+    from oracle import port
+    torch.manual_seed(5)
+    C, H, HH, nl, L, B = 4, 6, 8, 2, 8, 5
+    func = ancde_b200.FinalTanh(C, H, HH, nl)
+    times = torch.tensor([0.0, 0.4, 1.0, 1.3, 2.1, 2.2, 3.0, 3.7])
+    X = 0.3 * torch.randn(B, L, C).cumsum(1)
+    coeffs = port.natural_cubic_spline_coeffs(times, X)
+    z0 = torch.randn(B, H)
+    t = torch.tensor([0.0, 1.0, 2.1, 3.7])
+    grid = torch.tensor([0.0, 0.25, 0.6, 1.0, 1.1, 1.9, 2.1, 2.8, 3.3, 3.7])
+    w = loss_weights((t.numel(), B, H))
+    for constructor in (None, lambda f, y0, tt: grid.to(tt.device)):
+        sd = {'func.' + k: v.detach().clone().requires_grad_(True) for k, v in func.state_dict().items()}
+        z0r = z0.clone().requires_grad_(True)
+        ref = port.cdeint_port(sd, times, coeffs, z0r, t, None, H, C, prefix='func',
+                               grid=None if constructor is None else grid)
+        (ref * w).sum().backward()
+        fg = ancde_b200.FinalTanh(C, H, HH, nl)
+        fg.load_state_dict(func.state_dict())
+        fg = fg.cuda()
+        sp = ancde_b200.NaturalCubicSpline(times.cuda(), tuple(c.cuda() for c in coeffs))
+        z0g = z0.cuda().requires_grad_(True)
+        options = {} if constructor is None else dict(grid_constructor=constructor)
+        got = ancde_b200.cdeint(sp.derivative, z0g, fg, t.cuda(), adjoint=False, method='rk4', options=options)
+        (got * w.cuda()).sum().backward()
+        assert rel_err(got, ref) < FWD_TOL
+        assert rel_err(z0g.grad, z0r.grad) < GRAD_TOL
+        for k, p in fg.named_parameters():
+            assert rel_err(p.grad, sd['func.' + k].grad) < GRAD_TOL, k
+
+
+def test_grid_that_misses_the_last_time_raises_like_torchdiffeq():
+    """float32 arange(n) * step + t0 can end one ulp short of t[-1]; torchdiffeq asserts time_grid[-1] == t[-1]."""
+    import ancde_b200
+    func = ancde_b200.FinalTanh(3, 4, 5, 2).cuda()
+    times = torch.linspace(0, 10, 4).cuda()
+    coeffs = ancde_b200.natural_cubic_spline_coeffs(times, torch.randn(2, 4, 3).cuda())
+    sp = ancde_b200.NaturalCubicSpline(times, coeffs)
+    step = float((times[1:] - times[:-1]).min())
+    th = times.cpu()
+    n = int(torch.ceil((th[-1] - th[0]) / torch.tensor(step) + 1))
+    last = torch.tensor(float(n - 1)) * torch.tensor(step) + th[0]
+    if bool(last >= th[-1]):
+        pytest.skip('this grid reaches t[-1] in float32 on this build')
+    with pytest.raises(AssertionError):
+        ancde_b200.cdeint(sp.derivative, torch.randn(2, 4).cuda(), func, times, method='rk4', options=dict(step_size=step))
+
+
+def test_h_prime_of_another_batch_is_refused():
+    """ancde() validates h_prime against the batch and channel count of the control (the kernel indexes it as
+    (calls, B, C)); a stale h' of another batch must never be read out of bounds."""
+    import ancde_b200
+    g = dual_case('mujoco_soft_tw')
+    cfg = g['cfg']
+    func_g = ancde_b200.FinalTanh(cfg['C'], cfg['H'], cfg['HH'], cfg['nl']).cuda()
+    times = g['times'].cuda()
+    sp = ancde_b200.NaturalCubicSpline(times, tuple(c.cuda() for c in g['coeffs']))
+    B, C = g['coeffs'][0].shape[0], cfg['C']
+    att = torch.rand(times.numel(), B, C).cuda()
+    z0 = torch.randn(B, cfg['H']).cuda()
+    kw = dict(method='rk4', options=dict(step_size=1.0))
+    for bad in (torch.zeros(4 * (times.numel() - 1), B + 1, C), torch.zeros(4 * (times.numel() - 1), B, C + 1),
+                torch.zeros(1, B, C)):
+        with pytest.raises(ValueError):
+            ancde_b200.ancde(sp.derivative, att, z0, sp, func_g, bad.cuda(), times, False, **kw)
+    with pytest.raises(IndexError):       # 2-D h_prime and no bottom solve on this spline: what the reference raises
+        ancde_b200.ancde(sp.derivative, att, z0, sp, func_g, torch.zeros(1, C).cuda(), times, True, **kw)
+
+
+def _two_gpu_worker(rank, world, port_no, out):
+    import os
+    import torch.distributed as dist
+    from ancde_b200 import synthetic
+    from ancde_b200.train import DualNcdeTrainer
+    import ancde_b200
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port_no)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    tr = DualNcdeTrainer('mujoco', dev, seed=2021)
+    bt = synthetic.make_batch('mujoco', B=32, seed=11)
+    sl = slice(rank * 16, (rank + 1) * 16)
+    times = bt['times'].to(dev)
+    coeffs = ancde_b200.natural_cubic_spline_coeffs(times, bt['X'][sl].to(dev))
+    batch = dict(times=times, coeffs=coeffs, final_index=bt['final_index'][sl].to(dev), y=bt['y'][sl].to(dev))
+    tr.bucket.zero()
+    from ancde_b200 import solver
+    from ancde_b200.train import task_loss
+    loss = task_loss(tr.cfg, tr.forward(batch), batch['y'])
+    with solver.accumulate_into_param_grads():
+        loss.backward()
+    tr.bucket.all_reduce_mean()
+    torch.cuda.synchronize(dev)
+    if rank == 0:
+        torch.save(tr.bucket.flat.cpu(), out)
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_gradient_equals_single_gpu_gradient(tmp_path):
+    """N-rank sharded flat gradient (NCCL all-reduce, mean) == the single-GPU gradient of the whole batch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import socket
+    import torch.multiprocessing as mp
+    import ancde_b200
+    from ancde_b200 import synthetic, solver
+    from ancde_b200.train import DualNcdeTrainer, task_loss
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port_no = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / 'flat.pt')
+    mp.spawn(_two_gpu_worker, args=(2, port_no, out), nprocs=2, join=True)
+    sharded = torch.load(out)
+    dev = torch.device('cuda', 0)
+    tr = DualNcdeTrainer('mujoco', dev, seed=2021)
+    bt = synthetic.make_batch('mujoco', B=32, seed=11)
+    times = bt['times'].to(dev)
+    coeffs = ancde_b200.natural_cubic_spline_coeffs(times, bt['X'].to(dev))
+    batch = dict(times=times, coeffs=coeffs, final_index=bt['final_index'].to(dev), y=bt['y'].to(dev))
+    tr.bucket.zero()
+    loss = task_loss(tr.cfg, tr.forward(batch), batch['y'])
+    with solver.accumulate_into_param_grads():
+        loss.backward()
+    torch.cuda.synchronize()
+    assert rel_err(sharded, tr.bucket.flat) < 1e-5
