@@ -17,6 +17,8 @@
 // Matches autograd through torchdiffeq's rk4_alt_step_func + the reference vector fields
 // (cdeint_module.py:25-32,56-72,103-138; vector_fields.py:205-218,237-250) to FP32 round-off.
 #include "mma_common.cuh"
+#include "bwd_hidden.cuh"
+#include "ncde_bwd4.cuh"
 
 namespace ancde {
 
@@ -56,92 +58,6 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&v)[V], int lane)
 __device__ __forceinline__ void cp_async16_b(void* smem_dst, const void* gsrc)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-
-// The hidden ReLU layers backwards as ONE warp-synchronous chain (the mirror image of hidden_chain in ncde_fwd.cu):
-// a warp owns SPW samples for all layers, lane = input unit k of layer l, and per 4 outputs reads one 128-bit piece of
-// the transposed weight row Wt_l[k][o..o+3] plus one 128-bit broadcast per sample of the layer's cotangent
-// [sample][unit]; delta_{l-1} = (W_l^T delta_l) * relu'(h_{l-1}) goes to the next layer through shared memory behind a
-// __syncwarp.  FP32 FMA: these layers are far too small for the tensor cores (measured: 1.0-1.2 k cycles per layer
-// with mma.sync, one CTA barrier per layer and FP16 hi/lo operand conversions, 5.1 k cycles per stage for the Sepsis
-// bottom network).
-//   sLp[8*l ..] = {ceil(width / 4), in_dim, row stride, off_wt, act_off_h[l-1], act_off_delta[l-1], -, -}
-template <int TS>
-__device__ __forceinline__ void hidden_chain_bwd(const int* __restrict__ sLp, int n_hidden, const float* __restrict__ sW,
-                                                 float* __restrict__ sD0, float* __restrict__ sD1,
-                                                 const float* __restrict__ sAct, float* __restrict__ act,
-                                                 float* __restrict__ sZb, int HP, int warp, int NW, int lane)
-{
-    constexpr int SPW = (TS >= 2) ? 2 : 1;
-    constexpr int NCW = TS / SPW;
-    for (int cw = warp; cw < NCW; cw += NW) {
-        const int s0 = cw * SPW;
-        const float* in = sD0 + s0 * HP;
-        int pp = 1;
-        for (int l = n_hidden - 1; l >= 0; --l) {
-            const int4 q0 = *reinterpret_cast<const int4*>(sLp + 8 * l);
-            const int2 q1 = *reinterpret_cast<const int2*>(sLp + 8 * l + 4);
-            const int nk4 = q0.x, N = q0.y;
-            float* out = (pp ? sD1 : sD0) + s0 * HP;
-            const int N4 = pad4(N);
-            for (int k0 = 0; k0 < N4; k0 += 32) {
-                const int k = k0 + lane;
-                const bool valid = k < N;
-                const int kc = valid ? k : N - 1;
-                const float4* wr = reinterpret_cast<const float4*>(sW + q0.w + kc * q0.z);
-                const float4* x0 = reinterpret_cast<const float4*>(in);
-                const float4* x1 = reinterpret_cast<const float4*>(in + (SPW - 1) * HP);
-                float h[SPW];
-#pragma unroll
-                for (int e = 0; e < SPW; ++e) h[e] = 1.0f;
-                if (l > 0) Vec<SPW>::ld(sAct + q1.x + kc * TS + s0, h);
-                float accA[SPW], accB[SPW];
-#pragma unroll
-                for (int e = 0; e < SPW; ++e) { accA[e] = 0.f; accB[e] = 0.f; }
-                float4 w = wr[0], xa = x0[0], xb = x1[0];
-#pragma unroll 2
-                for (int q = 1; q < nk4; ++q) {
-                    const float4 wn = wr[q], xan = x0[q], xbn = x1[q];
-                    accA[0] = fmaf(w.x, xa.x, accA[0]);
-                    accB[0] = fmaf(w.y, xa.y, accB[0]);
-                    accA[0] = fmaf(w.z, xa.z, accA[0]);
-                    accB[0] = fmaf(w.w, xa.w, accB[0]);
-                    if (SPW == 2) {
-                        accA[SPW - 1] = fmaf(w.x, xb.x, accA[SPW - 1]);
-                        accB[SPW - 1] = fmaf(w.y, xb.y, accB[SPW - 1]);
-                        accA[SPW - 1] = fmaf(w.z, xb.z, accA[SPW - 1]);
-                        accB[SPW - 1] = fmaf(w.w, xb.w, accB[SPW - 1]);
-                    }
-                    w = wn; xa = xan; xb = xbn;
-                }
-                accA[0] = fmaf(w.x, xa.x, accA[0]);
-                accB[0] = fmaf(w.y, xa.y, accB[0]);
-                accA[0] = fmaf(w.z, xa.z, accA[0]);
-                accB[0] = fmaf(w.w, xa.w, accB[0]);
-                if (SPW == 2) {
-                    accA[SPW - 1] = fmaf(w.x, xb.x, accA[SPW - 1]);
-                    accB[SPW - 1] = fmaf(w.y, xb.y, accB[SPW - 1]);
-                    accA[SPW - 1] = fmaf(w.z, xb.z, accA[SPW - 1]);
-                    accB[SPW - 1] = fmaf(w.w, xb.w, accB[SPW - 1]);
-                }
-                float v[SPW];
-#pragma unroll
-                for (int e = 0; e < SPW; ++e) v[e] = (valid && h[e] > 0.f) ? accA[e] + accB[e] : 0.f;
-                if (l > 0) {
-                    if (k < N4) {
-#pragma unroll
-                        for (int e = 0; e < SPW; ++e) out[e * HP + k] = v[e];
-                    }
-                    if (valid) Vec<SPW>::st(act + q1.y + k * TS + s0, v);     // for the hidden weight-gradient kernel
-                } else if (valid) {
-                    Vec<SPW>::st(sZb + k * TS + s0, v);                       // cotangent of the stage input
-                }
-            }
-            __syncwarp();
-            in = out;
-            pp ^= 1;
-        }
-    }
 }
 
 constexpr int BW_MTK_MAX = 4;      // output-layer reduction size K <= 64
@@ -732,6 +648,37 @@ static int side_stream(SideStream** out)
     return ANCDE_OK;
 }
 
+// The weight-gradient kernels of a backward call (they read the stage / layer cotangents the recurrent kernel left in
+// save_act and depend on nothing else).
+static int launch_wgrads(const ancde_ncde_desc* d, const SolveArgs& a, cudaStream_t stream)
+{
+    const NcdeLayout& lo = a.lo;
+    // With async_wgrad they go to the side stream and run next to whatever the caller enqueues after
+    // this call -- in a training step the recurrent backward of the OTHER network, which leaves 20 of the 148 SMs idle
+    {
+        cudaStream_t ws = stream;
+        SideStream* ss = nullptr;
+        if (d->async_wgrad) {
+            int rc = side_stream(&ss);
+            if (rc != ANCDE_OK) return rc;
+            ANCDE_CUDA(cudaEventRecord(ss->fork, stream));
+            ANCDE_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+            ws = ss->s;
+        }
+        int rc = launch_wgrad(a, d->grad_W[lo.n_hidden], d->grad_bias[lo.n_hidden], ws);
+        if (rc != ANCDE_OK) return rc;
+        HiddenGradPtrs hp;
+        for (int l = 0; l < lo.n_hidden; ++l) { hp.gW[l] = d->grad_W[l]; hp.gB[l] = d->grad_bias[l]; }
+        rc = launch_hidden_wgrad(a, hp, ws);
+        if (rc != ANCDE_OK) return rc;
+        if (ss) {
+            ANCDE_CUDA(cudaEventRecord(ss->done, ss->s));
+            ss->pending = true;
+        }
+    }
+    return ANCDE_OK;
+}
+
 template <int TS>
 static int launch_bwd(const ancde_ncde_desc* d, SolveArgs& a, cudaStream_t stream)
 {
@@ -768,31 +715,7 @@ static int launch_bwd(const ancde_ncde_desc* d, SolveArgs& a, cudaStream_t strea
     count_launch();
     ANCDE_CUDA(cudaGetLastError());
 
-    // weight gradients (read the stage / layer cotangents the kernel above left in save_act).  They depend on nothing
-    // but that kernel: with async_wgrad they go to the side stream and run next to whatever the caller enqueues after
-    // this call -- in a training step the recurrent backward of the OTHER network, which leaves 20 of the 148 SMs idle
-    {
-        cudaStream_t ws = stream;
-        SideStream* ss = nullptr;
-        if (d->async_wgrad) {
-            int rc = side_stream(&ss);
-            if (rc != ANCDE_OK) return rc;
-            ANCDE_CUDA(cudaEventRecord(ss->fork, stream));
-            ANCDE_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
-            ws = ss->s;
-        }
-        int rc = launch_wgrad(a, d->grad_W[lo.n_hidden], d->grad_bias[lo.n_hidden], ws);
-        if (rc != ANCDE_OK) return rc;
-        HiddenGradPtrs hp;
-        for (int l = 0; l < lo.n_hidden; ++l) { hp.gW[l] = d->grad_W[l]; hp.gB[l] = d->grad_bias[l]; }
-        rc = launch_hidden_wgrad(a, hp, ws);
-        if (rc != ANCDE_OK) return rc;
-        if (ss) {
-            ANCDE_CUDA(cudaEventRecord(ss->done, ss->s));
-            ss->pending = true;
-        }
-    }
-    return ANCDE_OK;
+    return launch_wgrads(d, a, stream);
 }
 
 }  // namespace ancde
@@ -810,6 +733,34 @@ extern "C" int ancde_ncde_join(void* stream_)
         ss->pending = false;
     }
     return ANCDE_OK;
+}
+
+namespace ancde {
+static int g_force_bwd_engine = 0;       // 0 = automatic, 1 = streamed kernel, 4 = cluster / tcgen05 kernel
+static int g_force_bwd_cs = 0;           // cluster size of the tcgen05 backward (0 = automatic)
+
+int64_t bwd4_img_offset(const ancde_ncde_desc* d, const NcdeLayout& st);      // ncde_host.cu
+
+// Which recurrent backward kernel runs for this descriptor (the layout is filled when the answer is 4).
+static int bwd_engine_of(const ancde_ncde_desc* d, const NcdeLayout& lo, V4Layout* v4)
+{
+    if (g_force_bwd_engine == 1) return 1;
+    const bool need_att = d->mode == ANCDE_MODE_TOP && d->grad_attention != nullptr;
+    if (make_layout4(d, lo, need_att, g_force_bwd_cs, v4) != ANCDE_OK) return g_force_bwd_engine == 4 ? -1 : 1;
+    if (g_force_bwd_engine == 4) return 4;
+    // Measured on B200 (round 2): the cluster kernel wins where the streamed one is bound by re-streaming W_out^T through
+    // shared memory for 8 samples -- a large output layer and enough samples to fill clusters; small shapes stay put.
+    if ((int64_t)lo.NCP * lo.K >= 20000 && lo.B >= 2 * v4->NS) return 4;
+    return 1;
+}
+}  // namespace ancde
+
+extern "C" int ancde_debug_force_bwd_engine(int engine, int cluster_size)
+{
+    const int old = ancde::g_force_bwd_engine;
+    ancde::g_force_bwd_engine = engine;
+    ancde::g_force_bwd_cs = cluster_size;
+    return old;
 }
 
 extern "C" int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream_)
@@ -830,6 +781,20 @@ extern "C" int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream_)
     if (rc != ANCDE_OK) return rc;
     rc = pack_weights(d, lo, stream);   // the packed weights of the forward may have been reused
     if (rc != ANCDE_OK) return rc;
+    V4Layout v4;
+    const int engine = bwd_engine_of(d, lo, &v4);
+    if (engine < 0) {
+        set_error("ncde_backward: this shape is not supported by the cluster (tcgen05) backward");
+        return ANCDE_EUNSUPPORTED;
+    }
+    if (engine == 4) {
+        unsigned char* img = reinterpret_cast<unsigned char*>(d->wpack + bwd4_img_offset(d, lo));
+        rc = pack_weights4(d, lo, v4, img, stream);
+        if (rc != ANCDE_OK) return rc;
+        rc = launch_bwd4(a, v4, img, stream);
+        if (rc != ANCDE_OK) return rc;
+        return launch_wgrads(d, a, stream);
+    }
     switch (lo.TS) {
         case 8: return launch_bwd<8>(d, a, stream);
         case 4: return launch_bwd<4>(d, a, stream);

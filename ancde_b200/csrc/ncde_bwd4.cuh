@@ -1,0 +1,63 @@
+// Cluster / tcgen05 ("v4") recurrent backward of the fused NCDE solve: shared definitions.
+//
+// The streamed backward (ncde_bwd.cu) re-streams all of W_out^T (~500 KB as FP16 hi/lo fragments) through shared memory
+// every RK4 stage for the 8 samples of a CTA and is bound by that shared-memory round trip.  Here a thread-block CLUSTER
+// of CS CTAs walks NS = 8*CS samples backwards together, weight stationary:
+//   * every CTA keeps a 1/CS slice of W_out^T RESIDENT in shared memory for the whole solve.  The slice is cut along
+//     the REDUCTION index p = i*C4 + j of  hbar[u] = sum_p W_out[p][u] * prebar[p]  (k steps of 16 columns), and stored
+//     as ONE FP16 matrix of 128 rows in the tensor core's canonical K-major layout (umma.cuh): row 32*q + l holds the
+//     hi half (l < 16) or the lo half (l >= 16) of 64 * W_out[.][u], u = 16*q + (l & 15);
+//   * per stage every CTA builds the pre-activation cotangent  prebar[p][n] = gbar[i][n] * dU[j][n] * (1 - G[p][n]^2)  of
+//     its slice for ALL NS samples straight from the saved tanh outputs (HBM / L2 -> registers), splits it into FP16
+//     hi/lo and writes it as the B operand [prebar_hi ; prebar_lo] (2*NS rows) into a small ring of shared-memory
+//     chunks; one elected thread issues tcgen05.mma (M = 128, N = 2*NS, K = 16) per k step, accumulating the four
+//     hi/lo products in tensor memory (the lo*lo quadrant is simply not read);
+//   * the accumulator is read back with tcgen05.ld, the three useful quadrants are summed with one shuffle, and the
+//     partial sums are REDUCE-SCATTERED through distributed shared memory (st.async + mbarrier transaction counts): CTA r
+//     receives the CS partial hbar of ITS 8 samples;
+//   * the hidden ReLU layers backwards, the RK4 adjoint recurrence (state in registers) and the saved cotangents for the
+//     weight-gradient kernels are per CTA for its own 8 samples, exactly as in the streamed kernel; the stage cotangent
+//     gbar of the next stage is broadcast to the cluster (st.async) for the next operand build.
+// Buffers read and written in HBM are those of the streamed engine (tiles of 8 samples, ncde_layout.cuh), so either
+// forward engine and all weight-gradient kernels work unchanged.
+#pragma once
+#include "ncde_common.cuh"
+
+namespace ancde {
+
+constexpr int V4_THREADS = 512;
+constexpr int V4_MAX_CS = 8;
+
+struct V4Layout {
+    int CS, NS, nclusters;
+    int QW;                         // warps per tile in the operand build = 16 / CS
+    int CK;                         // k steps (of 16 columns) per ring chunk = 32 / CS: one (sample, 8 columns) item per thread
+    int ks_begin[V4_MAX_CS + 1];    // k-step range of every cluster rank
+    int nks_max, nchunks_max;
+    int SBOa, a_bytes;              // per-rank A image: 128 rows x 16*nks_max columns, SBO = nks_max * 256 bytes
+    int64_t img_bytes;              // CS * a_bytes
+    int SBOb, ring_bytes;           // one ring chunk: 2*NS rows x 16*CK columns
+    int tmem_cols;                  // power of two >= max(32, 2*NS)
+    int GSTR;                       // row stride (floats) of the gathered stage cotangent [Hd][GSTR]
+    int dub;                        // floats of one tile's dU (| dU/da) block
+    int act_ld;                     // floats of a saved-activation block staged in shared memory (z_s | h_1 .. h_n)
+    int KP, HP;                     // hidden-layer buffers (see ncde_bwd.cu)
+    int chain;                      // 1: FP32 warp-synchronous hidden chain (all widths <= 32), 0: mma.sync
+    int need_att;                   // timewise attention cotangent requested
+    // shared-memory carve-up (byte offsets)
+    int o_bars, o_A, o_ring, o_hid, o_recv, o_recvatt, o_gall, o_du, o_act, o_zb, o_bd, o_max, o_lp, o_tab;
+    int smem_total;
+};
+
+struct Bwd4Args {
+    SolveArgs s;
+    V4Layout v;
+    const unsigned char* img;
+};
+
+// Fills the layout when the shape is supported by this engine (ANCDE_EUNSUPPORTED otherwise, quietly).
+int make_layout4(const ancde_ncde_desc* d, const NcdeLayout& st, bool need_att, int force_cs, V4Layout* v);
+int pack_weights4(const ancde_ncde_desc* d, const NcdeLayout& st, const V4Layout& v, unsigned char* img, cudaStream_t stream);
+int launch_bwd4(const SolveArgs& a, const V4Layout& v, const unsigned char* img, cudaStream_t stream);
+
+}  // namespace ancde

@@ -2,6 +2,7 @@
 // argument marshalling and the C-ABI entry points for the forward.
 #include "mma_common.cuh"
 #include "ncde3_common.cuh"
+#include "ncde_bwd4.cuh"
 
 namespace ancde {
 
@@ -305,6 +306,32 @@ extern "C" int ancde_ncde_engine(const ancde_ncde_desc* d)
     return engine_of(d);
 }
 
+namespace ancde {
+// float offset of the cluster backward's operand image inside wpack: behind everything the forward engines use
+int64_t bwd4_img_offset(const ancde_ncde_desc* d, const NcdeLayout& st)
+{
+    int64_t end = st.wpack_floats;
+    if (engine_of(d) == ANCDE_ENGINE_UMMA) {
+        V3Layout l3;
+        if (make_layout3(d, &st, &l3) == ANCDE_OK) end = umma_img_offset(st) + (l3.img_bytes + 3) / 4;
+    }
+    return (end + 31) & ~(int64_t)31;          // 128-byte aligned
+}
+// floats the cluster backward's image needs (0 when the shape is not supported by it, whatever the attention mode)
+static int64_t bwd4_img_floats(const ancde_ncde_desc* d, const NcdeLayout& st)
+{
+    V4Layout v4;
+    int64_t best = 0;
+    for (int att = 0; att < 2; ++att) {
+        if (att && (d->mode != ANCDE_MODE_TOP || d->att_C != 1)) continue;
+        if (make_layout4(d, st, att != 0, 0, &v4) == ANCDE_OK && v4.img_bytes > best) best = v4.img_bytes;
+        for (int cs = 2; cs <= 8; cs *= 2)
+            if (make_layout4(d, st, att != 0, cs, &v4) == ANCDE_OK && v4.img_bytes > best) best = v4.img_bytes;
+    }
+    return (best + 3) / 4;
+}
+}  // namespace ancde
+
 extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
 {
     if (engine_of(d) < 0) { set_error("ncde: this shape is not supported by the UMMA engine"); return -1; }
@@ -313,9 +340,8 @@ extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
     if (engine_of(d) == ANCDE_ENGINE_UMMA) {
         V3Layout l3;
         if (make_layout3(d, &lo, &l3) != ANCDE_OK) return -1;
-        return umma_img_offset(lo) + (l3.img_bytes + 3) / 4;
     }
-    return lo.wpack_floats;
+    return bwd4_img_offset(d, lo) + bwd4_img_floats(d, lo);
 }
 
 extern "C" int64_t ancde_ncde_save_act_floats(const ancde_ncde_desc* d)

@@ -212,12 +212,13 @@ def cpu_reference_step_fn(workload, sample_B, adjoint=False):
         def one():
             model.zero_grad(set_to_none=True)
             kw = dict(stream=cfg['stream'], adjoint=adjoint)
-            if cfg['static']:
-                pred = model(bt['times'], coeffs32, bt['final_index'], 1.0, bt['static'], **kw)
-            else:
-                pred = model(bt['times'], coeffs32, bt['final_index'], 1.0, **kw)
-            loss = task_loss(cfg, pred, bt['y'])
-            loss.backward()
+            with reference_loader.cpu_only():             # the reference hard-codes .cuda() on its vector fields
+                if cfg['static']:
+                    pred = model(bt['times'], coeffs32, bt['final_index'], 1.0, bt['static'], **kw)
+                else:
+                    pred = model(bt['times'], coeffs32, bt['final_index'], 1.0, **kw)
+                loss = task_loss(cfg, pred, bt['y'])
+                loss.backward()
             return float(loss.detach())
         return one, 'reference', cores
 

@@ -173,6 +173,12 @@ int ancde_profile_get(int i, char* name, size_t len, float* ms);
  * instead of the tcgen05 kernel (ncde_wgrad_umma.cu), which is the default for tiles of 8 samples.  Returns the old value. */
 int ancde_debug_force_wgrad_mma_sync(int on);
 
+/* Development / test aid: which recurrent backward kernel ancde_ncde_backward runs.  engine 0 = automatic (the cluster /
+ * tcgen05 kernel of ncde_bwd4.cu for large output layers, the streamed kernel of ncde_bwd.cu otherwise), 1 = streamed,
+ * 4 = cluster (ANCDE_EUNSUPPORTED for shapes it cannot run); cluster_size 0 = automatic, else 2, 4 or 8.  Returns the old
+ * engine value. */
+int ancde_debug_force_bwd_engine(int engine, int cluster_size);
+
 /* Development aid: 64 int64 counters in device memory that kernels built with -DANCDE_PHASE_TIMING
  * fill with per-phase clock64() totals (normal builds never touch the buffer). NULL disables. */
 int ancde_debug_set_buffer(long long* dev_counters);

@@ -127,6 +127,21 @@ def load_models_on_dropin():
     return ref_models
 
 
+class cpu_only:
+    """Context manager for running the reference on the host cores of a box that HAS a GPU: the reference hard-codes
+    `.cuda()` on its vector fields (cdeint_module.py:163,253), which would move the weights away from the CPU inputs.
+    Inside the context `torch.nn.Module.cuda` is the identity (restored afterwards)."""
+
+    def __enter__(self):
+        self._old = torch.nn.Module.cuda
+        torch.nn.Module.cuda = lambda module, *a, **k: module
+        return self
+
+    def __exit__(self, *exc):
+        torch.nn.Module.cuda = self._old
+        return False
+
+
 def _install_q7_repair(ref_cde):
     orig_bottom, orig_top = ref_cde.ancde_bottom, ref_cde.ancde
     state = {}
