@@ -45,7 +45,7 @@ _lib = None
 
 EXPORTS = ['ancde_abi_version', 'ancde_last_error', 'ancde_spline_coeffs_f32', 'ancde_spline_coeffs_f64',
            'ancde_ncde_wpack_floats', 'ancde_ncde_save_act_floats', 'ancde_ncde_save_G_floats',
-           'ancde_ncde_engine', 'ancde_ncde_forward', 'ancde_ncde_backward', 'ancde_ncde_join', 'ancde_debug_force_wgrad_mma_sync', 'ancde_debug_force_bwd_engine', 'ancde_last_launch_count', 'ancde_fp32_peak_kernel',
+           'ancde_ncde_engine', 'ancde_ncde_forward', 'ancde_ncde_backward', 'ancde_ncde_join', 'ancde_debug_force_wgrad_mma_sync', 'ancde_debug_force_bwd_engine', 'ancde_debug_bwd4_launches', 'ancde_last_launch_count', 'ancde_fp32_peak_kernel',
            'ancde_profile_enable', 'ancde_profile_count', 'ancde_profile_get']
 
 

@@ -736,7 +736,8 @@ extern "C" int ancde_ncde_join(void* stream_)
 }
 
 namespace ancde {
-static int g_force_bwd_engine = 0;       // 0 = automatic, 1 = streamed kernel, 4 = cluster / tcgen05 kernel
+static int g_force_bwd_engine = 0;       // 0 = automatic, 1 = streamed kernel, 4 = cluster / tcgen05 kernel, 5 = cluster where supported
+static int g_bwd4_launches = 0;
 static int g_force_bwd_cs = 0;           // cluster size of the tcgen05 backward (0 = automatic)
 
 int64_t bwd4_img_offset(const ancde_ncde_desc* d, const NcdeLayout& st);      // ncde_host.cu
@@ -746,8 +747,8 @@ static int bwd_engine_of(const ancde_ncde_desc* d, const NcdeLayout& lo, V4Layou
 {
     if (g_force_bwd_engine == 1) return 1;
     const bool need_att = d->mode == ANCDE_MODE_TOP && d->grad_attention != nullptr;
-    if (make_layout4(d, lo, need_att, g_force_bwd_cs, v4) != ANCDE_OK) return g_force_bwd_engine == 4 ? -1 : 1;
-    if (g_force_bwd_engine == 4) return 4;
+    if (choose_layout4(d, lo, need_att, g_force_bwd_cs, v4) != ANCDE_OK) return g_force_bwd_engine == 4 ? -1 : 1;
+    if (g_force_bwd_engine >= 4) return 4;
     // Measured on B200 (round 2): the cluster kernel wins where the streamed one is bound by re-streaming W_out^T through
     // shared memory for 8 samples -- a large output layer and enough samples to fill clusters; small shapes stay put.
     if ((int64_t)lo.NCP * lo.K >= 20000 && lo.B >= 2 * v4->NS) return 4;
@@ -762,6 +763,8 @@ extern "C" int ancde_debug_force_bwd_engine(int engine, int cluster_size)
     ancde::g_force_bwd_cs = cluster_size;
     return old;
 }
+
+extern "C" int ancde_debug_bwd4_launches(void) { return ancde::g_bwd4_launches; }
 
 extern "C" int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream_)
 {
@@ -793,6 +796,7 @@ extern "C" int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream_)
         if (rc != ANCDE_OK) return rc;
         rc = launch_bwd4(a, v4, img, stream);
         if (rc != ANCDE_OK) return rc;
+        ++g_bwd4_launches;
         return launch_wgrads(d, a, stream);
     }
     switch (lo.TS) {

@@ -29,16 +29,19 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float a, float
                  : "memory");
 }
 
+// Named barrier over the worker warps (the issuer warp never joins).
+__device__ __forceinline__ void workers_sync() { named_bar_sync(1, V4_WORKERS); }
+
 template <bool CHAIN>
 __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_constant__ Bwd4Args p)
 {
     const NcdeLayout& lo = p.s.lo;            // streamed layout with tiles of 8 samples
     const V4Layout& v = p.v;
-    constexpr int TS = 8, NT = V4_THREADS, NW = NT / 32;
+    constexpr int TS = 8, NT = V4_WORKERS, NW = NT / 32;      // worker threads; warp NW is the MMA issuer
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform (uniform datapath for the MMA issue)
     const int wq = warp & 3, wg = warp >> 2;
-    const int CS = v.CS, NS = v.NS, CK = v.CK;
+    const int CS = v.CS, NS = v.NS, CK = v.CK, NSLOT = v.nslots;
     const int rank = (int)cluster_ctarank();
     const int cl = blockIdx.x / CS;
     const int tile = cl * CS + rank;          // the tile of 8 samples this CTA owns
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
     uint64_t* bar_du = bar_g + 1;                                             // dU blocks of the stage have landed (TMA)
     uint64_t* bar_act = bar_g + 2;                                            // own saved activations have landed (TMA)
     uint64_t* bar_recv = bar_g + 3;                                           // partial sums of my samples complete (tx bytes)
-    uint64_t* bar_built = bar_g + 4;                                          // [2] ring chunk written by all warps
+    uint64_t* bar_built = bar_g + 4;                                          // [2] ring chunk written by all worker warps
     uint64_t* bar_free = bar_g + 6;                                           // [2] products of a ring chunk complete
     uint32_t* tslot = reinterpret_cast<uint32_t*>(bar_g + 8);
     unsigned char* sA = smem_raw + v.o_A;
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
     const int pbase = 16 * v.ks_begin[rank];
 
     // ---- prologue: resident operands, tables, barriers, tensor memory
-    {
+    if (tid < NT) {
         const uint4* src = reinterpret_cast<const uint4*>(p.img + (size_t)rank * v.a_bytes);
         uint4* dst = reinterpret_cast<uint4*>(sA);
         for (int i = tid; i < v.a_bytes / 16; i += NT) dst[i] = __ldg(src + i);
@@ -95,6 +98,9 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
             uint32_t* zb = reinterpret_cast<uint32_t*>(sBd);
             for (int i = tid; i < 2 * 8 * v.KP; i += NT) zb[i] = 0u;      // 4 matrices of 8*KP halfs
         }
+        // operand rows / columns that are never written stay zero (0 * finite garbage would be fine, 0 * NaN is not)
+        uint4* zr = reinterpret_cast<uint4*>(sRing);
+        for (int i = tid; i < NSLOT * v.ring_bytes / 16; i += NT) zr[i] = make_uint4(0u, 0u, 0u, 0u);
         for (int i = tid; i < Hd * v.GSTR; i += NT) sGall[i] = 0.f;
         for (int i = tid; i < CS * v.dub; i += NT) sDU[i] = 0.f;          // tiles behind the batch stay zero
         for (int i = tid; i < v.act_ld; i += NT) sAct[i] = 0.f;
@@ -121,7 +127,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
                 const bool ok = gq < 2 * nks && pp < NCP;
                 const int i = pp / lo.C4, j0 = pp - i * lo.C4;
                 e[2 * h] = ok ? i * v.GSTR : -1;
-                e[2 * h + 1] = ok ? (j0 >> 2) * DUS : 0;
+                e[2 * h + 1] = ok ? (j0 >> 2) * 8 : 0;        // float4 index of the 4 channels in the re-laid-out controls
             }
             sTab[gq] = make_int4(e[0], e[1], e[2], e[3]);
         }
@@ -148,7 +154,10 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
     cluster_wait();
 
     auto act_block = [&](int n, int tl) { return p.s.save_act + ((int64_t)n * lo.ntiles + tl) * lo.act_floats; };
-    // dU (| dU/da) blocks of all tiles of the cluster for stage n: one TMA bulk copy per tile, ONE issuing thread
+    // dU (| dU/da) blocks of all tiles of the cluster for stage n: one TMA bulk copy per tile, ONE issuing thread.  They
+    // land in the operand buffer, which is idle between the last product of a stage and the operand build of the next,
+    // and are re-laid out from there at the start of the stage (below).
+    float* sStage = reinterpret_cast<float*>(sRing);
     auto issue_du = [&](int n) {
         uint32_t bytes = 0;
         for (int t = 0; t < CS; ++t)
@@ -156,32 +165,64 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
         mbar_arrive_expect_tx(bar_du, bytes);
         for (int t = 0; t < CS; ++t)
             if (cl * CS + t < lo.ntiles)
-                bulk_g2s(sDU + (size_t)t * v.dub, act_block(n, cl * CS + t) + lo.act_off_du, (uint32_t)(v.dub * 4), bar_du);
+                bulk_g2s(sStage + (size_t)t * v.dub, act_block(n, cl * CS + t) + lo.act_off_du, (uint32_t)(v.dub * 4), bar_du);
     };
     auto issue_act = [&](int n) {
         mbar_arrive_expect_tx(bar_act, (uint32_t)(v.act_ld * 4));
         bulk_g2s(sAct, act_block(n, tile), (uint32_t)(v.act_ld * 4), bar_act);
     };
+
+    if (warp_u == NW) {
+        // ================================ the issuer warp: products of every operand chunk ================================
+        const uint32_t idesc = umma_idesc_f16(128, 2 * NS, false);
+        const uint64_t dA = umma_smem_desc(smem_u32(sA), 128, (uint32_t)v.SBOa);
+        const uint64_t dB0 = umma_smem_desc(smem_u32(sRing), 128, (uint32_t)v.SBOb);
+        const uint64_t dB1 = umma_smem_desc(smem_u32(sRing) + (uint32_t)v.ring_bytes, 128, (uint32_t)v.SBOb);
+        uint32_t pb0 = 0, pb1 = 0;
+        int use = 0;                   // ring position of the next chunk (all stages)
+        for (int n = lo.n_stages - 1; n >= 0; --n) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int slot = (NSLOT == 2) ? (use & 1) : 0;
+                ++use;
+                mbar_wait(bar_built + slot, slot ? pb1 : pb0);
+                if (slot) pb1 ^= 1; else pb0 ^= 1;
+                if (elect_one()) {
+                    tc_fence_after();
+                    const int k0 = CK * c;
+                    const int kn = (nks - k0 < CK) ? nks - k0 : CK;
+                    const uint64_t dB = slot ? dB1 : dB0;
+#pragma unroll 4
+                    for (int ks = 0; ks < kn; ++ks)
+                        umma_f16(tbase, dA + (uint64_t)((k0 + ks) * 16), dB + (uint64_t)(ks * 16), idesc, (k0 + ks) != 0);
+                    umma_commit(bar_free + slot);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+    // ================================================ the worker warps ================================================
     if (tid == 0) {
         issue_du(lo.n_stages - 1);
         if (have_tile) issue_act(lo.n_stages - 1);
     }
 
-    // ---- constants of the operand build: thread = (sample nloc of the cluster, 8-column group q of a chunk)
-    const int n8 = tid & 7;
+    // ---- constants of the operand build: a thread converts (sample nloc of the cluster, 8 columns q of a chunk) items;
+    // the sample is the same for all its items: n8 = lane % 8 of tile `tile_t`, and q = 4 * (item warp / CS) + lane / 8
+    const int n8 = lane & 7;
+    const int cs_log2 = (CS == 8) ? 3 : (CS == 4 ? 2 : 1);
     const int tile_t = warp & (CS - 1);                      // tile of the cluster this thread's sample belongs to
     const int nloc = 8 * tile_t + n8;
-    const int q = ((tid >> 3) & 3) + 4 * (warp / CS);        // 0 .. 2*CK - 1
     const bool samp_ok = cl * CS + tile_t < lo.ntiles;
-    const uint32_t ring_hi = smem_u32(sRing) + (uint32_t)((nloc >> 3) * v.SBOb + q * 128 + (nloc & 7) * 16);
-    const uint32_t ring_lo = ring_hi + (uint32_t)((NS >> 3) * v.SBOb);
-    const float* sDUt = sDU + (size_t)tile_t * v.dub + n8;
-    const float* sDAt = sDUt + lo.du_floats;
+    const int wchunk = CS * (CK >> 1);                       // warp-items per chunk
+    const int nit = (wchunk + NW - 1) / NW;                  // iterations of a warp per chunk
+    const uint32_t ring_hi = smem_u32(sRing) + (uint32_t)((nloc >> 3) * v.SBOb + (nloc & 7) * 16);
+    const uint32_t ring_lo_off = (uint32_t)((NS >> 3) * v.SBOb);
+    const int NCH = lo.NCH;
+    const bool top = lo.mode == ANCDE_MODE_TOP;
+    // re-laid-out controls: float4 {channels 4*j4 .. 4*j4 + 3} per (tile, j4, sample); dU/da behind dU
+    const float4* sDUt = reinterpret_cast<const float4*>(sDU) + (size_t)tile_t * NCH * 8 + n8;
+    const float4* sDAt = sDUt + (size_t)CS * NCH * 8;
     const float* sGn = sGall + nloc;
-    const uint32_t idesc = umma_idesc_f16(128, 2 * NS, false);
-    const uint64_t dA = umma_smem_desc(smem_u32(sA), 128, (uint32_t)v.SBOa);
-    const uint64_t dB0 = umma_smem_desc(smem_u32(sRing), 128, (uint32_t)v.SBOb);
-    const uint64_t dB1 = umma_smem_desc(smem_u32(sRing) + (uint32_t)v.ring_bytes, 128, (uint32_t)v.SBOb);
     uint32_t gall_rank[V4_MAX_CS];
 #pragma unroll
     for (int r = 0; r < V4_MAX_CS; ++r) gall_rank[r] = map_to_rank(smem_u32(sGall), (uint32_t)(r < CS ? r : 0));
@@ -196,9 +237,16 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
     float lam = 0.f, mu = 0.f, v4 = 0.f, v3 = 0.f, v2 = 0.f;
     float gmax = 0.f;
     int jb = lo.n_out - 1;             // last output time whose cotangent has not been consumed yet
-    uint32_t par_g = 0, par_du = 0, par_act = 0, par_recv = 0, par_built0 = 0, par_built1 = 0;
-    int cnt0 = 0, cnt1 = 0;            // commits issued so far to ring slot 0 / 1 (the same in every thread)
+    uint32_t par_g = 0, par_du = 0, par_act = 0, par_recv = 0;
+    int use = 0;                       // ring position of the next chunk (all stages; the same in every thread)
     PH2_DECL();
+#ifdef ANCDE_PHASE_TIMING
+    if (tid == 0 && rank == 0 && p.s.dbg && cl < 32 && lo.mode == ANCDE_MODE_TOP) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.s.dbg[64 + cl] = (long long)gt;
+    }
+#endif
 
     for (int k = lo.n_steps - 1; k >= 0; --k) {
         const float t0 = grid_time(k, lo.n_steps, p.s.t_start, p.s.t_end, p.s.step, p.s.grid);
@@ -235,21 +283,33 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
                 else gv = dt * (0.125f * lam + v4 + (v2 - v3) * (1.0f / 3.0f));
                 if (act) act[lo.act_off_gbar + tid] = gv;        // the stage cotangent goes to HBM for the weight-gradient kernels
             }
+            // controls of this stage: [chunk j4][channel][sample] blocks of every tile -> float4 per (tile, j4, sample)
+            mbar_wait(bar_du, par_du);
+            par_du ^= 1;
+            for (int idx = tid; idx < CS * NCH * 8; idx += NT) {
+                const int t = idx / (NCH * 8), rem = idx - t * NCH * 8;
+                const float* src = sStage + (size_t)t * v.dub + (rem >> 3) * DUS + (rem & 7);
+                reinterpret_cast<float4*>(sDU)[idx] = make_float4(src[0], src[8], src[16], src[24]);
+                if (top) {
+                    src += lo.du_floats;
+                    reinterpret_cast<float4*>(sDU)[CS * NCH * 8 + idx] = make_float4(src[0], src[8], src[16], src[24]);
+                }
+            }
             float lmax = fabsf(gv);
             gmax = fmaxf(gmax, lmax);
             for (int o = 16; o >= 1; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
             if (lane == 0) sMax[warp] = lmax;
             // the tanh outputs of the NEXT stage towards L2 (this CTA reads a strided slice of every row)
             if (n >= 1) {
-                const int nrow = NS, per = (nks * 64 + 127) / 128 + 1;       // 128-byte lines per row slice
-                for (int item = tid; item < nrow * per; item += NT) {
+                const int per = (nks * 64 + 127) / 128 + 1;       // 128-byte lines per row slice
+                for (int item = tid; item < NS * per; item += NT) {
                     const int r = item / per, ln = item - r * per;
                     const int64_t row = (int64_t)cl * NS + r;
                     const int col = pbase + 32 * ln;
                     if (row < rows && col < NCP) prefetch_l2(p.s.save_G + ((int64_t)(n - 1) * rows + row) * NCP + col);
                 }
             }
-            __syncthreads();
+            workers_sync();
             float scale = 1.0f;
             {
                 const float4 m0 = *reinterpret_cast<const float4*>(sMax), m1 = *reinterpret_cast<const float4*>(sMax + 4);
@@ -272,93 +332,90 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
             if (tid == 0) mbar_arrive_expect_tx(bar_g, (uint32_t)(HT * CS * 4));
             mbar_wait(bar_g, par_g);
             par_g ^= 1;
-            mbar_wait(bar_du, par_du);
-            par_du ^= 1;
             PH2_MARK(0);
 
-            // ---- (1) operand build + products, chunk by chunk
+            // ---- (1) operand build, chunk by chunk; the issuer warp multiplies a chunk as soon as every warp has written it
             float att = 0.f;
             {
-                const float* grow = p.s.save_G + ((int64_t)n * rows + (int64_t)cl * NS + nloc) * NCP + pbase + 8 * q;
-                float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
-                int4 te = sTab[q];
-                if (samp_ok) {
-                    if (te.x >= 0) ga = __ldg(reinterpret_cast<const float4*>(grow));
-                    if (te.z >= 0) gb = __ldg(reinterpret_cast<const float4*>(grow + 4));
-                }
-                for (int c = 0; c < nchunks; ++c) {
-                    const int slot = c & 1;
-                    const float4 g0 = ga, g1 = gb;
-                    const int4 e = te;
-                    if (c + 1 < nchunks) {                   // the next chunk's tanh outputs are in flight while this one is converted
-                        te = sTab[2 * CK * (c + 1) + q];
-                        const float* gp = grow + 16 * CK * (c + 1);
-                        ga = make_float4(0.f, 0.f, 0.f, 0.f);
-                        gb = ga;
+                const float* grow = p.s.save_G + ((int64_t)n * rows + (int64_t)cl * NS + nloc) * NCP + pbase;
+                // two (chunk, iteration) units ahead: the tanh outputs of the next two items are in flight while one is converted
+                float4 ga0, gb0, ga1, gb1;
+                int4 te0, te1;
+                auto fetch = [&](int c, int it, float4& ga, float4& gb, int4& te) {
+                    ga = make_float4(0.f, 0.f, 0.f, 0.f);
+                    gb = ga;
+                    te = make_int4(-1, 0, -1, 0);
+                    while (it >= nit) { it -= nit; ++c; }
+                    const int wi = it * NW + warp;
+                    if (c < nchunks && wi < wchunk) {
+                        const int gq = 2 * CK * c + 4 * (wi >> cs_log2) + (lane >> 3);
+                        te = sTab[gq];
                         if (samp_ok) {
+                            const float* gp = grow + 8 * gq;
                             if (te.x >= 0) ga = __ldg(reinterpret_cast<const float4*>(gp));
                             if (te.z >= 0) gb = __ldg(reinterpret_cast<const float4*>(gp + 4));
                         }
                     }
-                    float pv[8];
-                    {
-                        const bool ok = e.x >= 0;
-                        const float gbv = ok ? sGn[e.x] : 0.f;
-                        const float* du = sDUt + e.y;
-                        pv[0] = gbv * du[0] * fmaf(-g0.x, g0.x, 1.0f);
-                        pv[1] = gbv * du[8] * fmaf(-g0.y, g0.y, 1.0f);
-                        pv[2] = gbv * du[16] * fmaf(-g0.z, g0.z, 1.0f);
-                        pv[3] = gbv * du[24] * fmaf(-g0.w, g0.w, 1.0f);
-                        if (need_att) {
-                            // sum_j dUbar[j] * dU/da[j] with dUbar[j] = sum_i gbar[i] * G[i][j]   
-                            const float* da = sDAt + e.y;
-                            att = fmaf(gbv, (g0.x * da[0] + g0.y * da[8]) + (g0.z * da[16] + g0.w * da[24]), att);
-                        }
-                    }
-                    {
-                        const bool ok = e.z >= 0;
-                        const float gbv = ok ? sGn[e.z] : 0.f;
-                        const float* du = sDUt + e.w;
-                        pv[4] = gbv * du[0] * fmaf(-g1.x, g1.x, 1.0f);
-                        pv[5] = gbv * du[8] * fmaf(-g1.y, g1.y, 1.0f);
-                        pv[6] = gbv * du[16] * fmaf(-g1.z, g1.z, 1.0f);
-                        pv[7] = gbv * du[24] * fmaf(-g1.w, g1.w, 1.0f);
-                        if (need_att) {
-                            const float* da = sDAt + e.w;
-                            att = fmaf(gbv, (g1.x * da[0] + g1.y * da[8]) + (g1.z * da[16] + g1.w * da[24]), att);
-                        }
-                    }
-                    uint32_t h[4], l[4];
+                };
+                fetch(0, 0, ga0, gb0, te0);
+                fetch(0, 1, ga1, gb1, te1);
+                for (int c = 0; c < nchunks; ++c) {
+                    const int slot = (NSLOT == 2) ? (use & 1) : 0;
+                    const int my_use = use;
+                    ++use;
+                    const uint32_t so = ring_hi + (uint32_t)(slot * v.ring_bytes);
+                    for (int it = 0; it < nit; ++it) {
+                        const float4 g0 = ga0, g1 = gb0;
+                        const int4 e = te0;
+                        const int wi = it * NW + warp;
+                        ga0 = ga1; gb0 = gb1; te0 = te1;
+                        fetch(c, it + 2, ga1, gb1, te1);
+                        uint32_t h[4], l[4];
+                        if (wi < wchunk) {
+                            float pv[8];
+                            {
+                                const bool ok = e.x >= 0;
+                                const float gbv = ok ? sGn[ok ? e.x : 0] : 0.f;
+                                const float4 du = sDUt[e.y];
+                                pv[0] = gbv * du.x * fmaf(-g0.x, g0.x, 1.0f);
+                                pv[1] = gbv * du.y * fmaf(-g0.y, g0.y, 1.0f);
+                                pv[2] = gbv * du.z * fmaf(-g0.z, g0.z, 1.0f);
+                                pv[3] = gbv * du.w * fmaf(-g0.w, g0.w, 1.0f);
+                                if (need_att) {
+                                    // sum_j dUbar[j] * dU/da[j] with dUbar[j] = sum_i gbar[i] * G[i][j]   
+                                    const float4 da = sDAt[e.y];
+                                    att = fmaf(gbv, (g0.x * da.x + g0.y * da.y) + (g0.z * da.z + g0.w * da.w), att);
+                                }
+                            }
+                            {
+                                const bool ok = e.z >= 0;
+                                const float gbv = ok ? sGn[ok ? e.z : 0] : 0.f;
+                                const float4 du = sDUt[e.w];
+                                pv[4] = gbv * du.x * fmaf(-g1.x, g1.x, 1.0f);
+                                pv[5] = gbv * du.y * fmaf(-g1.y, g1.y, 1.0f);
+                                pv[6] = gbv * du.z * fmaf(-g1.z, g1.z, 1.0f);
+                                pv[7] = gbv * du.w * fmaf(-g1.w, g1.w, 1.0f);
+                                if (need_att) {
+                                    const float4 da = sDAt[e.w];
+                                    att = fmaf(gbv, (g1.x * da.x + g1.y * da.y) + (g1.z * da.z + g1.w * da.w), att);
+                                }
+                            }
 #pragma unroll
-                    for (int x = 0; x < 4; ++x) split_pair(pv[2 * x], pv[2 * x + 1], h[x], l[x]);
-                    // the slot is free once the products of the chunk that used it last have completed
-                    const int cnt = slot ? cnt1 : cnt0;
-                    if (cnt > 0) mbar_wait(bar_free + slot, (uint32_t)((cnt - 1) & 1));
-                    const uint32_t so = (uint32_t)(slot * v.ring_bytes);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(ring_hi + so), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(ring_lo + so), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+                            for (int x = 0; x < 4; ++x) split_pair(pv[2 * x], pv[2 * x + 1], h[x], l[x]);
+                        }
+                        // the buffer is free once the products of the chunk that used it last have completed: chunk number
+                        // use - NSLOT (0-based over the whole solve) is completion number (use - NSLOT) / NSLOT of its barrier
+                        if (it == 0 && my_use >= NSLOT) mbar_wait(bar_free + slot, (uint32_t)(((my_use - NSLOT) / NSLOT) & 1));
+                        if (wi < wchunk) {
+                            const uint32_t dst = so + (uint32_t)((4 * (wi >> cs_log2) + (lane >> 3)) * 128);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + ring_lo_off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+                        }
+                    }
                     fence_async_smem();
+                    tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_built + slot);
-                    if (slot) ++cnt1; else ++cnt0;
-                    if (warp_u == 0) {
-                        const uint32_t par = slot ? par_built1 : par_built0;
-                        mbar_wait(bar_built + slot, par);
-                        if (slot) par_built1 ^= 1; else par_built0 ^= 1;
-                        if (elect_one()) {
-                            tc_fence_after();
-                            const int k0 = CK * c;
-                            const int kn = (nks - k0 < CK) ? nks - k0 : CK;
-                            const uint64_t dB = slot ? dB1 : dB0;
-#pragma unroll 4
-                            for (int ks = 0; ks < kn; ++ks)
-                                umma_f16(tbase, dA + (uint64_t)((k0 + ks) * 16), dB + (uint64_t)(ks * 16), idesc, (k0 + ks) != 0);
-                            umma_commit(bar_free + slot);
-                            // every warp has finished reading this stage's dU blocks: fetch the next stage's
-                            if (c == nchunks - 1 && n >= 1) issue_du(n - 1);
-                        }
-                        __syncwarp();
-                    }
                 }
             }
             PH2_MARK(1);
@@ -368,21 +425,23 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
                 att += __shfl_xor_sync(0xffffffffu, att, 16);
                 if (lane < 8) {
                     const uint32_t base = recv_att_dst;
-                    st_async_f32(base + ratt_delta + (uint32_t)(((rank * v.QW + warp / CS) * 8 + lane) * 4), att, base + barr_delta);
+                    st_async_f32(base + ratt_delta + (uint32_t)(((rank * v.QW + (warp >> cs_log2)) * 8 + lane) * 4), att, base + barr_delta);
                 }
             }
 
             // ---- (2) accumulator -> registers -> reduce-scatter of the partial sums over the cluster
             {
-                const int last = (nchunks - 1) & 1;
-                const int cnt = last ? cnt1 : cnt0;
-                mbar_wait(bar_free + last, (uint32_t)((cnt - 1) & 1));
+                const int last_use = use - 1;             // the stage's last chunk
+                const int last = (NSLOT == 2) ? (last_use & 1) : 0;
+                mbar_wait(bar_free + last, (uint32_t)((last_use / NSLOT) & 1));
                 tc_fence_after();
+                // every product of this stage has completed: the operand buffer is idle, the next stage's controls land in it
+                if (tid == 0 && n >= 1) issue_du(n - 1);
                 PH2_MARK(2);
                 if (wg < (NS >> 4)) {
                     float a[16], b2[16];
                     tmem_ld16x2(tlane + 16 * wg, tlane + NS + 16 * wg, a, b2);
-                    const bool hi = lane < 16;
+                    const bool hi = (lane & 8) == 0;
                     float out[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
@@ -392,9 +451,9 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
                         const float s_hi = hi ? a[8 + e] + b2[8 + e] : a[8 + e];
                         const float send = hi ? s_hi : s_lo;
                         const float keep = hi ? s_lo : s_hi;
-                        out[e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                        out[e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
                     }
-                    const int u = 16 * wq + (lane & 15);
+                    const int u = 16 * wq + 8 * (lane >> 4) + (lane & 7);
                     const int owner = 2 * wg + (hi ? 0 : 1);
                     if (u < K) {
                         const uint32_t base = map_to_rank(smem_u32(sRecv), (uint32_t)owner);
@@ -445,12 +504,12 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
                         atomicAdd(p.s.grad_attention + (int64_t)qa * lo.B + b0 + lane, a * inv_scale);
                 }
             }
-            __syncthreads();
+            workers_sync();
             if constexpr (CHAIN) {
                 hidden_chain_bwd<TS>(sLp, lo.n_hidden, sWtb, sD0, sD1, sAct, act, sZb, v.HP, warp, NW, lane);
-                __syncthreads();
+                workers_sync();
             } else {
-                hidden_mma_bwd<TS>(sLp, lo.n_hidden, sWhb, sBd, v.KP, sAct, act, sZb, inv_scale, warp, lane, [] { __syncthreads(); });
+                hidden_mma_bwd<TS>(sLp, lo.n_hidden, sWhb, sBd, v.KP, sAct, act, sZb, inv_scale, warp, lane, [] { workers_sync(); });
             }
             // the saved activations of this stage are consumed: fetch the next stage's (this kernel walks n downwards)
             if (tid == 0 && n >= 1 && have_tile) issue_act(n - 1);
@@ -470,7 +529,15 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
             PH2_MARK(5);
         }
     }
-    PH2_FLUSH(lo.mode == ANCDE_MODE_TOP ? 40 : 32);
+#ifdef ANCDE_PHASE_TIMING
+    if (tid == 0 && blockIdx.x == 0 && p.s.dbg)
+        for (int i = 0; i < 8; ++i) p.s.dbg[(lo.mode == ANCDE_MODE_TOP ? 40 : 32) + i] += ph2_acc[i];
+    if (tid == 0 && rank == 0 && p.s.dbg && cl < 32 && lo.mode == ANCDE_MODE_TOP) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.s.dbg[96 + cl] = (long long)gt;
+    }
+#endif
     // ---- results
     for (int o = 16; o >= 1; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
     if (lane == 0 && have_tile && gmax > 0.f && gmax < 3.0e38f)
@@ -479,6 +546,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
         const int bg = b0 + sb;
         if (bg < lo.B) p.s.grad_z0[(int64_t)bg * Hd + si] = lam + __ldg(p.s.grad_z_out + (int64_t)bg * Hd + si);
     }
+    }   // worker warps
     tc_fence_before();
     cluster_arrive();     // nobody leaves while a peer may still address its shared memory
     cluster_wait();
@@ -504,13 +572,13 @@ int make_layout4(const ancde_ncde_desc* d, const NcdeLayout& st, bool need_att, 
 {
     *v = V4Layout();
     if (st.TS != 8 || d->single_stage || st.n_stages < 4) return ANCDE_EUNSUPPORTED;
-    if (st.K > 64 || st.Hd * 8 > V4_THREADS || st.K * 8 > V4_THREADS) return ANCDE_EUNSUPPORTED;
+    if (st.K > 64 || st.Hd * 8 > V4_WORKERS || st.K * 8 > V4_WORKERS) return ANCDE_EUNSUPPORTED;
     if (need_att && st.att_C != 1) return ANCDE_EUNSUPPORTED;       // elementwise attention cotangents: streamed kernel
     if ((int64_t)st.ntiles * 8 * st.NCP * st.n_stages >= ((int64_t)1 << 40)) return ANCDE_EUNSUPPORTED;
     const bool chain = chain4(st);
     int maxmt = 1;
     for (int l = 0; l < st.n_hidden; ++l) maxmt = st.hbp[l].mtiles > maxmt ? st.hbp[l].mtiles : maxmt;
-    if (!chain && maxmt > V4_THREADS / 32) return ANCDE_EUNSUPPORTED;
+    if (!chain && maxmt > V4_WORKERS / 32) return ANCDE_EUNSUPPORTED;
     const int nks_total = (st.NCP + 15) / 16;
     static const int cand[3] = {8, 4, 2};
     for (int c = 0; c < 3; ++c) {
@@ -520,19 +588,16 @@ int make_layout4(const ancde_ncde_desc* d, const NcdeLayout& st, bool need_att, 
         v->CS = CS;
         v->NS = 8 * CS;
         v->QW = 16 / CS;
-        v->CK = 32 / CS;
         v->nclusters = (st.ntiles + CS - 1) / CS;
         const int base = nks_total / CS, extra = nks_total % CS;
         v->ks_begin[0] = 0;
         for (int r = 0; r < CS; ++r) v->ks_begin[r + 1] = v->ks_begin[r] + base + (r < extra ? 1 : 0);
         for (int r = CS; r < V4_MAX_CS; ++r) v->ks_begin[r + 1] = v->ks_begin[CS];
         v->nks_max = base + (extra ? 1 : 0);
-        v->nchunks_max = (v->nks_max + v->CK - 1) / v->CK;
         v->SBOa = v->nks_max * 256;
-        v->a_bytes = 16 * v->SBOa;
+        v->a_groups = 2 * ((st.K + 7) / 8);
+        v->a_bytes = v->a_groups * v->SBOa;
         v->img_bytes = (int64_t)CS * v->a_bytes;
-        v->SBOb = v->CK * 256;
-        v->ring_bytes = (2 * v->NS / 8) * v->SBOb;
         v->tmem_cols = pow2ceil4(2 * v->NS);
         v->GSTR = v->NS + 4;
         v->dub = st.du_floats * (st.mode == ANCDE_MODE_TOP ? 2 : 1);
@@ -541,26 +606,43 @@ int make_layout4(const ancde_ncde_desc* d, const NcdeLayout& st, bool need_att, 
         v->HP = pad4(st.Hmax);
         v->chain = chain ? 1 : 0;
         v->need_att = need_att ? 1 : 0;
-        auto up = [](size_t x) { return (x + 127) & ~(size_t)127; };
-        size_t o = 0;
-        v->o_bars = (int)o;    o = up(o + 128);
-        v->o_A = (int)o;       o = up(o + (size_t)v->a_bytes);
-        v->o_ring = (int)o;    o = up(o + 2 * (size_t)v->ring_bytes);
-        v->o_hid = (int)o;     o = up(o + (chain ? (size_t)pad4(st.hiddenb_floats) * 4 : (size_t)st.hb_u4 * 16));
-        v->o_recv = (int)o;    o = up(o + (size_t)CS * st.K * 8 * 4);
-        v->o_recvatt = (int)o; o = up(o + (size_t)CS * v->QW * 8 * 4);
-        v->o_gall = (int)o;    o = up(o + (size_t)st.Hd * v->GSTR * 4);
-        v->o_du = (int)o;      o = up(o + (size_t)CS * v->dub * 4);
-        v->o_act = (int)o;     o = up(o + (size_t)v->act_ld * 4);
-        v->o_zb = (int)o;      o = up(o + (size_t)pad4(st.Hd * 8) * 4);
-        v->o_bd = (int)o;      o = up(o + (chain ? (size_t)2 * 8 * v->HP * 4 : (size_t)4 * 8 * v->KP * 2));
-        v->o_max = (int)o;     o = up(o + 128);
-        v->o_lp = (int)o;      o = up(o + 8 * ANCDE_MAX_LAYERS * 4);
-        v->o_tab = (int)o;     o = up(o + (size_t)2 * v->CK * v->nchunks_max * 16);
-        v->smem_total = (int)o;
-        if (o > 227 * 1024) continue;
         if ((v->dub * 4) % 16 || (v->act_ld * 4) % 16 || (st.act_off_du * 4) % 16 || (st.act_floats * 4) % 16) continue;
-        return ANCDE_OK;
+        // the operand of a stage in as few chunks as fit: every chunk costs a proxy fence, a barrier round and an issue latency
+        for (int nch = 1; nch <= 8; ++nch) {
+            int CK = (v->nks_max + nch - 1) / nch;
+            CK += CK & 1;
+            const int nchunks = (v->nks_max + CK - 1) / CK;
+            for (int nslots = (nchunks > 1 ? 2 : 1); nslots >= 1; --nslots) {
+                v->CK = CK;
+                v->nslots = nslots;
+                v->nchunks_max = nchunks;
+                v->SBOb = CK * 256;
+                v->ring_bytes = (2 * v->NS / 8) * v->SBOb;
+                auto up = [](size_t x) { return (x + 127) & ~(size_t)127; };
+                size_t o = 0;
+                v->o_bars = (int)o;    o = up(o + 128);
+                v->o_A = (int)o;       o = up(o + (size_t)v->a_bytes);
+                v->o_ring = (int)o;    o = up(o + (size_t)nslots * v->ring_bytes);
+                v->o_hid = (int)o;     o = up(o + (chain ? (size_t)pad4(st.hiddenb_floats) * 4 : (size_t)st.hb_u4 * 16));
+                v->o_recv = (int)o;    o = up(o + (size_t)CS * st.K * 8 * 4);
+                v->o_recvatt = (int)o; o = up(o + (size_t)CS * v->QW * 8 * 4);
+                v->o_gall = (int)o;    o = up(o + (size_t)st.Hd * v->GSTR * 4);
+                v->o_du = (int)o;      o = up(o + (size_t)CS * v->dub * 4);
+                v->o_act = (int)o;     o = up(o + (size_t)v->act_ld * 4);
+                v->o_zb = (int)o;      o = up(o + (size_t)pad4(st.Hd * 8) * 4);
+                v->o_bd = (int)o;      o = up(o + (chain ? (size_t)2 * 8 * v->HP * 4 : (size_t)4 * 8 * v->KP * 2));
+                v->o_max = (int)o;     o = up(o + 128);
+                v->o_lp = (int)o;      o = up(o + 8 * ANCDE_MAX_LAYERS * 4);
+                v->o_tab = (int)o;     o = up(o + (size_t)2 * CK * nchunks * 16);
+                // the products read 16 groups of rows from the A image's base: that range must lie inside the allocation
+                const size_t a_end = (size_t)v->o_A + 16 * (size_t)v->SBOa;
+                if (o < a_end) o = up(a_end);
+                v->smem_total = (int)o;
+                // the controls of the next stage are staged in the operand buffer
+                if ((size_t)CS * v->dub * 4 > (size_t)nslots * v->ring_bytes) continue;
+                if (o <= 227 * 1024) return ANCDE_OK;
+            }
+        }
     }
     return ANCDE_EUNSUPPORTED;
 }
@@ -572,19 +654,20 @@ struct Pack4Args {
     unsigned char* img;
 };
 
-// A image of rank r: row m = 32*q + l -> unit u = 16*q + (l & 15), hi half for l < 16, lo half for l >= 16; column pl ->
-// reduction index p = 16*ks_begin[r] + pl = i*C4 + j.  Values are 64 * W_out[(i*C + j)][u].
+// A image of rank r: unit u -> rows 16*(u/8) + u%8 (hi half) and + 8 (lo half); column pl -> reduction index
+// p = 16*ks_begin[r] + pl = i*C4 + j.  Values are 64 * W_out[(i*C + j)][u].
 __global__ void pack_weights4_kernel(const __grid_constant__ Pack4Args a)
 {
     const NcdeLayout& lo = a.lo;
     const V4Layout& v = a.v;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     const int P = 16 * v.nks_max;
-    const int64_t total = (int64_t)v.CS * 64 * P;
+    const int NU = 4 * v.a_groups;             // units with rows in the image (a multiple of 8 >= K)
+    const int64_t total = (int64_t)v.CS * NU * P;
     for (int64_t idx = gtid; idx < total; idx += gsz) {
         const int pl = (int)(idx % P);
-        const int u = (int)((idx / P) % 64);
-        const int r = (int)(idx / ((int64_t)P * 64));
+        const int u = (int)((idx / P) % NU);
+        const int r = (int)(idx / ((int64_t)P * NU));
         const int pp = 16 * v.ks_begin[r] + pl;
         float w = 0.f;
         if (u < lo.K && pl < 16 * (v.ks_begin[r + 1] - v.ks_begin[r]) && pp < lo.NCP) {
@@ -593,7 +676,7 @@ __global__ void pack_weights4_kernel(const __grid_constant__ Pack4Args a)
         }
         const __half h = __float2half_rn(w);
         const __half l = __float2half_rn(w - __half2float(h));
-        const int mh = 32 * (u >> 4) + (u & 15), ml = mh + 16;
+        const int mh = 16 * (u >> 3) + (u & 7), ml = mh + 8;
         unsigned char* base = a.img + (size_t)r * v.a_bytes + (size_t)(pl >> 3) * 128 + (pl & 7) * 2;
         *reinterpret_cast<__half*>(base + (size_t)(mh >> 3) * v.SBOa + (mh & 7) * 16) = h;
         *reinterpret_cast<__half*>(base + (size_t)(ml >> 3) * v.SBOa + (ml & 7) * 16) = l;
@@ -615,6 +698,64 @@ int pack_weights4(const ancde_ncde_desc* d, const NcdeLayout& st, const V4Layout
     return ANCDE_OK;
 }
 
+static void launch_config4(const V4Layout& v, cudaStream_t stream, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at)
+{
+    *cfg = cudaLaunchConfig_t();
+    cfg->gridDim = dim3((unsigned)(v.nclusters * v.CS));
+    cfg->blockDim = dim3(V4_THREADS);
+    cfg->dynamicSmemBytes = (size_t)v.smem_total;
+    cfg->stream = stream;
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)v.CS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg->attrs = at;
+    cfg->numAttrs = 1;
+}
+
+// Clusters of this layout that can be resident at the same time (0 when the query fails).  A cluster of 8 CTAs with
+// one CTA per SM fits 15 times on a B200 (measured: the 16th cluster of a 1024-sample batch ran as a second wave and
+// doubled the kernel time), a cluster of 4 fits 33 times.
+static int max_active_clusters4(const V4Layout& v)
+{
+    static int cache[2][V4_MAX_CS + 1][8] = {};          // [chain][CS][smem / 32 KB] -> clusters + 1
+    const int bucket = v.smem_total / (32 * 1024);
+    int& slot = cache[v.chain][v.CS][bucket > 7 ? 7 : bucket];
+    if (slot) return slot - 1;
+    auto kern = v.chain ? ncde_bwd4_kernel<true> : ncde_bwd4_kernel<false>;
+    int n = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess) {
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute at[1];
+        V4Layout q = v;
+        q.smem_total = (bucket + 1) * 32 * 1024 - 1 > 227 * 1024 ? 227 * 1024 : (bucket + 1) * 32 * 1024 - 1;
+        q.nclusters = 64;
+        launch_config4(q, nullptr, &cfg, at);
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
+    }
+    cudaGetLastError();
+    slot = n + 1;
+    return n;
+}
+
+// The cluster size whose clusters run in the fewest waves (ties: the larger cluster, whose CTAs hold a smaller slice).
+int choose_layout4(const ancde_ncde_desc* d, const NcdeLayout& st, bool need_att, int force_cs, V4Layout* v)
+{
+    if (force_cs) return make_layout4(d, st, need_att, force_cs, v);
+    int best_waves = 0;
+    V4Layout cand;
+    for (int cs = V4_MAX_CS; cs >= 2; cs /= 2) {
+        if (make_layout4(d, st, need_att, cs, &cand) != ANCDE_OK) continue;
+        const int act = max_active_clusters4(cand);
+        const int waves = act > 0 ? (cand.nclusters + act - 1) / act : 1 << 20;
+        if (best_waves == 0 || waves < best_waves) {
+            best_waves = waves;
+            *v = cand;
+        }
+    }
+    return best_waves ? ANCDE_OK : ANCDE_EUNSUPPORTED;
+}
+
 int launch_bwd4(const SolveArgs& a, const V4Layout& v, const unsigned char* img, cudaStream_t stream)
 {
     Bwd4Args ba;
@@ -623,18 +764,9 @@ int launch_bwd4(const SolveArgs& a, const V4Layout& v, const unsigned char* img,
     ba.img = img;
     auto kern = v.chain ? ncde_bwd4_kernel<true> : ncde_bwd4_kernel<false>;
     ANCDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem_total));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(v.nclusters * v.CS));
-    cfg.blockDim = dim3(V4_THREADS);
-    cfg.dynamicSmemBytes = (size_t)v.smem_total;
-    cfg.stream = stream;
+    cudaLaunchConfig_t cfg;
     cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)v.CS;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
+    launch_config4(v, stream, &cfg, at);
     static const char* names[3] = {"ncde_bwd_plain", "ncde_bwd_bottom", "ncde_bwd_top"};
     prof_begin(names[a.lo.mode], stream);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ba);

@@ -5,13 +5,17 @@
 // of CS CTAs walks NS = 8*CS samples backwards together, weight stationary:
 //   * every CTA keeps a 1/CS slice of W_out^T RESIDENT in shared memory for the whole solve.  The slice is cut along
 //     the REDUCTION index p = i*C4 + j of  hbar[u] = sum_p W_out[p][u] * prebar[p]  (k steps of 16 columns), and stored
-//     as ONE FP16 matrix of 128 rows in the tensor core's canonical K-major layout (umma.cuh): row 32*q + l holds the
-//     hi half (l < 16) or the lo half (l >= 16) of 64 * W_out[.][u], u = 16*q + (l & 15);
+//     as ONE FP16 matrix in the tensor core's canonical K-major layout (umma.cuh): groups of 8 rows alternate between the
+//     hi halves and the lo halves of 64 * W_out[.][u] for 8 hidden units u (row 16*(u/8) + u%8 and + 8), so that the two
+//     halves of a unit sit in lanes l and l + 8 of the same warp when the accumulator is read back.  Only the
+//     2*ceil(K/8) groups that hold units are stored; the products run over M = 128 rows and simply compute garbage for
+//     the rest (rows of the accumulator that are never read);
 //   * per stage every CTA builds the pre-activation cotangent  prebar[p][n] = gbar[i][n] * dU[j][n] * (1 - G[p][n]^2)  of
 //     its slice for ALL NS samples straight from the saved tanh outputs (HBM / L2 -> registers), splits it into FP16
-//     hi/lo and writes it as the B operand [prebar_hi ; prebar_lo] (2*NS rows) into a small ring of shared-memory
-//     chunks; one elected thread issues tcgen05.mma (M = 128, N = 2*NS, K = 16) per k step, accumulating the four
-//     hi/lo products in tensor memory (the lo*lo quadrant is simply not read);
+//     hi/lo and writes it as the B operand [prebar_hi ; prebar_lo] (2*NS rows) into shared memory, in one pass or, where
+//     the operand does not fit, in a few chunks; a dedicated issuer warp multiplies each chunk as soon as all worker
+//     warps have written it: tcgen05.mma (M = 128, N = 2*NS, K = 16) per k step, the four hi/lo products accumulate in
+//     tensor memory (the lo*lo quadrant is simply not read);
 //   * the accumulator is read back with tcgen05.ld, the three useful quadrants are summed with one shuffle, and the
 //     partial sums are REDUCE-SCATTERED through distributed shared memory (st.async + mbarrier transaction counts): CTA r
 //     receives the CS partial hbar of ITS 8 samples;
@@ -25,18 +29,20 @@
 
 namespace ancde {
 
-constexpr int V4_THREADS = 512;
+constexpr int V4_WORKERS = 512;             // 16 worker warps
+constexpr int V4_THREADS = V4_WORKERS + 32;  // + the MMA issuer warp
 constexpr int V4_MAX_CS = 8;
 
 struct V4Layout {
     int CS, NS, nclusters;
     int QW;                         // warps per tile in the operand build = 16 / CS
-    int CK;                         // k steps (of 16 columns) per ring chunk = 32 / CS: one (sample, 8 columns) item per thread
+    int CK;                         // k steps (of 16 columns) per operand chunk (even)
+    int nslots;                     // chunk buffers (1 or 2)
     int ks_begin[V4_MAX_CS + 1];    // k-step range of every cluster rank
     int nks_max, nchunks_max;
-    int SBOa, a_bytes;              // per-rank A image: 128 rows x 16*nks_max columns, SBO = nks_max * 256 bytes
+    int SBOa, a_groups, a_bytes;    // per-rank A image: a_groups groups of 8 rows x 16*nks_max columns, SBO = nks_max * 256 bytes
     int64_t img_bytes;              // CS * a_bytes
-    int SBOb, ring_bytes;           // one ring chunk: 2*NS rows x 16*CK columns
+    int SBOb, ring_bytes;           // one chunk buffer: 2*NS rows x 16*CK columns
     int tmem_cols;                  // power of two >= max(32, 2*NS)
     int GSTR;                       // row stride (floats) of the gathered stage cotangent [Hd][GSTR]
     int dub;                        // floats of one tile's dU (| dU/da) block
@@ -57,6 +63,8 @@ struct Bwd4Args {
 
 // Fills the layout when the shape is supported by this engine (ANCDE_EUNSUPPORTED otherwise, quietly).
 int make_layout4(const ancde_ncde_desc* d, const NcdeLayout& st, bool need_att, int force_cs, V4Layout* v);
+// make_layout4 with the cluster size chosen for co-residency (force_cs = 0) or given.
+int choose_layout4(const ancde_ncde_desc* d, const NcdeLayout& st, bool need_att, int force_cs, V4Layout* v);
 int pack_weights4(const ancde_ncde_desc* d, const NcdeLayout& st, const V4Layout& v, unsigned char* img, cudaStream_t stream);
 int launch_bwd4(const SolveArgs& a, const V4Layout& v, const unsigned char* img, cudaStream_t stream);
 

@@ -175,9 +175,11 @@ int ancde_debug_force_wgrad_mma_sync(int on);
 
 /* Development / test aid: which recurrent backward kernel ancde_ncde_backward runs.  engine 0 = automatic (the cluster /
  * tcgen05 kernel of ncde_bwd4.cu for large output layers, the streamed kernel of ncde_bwd.cu otherwise), 1 = streamed,
- * 4 = cluster (ANCDE_EUNSUPPORTED for shapes it cannot run); cluster_size 0 = automatic, else 2, 4 or 8.  Returns the old
- * engine value. */
+ * 4 = cluster (ANCDE_EUNSUPPORTED for shapes it cannot run), 5 = cluster wherever it supports the shape, else streamed;
+ * cluster_size 0 = automatic, else 2, 4 or 8.  Returns the old engine value.  ancde_debug_bwd4_launches counts the
+ * launches of the cluster kernel since the library was loaded. */
 int ancde_debug_force_bwd_engine(int engine, int cluster_size);
+int ancde_debug_bwd4_launches(void);
 
 /* Development aid: 64 int64 counters in device memory that kernels built with -DANCDE_PHASE_TIMING
  * fill with per-phase clock64() totals (normal builds never touch the buffer). NULL disables. */

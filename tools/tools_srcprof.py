@@ -3,6 +3,7 @@
 usage: python tools_srcprof.py report.ncu-rep [topN]
 """
 import csv
+import os
 import subprocess
 import sys
 
@@ -48,7 +49,7 @@ for func, a in agg.items():
     ti = sum(x['inst'] for x in a) or 1
     print('=' * 20, func[:90], ' samples', ts, ' warp-inst', ti)
     print('%7s %7s | %5s %5s %5s %5s %5s %5s %5s | %9s | %s' % ('samp%', 'inst%', 'bar', 'lsb', 'ssb', 'wait', 'mio', 'nsel', 'sel', 'smem_exc', 'source'))
-    for x in sorted(a, key=lambda x: -x['samples'])[:topn]:
+    for x in sorted(a, key=lambda x: -x[os.environ.get('SORT', 'samples')])[:topn]:
         s = max(x['samples'], 1)
         print('%6.2f%% %6.2f%% | %5.0f %5.0f %5.0f %5.0f %5.0f %5.0f %5.0f | %9d | %s:%s %s' % (
             100 * x['samples'] / ts, 100 * x['inst'] / ti, 100 * x['bar'] / s, 100 * x['lsb'] / s, 100 * x['ssb'] / s,
