@@ -13,13 +13,13 @@ namespace ancde {
 // with mma.sync, one CTA barrier per layer and FP16 hi/lo operand conversions, 5.1 k cycles per stage for the Sepsis
 // bottom network).
 //   sLp[8*l ..] = {ceil(width / 4), in_dim, row stride, off_wt, act_off_h[l-1], act_off_delta[l-1], -, -}
-template <int TS>
+template <int TS, int SPW_ = 0>
 __device__ __forceinline__ void hidden_chain_bwd(const int* __restrict__ sLp, int n_hidden, const float* __restrict__ sW,
                                                  float* __restrict__ sD0, float* __restrict__ sD1,
                                                  const float* __restrict__ sAct, float* __restrict__ act,
                                                  float* __restrict__ sZb, int HP, int warp, int NW, int lane)
 {
-    constexpr int SPW = (TS >= 2) ? 2 : 1;
+    constexpr int SPW = SPW_ ? SPW_ : ((TS >= 2) ? 2 : 1);      // samples per warp
     constexpr int NCW = TS / SPW;
     for (int cw = warp; cw < NCW; cw += NW) {
         const int s0 = cw * SPW;

@@ -13,6 +13,7 @@
 // Matches autograd through torchdiffeq's rk4_alt_step_func + the reference vector fields
 // (cdeint_module.py:25-32,56-72,103-138) to FP32 round-off, like the streamed kernel it replaces.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "bwd_hidden.cuh"
 #include "mma_common.cuh"
@@ -27,6 +28,14 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float a, float
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(remote_addr),
                  "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)), "r"(remote_mbar)
                  : "memory");
+}
+
+// Waits on an mbarrier: every thread suspends in mbarrier.try_wait.  (Measured alternative: one lane per warp
+// busy-polling test_wait while the others sit behind __syncwarp made every stage 4 k cycles SLOWER -- the polling warps
+// take issue slots and shared-memory bandwidth from the few warps that work in the latency-bound phases.)
+__device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity, int)
+{
+    mbar_wait(bar, parity);
 }
 
 // Named barrier over the worker warps (the issuer warp never joins).
@@ -59,8 +68,8 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
     uint64_t* bar_recv = bar_g + 3;                                           // partial sums of my samples complete (tx bytes)
     uint64_t* bar_built = bar_g + 4;                                          // [2] ring chunk written by all worker warps
     uint64_t* bar_free = bar_g + 6;                                           // [2] products of a ring chunk complete
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(bar_g + 8);
-    unsigned char* sA = smem_raw + v.o_A;
+    uint64_t* bar_gin = bar_g + 8;                                            // tanh outputs of the stage have landed (TMA)
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bar_g + 9);
     unsigned char* sRing = smem_raw + v.o_ring;
     const float* sWtb = reinterpret_cast<const float*>(smem_raw + v.o_hid);  // CHAIN: transposed hidden weights (FP32)
     const uint4* sWhb = reinterpret_cast<const uint4*>(smem_raw + v.o_hid);  // !CHAIN: W_l^T as FP16 hi/lo A fragments
@@ -75,17 +84,15 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
     float* sD1 = sD0 + TS * v.HP;                                             //        pong
     float* sMax = reinterpret_cast<float*>(smem_raw + v.o_max);
     int* sLp = reinterpret_cast<int*>(smem_raw + v.o_lp);
-    int4* sTab = reinterpret_cast<int4*>(smem_raw + v.o_tab);                // per 8 columns: {gbar row, dU offset} x 2 halves
+    float* sGst = reinterpret_cast<float*>(smem_raw + v.o_gst);              // staged tanh outputs [NS rows][GROW floats]
+    int4* sTab = reinterpret_cast<int4*>(smem_raw + v.o_tab);                // per run of 4 columns: {gbar row, dU index, G column, -}
 
     const int nks = v.ks_begin[rank + 1] - v.ks_begin[rank];
-    const int nchunks = (nks + CK - 1) / CK;
+    const int nchunks = ((nks + v.PASSK - 1) / v.PASSK + v.PPC - 1) / v.PPC;       // CK = PPC * PASSK k steps per chunk
     const int pbase = 16 * v.ks_begin[rank];
 
     // ---- prologue: resident operands, tables, barriers, tensor memory
     if (tid < NT) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.img + (size_t)rank * v.a_bytes);
-        uint4* dst = reinterpret_cast<uint4*>(sA);
-        for (int i = tid; i < v.a_bytes / 16; i += NT) dst[i] = __ldg(src + i);
         if constexpr (CHAIN) {
             const float4* hs = reinterpret_cast<const float4*>(p.s.wpack + lo.off_hiddenb);
             float4* hd = reinterpret_cast<float4*>(smem_raw + v.o_hid);
@@ -101,7 +108,8 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
         // operand rows / columns that are never written stay zero (0 * finite garbage would be fine, 0 * NaN is not)
         uint4* zr = reinterpret_cast<uint4*>(sRing);
         for (int i = tid; i < NSLOT * v.ring_bytes / 16; i += NT) zr[i] = make_uint4(0u, 0u, 0u, 0u);
-        for (int i = tid; i < Hd * v.GSTR; i += NT) sGall[i] = 0.f;
+        for (int i = tid; i < NS * v.GROW; i += NT) sGst[i] = 0.f;              // rows behind the batch stay zero
+        for (int i = tid; i < (Hd + 1) * v.GSTR; i += NT) sGall[i] = 0.f;      // row Hd stays zero
         for (int i = tid; i < CS * v.dub; i += NT) sDU[i] = 0.f;          // tiles behind the batch stay zero
         for (int i = tid; i < v.act_ld; i += NT) sAct[i] = 0.f;
         for (int i = tid; i < HT; i += NT) sZb[i] = 0.f;
@@ -118,18 +126,18 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
                 q[6] = l > 0 ? lo.act_off_h[l - 1] : 0; q[7] = l > 0 ? lo.act_off_delta[l - 1] : 0;
             }
         }
-        // columns 8*gq .. 8*gq + 7 of this rank's slice = two runs of 4 control channels of one field row each
-        for (int gq = tid; gq < 2 * CK * v.nchunks_max; gq += NT) {
-            int e[4];
+        // columns 8*gq .. 8*gq + 7 of this rank's slice = two runs of 4 control channels of one field row each; per run
+        // {offset of the field row in the gathered cotangent, float4 index of the 4 channels in the re-laid-out controls,
+        // column offset in the saved tanh outputs}.  Columns behind the slice or behind the last field row point at the ZERO
+        // row of the gathered cotangent (and at column 0): no predicates in the conversion loop.
+        for (int gq = tid; gq < 2 * v.PASSK * v.npass_max; gq += NT) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int pp = pbase + 8 * gq + 4 * h;
                 const bool ok = gq < 2 * nks && pp < NCP;
                 const int i = pp / lo.C4, j0 = pp - i * lo.C4;
-                e[2 * h] = ok ? i * v.GSTR : -1;
-                e[2 * h + 1] = ok ? (j0 >> 2) * 8 : 0;        // float4 index of the 4 channels in the re-laid-out controls
+                sTab[2 * gq + h] = ok ? make_int4(i * v.GSTR, (j0 >> 2) * 8, 8 * gq + 4 * h, 0) : make_int4(Hd * v.GSTR, 0, 0, 0);
             }
-            sTab[gq] = make_int4(e[0], e[1], e[2], e[3]);
         }
         if (tid == 0) {
             mbar_init(bar_g, 1);
@@ -140,6 +148,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
             mbar_init(bar_built + 1, NW);
             mbar_init(bar_free + 0, 1);
             mbar_init(bar_free + 1, 1);
+            mbar_init(bar_gin, 1);
             mbar_fence_init();
         }
         if (warp == 0) tmem_alloc(tslot, (uint32_t)v.tmem_cols);
@@ -149,6 +158,21 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tbase = *tslot;
     const uint32_t tlane = tbase + ((uint32_t)(32 * wq) << 16);
+    if (tid < NT) {
+        // resident A operand: row m = TMEM lane m (this warp's quarter), 16 FP16 of the row per 8 columns; the four warps of
+        // a lane quarter share the k steps
+        const int m = 32 * wq + lane;
+        const uint4* src = reinterpret_cast<const uint4*>(p.img + (size_t)rank * v.a_bytes + (size_t)m * v.nks_max * 32);
+        for (int ks = wg; ks < v.nks_max; ks += 4) {
+            const uint4 x0 = __ldg(src + 2 * ks), x1 = __ldg(src + 2 * ks + 1);
+            const uint32_t r[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            tmem_st8(tlane + (uint32_t)(v.a_col + 8 * ks), r);
+        }
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
     fence_async_smem();
     cluster_arrive();     // every CTA of the cluster has initialised its shared memory and barriers before anyone writes into it
     cluster_wait();
@@ -167,6 +191,17 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
             if (cl * CS + t < lo.ntiles)
                 bulk_g2s(sStage + (size_t)t * v.dub, act_block(n, cl * CS + t) + lo.act_off_du, (uint32_t)(v.dub * 4), bar_du);
     };
+    // The slice of the saved tanh outputs this CTA converts in stage n: one TMA bulk copy per sample row (rows padded by 16
+    // bytes in shared memory: the 8 rows a quarter warp reads fall into 8 different bank groups).  Called by a whole warp.
+    const int g_cols = (pbase + 16 * nks <= NCP) ? 16 * nks : NCP - pbase;          // floats of a row slice
+    auto issue_g = [&](int n) {
+        const int64_t r0 = (int64_t)cl * NS;
+        const int nrows = (rows - r0 < NS) ? (int)(rows - r0) : NS;
+        if (lane == 0) mbar_arrive_expect_tx(bar_gin, (uint32_t)(nrows * g_cols * 4));
+        __syncwarp();
+        for (int r = lane; r < nrows; r += 32)
+            bulk_g2s(sGst + (size_t)r * v.GROW, p.s.save_G + ((int64_t)n * rows + r0 + r) * NCP + pbase, (uint32_t)(g_cols * 4), bar_gin);
+    };
     auto issue_act = [&](int n) {
         mbar_arrive_expect_tx(bar_act, (uint32_t)(v.act_ld * 4));
         bulk_g2s(sAct, act_block(n, tile), (uint32_t)(v.act_ld * 4), bar_act);
@@ -175,16 +210,17 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
     if (warp_u == NW) {
         // ================================ the issuer warp: products of every operand chunk ================================
         const uint32_t idesc = umma_idesc_f16(128, 2 * NS, false);
-        const uint64_t dA = umma_smem_desc(smem_u32(sA), 128, (uint32_t)v.SBOa);
+        const uint32_t tA = tbase + (uint32_t)v.a_col;
         const uint64_t dB0 = umma_smem_desc(smem_u32(sRing), 128, (uint32_t)v.SBOb);
         const uint64_t dB1 = umma_smem_desc(smem_u32(sRing) + (uint32_t)v.ring_bytes, 128, (uint32_t)v.SBOb);
         uint32_t pb0 = 0, pb1 = 0;
         int use = 0;                   // ring position of the next chunk (all stages)
+        issue_g(lo.n_stages - 1);
         for (int n = lo.n_stages - 1; n >= 0; --n) {
             for (int c = 0; c < nchunks; ++c) {
                 const int slot = (NSLOT == 2) ? (use & 1) : 0;
                 ++use;
-                mbar_wait(bar_built + slot, slot ? pb1 : pb0);
+                warp_wait(bar_built + slot, slot ? pb1 : pb0, lane);
                 if (slot) pb1 ^= 1; else pb0 ^= 1;
                 if (elect_one()) {
                     tc_fence_after();
@@ -193,10 +229,12 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
                     const uint64_t dB = slot ? dB1 : dB0;
 #pragma unroll 4
                     for (int ks = 0; ks < kn; ++ks)
-                        umma_f16(tbase, dA + (uint64_t)((k0 + ks) * 16), dB + (uint64_t)(ks * 16), idesc, (k0 + ks) != 0);
+                        umma_f16_ts(tbase, tA + (uint32_t)((k0 + ks) * 8), dB + (uint64_t)(ks * 16), idesc, (k0 + ks) != 0);
                     umma_commit(bar_free + slot);
                 }
                 __syncwarp();
+                // every worker warp has converted its last item of this stage: the staging buffer takes the next stage's rows
+                if (c == nchunks - 1 && n >= 1) issue_g(n - 1);
             }
         }
     } else {
@@ -213,9 +251,12 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
     const int tile_t = warp & (CS - 1);                      // tile of the cluster this thread's sample belongs to
     const int nloc = 8 * tile_t + n8;
     const bool samp_ok = cl * CS + tile_t < lo.ntiles;
-    const int wchunk = CS * (CK >> 1);                       // warp-items per chunk
-    const int nit = (wchunk + NW - 1) / NW;                  // iterations of a warp per chunk
-    const uint32_t ring_hi = smem_u32(sRing) + (uint32_t)((nloc >> 3) * v.SBOb + (nloc & 7) * 16);
+    // one PASS of the 512 workers converts 8 * PASSK columns... (PASSK = 32 / CS k steps) for all NS samples: a thread's
+    // items of a stage are the same (sample, 8-column group of the pass) in every pass
+    const int PASSK = v.PASSK, PPC = v.PPC;
+    const int npass = (nks + PASSK - 1) / PASSK;
+    const int qpass = 4 * (warp >> cs_log2) + (lane >> 3);   // 0 .. 2*PASSK - 1
+    const uint32_t ring_hi = smem_u32(sRing) + (uint32_t)((nloc >> 3) * v.SBOb + (nloc & 7) * 16 + qpass * 128);
     const uint32_t ring_lo_off = (uint32_t)((NS >> 3) * v.SBOb);
     const int NCH = lo.NCH;
     const bool top = lo.mode == ANCDE_MODE_TOP;
@@ -231,13 +272,29 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
     const uint32_t barr_delta = smem_u32(bar_recv) - smem_u32(sRecv);
     const uint32_t ratt_delta = smem_u32(sRecvAtt) - smem_u32(sRecv);
 
+    // Controls of a stage: the TMA-staged [chunk j4][channel][sample] blocks of every tile -> float4 per (tile, j4, sample).
+    // `first`, `count`: the calling threads' index and number (all workers before the first stage, the idle warps during the
+    // hidden layers).
+    auto stage_in = [&](int n, int first, int count) {
+        for (int idx = first; idx < CS * NCH * 8; idx += count) {
+            const int t = idx / (NCH * 8), rem = idx - t * NCH * 8;
+            const float* src = sStage + (size_t)t * v.dub + (rem >> 3) * DUS + (rem & 7);
+            reinterpret_cast<float4*>(sDU)[idx] = make_float4(src[0], src[8], src[16], src[24]);
+            if (top) {
+                src += lo.du_floats;
+                reinterpret_cast<float4*>(sDU)[CS * NCH * 8 + idx] = make_float4(src[0], src[8], src[16], src[24]);
+            }
+        }
+    };
+    const int CW = v.chain_warps;       // warps that walk the hidden layers backwards; the others prepare the next stage meanwhile
+
     // ---- RK4 adjoint state in registers: thread tid < Hd*8 owns element (i = tid / 8, b = tid % 8) of its tile
     const bool st_thr = tid < HT;
     const int si = tid >> 3, sb = tid & 7;
     float lam = 0.f, mu = 0.f, v4 = 0.f, v3 = 0.f, v2 = 0.f;
     float gmax = 0.f;
     int jb = lo.n_out - 1;             // last output time whose cotangent has not been consumed yet
-    uint32_t par_g = 0, par_du = 0, par_act = 0, par_recv = 0;
+    uint32_t par_g = 0, par_du = 0, par_act = 0, par_recv = 0, par_gin = 0;
     int use = 0;                       // ring position of the next chunk (all stages; the same in every thread)
     PH2_DECL();
 #ifdef ANCDE_PHASE_TIMING
@@ -247,6 +304,9 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
         p.s.dbg[64 + cl] = (long long)gt;
     }
 #endif
+    warp_wait(bar_du, par_du, lane);          // controls of the last stage (the first one this kernel visits)
+    par_du ^= 1;
+    stage_in(lo.n_stages - 1, tid, NT);
 
     for (int k = lo.n_steps - 1; k >= 0; --k) {
         const float t0 = grid_time(k, lo.n_steps, p.s.t_start, p.s.t_end, p.s.step, p.s.grid);
@@ -283,32 +343,10 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
                 else gv = dt * (0.125f * lam + v4 + (v2 - v3) * (1.0f / 3.0f));
                 if (act) act[lo.act_off_gbar + tid] = gv;        // the stage cotangent goes to HBM for the weight-gradient kernels
             }
-            // controls of this stage: [chunk j4][channel][sample] blocks of every tile -> float4 per (tile, j4, sample)
-            mbar_wait(bar_du, par_du);
-            par_du ^= 1;
-            for (int idx = tid; idx < CS * NCH * 8; idx += NT) {
-                const int t = idx / (NCH * 8), rem = idx - t * NCH * 8;
-                const float* src = sStage + (size_t)t * v.dub + (rem >> 3) * DUS + (rem & 7);
-                reinterpret_cast<float4*>(sDU)[idx] = make_float4(src[0], src[8], src[16], src[24]);
-                if (top) {
-                    src += lo.du_floats;
-                    reinterpret_cast<float4*>(sDU)[CS * NCH * 8 + idx] = make_float4(src[0], src[8], src[16], src[24]);
-                }
-            }
             float lmax = fabsf(gv);
             gmax = fmaxf(gmax, lmax);
             for (int o = 16; o >= 1; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
             if (lane == 0) sMax[warp] = lmax;
-            // the tanh outputs of the NEXT stage towards L2 (this CTA reads a strided slice of every row)
-            if (n >= 1) {
-                const int per = (nks * 64 + 127) / 128 + 1;       // 128-byte lines per row slice
-                for (int item = tid; item < NS * per; item += NT) {
-                    const int r = item / per, ln = item - r * per;
-                    const int64_t row = (int64_t)cl * NS + r;
-                    const int col = pbase + 32 * ln;
-                    if (row < rows && col < NCP) prefetch_l2(p.s.save_G + ((int64_t)(n - 1) * rows + row) * NCP + col);
-                }
-            }
             workers_sync();
             float scale = 1.0f;
             {
@@ -330,92 +368,96 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
                     if (r < CS) st_async_f32(gall_rank[r] + off, val, gall_rank[r] + barg_delta);
             }
             if (tid == 0) mbar_arrive_expect_tx(bar_g, (uint32_t)(HT * CS * 4));
-            mbar_wait(bar_g, par_g);
+            warp_wait(bar_g, par_g, lane);
             par_g ^= 1;
             PH2_MARK(0);
 
-            // ---- (1) operand build, chunk by chunk; the issuer warp multiplies a chunk as soon as every warp has written it
+            // ---- (1) operand build, pass by pass; the issuer warp multiplies a chunk as soon as every warp has written it
             float att = 0.f;
             {
-                const float* grow = p.s.save_G + ((int64_t)n * rows + (int64_t)cl * NS + nloc) * NCP + pbase;
-                // two (chunk, iteration) units ahead: the tanh outputs of the next two items are in flight while one is converted
-                float4 ga0, gb0, ga1, gb1;
-                int4 te0, te1;
-                auto fetch = [&](int c, int it, float4& ga, float4& gb, int4& te) {
-                    ga = make_float4(0.f, 0.f, 0.f, 0.f);
-                    gb = ga;
-                    te = make_int4(-1, 0, -1, 0);
-                    while (it >= nit) { it -= nit; ++c; }
-                    const int wi = it * NW + warp;
-                    if (c < nchunks && wi < wchunk) {
-                        const int gq = 2 * CK * c + 4 * (wi >> cs_log2) + (lane >> 3);
-                        te = sTab[gq];
-                        if (samp_ok) {
-                            const float* gp = grow + 8 * gq;
-                            if (te.x >= 0) ga = __ldg(reinterpret_cast<const float4*>(gp));
-                            if (te.z >= 0) gb = __ldg(reinterpret_cast<const float4*>(gp + 4));
+                warp_wait(bar_gin, par_gin, lane);      // this stage's tanh outputs (copies issued a whole stage ago)
+                par_gin ^= 1;
+                const float* grow = sGst + (size_t)nloc * v.GROW;
+                const int4* tp = sTab + 2 * qpass;
+                const int tstep = 4 * PASSK;                  // table entries per pass
+                // two passes ahead: the tanh outputs of the next two items are in flight while one is converted
+                float4 gA0, gB0, gA1, gB1;
+                int4 tA0, tB0, tA1, tB1;
+                auto fetch = [&](int pass, float4& ga, float4& gb, int4& ta, int4& tb) {
+                    const int pz = pass < npass ? pass : npass - 1;          // (past the end: a harmless reload)
+                    ta = tp[pz * tstep];
+                    tb = tp[pz * tstep + 1];
+                    ga = *reinterpret_cast<const float4*>(grow + ta.z);
+                    gb = *reinterpret_cast<const float4*>(grow + tb.z);
+                };
+                fetch(0, gA0, gB0, tA0, tB0);
+                fetch(1, gA1, gB1, tA1, tB1);
+                int pic = 0;                                   // pass inside the current chunk
+                int slot = (NSLOT == 2) ? (use & 1) : 0;
+                uint32_t so = ring_hi + (uint32_t)(slot * v.ring_bytes);
+                auto convert = [&](int pass, const float4& g0, const float4& g1, const int4& ta, const int4& tb) {
+                    float pv[8];
+                    {
+                        const float gbv = sGn[ta.x];
+                        const float4 du = sDUt[ta.y];
+                        pv[0] = gbv * du.x * fmaf(-g0.x, g0.x, 1.0f);
+                        pv[1] = gbv * du.y * fmaf(-g0.y, g0.y, 1.0f);
+                        pv[2] = gbv * du.z * fmaf(-g0.z, g0.z, 1.0f);
+                        pv[3] = gbv * du.w * fmaf(-g0.w, g0.w, 1.0f);
+                        if (need_att) {
+                            // sum_j dUbar[j] * dU/da[j] with dUbar[j] = sum_i gbar[i] * G[i][j]   
+                            const float4 da = sDAt[ta.y];
+                            att = fmaf(gbv, (g0.x * da.x + g0.y * da.y) + (g0.z * da.z + g0.w * da.w), att);
                         }
                     }
-                };
-                fetch(0, 0, ga0, gb0, te0);
-                fetch(0, 1, ga1, gb1, te1);
-                for (int c = 0; c < nchunks; ++c) {
-                    const int slot = (NSLOT == 2) ? (use & 1) : 0;
-                    const int my_use = use;
-                    ++use;
-                    const uint32_t so = ring_hi + (uint32_t)(slot * v.ring_bytes);
-                    for (int it = 0; it < nit; ++it) {
-                        const float4 g0 = ga0, g1 = gb0;
-                        const int4 e = te0;
-                        const int wi = it * NW + warp;
-                        ga0 = ga1; gb0 = gb1; te0 = te1;
-                        fetch(c, it + 2, ga1, gb1, te1);
-                        uint32_t h[4], l[4];
-                        if (wi < wchunk) {
-                            float pv[8];
-                            {
-                                const bool ok = e.x >= 0;
-                                const float gbv = ok ? sGn[ok ? e.x : 0] : 0.f;
-                                const float4 du = sDUt[e.y];
-                                pv[0] = gbv * du.x * fmaf(-g0.x, g0.x, 1.0f);
-                                pv[1] = gbv * du.y * fmaf(-g0.y, g0.y, 1.0f);
-                                pv[2] = gbv * du.z * fmaf(-g0.z, g0.z, 1.0f);
-                                pv[3] = gbv * du.w * fmaf(-g0.w, g0.w, 1.0f);
-                                if (need_att) {
-                                    // sum_j dUbar[j] * dU/da[j] with dUbar[j] = sum_i gbar[i] * G[i][j]   
-                                    const float4 da = sDAt[e.y];
-                                    att = fmaf(gbv, (g0.x * da.x + g0.y * da.y) + (g0.z * da.z + g0.w * da.w), att);
-                                }
-                            }
-                            {
-                                const bool ok = e.z >= 0;
-                                const float gbv = ok ? sGn[ok ? e.z : 0] : 0.f;
-                                const float4 du = sDUt[e.w];
-                                pv[4] = gbv * du.x * fmaf(-g1.x, g1.x, 1.0f);
-                                pv[5] = gbv * du.y * fmaf(-g1.y, g1.y, 1.0f);
-                                pv[6] = gbv * du.z * fmaf(-g1.z, g1.z, 1.0f);
-                                pv[7] = gbv * du.w * fmaf(-g1.w, g1.w, 1.0f);
-                                if (need_att) {
-                                    const float4 da = sDAt[e.w];
-                                    att = fmaf(gbv, (g1.x * da.x + g1.y * da.y) + (g1.z * da.z + g1.w * da.w), att);
-                                }
-                            }
-#pragma unroll
-                            for (int x = 0; x < 4; ++x) split_pair(pv[2 * x], pv[2 * x + 1], h[x], l[x]);
+                    {
+                        const float gbv = sGn[tb.x];
+                        const float4 du = sDUt[tb.y];
+                        pv[4] = gbv * du.x * fmaf(-g1.x, g1.x, 1.0f);
+                        pv[5] = gbv * du.y * fmaf(-g1.y, g1.y, 1.0f);
+                        pv[6] = gbv * du.z * fmaf(-g1.z, g1.z, 1.0f);
+                        pv[7] = gbv * du.w * fmaf(-g1.w, g1.w, 1.0f);
+                        if (need_att) {
+                            const float4 da = sDAt[tb.y];
+                            att = fmaf(gbv, (g1.x * da.x + g1.y * da.y) + (g1.z * da.z + g1.w * da.w), att);
                         }
+                    }
+                    uint32_t h[4], l[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) split_pair(pv[2 * x], pv[2 * x + 1], h[x], l[x]);
+                    if (pic == 0) {
                         // the buffer is free once the products of the chunk that used it last have completed: chunk number
                         // use - NSLOT (0-based over the whole solve) is completion number (use - NSLOT) / NSLOT of its barrier
-                        if (it == 0 && my_use >= NSLOT) mbar_wait(bar_free + slot, (uint32_t)(((my_use - NSLOT) / NSLOT) & 1));
-                        if (wi < wchunk) {
-                            const uint32_t dst = so + (uint32_t)((4 * (wi >> cs_log2) + (lane >> 3)) * 128);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + ring_lo_off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
-                        }
+                        if (use >= NSLOT) warp_wait(bar_free + slot, (uint32_t)(((use - NSLOT) / NSLOT) & 1), lane);
+                        ++use;
                     }
-                    fence_async_smem();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_built + slot);
+                    const uint32_t dst = so + (uint32_t)(pic * 2 * PASSK * 128);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + ring_lo_off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+                    if (++pic == PPC || pass == npass - 1) {
+                        // chunk complete (for this warp)
+                        fence_async_smem();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_built + slot);
+                        pic = 0;
+                        slot = (NSLOT == 2) ? (use & 1) : 0;
+                        so = ring_hi + (uint32_t)(slot * v.ring_bytes);
+                    }
+                };
+                for (int pass = 0; pass < npass; pass += 2) {
+                    {
+                        const float4 g0 = gA0, g1 = gB0;
+                        const int4 ta = tA0, tb = tB0;
+                        fetch(pass + 2, gA0, gB0, tA0, tB0);
+                        convert(pass, g0, g1, ta, tb);
+                    }
+                    if (pass + 1 < npass) {
+                        const float4 g0 = gA1, g1 = gB1;
+                        const int4 ta = tA1, tb = tB1;
+                        fetch(pass + 3, gA1, gB1, tA1, tB1);
+                        convert(pass + 1, g0, g1, ta, tb);
+                    }
                 }
             }
             PH2_MARK(1);
@@ -433,7 +475,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
             {
                 const int last_use = use - 1;             // the stage's last chunk
                 const int last = (NSLOT == 2) ? (last_use & 1) : 0;
-                mbar_wait(bar_free + last, (uint32_t)((last_use / NSLOT) & 1));
+                warp_wait(bar_free + last, (uint32_t)((last_use / NSLOT) & 1), lane);
                 tc_fence_after();
                 // every product of this stage has completed: the operand buffer is idle, the next stage's controls land in it
                 if (tid == 0 && n >= 1) issue_du(n - 1);
@@ -467,10 +509,10 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
             }
 
             // ---- (3) my samples: sum of the partial hbar, hidden layers backwards
-            mbar_wait(bar_recv, par_recv);
+            warp_wait(bar_recv, par_recv, lane);
             par_recv ^= 1;
             if (have_tile) {
-                mbar_wait(bar_act, par_act);
+                warp_wait(bar_act, par_act, lane);
                 par_act ^= 1;
             }
             PH2_MARK(3);
@@ -505,12 +547,22 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
                 }
             }
             workers_sync();
-            if constexpr (CHAIN) {
-                hidden_chain_bwd<TS>(sLp, lo.n_hidden, sWtb, sD0, sD1, sAct, act, sZb, v.HP, warp, NW, lane);
-                workers_sync();
-            } else {
-                hidden_mma_bwd<TS>(sLp, lo.n_hidden, sWhb, sBd, v.KP, sAct, act, sZb, inv_scale, warp, lane, [] { workers_sync(); });
+            if (warp < CW) {
+                if constexpr (CHAIN) {
+                    hidden_chain_bwd<TS, 1>(sLp, lo.n_hidden, sWtb, sD0, sD1, sAct, act, sZb, v.HP, warp, CW, lane);
+                } else {
+                    const int cthreads = 32 * CW;
+                    hidden_mma_bwd<TS>(sLp, lo.n_hidden, sWhb, sBd, v.KP, sAct, act, sZb, inv_scale, warp, lane,
+                                       [cthreads] { named_bar_sync(2, cthreads); });
+                }
+            } else if (n >= 1) {
+                // meanwhile the other warps bring in the next stage: its controls (TMA issued after this stage's last product)
+                // into the layout of the operand build, its tanh outputs towards L2
+                warp_wait(bar_du, par_du, lane);
+                stage_in(n - 1, tid - 32 * CW, NT - 32 * CW);
             }
+            par_du ^= 1;
+            workers_sync();
             // the saved activations of this stage are consumed: fetch the next stage's (this kernel walks n downwards)
             if (tid == 0 && n >= 1 && have_tile) issue_act(n - 1);
             PH2_MARK(4);
@@ -594,25 +646,37 @@ int make_layout4(const ancde_ncde_desc* d, const NcdeLayout& st, bool need_att, 
         for (int r = 0; r < CS; ++r) v->ks_begin[r + 1] = v->ks_begin[r] + base + (r < extra ? 1 : 0);
         for (int r = CS; r < V4_MAX_CS; ++r) v->ks_begin[r + 1] = v->ks_begin[CS];
         v->nks_max = base + (extra ? 1 : 0);
-        v->SBOa = v->nks_max * 256;
-        v->a_groups = 2 * ((st.K + 7) / 8);
-        v->a_bytes = v->a_groups * v->SBOa;
+        v->a_bytes = 128 * 16 * v->nks_max * 2;
         v->img_bytes = (int64_t)CS * v->a_bytes;
-        v->tmem_cols = pow2ceil4(2 * v->NS);
+        v->a_col = 2 * v->NS;
+        v->tmem_cols = pow2ceil4(2 * v->NS + 8 * v->nks_max);
+        if (v->tmem_cols > 512) continue;
         v->GSTR = v->NS + 4;
+        v->GROW = 16 * v->nks_max + 4;
         v->dub = st.du_floats * (st.mode == ANCDE_MODE_TOP ? 2 : 1);
         v->act_ld = st.act_off_du;
         v->KP = 16 * st.KSB + 8;
         v->HP = pad4(st.Hmax);
         v->chain = chain ? 1 : 0;
+        v->chain_warps = chain ? 8 : maxmt;
         v->need_att = need_att ? 1 : 0;
         if ((v->dub * 4) % 16 || (v->act_ld * 4) % 16 || (st.act_off_du * 4) % 16 || (st.act_floats * 4) % 16) continue;
-        // the operand of a stage in as few chunks as fit: every chunk costs a proxy fence, a barrier round and an issue latency
-        for (int nch = 1; nch <= 8; ++nch) {
-            int CK = (v->nks_max + nch - 1) / nch;
-            CK += CK & 1;
-            const int nchunks = (v->nks_max + CK - 1) / CK;
-            for (int nslots = (nchunks > 1 ? 2 : 1); nslots >= 1; --nslots) {
+        // Operand chunks: whole passes.  Two chunks in two buffers where they fit (the products of the first half run while
+        // the second is converted), else as few chunks as fit: every chunk costs the workers a proxy fence and a barrier
+        // round, and the issuer its wake-up.
+        v->PASSK = 32 / CS;
+        v->npass_max = (v->nks_max + v->PASSK - 1) / v->PASSK;
+        const char* env_nch = getenv("ANCDE_BWD4_NCH");        // development: operand chunks per stage
+        int want = env_nch ? atoi(env_nch) : 2;
+        if (want > v->npass_max) want = v->npass_max;
+        if (want < 1) want = 1;
+        for (int nch = want, first = 1; nch <= v->npass_max; nch = first ? 1 : nch + 1, first = 0) {
+            const int PPC = (v->npass_max + nch - 1) / nch;
+            const int nchunks = (v->npass_max + PPC - 1) / PPC;
+            if (nchunks != nch) continue;
+            for (int nslots = (nchunks > 1 ? 2 : 1); nslots >= (first && nchunks > 1 ? 2 : 1); --nslots) {
+                const int CK = PPC * v->PASSK;
+                v->PPC = PPC;
                 v->CK = CK;
                 v->nslots = nslots;
                 v->nchunks_max = nchunks;
@@ -621,26 +685,28 @@ int make_layout4(const ancde_ncde_desc* d, const NcdeLayout& st, bool need_att, 
                 auto up = [](size_t x) { return (x + 127) & ~(size_t)127; };
                 size_t o = 0;
                 v->o_bars = (int)o;    o = up(o + 128);
-                v->o_A = (int)o;       o = up(o + (size_t)v->a_bytes);
                 v->o_ring = (int)o;    o = up(o + (size_t)nslots * v->ring_bytes);
                 v->o_hid = (int)o;     o = up(o + (chain ? (size_t)pad4(st.hiddenb_floats) * 4 : (size_t)st.hb_u4 * 16));
                 v->o_recv = (int)o;    o = up(o + (size_t)CS * st.K * 8 * 4);
                 v->o_recvatt = (int)o; o = up(o + (size_t)CS * v->QW * 8 * 4);
-                v->o_gall = (int)o;    o = up(o + (size_t)st.Hd * v->GSTR * 4);
+                v->o_gall = (int)o;    o = up(o + (size_t)(st.Hd + 1) * v->GSTR * 4);
                 v->o_du = (int)o;      o = up(o + (size_t)CS * v->dub * 4);
                 v->o_act = (int)o;     o = up(o + (size_t)v->act_ld * 4);
                 v->o_zb = (int)o;      o = up(o + (size_t)pad4(st.Hd * 8) * 4);
                 v->o_bd = (int)o;      o = up(o + (chain ? (size_t)2 * 8 * v->HP * 4 : (size_t)4 * 8 * v->KP * 2));
                 v->o_max = (int)o;     o = up(o + 128);
                 v->o_lp = (int)o;      o = up(o + 8 * ANCDE_MAX_LAYERS * 4);
-                v->o_tab = (int)o;     o = up(o + (size_t)2 * CK * nchunks * 16);
-                // the products read 16 groups of rows from the A image's base: that range must lie inside the allocation
-                const size_t a_end = (size_t)v->o_A + 16 * (size_t)v->SBOa;
-                if (o < a_end) o = up(a_end);
+                v->o_tab = (int)o;     o = up(o + (size_t)4 * v->PASSK * v->npass_max * 16);
+                v->o_gst = (int)o;     o = up(o + (size_t)v->NS * v->GROW * 4);
                 v->smem_total = (int)o;
                 // the controls of the next stage are staged in the operand buffer
                 if ((size_t)CS * v->dub * 4 > (size_t)nslots * v->ring_bytes) continue;
-                if (o <= 227 * 1024) return ANCDE_OK;
+                if (o <= 227 * 1024) {
+                    if (getenv("ANCDE_DEBUG_LAYOUT"))
+                        fprintf(stderr, "bwd4 layout: mode %d CS %d nks_max %d passes %d per chunk %d chunks %d slots %d tmem cols %d ring %d smem %d\n",
+                                st.mode, CS, v->nks_max, v->npass_max, PPC, nchunks, nslots, v->tmem_cols, v->ring_bytes, v->smem_total);
+                    return ANCDE_OK;
+                }
             }
         }
     }
@@ -654,20 +720,20 @@ struct Pack4Args {
     unsigned char* img;
 };
 
-// A image of rank r: unit u -> rows 16*(u/8) + u%8 (hi half) and + 8 (lo half); column pl -> reduction index
-// p = 16*ks_begin[r] + pl = i*C4 + j.  Values are 64 * W_out[(i*C + j)][u].
+// A image of rank r, row-major [128 rows][16*nks_max FP16]: unit u -> rows 16*(u/8) + u%8 (hi half) and + 8 (lo half);
+// column pl -> reduction index p = 16*ks_begin[r] + pl = i*C4 + j.  Values are 64 * W_out[(i*C + j)][u]; rows without a
+// unit and columns behind the slice are zero.
 __global__ void pack_weights4_kernel(const __grid_constant__ Pack4Args a)
 {
     const NcdeLayout& lo = a.lo;
     const V4Layout& v = a.v;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     const int P = 16 * v.nks_max;
-    const int NU = 4 * v.a_groups;             // units with rows in the image (a multiple of 8 >= K)
-    const int64_t total = (int64_t)v.CS * NU * P;
+    const int64_t total = (int64_t)v.CS * 64 * P;
     for (int64_t idx = gtid; idx < total; idx += gsz) {
         const int pl = (int)(idx % P);
-        const int u = (int)((idx / P) % NU);
-        const int r = (int)(idx / ((int64_t)P * NU));
+        const int u = (int)((idx / P) % 64);
+        const int r = (int)(idx / ((int64_t)P * 64));
         const int pp = 16 * v.ks_begin[r] + pl;
         float w = 0.f;
         if (u < lo.K && pl < 16 * (v.ks_begin[r + 1] - v.ks_begin[r]) && pp < lo.NCP) {
@@ -677,9 +743,9 @@ __global__ void pack_weights4_kernel(const __grid_constant__ Pack4Args a)
         const __half h = __float2half_rn(w);
         const __half l = __float2half_rn(w - __half2float(h));
         const int mh = 16 * (u >> 3) + (u & 7), ml = mh + 8;
-        unsigned char* base = a.img + (size_t)r * v.a_bytes + (size_t)(pl >> 3) * 128 + (pl & 7) * 2;
-        *reinterpret_cast<__half*>(base + (size_t)(mh >> 3) * v.SBOa + (mh & 7) * 16) = h;
-        *reinterpret_cast<__half*>(base + (size_t)(ml >> 3) * v.SBOa + (ml & 7) * 16) = l;
+        __half* base = reinterpret_cast<__half*>(a.img + (size_t)r * v.a_bytes);
+        base[(size_t)mh * P + pl] = h;
+        base[(size_t)ml * P + pl] = l;
     }
 }
 

@@ -3,13 +3,13 @@
 // The streamed backward (ncde_bwd.cu) re-streams all of W_out^T (~500 KB as FP16 hi/lo fragments) through shared memory
 // every RK4 stage for the 8 samples of a CTA and is bound by that shared-memory round trip.  Here a thread-block CLUSTER
 // of CS CTAs walks NS = 8*CS samples backwards together, weight stationary:
-//   * every CTA keeps a 1/CS slice of W_out^T RESIDENT in shared memory for the whole solve.  The slice is cut along
-//     the REDUCTION index p = i*C4 + j of  hbar[u] = sum_p W_out[p][u] * prebar[p]  (k steps of 16 columns), and stored
-//     as ONE FP16 matrix in the tensor core's canonical K-major layout (umma.cuh): groups of 8 rows alternate between the
-//     hi halves and the lo halves of 64 * W_out[.][u] for 8 hidden units u (row 16*(u/8) + u%8 and + 8), so that the two
-//     halves of a unit sit in lanes l and l + 8 of the same warp when the accumulator is read back.  Only the
-//     2*ceil(K/8) groups that hold units are stored; the products run over M = 128 rows and simply compute garbage for
-//     the rest (rows of the accumulator that are never read);
+//   * every CTA keeps a 1/CS slice of W_out^T RESIDENT in TENSOR MEMORY for the whole solve (the A operand of
+//     tcgen05.mma may come from tensor memory: no shared-memory fetch of the weights at all, and 100 KB of shared memory
+//     less than a resident copy there).  The slice is cut along the REDUCTION index p = i*C4 + j of
+//     hbar[u] = sum_p W_out[p][u] * prebar[p]  (k steps of 16 columns).  It is ONE FP16 matrix of 128 rows: groups of 8
+//     rows alternate between the hi halves and the lo halves of 64 * W_out[.][u] for 8 hidden units u (row
+//     16*(u/8) + u%8 and + 8), so that the two halves of a unit sit in lanes l and l + 8 of the same warp when the
+//     accumulator is read back; row m is TMEM lane m, two consecutive p per 32-bit column;
 //   * per stage every CTA builds the pre-activation cotangent  prebar[p][n] = gbar[i][n] * dU[j][n] * (1 - G[p][n]^2)  of
 //     its slice for ALL NS samples straight from the saved tanh outputs (HBM / L2 -> registers), splits it into FP16
 //     hi/lo and writes it as the B operand [prebar_hi ; prebar_lo] (2*NS rows) into shared memory, in one pass or, where
@@ -36,22 +36,27 @@ constexpr int V4_MAX_CS = 8;
 struct V4Layout {
     int CS, NS, nclusters;
     int QW;                         // warps per tile in the operand build = 16 / CS
-    int CK;                         // k steps (of 16 columns) per operand chunk (even)
+    int PASSK;                      // k steps one pass of the 512 workers converts = 32 / CS (one item per thread)
+    int PPC, npass_max;             // passes per operand chunk; passes of the longest slice
+    int CK;                         // k steps (of 16 columns) per operand chunk = PPC * PASSK
     int nslots;                     // chunk buffers (1 or 2)
     int ks_begin[V4_MAX_CS + 1];    // k-step range of every cluster rank
     int nks_max, nchunks_max;
-    int SBOa, a_groups, a_bytes;    // per-rank A image: a_groups groups of 8 rows x 16*nks_max columns, SBO = nks_max * 256 bytes
+    int a_bytes;                    // per-rank A image in global memory: 128 rows x 16*nks_max FP16, row-major
     int64_t img_bytes;              // CS * a_bytes
+    int a_col;                      // first TMEM column of the resident A slice (8 columns per k step); the accumulator sits at column 0
     int SBOb, ring_bytes;           // one chunk buffer: 2*NS rows x 16*CK columns
     int tmem_cols;                  // power of two >= max(32, 2*NS)
     int GSTR;                       // row stride (floats) of the gathered stage cotangent [Hd][GSTR]
+    int GROW;                       // row stride (floats) of the staged tanh outputs [NS][GROW] = slice + 16 bytes
     int dub;                        // floats of one tile's dU (| dU/da) block
     int act_ld;                     // floats of a saved-activation block staged in shared memory (z_s | h_1 .. h_n)
     int KP, HP;                     // hidden-layer buffers (see ncde_bwd.cu)
     int chain;                      // 1: FP32 warp-synchronous hidden chain (all widths <= 32), 0: mma.sync
+    int chain_warps;                // warps that run the hidden layers (chain: one per sample; mma.sync: one per 16 inputs)
     int need_att;                   // timewise attention cotangent requested
     // shared-memory carve-up (byte offsets)
-    int o_bars, o_A, o_ring, o_hid, o_recv, o_recvatt, o_gall, o_du, o_act, o_zb, o_bd, o_max, o_lp, o_tab;
+    int o_bars, o_ring, o_hid, o_recv, o_recvatt, o_gall, o_du, o_act, o_zb, o_bd, o_max, o_lp, o_tab, o_gst;
     int smem_total;
 };
 

@@ -72,6 +72,26 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
     // asm volatile statements keep their order; a clobber would only make the single issuing thread reload every
     // loop-invariant value between two products
 }
+// The same with the A operand in TENSOR MEMORY (lane = row m, two FP16 of consecutive k per 32-bit column, 8 columns per
+// K = 16 step): no shared-memory fetch of A, which bounds the small-N products of this library (measured on B200,
+// M = 128, N = 64: ~110 cycles per product from shared memory).  A from tensor memory is always K-major.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate));
+}
+// Registers -> 8 consecutive 32-bit columns of this thread's TMEM lane (lane = 32 * (warp % 4) + laneid in taddr[31:16]).
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
 // Arrives once on the mbarrier when every tcgen05.mma issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
 {
