@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get('ANCDE_LIB') or os.path.join(_HERE, 'libancde_b200.so'
 MAX_LAYERS = 8
 MODE_PLAIN, MODE_BOTTOM, MODE_TOP = 0, 1, 2
 ENGINE_STREAMED, ENGINE_UMMA = 1, 3
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _f32p = ctypes.POINTER(ctypes.c_float)
 
@@ -41,12 +41,38 @@ class NcdeDesc(ctypes.Structure):
     ]
 
 
+class HeadDesc(ctypes.Structure):
+    """Mirror of `ancde_head_desc`."""
+    _fields_ = [
+        ('L', ctypes.c_int32), ('B', ctypes.c_int32), ('C', ctypes.c_int32), ('H', ctypes.c_int32),
+        ('timewise', ctypes.c_int32), ('kind', ctypes.c_int32), ('slope', ctypes.c_float),
+        ('raw', ctypes.c_void_p), ('ta_w', ctypes.c_void_p), ('ta_b', ctypes.c_void_p),
+        ('x0', ctypes.c_void_p), ('x0_stride', ctypes.c_int64),
+        ('fe_w', ctypes.c_void_p), ('fe_b', ctypes.c_void_p),
+        ('attention', ctypes.c_void_p), ('y0', ctypes.c_void_p),
+        ('grad_attention', ctypes.c_void_p), ('grad_y0', ctypes.c_void_p), ('grad_raw', ctypes.c_void_p),
+        ('grad_ta_w', ctypes.c_void_p), ('grad_ta_b', ctypes.c_void_p), ('grad_fe_w', ctypes.c_void_p), ('grad_fe_b', ctypes.c_void_p),
+    ]
+
+
+class TailDesc(ctypes.Structure):
+    """Mirror of `ancde_tail_desc`."""
+    _fields_ = [
+        ('n_out', ctypes.c_int32), ('B', ctypes.c_int32), ('H', ctypes.c_int32), ('O', ctypes.c_int32),
+        ('kind', ctypes.c_int32), ('T', ctypes.c_int32), ('pos_weight', ctypes.c_float), ('loss_scale', ctypes.c_float),
+        ('z_t', ctypes.c_void_p), ('final_index', ctypes.c_void_p), ('W', ctypes.c_void_p), ('b', ctypes.c_void_p),
+        ('target', ctypes.c_void_p), ('pred', ctypes.c_void_p), ('loss', ctypes.c_void_p), ('grad_z_t', ctypes.c_void_p),
+        ('grad_W', ctypes.c_void_p), ('grad_b', ctypes.c_void_p),
+    ]
+
+
 _lib = None
 
 EXPORTS = ['ancde_abi_version', 'ancde_last_error', 'ancde_spline_coeffs_f32', 'ancde_spline_coeffs_f64',
            'ancde_ncde_wpack_floats', 'ancde_ncde_save_act_floats', 'ancde_ncde_save_G_floats',
            'ancde_ncde_engine', 'ancde_ncde_forward', 'ancde_ncde_backward', 'ancde_ncde_join', 'ancde_debug_force_wgrad_mma_sync', 'ancde_debug_force_bwd_engine', 'ancde_debug_bwd4_launches', 'ancde_last_launch_count', 'ancde_fp32_peak_kernel',
-           'ancde_profile_enable', 'ancde_profile_count', 'ancde_profile_get']
+           'ancde_profile_enable', 'ancde_profile_count', 'ancde_profile_get',
+           'ancde_head_forward', 'ancde_head_backward', 'ancde_tail_forward_backward', 'ancde_weight_regulariser']
 
 
 def lib():
@@ -76,6 +102,11 @@ def lib():
     L.ancde_ncde_forward.argtypes = [ctypes.POINTER(NcdeDesc), vp]
     L.ancde_ncde_backward.argtypes = [ctypes.POINTER(NcdeDesc), vp]
     L.ancde_ncde_join.argtypes = [vp]
+    L.ancde_head_forward.argtypes = [ctypes.POINTER(HeadDesc), vp]
+    L.ancde_head_backward.argtypes = [ctypes.POINTER(HeadDesc), vp]
+    L.ancde_tail_forward_backward.argtypes = [ctypes.POINTER(TailDesc), vp]
+    L.ancde_weight_regulariser.argtypes = [vp, vp, vp, ci, vp, ctypes.c_float, vp, vp]
+    L.ancde_debug_force_bwd_engine.argtypes = [ci, ci]
     L.ancde_fp32_peak_kernel.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double), vp]
     L.ancde_profile_get.argtypes = [ci, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_float)]
     _lib = L

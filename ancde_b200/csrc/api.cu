@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters)
 
 }  // namespace ancde
 
-extern "C" int ancde_abi_version(void) { return 6; }
+extern "C" int ancde_abi_version(void) { return 7; }
 
 // development aid: device buffer of 64 int64 counters for -DANCDE_PHASE_TIMING builds
 extern "C" int ancde_debug_set_buffer(long long* dev_ptr) { ancde::g_dbg = dev_ptr; return ANCDE_OK; }

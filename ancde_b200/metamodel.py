@@ -9,6 +9,7 @@ through the `.npy` file of the reference (metamodel.py:326,648).
 import torch
 
 from . import cdeint_module as _cde
+from . import heads
 from .interpolate import NaturalCubicSpline
 
 
@@ -100,7 +101,8 @@ class _AttentiveBase(torch.nn.Module):
                "".format(self.input_channels, self.hidden_channels, self.output_channels, self.initial)
 
     def _attention_head(self, attention, slope):
-        """Reference: metamodel.py:327-343 / :650-666."""
+        """Reference: metamodel.py:327-343 / :650-666 (plain torch ops; the forward pass uses the fused kernel of
+        ancde_b200/heads.py, this stays as the readable statement of what that kernel computes)."""
         if self.timewise:
             attention = self.time_attention(attention)
         if self.soft:
@@ -109,7 +111,9 @@ class _AttentiveBase(torch.nn.Module):
             return self.binarizer(self.STE(slope * attention))
         return self.binarizer(torch.sigmoid(attention))
 
-    def forward(self, times, coeffs, final_index, slope, z0=None, stream=False, **kwargs):
+    def hidden(self, times, coeffs, final_index, slope, z0=None, stream=False, **kwargs):
+        """The hot path up to the top solve: z_t (len(times), batch, hidden) at EVERY knot (see _solve_times).
+        Reference: metamodel.py:238-358 / :565-680."""
         coeff, _, _, _ = coeffs
         batch_dims = coeff.shape[:-2]
         if not stream:
@@ -117,7 +121,11 @@ class _AttentiveBase(torch.nn.Module):
                                                     "coeff.shape[:-2]={}, final_index.shape={}" \
                                                     "".format(batch_dims, final_index.shape)
         cubic_spline = NaturalCubicSpline(times, coeffs)
-        x0 = cubic_spline.evaluate(times[0]).float()
+        # X(t0) = a + (b + ...) * 0: the `a` coefficient of the first piece (a strided view, no kernel) when that is exact
+        if coeff.dtype == torch.float32 and coeff.dim() == 3 and coeff.is_cuda:
+            x0 = coeff[:, 0, :]
+        else:
+            x0 = cubic_spline.evaluate(times[0]).float()
         if z0 is None:
             assert self.initial, "Was not expecting to be given no value of z0."
             z0 = self.initial_network(x0)
@@ -127,16 +135,20 @@ class _AttentiveBase(torch.nn.Module):
         kwargs = _default_rk4(times, kwargs)
         adjoint = kwargs.pop('adjoint', True)
 
-        attention = _cde.ancde_bottom(dX_dt=cubic_spline.derivative, z0=z0, func=self.func_f, t=times,
-                                      file=self.file, adjoint=adjoint, **kwargs)
+        raw = _cde.ancde_bottom(dX_dt=cubic_spline.derivative, z0=z0, func=self.func_f, t=times,
+                                file=self.file, adjoint=adjoint, **kwargs)
         # the bottom solve's stage derivatives, still in HBM (reference: np.load(self.file)); the model keeps the latest one
         # alive (controldiffeq.load_h_prime(self.file) finds it), the previous one is released
-        h_prime = self._h_prime = attention.h_prime
-        attention = self._attention_head(attention, slope)
-        y0 = self.feature_extractor(x0 * attention[0, :, :])
-        z_t = _cde.ancde(dX_dt=cubic_spline.derivative, attention=attention, z0=y0, X_s=cubic_spline,
-                         func_g=self.func_g, h_prime=h_prime, t=t, timewise=self.timewise, adjoint=adjoint,
-                         **kwargs)
+        h_prime = self._h_prime = raw.h_prime
+        # attention = act(time_attention(raw)), y0 = feature_extractor(X(t0) * attention[0]): ONE kernel (heads.cu)
+        attention, y0 = heads.attention_head(raw, self.time_attention, x0, self.feature_extractor, self.timewise, self.soft,
+                                             self.slope_check, slope)
+        return _cde.ancde(dX_dt=cubic_spline.derivative, attention=attention, z0=y0, X_s=cubic_spline,
+                          func_g=self.func_g, h_prime=h_prime, t=t, timewise=self.timewise, adjoint=adjoint,
+                          **kwargs)
+
+    def forward(self, times, coeffs, final_index, slope, z0=None, stream=False, **kwargs):
+        z_t = self.hidden(times, coeffs, final_index, slope, z0=z0, stream=stream, **kwargs)
         z_t = _readout(z_t, final_index, stream)
         if self.forecasting:
             input_time = z_t.shape[1]
@@ -239,6 +251,12 @@ class InitialValueNetwork(torch.nn.Module):
         *coeffs, static = coeffs
         z0 = self.linear2(torch.relu(self.linear1(static)))
         return self.model(times, coeffs, final_index, slope_check, z0=z0, **kwargs)
+
+    def hidden(self, times, coeffs, final_index, slope_check, **kwargs):
+        """The wrapped model's `hidden` (all-knot top states) with z0 from the static features."""
+        *coeffs, static = coeffs
+        z0 = self.linear2(torch.relu(self.linear1(static)))
+        return self.model.hidden(times, coeffs, final_index, slope_check, z0=z0, **kwargs)
 
 
 def make_model(name, input_channels, output_channels, hidden_channels, hidden_hidden_channels, attention_channel,

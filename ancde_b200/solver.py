@@ -46,6 +46,17 @@ def accumulate_into_param_grads(async_wgrad=True):
         join()
 
 
+def accumulating_into_param_grads():
+    return _ACCUMULATE_INTO_PARAM_GRADS
+
+
+def grad_is_accumulable(p, dev):
+    """True when kernels may atomically add into `p.grad` in place (an existing contiguous float32 gradient on `dev`)."""
+    g = getattr(p, 'grad', None)
+    return (isinstance(p, torch.nn.Parameter) and g is not None and g.dtype == torch.float32 and g.is_contiguous()
+            and g.device == dev and g.shape == p.shape)
+
+
 def join():
     """Makes the current stream of every device with pending asynchronous weight gradients wait for them."""
     if not _pending:

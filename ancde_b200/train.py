@@ -7,7 +7,7 @@ add one flat-gradient all-reduce between backward and the optimizer step (ancde_
 """
 import torch
 
-from . import metamodel, solver, synthetic
+from . import heads, metamodel, solver, synthetic
 from .dp import FlatGradBucket
 
 
@@ -50,23 +50,66 @@ class DualNcdeTrainer:
         # parameter sizes in flat-buffer order (the order `seg` numbers them in); computed here because bincount
         # synchronises with the host, which a CUDA-graph capture of step() would not survive
         self._reg_lengths = torch.bincount(self._reg[2], minlength=len(self.reg_params)) if self._reg else None
+        # fused tail (read-out + linear + loss + their gradients in one launch) and regulariser (two launches): GPU only
+        self.fused = fused
+        self.regulariser = heads.WeightRegulariser(self.bucket, self.reg_params, self.reg_scaling) if (fused and self.reg_params) else None
+        core = self.model.model if self.cfg['static'] else self.model
+        self.readout_linear = core.linear
+        if self.cfg['kind'] == 'ancde_forecasting':
+            self.tail_kind = heads.TAIL_MSE
+        else:
+            self.tail_kind = heads.TAIL_BCE if self.cfg['out'] == 1 else heads.TAIL_CE
+
+    def _coeffs(self, batch):
+        if 'coeffs' in batch:
+            return batch['coeffs']
+        # raw paths: the spline coefficients of the batch are built on the GPU inside the step (one kernel launch,
+        # datasets_common.coefficients_on_the_fly) instead of being read from a 4x larger precomputed cache
+        from .datasets_common import coefficients_on_the_fly
+        return coefficients_on_the_fly(batch['times'], batch['X'])
 
     def forward(self, batch, slope=1.0):
         cfg = self.cfg
-        if 'coeffs' in batch:
-            coeffs = batch['coeffs']
-        else:
-            # raw paths: the spline coefficients of the batch are built on the GPU inside the step (one kernel launch,
-            # datasets_common.coefficients_on_the_fly) instead of being read from a 4x larger precomputed cache
-            from .datasets_common import coefficients_on_the_fly
-            coeffs = coefficients_on_the_fly(batch['times'], batch['X'])
+        coeffs = self._coeffs(batch)
         kw = dict(stream=cfg['stream'], adjoint=self.adjoint)
         if cfg['static']:
             return self.model(batch['times'], tuple(coeffs) + (batch['static'],), batch['final_index'], slope, **kw)
         return self.model(batch['times'], tuple(coeffs), batch['final_index'], slope, **kw)
 
+    def hidden(self, batch, slope=1.0):
+        """The top NCDE's states at every knot, (L, B, H), with the autograd graph of both solves behind them."""
+        cfg = self.cfg
+        kw = dict(stream=cfg['stream'], adjoint=self.adjoint)
+        coeffs = self._coeffs(batch)
+        if cfg['static']:
+            return self.model.hidden(batch['times'], tuple(coeffs) + (batch['static'],), batch['final_index'], slope, **kw)
+        return self.model.hidden(batch['times'], tuple(coeffs), batch['final_index'], slope, **kw)
+
     def step(self, batch, slope=1.0):
-        """forward + loss + backward + gradient all-reduce + Adam. Returns the (detached) loss."""
+        """forward + loss + backward + gradient all-reduce + Adam. Returns the (detached) loss.
+
+        On the GPU the tail of the step is fused: read-out, final linear layer, task loss and the gradients of all three are
+        ONE launch (heads.readout_loss), the backward pass continues from the cotangent of the top solve's states, and the
+        weight regulariser (value and gradient) is two launches on the flat buffers."""
+        if self.fused:
+            return self.step_fused(batch, slope)
+        return self.step_eager(batch, slope)
+
+    def step_fused(self, batch, slope=1.0):
+        self.bucket.zero()
+        z_t = self.hidden(batch, slope)
+        loss, _, grad_z = heads.readout_loss(z_t, batch['final_index'], self.readout_linear, batch['y'], self.tail_kind,
+                                             output_time=self.cfg['output_time'], pos_weight=10.0)
+        with solver.accumulate_into_param_grads():      # the solver's weight gradients go straight into the flat bucket
+            z_t.backward(grad_z)
+        if self.regulariser is not None:
+            self.regulariser.add(loss)
+        self.bucket.all_reduce_mean()
+        self.opt.step()
+        return loss
+
+    def step_eager(self, batch, slope=1.0):
+        """The same step with the tail as plain torch ops (the reference's formulation; CPU tests and cross-checks)."""
         self.bucket.zero()
         pred = self.forward(batch, slope)
         loss = task_loss(self.cfg, pred, batch['y'])

@@ -28,7 +28,7 @@ extern "C" {
 
 #define ANCDE_MAX_LAYERS 8      /* hidden (ReLU) layers in a vector-field MLP */
 
-/* ABI version; bumped when a struct below changes.  6: ancde_ncde_desc gained `grid`.  5: ancde_ncde_desc gained single_stage, grad_k_out (ABI 5) and
+/* ABI version; bumped when a struct below changes.  7: head / tail / regulariser entry points.  6: ancde_ncde_desc gained `grid`.  5: ancde_ncde_desc gained single_stage, grad_k_out (ABI 5) and
  * async_wgrad (ABI 4, with ancde_ncde_join). */
 int ancde_abi_version(void);
 
@@ -158,6 +158,81 @@ int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream);
 /* Makes `stream` wait for every weight-gradient kernel that backward calls with async_wgrad = 1 put on the side stream
  * of the current device (an event wait: no host synchronisation, capturable in a CUDA graph).  No-op when none is pending. */
 int ancde_ncde_join(void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The small layers either side of the two solves, fused.
+ *
+ * HEAD -- experiments/models/metamodel.py:327-348 (ANCDE) / :650-671 (ANCDE_forecasting):
+ *   attention = act(time_attention(raw))  (timewise, one value per knot and sample)  or  act(raw)  (elementwise),
+ *   act = sigmoid (soft, :332-333) | round(Hardsigmoid(slope * x)) (hard, slope_check, :335-338) | round(sigmoid(x)) (:340-343),
+ *   the rounding with the straight-through gradient of RoundFunctionST (:148-161), Hardsigmoid = (hardtanh + 1) / 2 (:139-146);
+ *   y0 = feature_extractor(X(t0) * attention[0])  (:345-348).
+ * ------------------------------------------------------------------------------------------- */
+#define ANCDE_HEAD_SOFT         0
+#define ANCDE_HEAD_HARD_STE     1
+#define ANCDE_HEAD_HARD_SIGMOID 2
+
+typedef struct ancde_head_desc {
+    int32_t L, B, C, H;         /* knots, samples, channels (= bottom state size), top state size */
+    int32_t timewise;           /* 1: attention (L, B, 1) = act(raw . ta_w + ta_b); 0: attention (L, B, C) = act(raw) */
+    int32_t kind;               /* ANCDE_HEAD_* */
+    float   slope;              /* ANCDE_HEAD_HARD_STE only */
+    const float* raw;           /* (L, B, C) bottom NCDE states */
+    const float* ta_w;          /* (C)  time_attention.weight, timewise only */
+    const float* ta_b;          /* (1)  time_attention.bias */
+    const float* x0;            /* X(t0): sample b, channel c at x0[b * x0_stride + c] (e.g. the `a` coefficient of the first piece) */
+    int64_t x0_stride;
+    const float* fe_w;          /* (H, C) feature_extractor.weight */
+    const float* fe_b;          /* (H) */
+    float* attention;           /* out (L, B, 1 | C) */
+    float* y0;                  /* out (B, H) */
+    /* backward only */
+    const float* grad_attention;/* (L, B, 1 | C) or NULL (adjoint-mode gradient flow: only y0 carries a cotangent) */
+    const float* grad_y0;       /* (B, H) */
+    float* grad_raw;            /* (L, B, C) written */
+    float* grad_ta_w;           /* accumulated into (caller zeroes); timewise only */
+    float* grad_ta_b;
+    float* grad_fe_w;
+    float* grad_fe_b;
+} ancde_head_desc;
+
+int ancde_head_forward(const ancde_head_desc* d, void* stream);
+/* Reads `attention` as written by the forward (row 0) and recomputes the pre-activations from `raw`. */
+int ancde_head_backward(const ancde_head_desc* d, void* stream);
+
+/* TAIL -- read-out, final linear layer, task loss and the gradients of all three in ONE launch:
+ *   classification (metamodel.py:360-371): z = z_t[final_index[b], b, :], pred = linear(z);
+ *   forecasting    (metamodel.py:683-696): pred[b, q] = linear(z_t[n_out - T + q, b, :]), q < T = output_time;
+ *   loss = BCEWithLogits(pos_weight) (experiments/common.py:677-678) | cross entropy (:680) | MSE (:766), mean reduced. */
+#define ANCDE_TAIL_BCE 0
+#define ANCDE_TAIL_CE  1
+#define ANCDE_TAIL_MSE 2
+
+typedef struct ancde_tail_desc {
+    int32_t n_out, B, H, O;     /* z_t is (n_out, B, H); the linear layer maps H -> O */
+    int32_t kind;               /* ANCDE_TAIL_* */
+    int32_t T;                  /* ANCDE_TAIL_MSE: output_time */
+    float   pos_weight;         /* ANCDE_TAIL_BCE */
+    float   loss_scale;         /* cotangent of the loss (1 for loss.backward()) */
+    const float* z_t;
+    const int64_t* final_index; /* (B), classification */
+    const float* W;             /* (O, H) */
+    const float* b;             /* (O) */
+    const void* target;         /* BCE: float (B); CE: int64 (B); MSE: float (B, T, O) */
+    float* pred;                /* out (B, O) | (B, T, O) */
+    float* loss;                /* out (1): written */
+    float* grad_z_t;            /* out (n_out, B, H), written completely (zero where nothing is read out), or NULL */
+    float* grad_W;              /* accumulated into (caller zeroes) */
+    float* grad_b;
+} ancde_tail_desc;
+
+int ancde_tail_forward_backward(const ancde_tail_desc* d, void* stream);
+
+/* REG -- experiments/common.py:47-58: loss + scaling * sum_p ||p||_2 over parameters that are segments
+ * [seg_begin[s], seg_begin[s+1]) of one flat buffer: adds scaling * p / ||p|| to flat_grad and scaling * sum ||p|| to *loss
+ * (loss may be NULL).  sumsq: nseg floats of scratch. */
+int ancde_weight_regulariser(const float* flat_param, float* flat_grad, const int32_t* seg_begin, int32_t nseg, float* sumsq,
+                             float scaling, float* loss, void* stream);
 
 /* Number of kernel launches the last forward / backward call of this thread issued. */
 int ancde_last_launch_count(void);
