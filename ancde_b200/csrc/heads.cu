@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_bwd_kernel(const ancde_head
 }
 
 // Feature extractor: grad_W[h][c] = sum_b grad_y0[b][h] * x0[b][c] * attention[0][b][c|0], grad_b[h] = sum_b grad_y0[b][h].
-// One block per output unit h, lanes over the channels, the batch split over the warps.
+// Grid (H, slices of the batch): one output unit h per block row, lanes over the channels, the block's slice of the batch
+// split over its warps (x0 rows are a spline-coefficient stride apart: many short independent loops, not one long one).
 __global__ void __launch_bounds__(HEAD_THREADS) head_fe_grad_kernel(const ancde_head_desc d)
 {
     __shared__ float s_acc[HEAD_THREADS / 32][HEAD_MAXC + 1];
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_fe_grad_kernel(const ancde_
 #pragma unroll
     for (int q = 0; q < HEAD_MAXC / 32; ++q) acc[q] = 0.f;
     const int attC = d.timewise ? 1 : d.C;
-    for (int b = warp; b < d.B; b += HEAD_THREADS / 32) {
+    for (int b = blockIdx.y * (HEAD_THREADS / 32) + warp; b < d.B; b += gridDim.y * (HEAD_THREADS / 32)) {
         const float gy = __ldg(d.grad_y0 + (int64_t)b * d.H + h);
         gb += gy;
 #pragma unroll
@@ -447,7 +448,11 @@ extern "C" int ancde_head_backward(const ancde_head_desc* d, void* stream_)
     count_launch();
     ANCDE_CUDA(cudaGetLastError());
     prof_begin("head_fe_grad", stream);
-    head_fe_grad_kernel<<<d->H, HEAD_THREADS, 0, stream>>>(*d);
+    {
+        int slices = (d->B + 63) / 64;             // ~8 samples per warp
+        if (slices > 64) slices = 64;
+        head_fe_grad_kernel<<<dim3((unsigned)d->H, (unsigned)slices), HEAD_THREADS, 0, stream>>>(*d);
+    }
     prof_end(stream);
     count_launch();
     ANCDE_CUDA(cudaGetLastError());

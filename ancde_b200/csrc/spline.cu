@@ -25,12 +25,22 @@
 //  * a tile kernel -- one CTA per sample, X block and every scratch value in shared memory, thread = channel for the
 //    compaction and the Thomas sweeps, thread = (interval, channel) element for the expansion, fully coalesced 128-bit
 //    loads and 128-byte stores, bit-identical results: 0.951 ms (the per-channel phases keep 35 of 128 threads busy and
-//    serialise ~15 k cycles per sample).
+//    serialise ~15 k cycles per sample);
+//  * (round 2) the same tile idea with one WARP per path -- ballot/popc compaction, per-ordinal terms and piece
+//    coefficients one per lane, lane 0 alone in the two Thomas sweeps, intervals one per lane, outputs staged in shared
+//    memory and stored as contiguous runs, bit-identical: 1.56 ms.  The serial sweeps (one division per ordinal on ONE
+//    lane) and five paths per warp in sequence leave ~44 k cycles per sample and CTA; 32 independent paths per warp, as
+//    here, hide that latency far better.
+// What this kernel does instead about the expensive piece set-up in the interval loop: paths with at most SPL_MAXP pieces
+// (sparse data: Sepsis has ~8 of 71) compute every piece's coefficients in the back-substitution loop, where all lanes of
+// a warp are busy, and park them in shared memory; the interval loop then enters a piece with four loads.
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace ancde {
+
+constexpr int SPL_MAXP = 16;     // pieces per path whose coefficients are parked in shared memory
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -43,7 +53,10 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
     const int tid = threadIdx.x;
     T* sT = reinterpret_cast<T*>(smem_raw);
     const int Lp = (L + 3) & ~3;
-    unsigned short* sidx = reinterpret_cast<unsigned short*>(sT + Lp);   // [L+2][NT] knot index per ordinal
+    T* sPB = sT + Lp;                                                    // [SPL_MAXP][NT] parked piece coefficients b, two_c, three_d
+    T* sPC = sPB + SPL_MAXP * NT;
+    T* sPD = sPC + SPL_MAXP * NT;
+    unsigned short* sidx = reinterpret_cast<unsigned short*>(sPD + SPL_MAXP * NT);   // [L+2][NT] knot index per ordinal
 
     for (int i = tid; i < L; i += NT) sT[i] = times[i];
     __syncthreads();
@@ -112,9 +125,12 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
     // Scratch of the Thomas solve: the modified diagonal / rhs of ordinal j live in interval slot j of this
     // path's OWN output arrays (D3 / Bc, coalesced, L1/L2 resident) until pass 3 overwrites them; only m of the
     // L-1 slots are touched.  The last ordinal (m-1 can be L-1, one past the slots) stays in registers.
-    T* sd = D3 + obase;
-    T* sb = Bc + obase;
-    const int64_t SC = C;       // stride between interval slots
+    // Paths with at most SPL_MAXP pieces keep that scratch in SHARED memory instead (the slots that later hold the parked
+    // piece coefficients): no global round trip inside the two dependent sweeps.
+    const bool park = (m - 1 <= SPL_MAXP) && (m > 2);     // (a single linear piece takes the general path)
+    T* sd = park ? sPC + tid : D3 + obase;
+    T* sb = park ? sPB + tid : Bc + obase;
+    const int64_t SC = park ? NT : C;       // stride between ordinal slots
     T k_last;
     // ---- pass 1: forward sweep over the ordinals (misc.py:57-61).  Row j of the system
     // (interpolate.py:31-43) is D_j = 2 (r_j + r_{j-1}), rhs_j = pds_j + pds_{j-1}.
@@ -153,16 +169,28 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
         T knext = O::div(rhs, D);
         k_last = knext;
         int inext = iprev;
+        T xnext = park ? xval(m - 1, inext) : T(0);
 #pragma unroll 4
         for (int j = m - 2; j >= 0; --j) {
             const int ij = jx[j * NT];
             T r, r2;
             recip(inext, ij, r, r2);
+            const T k1 = knext;
             knext = O::div(O::sub(sb[j * SC], O::mul(r, knext)), sd[j * SC]);
-            sb[j * SC] = knext;
+            if (!park) sb[j * SC] = knext;
+            if (park) {
+                // coefficients of piece j (interpolate.py:46-53), the same operations as in the interval loop below
+                const T v = xval(j, ij);
+                const T six_pd = O::mul(T(2), O::mul(T(3), O::sub(xnext, v)));
+                sPB[j * NT + tid] = knext;
+                sPC[j * NT + tid] = O::mul(O::sub(O::sub(O::mul(six_pd, r), O::mul(T(4), knext)), O::mul(T(2), k1)), r);
+                sPD[j * NT + tid] = O::mul(O::add(O::mul(-six_pd, r), O::mul(T(3), O::add(knext, k1))), r2);
+                xnext = v;
+            }
             inext = ij;
         }
     }
+    const bool parked = park;
     // ---- pass 3: coefficients of each observed piece (interpolate.py:46-53), expanded to every
     // interval with offset = t_observed - t_i (interpolate.py:136-148).  All lanes walk i in lock step,
     // BACKWARDS: piece jj is entered at its last interval idx[jj+1]-1 >= jj, when slots jj+1.. are the only
@@ -177,6 +205,12 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
             --jj;
             const int ni = icur;
             icur = jx[jj * NT];
+            if (parked) {
+                pa = xval(jj, icur);
+                pb = sPB[jj * NT + tid];
+                pc = sPC[jj * NT + tid];
+                pd = sPD[jj * NT + tid];
+            } else {
             const T v = xval(jj, icur), x1 = xval(jj + 1, ni);
             pa = v;
             const T k0 = sb[jj * SC], k1 = k_hi;
@@ -195,6 +229,7 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
                 pc = O::mul(O::sub(O::sub(O::mul(six_pd, r), O::mul(T(4), k0)), O::mul(T(2), k1)), r);
                 // three_d = (-six_pd * r + 3 (k0 + k1)) * r^2
                 pd = O::mul(O::add(O::mul(-six_pd, r), O::mul(T(3), O::add(k0, k1))), r2);
+            }
             }
         }
         const T off = tf32 ? (T)__fsub_rn((float)sT[icur], (float)sT[i]) : O::sub(sT[icur], sT[i]);
@@ -216,14 +251,14 @@ static int launch_spline(const T* times, const T* X, T* a, T* b, T* c2, T* d3, i
     ANCDE_CHECK_ARG(L >= 2, "spline_coeffs: Must have a time dimension of size at least 2.");
     ANCDE_CHECK_ARG(C >= 1 && N >= 0, "spline_coeffs: bad shape N=%lld C=%d", (long long)N, C);
     if (N == 0) return ANCDE_OK;
+    ANCDE_CHECK_ARG(L <= 65535, "spline_coeffs: L=%d too long (max 65535 knots)", L);
     const int64_t P = N * (int64_t)C;
     const int Lp = (L + 3) & ~3;
     // the only shared scratch is the 16-bit ordinal -> knot index list; the Thomas scratch lives in the outputs
-    ANCDE_CHECK_ARG(L <= 65535, "spline_coeffs: L=%d too long (max 65535 knots)", L);
     int nt = 128;
     size_t smem = 0;
     for (;; nt /= 2) {
-        smem = (size_t)Lp * sizeof(T) + (size_t)(L + 2) * nt * sizeof(unsigned short);
+        smem = (size_t)Lp * sizeof(T) + 3 * (size_t)SPL_MAXP * nt * sizeof(T) + (size_t)(L + 2) * nt * sizeof(unsigned short);
         if (smem <= 56 * 1024 || nt == 32) break;
     }
     if (smem > 227 * 1024) {

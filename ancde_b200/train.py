@@ -7,11 +7,14 @@ add one flat-gradient all-reduce between backward and the optimizer step (ancde_
 """
 import torch
 
+import os
+
 from . import heads, metamodel, solver, synthetic
 from .dp import FlatGradBucket
 
 
 _pos_weight = {}
+ASYNC_WGRAD = os.environ.get('ANCDE_ASYNC_WGRAD', '1') not in ('', '0')     # weight-gradient kernels on the library's side stream
 
 
 def task_loss(cfg, pred, y):
@@ -100,7 +103,7 @@ class DualNcdeTrainer:
         z_t = self.hidden(batch, slope)
         loss, _, grad_z = heads.readout_loss(z_t, batch['final_index'], self.readout_linear, batch['y'], self.tail_kind,
                                              output_time=self.cfg['output_time'], pos_weight=10.0)
-        with solver.accumulate_into_param_grads():      # the solver's weight gradients go straight into the flat bucket
+        with solver.accumulate_into_param_grads(async_wgrad=ASYNC_WGRAD):      # the solver's weight gradients go straight into the flat bucket
             z_t.backward(grad_z)
         if self.regulariser is not None:
             self.regulariser.add(loss)

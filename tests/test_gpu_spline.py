@@ -97,3 +97,4 @@ def test_errors_match_reference():
         ancde_b200.natural_cubic_spline_coeffs(t.cpu(), torch.randn(2, 4, 3))   # no CPU path
     out = ancde_b200.natural_cubic_spline_coeffs(t, torch.randn(0, 4, 3).cuda())      # empty batch
     assert out[0].shape == (0, 3, 3)
+
