@@ -12,6 +12,7 @@ python, so the opaque callables of the reference API are recognised structurally
 
 Anything else raises NotImplementedError -- there is no eager fallback.
 """
+import math
 import os
 import weakref
 
@@ -81,8 +82,33 @@ def _plan(mode, sp, t, func, z0, step, constructor, **kw):
     return SolvePlan(mode, sp._times, (sp._b, sp._two_c, sp._three_d), t, step, grid=grid, **kw)
 
 
+def _time_of(t):
+    """A solver time as a python float (torchdiffeq hands the vector field 0-d tensors; one read-back, like the reference's
+    `t.item()` at cdeint_module.py:108)."""
+    return float(t.item()) if torch.is_tensor(t) else float(t)
+
+
+def _field_at(dX_dt, func, t, z):
+    """func(z) @ dX_dt(t) as ONE launch of the solver kernel in its single-stage mode."""
+    from .solver import FieldPlan, field
+    sp = _spline_of(dX_dt)
+    return field(FieldPlan(sp._times, (sp._b, sp._two_c, sp._three_d), _time_of(t)), func, z.float())
+
+
+def _field_with_control(func, z, dU):
+    """func(z) @ dU for an explicit control vector dU (batch, channels): the same kernel, on a one-piece "spline" whose
+    derivative is dU.  No gradient flows into dU (the control of the fused kernels is a constant)."""
+    from .solver import FieldPlan, field
+    dU = dU.detach().float().contiguous()
+    B, C = dU.shape
+    zeros = dU.new_zeros(B, 1, C)
+    times = torch.tensor([0.0, 1.0], dtype=torch.float32, device=dU.device)
+    return field(FieldPlan(times, (dU.view(B, 1, C), zeros, zeros), 0.0), func, z.float())
+
+
 class VectorField(torch.nn.Module):
-    """Descriptor of f(z) dX/dt (reference: cdeint_module.py:9-32). Evaluated inside the fused kernel."""
+    """f(z) dX/dt (reference: cdeint_module.py:9-32).  The solves evaluate it inside the fused kernels; called directly
+    (`field(t, z)`, what torchdiffeq does with it) it is one launch of the same kernel in single-stage mode."""
 
     def __init__(self, dX_dt, func):
         super(VectorField, self).__init__()
@@ -92,20 +118,36 @@ class VectorField(torch.nn.Module):
         self.func = func
 
     def forward(self, t, z):
-        raise NotImplementedError('vector fields are evaluated inside the fused kernel; call cdeint()')
+        return _field_at(self.dX_dt, self.func, t, z)
 
 
 class VectorField_stack(VectorField):
-    """Bottom field that also records h' (reference: cdeint_module.py:34-72)."""
+    """Bottom field that also records h' = its outputs in call order (reference: cdeint_module.py:34-72).  The list lives
+    on the instance (the reference appends to a module-global tensor); with ANCDE_WRITE_H_PRIME=1 it is written to `file`
+    once the final time is reached, like the reference (:69-70)."""
 
     def __init__(self, dX_dt, func, final_time, file):
         super(VectorField_stack, self).__init__(dX_dt, func)
         self.final_time = final_time
         self.file = file
+        self.h_prime_list = []
+
+    def forward(self, t, z):
+        out = _field_at(self.dX_dt, self.func, t, z)
+        self.h_prime_list.append(out.detach())
+        if _time_of(self.final_time) - _time_of(t) <= 0.1 and os.environ.get('ANCDE_WRITE_H_PRIME', '0') not in ('', '0'):
+            np.save(self.file, torch.stack(self.h_prime_list).cpu().numpy())
+        return out
+
+    def h_prime(self):
+        return torch.stack(self.h_prime_list)
 
 
 class AttentiveVectorField(torch.nn.Module):
-    """Top field g(z) dY/dt with attention (reference: cdeint_module.py:74-138)."""
+    """Top field g(z) dY/dt with dY = dX a + a (1 - a) dX h'[call counter], a = attention[floor(t) - 1]
+    (reference: cdeint_module.py:74-138).  Inside `ancde` (rk4) the fused kernels evaluate it; called
+    directly it forms dY with tensor ops and multiplies it with g(z) in one single-stage launch.  Attention and h' are
+    constants of a direct call (no gradient), as in the reference's adjoint mode (Q10)."""
 
     def __init__(self, dX_dt, func_g, X_s, h_prime, time, attention):
         super(AttentiveVectorField, self).__init__()
@@ -113,9 +155,24 @@ class AttentiveVectorField(torch.nn.Module):
             raise ValueError("func must be a torch.nn.Module.")
         self.dX_dt, self.func_g, self.X_s = dX_dt, func_g, X_s
         self.h_prime, self.timewise, self.attention = h_prime, time, attention
+        self.t_idx = 0
 
     def forward(self, t, z):
-        raise NotImplementedError('vector fields are evaluated inside the fused kernel; call ancde()')
+        tt = _time_of(t)
+        att = self.attention if self.attention.dim() == 3 else self.attention.unsqueeze(-1)
+        a_t = att[int(math.floor(tt)) - 1].detach().float()                 # python index: -1 wraps to the last knot (Q3)
+        dX = self.dX_dt(torch.as_tensor(tt, dtype=torch.float32, device=z.device)).float()
+        hp = self.h_prime
+        hp_t = hp[self.t_idx]
+        if isinstance(hp_t, np.ndarray):
+            hp_t = torch.from_numpy(hp_t)
+        hp_t = hp_t.to(device=z.device, dtype=torch.float32)
+        dY = dX * a_t + (a_t * (1 - a_t)) * dX * hp_t                         # "Xt" is dX/dt (Q4)
+        out = _field_with_control(self.func_g, z, dY)
+        self.t_idx += 1
+        if self.t_idx == len(hp) - 1:                                         # the reset rule of :136-137 (Q5)
+            self.t_idx = 0
+        return out
 
 
 def cdeint(dX_dt, z0, func, t, adjoint=True, **kwargs):
@@ -179,6 +236,8 @@ def ancde_bottom(dX_dt, z0, func, t, file, adjoint=True, **kwargs):
     sp = _spline_of(dX_dt)
     if 'method' not in kwargs:
         kwargs['method'] = 'rk4'
+    if kwargs['method'] == 'dopri5':
+        return _ancde_bottom_dopri5(sp, dX_dt, z0, func, t, file, adjoint, kwargs)
     step, constructor = _rk4_step(kwargs, 1.0)
     if adjoint and any(c.requires_grad for c in (sp._b, sp._two_c, sp._three_d)):
         raise ValueError("Gradients do not backpropagate through the control with adjoint=True. (This is a limitation "
@@ -204,6 +263,8 @@ def ancde(dX_dt, attention, z0, X_s, func_g, h_prime, t, timewise, adjoint=True,
     only differentiates func parameters and z0).
     """
     sp = _spline_of(dX_dt)
+    if kwargs.get('method', None) in (None, 'dopri5'):
+        return _ancde_dopri5(sp, dX_dt, attention, z0, X_s, func_g, h_prime, t, timewise, adjoint, kwargs)
     step, constructor = _rk4_step(kwargs, None)
     if isinstance(h_prime, np.ndarray):
         h_prime = torch.from_numpy(h_prime).to(z0.device)
@@ -221,3 +282,58 @@ def ancde(dX_dt, attention, z0, X_s, func_g, h_prime, t, timewise, adjoint=True,
     plan = _plan(_lib.MODE_TOP, sp, t, func_g, z0, step, constructor, h_prime=h_prime.detach(), att_grad=not adjoint)
     z_out, _ = solve(plan, func_g, z0, att)
     return z_out
+
+
+def _dopri5_args(kwargs, adjoint, bottom):
+    """rtol / atol / options of a dopri5 call: ancde_bottom sets atol 1e-12, rtol 1e-6 itself (cdeint_module.py:179-183);
+    elsewhere torchdiffeq 0.0.1's defaults apply (odeint 1e-7 / 1e-9, odeint_adjoint 1e-6 / 1e-12)."""
+    kwargs = dict(kwargs)
+    kwargs.pop('method', None)
+    options = dict(kwargs.pop('options', None) or {})
+    if bottom:
+        rtol, atol = kwargs.pop('rtol', 1e-6), kwargs.pop('atol', 1e-12)
+    else:
+        rtol, atol = kwargs.pop('rtol', 1e-6 if adjoint else 1e-7), kwargs.pop('atol', 1e-12 if adjoint else 1e-9)
+    if kwargs:
+        raise TypeError('unexpected solver arguments: %s' % sorted(kwargs))
+    allowed = {'first_step', 'safety', 'ifactor', 'dfactor', 'max_num_steps'}
+    if set(options) - allowed:
+        raise NotImplementedError('dopri5 options %s are not supported' % sorted(set(options) - allowed))
+    return rtol, atol, options
+
+
+def _ancde_bottom_dopri5(sp, dX_dt, z0, func, t, file, adjoint, kwargs):
+    """`ancde_bottom(..., method='dopri5')` (cdeint_module.py:179-183,222,239): host-driven adaptive steps around the
+    single-stage kernel; h' = EVERY field evaluation in call order, rejected steps included, exactly what the reference's
+    VectorField_stack records."""
+    from . import dopri5
+    rtol, atol, options = _dopri5_args(kwargs, adjoint, bottom=True)
+    vf = VectorField_stack(dX_dt, func, t[-1], file)
+    z_out = dopri5.odeint(lambda tt, z: vf(tt, z), z0.float(), solver_times(t), rtol=rtol, atol=atol, **options)
+    k_out = vf.h_prime()
+    z_out.h_prime = k_out
+    sp._ancde_h_prime = k_out
+    _H_PRIME[file] = k_out
+    if os.environ.get('ANCDE_WRITE_H_PRIME', '0') not in ('', '0'):
+        np.save(file, k_out.cpu().numpy())
+    return z_out
+
+
+def _ancde_dopri5(sp, dX_dt, attention, z0, X_s, func_g, h_prime, t, timewise, adjoint, kwargs):
+    """`ancde(..., method='dopri5')` (torchdiffeq's default when the caller names no method, cdeint_module.py:251-253): the
+    reference's call-counter indexing of h' and zero-order hold of the attention, whatever they mean on an adaptive grid
+    (well defined for hard attention, where a (1 - a) = 0).  Attention and h' are constants of this solve
+    (the reference's adjoint-mode gradient flow, Q10); asking for their gradient (adjoint=False with an attention that
+    requires grad) is refused rather than answered wrongly."""
+    from . import dopri5
+    if not adjoint and torch.is_tensor(attention) and attention.requires_grad:
+        raise NotImplementedError("ancde(method='dopri5', adjoint=False): the gradient with respect to the attention is not "
+                                  "implemented for the adaptive solver; use method='rk4' (the path every ANCDE experiment "
+                                  "takes) or adjoint=True")
+    rtol, atol, options = _dopri5_args(kwargs, adjoint, bottom=False)
+    if torch.is_tensor(h_prime) and h_prime.dim() == 2:
+        h_prime = getattr(sp, '_ancde_h_prime', None)
+        if h_prime is None:
+            raise IndexError('too many indices for tensor of dimension 2')
+    vf = AttentiveVectorField(dX_dt, func_g, X_s, h_prime, timewise, attention)
+    return dopri5.odeint(lambda tt, z: vf(tt, z), z0.float(), solver_times(t), rtol=rtol, atol=atol, **options)
