@@ -48,6 +48,21 @@ def _spline_of(dX_dt):
     return sp
 
 
+def _check_control_grad(sp, adjoint, bottom=False):
+    """The control is a constant of the fused kernels.  adjoint=True: the reference refuses a control that requires grad
+    too (ancde_bottom, cdeint_module.py:218-220, same message).  adjoint=False: the reference would backpropagate into the
+    spline coefficients; that gradient is not implemented here, and silently returning none would be wrong."""
+    if not any(c.requires_grad for c in (sp._b, sp._two_c, sp._three_d)):
+        return
+    if adjoint:
+        if bottom:
+            raise ValueError("Gradients do not backpropagate through the control with adjoint=True. (This is a limitation "
+                             "of the underlying torchdiffeq library.)")
+        return
+    raise NotImplementedError('gradients with respect to the control (spline coefficients that require grad, adjoint=False) '
+                              'are not implemented by the fused solver; detach the coefficients')
+
+
 def _rk4_step(kwargs, default_step):
     """Resolves the solver arguments the way the reference entry points and torchdiffeq's FixedGridODESolver do.
     Returns (step_size or None, grid_constructor or None): a step size makes the arithmetic grid t[0] + k * step, a
@@ -183,6 +198,7 @@ def cdeint(dX_dt, z0, func, t, adjoint=True, **kwargs):
     the solver's O(h^4)), see DESIGN.md.
     """
     sp = _spline_of(dX_dt)
+    _check_control_grad(sp, adjoint)
     if kwargs.get('method', None) in (None, 'dopri5'):
         # torchdiffeq's default solver (cdeint_module.py:146,149 forward **kwargs untouched): adaptive Dormand-Prince
         return _cdeint_dopri5(sp, z0, func, t, adjoint, kwargs)
@@ -234,14 +250,12 @@ def ancde_bottom(dX_dt, z0, func, t, file, adjoint=True, **kwargs):
     reference models (`np.load(self.file)`, metamodel.py:326,648) run on this package.
     """
     sp = _spline_of(dX_dt)
+    _check_control_grad(sp, adjoint, bottom=True)
     if 'method' not in kwargs:
         kwargs['method'] = 'rk4'
     if kwargs['method'] == 'dopri5':
         return _ancde_bottom_dopri5(sp, dX_dt, z0, func, t, file, adjoint, kwargs)
     step, constructor = _rk4_step(kwargs, 1.0)
-    if adjoint and any(c.requires_grad for c in (sp._b, sp._two_c, sp._three_d)):
-        raise ValueError("Gradients do not backpropagate through the control with adjoint=True. (This is a limitation "
-                         "of the underlying torchdiffeq library.)")
     plan = _plan(_lib.MODE_BOTTOM, sp, t, func, z0, step, constructor, want_k=True)
     z_out, k_out = solve(plan, func, z0)
     z_out.h_prime = k_out               # per-call handle: lives exactly as long as the result (or the spline) does
@@ -263,6 +277,7 @@ def ancde(dX_dt, attention, z0, X_s, func_g, h_prime, t, timewise, adjoint=True,
     only differentiates func parameters and z0).
     """
     sp = _spline_of(dX_dt)
+    _check_control_grad(sp, adjoint)
     if kwargs.get('method', None) in (None, 'dopri5'):
         return _ancde_dopri5(sp, dX_dt, attention, z0, X_s, func_g, h_prime, t, timewise, adjoint, kwargs)
     step, constructor = _rk4_step(kwargs, None)

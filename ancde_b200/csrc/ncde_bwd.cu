@@ -16,6 +16,8 @@
 //
 // Matches autograd through torchdiffeq's rk4_alt_step_func + the reference vector fields
 // (cdeint_module.py:25-32,56-72,103-138; vector_fields.py:205-218,237-250) to FP32 round-off.
+#include <mutex>
+
 #include "mma_common.cuh"
 #include "bwd_hidden.cuh"
 #include "ncde_bwd4.cuh"
@@ -632,6 +634,7 @@ struct SideStream {
     bool pending = false;
 };
 static SideStream g_side[64];
+static std::mutex g_side_mutex;       // creation and the pending flag; the library is otherwise single-threaded per device (header)
 
 static int side_stream(SideStream** out)
 {
@@ -639,6 +642,7 @@ static int side_stream(SideStream** out)
     ANCDE_CUDA(cudaGetDevice(&dev));
     ANCDE_CHECK_ARG(dev >= 0 && dev < 64, "ncde_backward: device index %d", dev);
     SideStream* ss = &g_side[dev];
+    std::lock_guard<std::mutex> lock(g_side_mutex);
     if (!ss->s) {
         ANCDE_CUDA(cudaStreamCreateWithFlags(&ss->s, cudaStreamNonBlocking));
         ANCDE_CUDA(cudaEventCreateWithFlags(&ss->fork, cudaEventDisableTiming));
@@ -673,6 +677,7 @@ static int launch_wgrads(const ancde_ncde_desc* d, const SolveArgs& a, cudaStrea
         if (rc != ANCDE_OK) return rc;
         if (ss) {
             ANCDE_CUDA(cudaEventRecord(ss->done, ss->s));
+            std::lock_guard<std::mutex> lock(g_side_mutex);
             ss->pending = true;
         }
     }
@@ -728,6 +733,7 @@ extern "C" int ancde_ncde_join(void* stream_)
     ANCDE_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return ANCDE_OK;
     ancde::SideStream* ss = &ancde::g_side[dev];
+    std::lock_guard<std::mutex> lock(ancde::g_side_mutex);
     if (ss->s && ss->pending) {
         ANCDE_CUDA(cudaStreamWaitEvent((cudaStream_t)stream_, ss->done, 0));
         ss->pending = false;

@@ -13,6 +13,8 @@ import torch
 from . import _lib
 
 _grid_cache = {}
+# fields of the reference with the arithmetic the kernels implement (experiments/models/vector_fields.py:115-250)
+FUSED_FIELD_CLASSES = {'FinalTanh', 'FinalTanh_ff6', 'FinalTanh_g', 'FinalTanh_hide'}
 import os
 FORCE_SAMPLES_PER_CTA = int(os.environ.get('ANCDE_SAMPLES_PER_CTA', '0'))   # 0 = library default; tests set 1/2/4/8
 ENGINE = int(os.environ.get('ANCDE_ENGINE', '0'))   # 0 = library default; 1 = streamed FP32 engine; 3 = UMMA (tcgen05) engine
@@ -198,6 +200,15 @@ def mlp_params(func):
     """
     if not isinstance(func, torch.nn.Module):
         raise ValueError("func must be a torch.nn.Module.")
+    # The kernels hard-wire the arithmetic ReLU(linear) ... ReLU(linear) -> linear -> view(Hd, C) -> tanh.  A module is
+    # only taken for that when it IS one of the reference's fields of this form (by class name: the reference's own classes
+    # and this package's mirrors) or says so itself (`ancde_relu_mlp_tanh = True`); attribute names alone prove nothing
+    # about the activations in between.
+    if type(func).__name__ not in FUSED_FIELD_CLASSES and not getattr(func, 'ancde_relu_mlp_tanh', False):
+        raise NotImplementedError(
+            'the fused B200 solver only understands FinalTanh / FinalTanh_ff6 shaped vector fields (ReLU MLP, tanh at the end); '
+            'got %s.  A module with exactly that arithmetic can opt in with the attribute `ancde_relu_mlp_tanh = True`.'
+            % type(func).__name__)
     try:
         layers = [func.linear_in]
         if hasattr(func, 'linear_test'):
@@ -208,6 +219,12 @@ def mlp_params(func):
         raise NotImplementedError(
             'the fused B200 solver only understands FinalTanh / FinalTanh_ff6 shaped vector fields '
             '(linear_in[, linear_test], linears, linear_out + tanh); got %s' % type(func).__name__)
+    for lin in layers + [out]:
+        if not isinstance(lin, torch.nn.Linear) or lin.bias is None:
+            raise NotImplementedError('vector field layers must be torch.nn.Linear with a bias; got %s' % type(lin).__name__)
+        if lin.weight.dtype != torch.float32 or lin.bias.dtype != torch.float32:
+            raise NotImplementedError('the fused B200 solver computes in float32: the vector field has %s parameters '
+                                      '(cast the module with .float())' % lin.weight.dtype)
     if len(layers) > _lib.MAX_LAYERS:
         raise NotImplementedError('at most %d hidden layers are supported' % _lib.MAX_LAYERS)
     Hd = layers[0].in_features

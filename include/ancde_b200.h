@@ -155,7 +155,12 @@ int ancde_ncde_forward(const ancde_ncde_desc* d, void* stream);
  * with the stage cotangents (consumed by the weight-gradient kernel launched from the same call). */
 int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream);
 
-/* Makes `stream` wait for every weight-gradient kernel that backward calls with async_wgrad = 1 put on the side stream
+/* Threading: one host thread per device at a time.  The side stream and its fork / done events are shared per device, so
+ * two host threads driving backward calls with async_wgrad = 1 on the SAME device would interleave their event records
+ * (creation and the pending flag are mutex-protected, the event order is not); use one thread per device, or
+ * async_wgrad = 0.  Calls on different devices are independent.
+ *
+ * Makes `stream` wait for every weight-gradient kernel that backward calls with async_wgrad = 1 put on the side stream
  * of the current device (an event wait: no host synchronisation, capturable in a CUDA graph).  No-op when none is pending. */
 int ancde_ncde_join(void* stream);
 

@@ -195,3 +195,40 @@ def test_dopri5_driver_matches_the_torchdiffeq_restatement_on_cpu():
         dopri5.odeint(Field(), torch.zeros(1, 5), [1.0, 0.0])
     with pytest.raises(AssertionError):
         dopri5.odeint(Field(), torch.zeros(1, 5), [0.0, 1.0, 0.5])
+
+
+def test_vector_fields_are_recognised_by_class_not_by_attribute_names():
+    """A module that merely has linear_in / linears / linear_out attributes may use other activations: it is refused unless
+    it is one of the reference's ReLU-MLP + tanh fields or opts in explicitly; float64 parameters are refused too."""
+    from ancde_b200 import solver
+
+    class LookAlike(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.linear_in = torch.nn.Linear(4, 5)
+            self.linears = torch.nn.ModuleList([torch.nn.Linear(5, 5)])
+            self.linear_out = torch.nn.Linear(5, 4 * 3)
+
+        def forward(self, z):
+            return torch.sin(self.linear_out(torch.nn.functional.gelu(self.linear_in(z)))).view(*z.shape[:-1], 4, 3)
+
+    with pytest.raises(NotImplementedError, match='FinalTanh'):
+        solver.mlp_params(LookAlike())
+    m = LookAlike()
+    m.ancde_relu_mlp_tanh = True
+    tensors, widths, Hd, C = solver.mlp_params(m)
+    assert (widths, Hd, C) == ([5, 5], 4, 3) and len(tensors) == 6
+    with pytest.raises(NotImplementedError, match='float32'):
+        solver.mlp_params(ancde_b200.FinalTanh(3, 4, 5, 2).double())
+    tensors, widths, Hd, C = solver.mlp_params(ancde_b200.FinalTanh_ff6(3, 4, 5, 2))
+    assert (widths, Hd, C) == ([5, 4, 4], 3, 3)
+
+
+def test_control_that_requires_grad_is_refused_without_adjoint_too():
+    times = torch.arange(5.)
+    coeffs = port.natural_cubic_spline_coeffs(times, torch.randn(2, 5, 3))
+    c2 = tuple(c.clone().requires_grad_(True) for c in coeffs)
+    sp = ancde_b200.NaturalCubicSpline(times, c2)
+    with pytest.raises(NotImplementedError, match='control'):
+        ancde_b200.cdeint(sp.derivative, torch.randn(2, 4), ancde_b200.FinalTanh(3, 4, 5, 2), times, adjoint=False,
+                          method='rk4', options=dict(step_size=1.0))
