@@ -42,7 +42,9 @@ namespace ancde {
 
 constexpr int SPL_MAXP = 16;     // pieces per path whose coefficients are parked in shared memory
 
-template <typename T>
+// IDX: type of the ordinal -> knot index list in shared memory (8 bit for L <= 256 knots: shared memory per CTA bounds the
+// resident warps of this latency-bound kernel)
+template <typename T, typename IDX>
 __global__ void __launch_bounds__(256)
 spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __restrict__ A,
                      T* Bc, T* __restrict__ C2, T* D3, int64_t P, int L, int C, int tf32)
@@ -56,7 +58,7 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
     T* sPB = sT + Lp;                                                    // [SPL_MAXP][NT] parked piece coefficients b, two_c, three_d
     T* sPC = sPB + SPL_MAXP * NT;
     T* sPD = sPC + SPL_MAXP * NT;
-    unsigned short* sidx = reinterpret_cast<unsigned short*>(sPD + SPL_MAXP * NT);   // [L+2][NT] knot index per ordinal
+    IDX* sidx = reinterpret_cast<IDX*>(sPD + SPL_MAXP * NT);   // [L+2][NT] knot index per ordinal
 
     for (int i = tid; i < L; i += NT) sT[i] = times[i];
     __syncthreads();
@@ -78,7 +80,7 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
             if (first < 0) { first = i; xfirst = v; }
             last = i;
             xlast = v;
-            sidx[pos * NT + tid] = (unsigned short)i;
+            sidx[pos * NT + tid] = (IDX)i;
             ++pos;
         }
     }
@@ -93,9 +95,9 @@ spline_coeffs_kernel(const T* __restrict__ times, const T* __restrict__ X, T* __
     const bool imp_first = first != 0, imp_last = last != L - 1;
     int base = 1;
     if (imp_first) { sidx[tid] = 0; base = 0; }
-    if (imp_last) { sidx[pos * NT + tid] = (unsigned short)(L - 1); ++pos; }
+    if (imp_last) { sidx[pos * NT + tid] = (IDX)(L - 1); ++pos; }
     const int m = pos - base;                        // observed knots after imputation, >= 2
-    const unsigned short* jx = sidx + base * NT + tid;     // jx[j*NT] = knot index of ordinal j
+    const IDX* jx = sidx + base * NT + tid;     // jx[j*NT] = knot index of ordinal j
     // value of ordinal j (knot i): read again from X (L1/L2 resident after pass 0) instead of a shared-memory copy --
     // shared memory per thread drops from 6 to 2 bytes per knot, which doubles the resident warps of this
     // latency-bound kernel (measured: 0.883 -> 0.825 ms on the Sepsis-size split); the two imputed ends come from
@@ -255,22 +257,23 @@ static int launch_spline(const T* times, const T* X, T* a, T* b, T* c2, T* d3, i
     const int64_t P = N * (int64_t)C;
     const int Lp = (L + 3) & ~3;
     // the only shared scratch is the 16-bit ordinal -> knot index list; the Thomas scratch lives in the outputs
+    const size_t isz = (L <= 256) ? 1 : 2;        // bytes per ordinal -> knot index
     int nt = 128;
     size_t smem = 0;
     for (;; nt /= 2) {
-        smem = (size_t)Lp * sizeof(T) + 3 * (size_t)SPL_MAXP * nt * sizeof(T) + (size_t)(L + 2) * nt * sizeof(unsigned short);
+        smem = (size_t)Lp * sizeof(T) + 3 * (size_t)SPL_MAXP * nt * sizeof(T) + (size_t)(L + 2) * nt * isz;
         if (smem <= 56 * 1024 || nt == 32) break;
     }
     if (smem > 227 * 1024) {
         set_error("spline_coeffs: L=%d needs %zu bytes of shared memory per CTA (max 227 KB)", L, smem);
         return ANCDE_EUNSUPPORTED;
     }
-    ANCDE_CUDA(cudaFuncSetAttribute(spline_coeffs_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
+    auto kern = (isz == 1) ? spline_coeffs_kernel<T, unsigned char> : spline_coeffs_kernel<T, unsigned short>;
+    ANCDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = (P + nt - 1) / nt;
     ANCDE_CHECK_ARG(grid <= 0x7fffffffLL, "spline_coeffs: too many paths");
     prof_begin(sizeof(T) == 4 ? "spline_coeffs_f32" : "spline_coeffs_f64", stream);
-    spline_coeffs_kernel<T><<<(unsigned)grid, nt, smem, stream>>>(times, X, a, b, c2, d3, P, L, C, tf32);
+    kern<<<(unsigned)grid, nt, smem, stream>>>(times, X, a, b, c2, d3, P, L, C, tf32);
     prof_end(stream);
     count_launch();
     ANCDE_CUDA(cudaGetLastError());

@@ -504,8 +504,12 @@ def run_ours(args):
     # ---- per-kernel roofline from the CUDA-event timings taken inside the timed region
     flops = kernel_flops(cfg, B)
     # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of one `ncu --set full` capture of this
-    # workload at this batch (profiles/r01f_ncu_set_full.txt); a measured constant, only valid for the captured shape
-    NCU_TRAFFIC = {('sepsis', 1024): {'ncde_fwd_bottom': 0.041357e9 + 1.659941e9, 'ncde_fwd_top': 0.094120e9 + 2.386643e9, 'ncde_bwd_top': 2.450084e9 + 0.280650e9, 'ncde_wgrad_top': 2.275437e9 + 0.005132e9, 'ncde_hidden_wgrad_top': 0.459675e9 + 0.003783e9, 'ncde_bwd_bottom': 1.684613e9 + 0.155929e9, 'ncde_wgrad_bottom': 1.583921e9 + 0.004289e9, 'ncde_hidden_wgrad_bottom': 0.254225e9 + 0.003811e9}}
+    # workload at this batch (profiles/r02_ncu_set_full.txt); a measured constant, only valid for the captured shape
+    NCU_TRAFFIC = {('sepsis', 1024): {
+        'ncde_fwd_bottom': 0.0415e9 + 1.6618e9, 'ncde_fwd_top': 0.0947e9 + 2.3874e9,
+        'ncde_bwd_top': 2.4501e9 + 0.2799e9, 'ncde_wgrad_top': 2.2732e9 + 0.0050e9, 'ncde_hidden_wgrad_top': 0.4597e9 + 0.0041e9,
+        'ncde_bwd_bottom': 1.6847e9 + 0.1542e9, 'ncde_wgrad_bottom': 1.5843e9 + 0.0048e9,
+        'ncde_hidden_wgrad_bottom': 0.2542e9 + 0.0045e9}}
     traffic = NCU_TRAFFIC.get((args.workload, B), {})
     agg = {}
     for name, t in prof:
@@ -533,7 +537,7 @@ def run_ours(args):
                     'peak_source': 'FFMA microbenchmark (ancde_fp32_peak_kernel) measured in this run; '
                                    'MEASURED_PEAKS.json holds no FP32 figure',
                     'traffic': traffic.get(dom['name']),
-                    'traffic_source': 'profiles/r01f_ncu_set_full.txt (bytes per launch)' if dom['name'] in traffic else None,
+                    'traffic_source': 'profiles/r02_ncu_set_full.txt (bytes per launch)' if dom['name'] in traffic else None,
                     'step_frac': round(total_flops * args.steps / (ms * 1e-3) / 1e12 / fp32_peak, 4),
                     'step_algorithmic_gflop': round(total_flops / 1e9, 2)}
 
@@ -623,8 +627,13 @@ def spline_roofline(device, cfg, n_paths_target=2 ** 20):
     nbytes = N * C * (L + 4 * (L - 1)) * 4           # algorithmic: read X once, write a, b, two_c, three_d once
     peak, src = hbm_peak()
     achieved = nbytes / (ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of exactly this input
+    # (profiles/r02_spline_ncu.txt); only valid for the captured shape
+    traffic = 1.5751e9 if (N, L, C) == (29959, 72, 35) else None
     return {'bound': 'hbm', 'kernel': 'spline_coeffs_f32', 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s',
-            'frac': round(achieved / peak, 4), 'traffic': None, 'peak_source': src, 'avg_ms': round(ms, 4),
+            'frac': round(achieved / peak, 4), 'traffic': traffic,
+            'traffic_source': 'profiles/r02_spline_ncu.txt (bytes per launch)' if traffic else None,
+            'peak_source': src, 'avg_ms': round(ms, 4),
             'paths': N * C, 'knots': L, 'algorithmic_bytes_per_launch': nbytes,
             'input': '%d x %d x %d float32, 90%% of entries missing' % (N, L, C)}
 

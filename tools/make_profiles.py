@@ -9,6 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, launches_csv, rep = sys.argv[1], sys.argv[2], sys.argv[3]
+CMD = sys.argv[4] if len(sys.argv) > 4 else 'python tools/one_step.py sepsis 3   (3 eager training steps, Sepsis shape, B = 1024, raw X in)'
 out_dir = os.path.join(ROOT, 'profiles')
 os.makedirs(out_dir, exist_ok=True)
 
@@ -35,8 +36,8 @@ tot = sum(a[0] for a in agg.values())
 ours = sum(a[0] for k, a in agg.items() if 'ancde::' in k and 'fp32_peak' not in k)
 step = sum(a[0] for k, a in agg.items() if 'fp32_peak' not in k)
 with open(os.path.join(out_dir, '%s_launch_list_summary.txt' % tag), 'w') as f:
-    f.write('ncu --metrics gpu__time_duration.sum --clock-control none -c %d  python bench.py --steps 5 --warmup 3 --no-cpu-baseline\n' % n)
-    f.write('(first %d launches of the command: warm-up + timed steps; per-launch times are cold-cache and serialised -- compare SHARES)\n' % n)
+    f.write('ncu --metrics gpu__time_duration.sum --clock-control none -c 400  %s\n' % CMD)
+    f.write('(all %d launches of the command; per-launch times are cold-cache and serialised -- compare SHARES)\n' % n)
     f.write('total %.3f ms; without the FP32-peak microbenchmark %.3f ms; library kernels %.3f ms = %.1f %% of that\n\n' %
             (tot / 1e6, step / 1e6, ours / 1e6, 100 * ours / step))
     f.write('%10s %6s %7s %9s  %s\n' % ('total ms', 'n', 'share', 'avg ms', 'kernel'))
@@ -64,7 +65,7 @@ want = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__regis
         'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio']
 with open(os.path.join(out_dir, '%s_ncu_set_full.txt' % tag), 'w') as f:
-    f.write('ncu --set full --clock-control none --import-source on  (python tools/fwd_time.py sepsis bwd: Sepsis shape, B = 1024, forward + backward)\n')
+    f.write('ncu --set full --clock-control none --import-source on  %s\n' % CMD)
     f.write('one column per profiled launch; dram__bytes_* are per launch (the "traffic" of bench.py\'s roofline object)\n\n')
     for w in want:
         if w not in h:
