@@ -757,7 +757,7 @@ static int bwd_engine_of(const ancde_ncde_desc* d, const NcdeLayout& lo, V4Layou
     if (g_force_bwd_engine >= 4) return 4;
     // Measured on B200 (round 2): the cluster kernel wins where the streamed one is bound by re-streaming W_out^T through
     // shared memory for 8 samples -- a large output layer and enough samples to fill clusters; small shapes stay put.
-    if ((int64_t)lo.NCP * lo.K >= 20000 && lo.B >= 2 * v4->NS) return 4;
+    if ((int64_t)lo.NCP * lo.K >= 20000 && lo.B >= v4->NS) return 4;
     return 1;
 }
 }  // namespace ancde

@@ -804,13 +804,16 @@ static int max_active_clusters4(const V4Layout& v)
     return n;
 }
 
-// The cluster size whose clusters run in the fewest waves (ties: the larger cluster, whose CTAs hold a smaller slice).
+// The cluster size whose clusters run in the fewest waves; ties go to clusters of 4, the size every measurement of
+// DESIGN.md was taken with (clusters of 8 were not faster where they fit in one wave).
 int choose_layout4(const ancde_ncde_desc* d, const NcdeLayout& st, bool need_att, int force_cs, V4Layout* v)
 {
     if (force_cs) return make_layout4(d, st, need_att, force_cs, v);
     int best_waves = 0;
     V4Layout cand;
-    for (int cs = V4_MAX_CS; cs >= 2; cs /= 2) {
+    static const int order[3] = {4, 8, 2};
+    for (int o = 0; o < 3; ++o) {
+        const int cs = order[o];
         if (make_layout4(d, st, need_att, cs, &cand) != ANCDE_OK) continue;
         const int act = max_active_clusters4(cand);
         const int waves = act > 0 ? (cand.nclusters + act - 1) / act : 1 << 20;
