@@ -92,6 +92,54 @@ __device__ __forceinline__ void hidden_chain_bwd(const int* __restrict__ sLp, in
 }
 
 
+// The same layers in FP32 with ONE (input unit k, sample b) output per thread: thread tid = 8*k + b of the calling
+// warps computes  delta_{l-1}[k][b] = relu'(h_{l-1}[k][b]) * sum_o Wt_l[k][o] * delta_l[o][b]  from 128-bit pieces of its
+// weight row (the 8 threads of a k share the address: broadcast) and of its sample's cotangent row, four accumulators,
+// one barrier of the calling warps per layer.  For layers of any width up to 64: a 49-unit layer is ~100 instructions
+// per thread and one barrier, against 15 mma.sync of ~50 cycles each on a fifth of the warps (hidden_mma_bwd below:
+// measured 1.25 k cycles per layer inside the cluster backward).  Buffers and parameters as hidden_chain_bwd.
+template <int TS, typename Sync>
+__device__ __forceinline__ void hidden_wide_bwd(const int* __restrict__ sLp, int n_hidden, const float* __restrict__ sW,
+                                                float* __restrict__ sD0, float* __restrict__ sD1,
+                                                const float* __restrict__ sAct, float* __restrict__ act,
+                                                float* __restrict__ sZb, int HP, int tid, Sync layer_sync)
+{
+    static_assert(TS == 8, "one output per thread: tid = 8 * unit + sample");
+    const int k = tid >> 3, b = tid & 7;
+    const float* in = sD0;
+    int pp = 1;
+    for (int l = n_hidden - 1; l >= 0; --l) {
+        const int4 q0 = *reinterpret_cast<const int4*>(sLp + 8 * l);
+        const int2 q1 = *reinterpret_cast<const int2*>(sLp + 8 * l + 4);
+        const int nk4 = q0.x, N = q0.y;               // ceil(width / 4), inputs of the layer
+        float* out = pp ? sD1 : sD0;
+        if (k < N) {
+            const float4* wr = reinterpret_cast<const float4*>(sW + q0.w + k * q0.z);
+            const float4* xr = reinterpret_cast<const float4*>(in + b * HP);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+            for (int q = 0; q < nk4; ++q) {
+                const float4 w = wr[q], x = xr[q];
+                a0 = fmaf(w.x, x.x, a0);
+                a1 = fmaf(w.y, x.y, a1);
+                a2 = fmaf(w.z, x.z, a2);
+                a3 = fmaf(w.w, x.w, a3);
+            }
+            float v = (a0 + a1) + (a2 + a3);
+            if (l > 0) {
+                v = (sAct[q1.x + tid] > 0.f) ? v : 0.f;       // h_{l-1}[k][b] sits at k * 8 + b = tid
+                out[b * HP + k] = v;
+                if (act) act[q1.y + tid] = v;                   // for the hidden weight-gradient kernel
+            } else {
+                sZb[tid] = v;                                   // cotangent of the stage input
+            }
+        }
+        layer_sync();
+        in = out;
+        pp ^= 1;
+    }
+}
+
 // The same layers on the tensor cores (mma.sync m16n8k16, FP16 hi/lo x3 = FP32-grade) for layers wider than 32 units:
 // every m-tile (16 inputs of layer l) has its own warp, one CTA barrier per layer.  The cotangents stay multiplied by the
 // stage's power-of-two `scale` inside the chain (FP16 range); delta_l = (W_{l+1}^T delta_{l+1}) * relu'(h_l), the

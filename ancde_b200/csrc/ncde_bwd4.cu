@@ -41,9 +41,12 @@ __device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity, int)
 // Named barrier over the worker warps (the issuer warp never joins).
 __device__ __forceinline__ void workers_sync() { named_bar_sync(1, V4_WORKERS); }
 
-template <bool CHAIN>
+// HM: how the hidden layers run backwards -- 0: FP32 warp-synchronous chain (a warp per sample, widths <= 32), 1: mma.sync
+// (a warp per 16 inputs), 2: FP32 with one (unit, sample) output per thread over all the warps a layer fills.
+template <int HM>
 __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_constant__ Bwd4Args p)
 {
+    constexpr bool CHAIN = HM != 1;       // FP32 buffers and transposed FP32 weights (modes 0 and 2)
     const NcdeLayout& lo = p.s.lo;            // streamed layout with tiles of 8 samples
     const V4Layout& v = p.v;
     constexpr int TS = 8, NT = V4_WORKERS, NW = NT / 32;      // worker threads; warp NW is the MMA issuer
@@ -548,8 +551,11 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
             }
             workers_sync();
             if (warp < CW) {
-                if constexpr (CHAIN) {
+                if constexpr (HM == 0) {
                     hidden_chain_bwd<TS, 1>(sLp, lo.n_hidden, sWtb, sD0, sD1, sAct, act, sZb, v.HP, warp, CW, lane);
+                } else if constexpr (HM == 2) {
+                    const int cthreads = 32 * CW;
+                    hidden_wide_bwd<TS>(sLp, lo.n_hidden, sWtb, sD0, sD1, sAct, act, sZb, v.HP, tid, [cthreads] { named_bar_sync(2, cthreads); });
                 } else {
                     const int cthreads = 32 * CW;
                     hidden_mma_bwd<TS>(sLp, lo.n_hidden, sWhb, sBd, v.KP, sAct, act, sZb, inv_scale, warp, lane,
@@ -657,8 +663,20 @@ int make_layout4(const ancde_ncde_desc* d, const NcdeLayout& st, bool need_att, 
         v->act_ld = st.act_off_du;
         v->KP = 16 * st.KSB + 8;
         v->HP = pad4(st.Hmax);
-        v->chain = chain ? 1 : 0;
-        v->chain_warps = chain ? 8 : maxmt;
+        {
+            // Hidden layers (measured per stage at the Sepsis shape): layers of <= 32 units in FP32 with one (unit,
+            // sample) output per thread (4.0 k cycles; a warp per sample: 4.2 k; mma.sync: 4.9 k); wider layers on mma.sync
+            // (49 units: 5.0 k; the FP32 form moves 26 128-bit shared-memory loads per output and is bound by the 128 B/clk
+            // of the shared-memory return path: 7.1 k).  ANCDE_BWD4_HID = 0 / 1 / 2 overrides (development).
+            const char* env = getenv("ANCDE_BWD4_HID");
+            int hm = env ? atoi(env) : (chain ? 2 : 1);
+            if (hm == 0 && !chain) hm = 2;
+            if (hm < 0 || hm > 2) hm = chain ? 2 : 1;
+            int in_max = st.Hd;
+            for (int l = 0; l < st.n_hidden; ++l) in_max = st.in_dim[l] > in_max ? st.in_dim[l] : in_max;
+            v->chain = hm;
+            v->chain_warps = hm == 0 ? 8 : (hm == 1 ? maxmt : (in_max * 8 + 31) / 32);
+        }
         v->need_att = need_att ? 1 : 0;
         if ((v->dub * 4) % 16 || (v->act_ld * 4) % 16 || (st.act_off_du * 4) % 16 || (st.act_floats * 4) % 16) continue;
         // Operand chunks: whole passes.  Two chunks in two buffers where they fit (the products of the first half run while
@@ -686,14 +704,14 @@ int make_layout4(const ancde_ncde_desc* d, const NcdeLayout& st, bool need_att, 
                 size_t o = 0;
                 v->o_bars = (int)o;    o = up(o + 128);
                 v->o_ring = (int)o;    o = up(o + (size_t)nslots * v->ring_bytes);
-                v->o_hid = (int)o;     o = up(o + (chain ? (size_t)pad4(st.hiddenb_floats) * 4 : (size_t)st.hb_u4 * 16));
+                v->o_hid = (int)o;     o = up(o + (v->chain != 1 ? (size_t)pad4(st.hiddenb_floats) * 4 : (size_t)st.hb_u4 * 16));
                 v->o_recv = (int)o;    o = up(o + (size_t)CS * st.K * 8 * 4);
                 v->o_recvatt = (int)o; o = up(o + (size_t)CS * v->QW * 8 * 4);
                 v->o_gall = (int)o;    o = up(o + (size_t)(st.Hd + 1) * v->GSTR * 4);
                 v->o_du = (int)o;      o = up(o + (size_t)CS * v->dub * 4);
                 v->o_act = (int)o;     o = up(o + (size_t)v->act_ld * 4);
                 v->o_zb = (int)o;      o = up(o + (size_t)pad4(st.Hd * 8) * 4);
-                v->o_bd = (int)o;      o = up(o + (chain ? (size_t)2 * 8 * v->HP * 4 : (size_t)4 * 8 * v->KP * 2));
+                v->o_bd = (int)o;      o = up(o + (v->chain != 1 ? (size_t)2 * 8 * v->HP * 4 : (size_t)4 * 8 * v->KP * 2));
                 v->o_max = (int)o;     o = up(o + 128);
                 v->o_lp = (int)o;      o = up(o + 8 * ANCDE_MAX_LAYERS * 4);
                 v->o_tab = (int)o;     o = up(o + (size_t)4 * v->PASSK * v->npass_max * 16);
@@ -784,11 +802,11 @@ static void launch_config4(const V4Layout& v, cudaStream_t stream, cudaLaunchCon
 // doubled the kernel time), a cluster of 4 fits 33 times.
 static int max_active_clusters4(const V4Layout& v)
 {
-    static int cache[2][V4_MAX_CS + 1][8] = {};          // [chain][CS][smem / 32 KB] -> clusters + 1
+    static int cache[3][V4_MAX_CS + 1][8] = {};          // [hidden-layer mode][CS][smem / 32 KB] -> clusters + 1
     const int bucket = v.smem_total / (32 * 1024);
     int& slot = cache[v.chain][v.CS][bucket > 7 ? 7 : bucket];
     if (slot) return slot - 1;
-    auto kern = v.chain ? ncde_bwd4_kernel<true> : ncde_bwd4_kernel<false>;
+    auto kern = v.chain == 0 ? ncde_bwd4_kernel<0> : (v.chain == 1 ? ncde_bwd4_kernel<1> : ncde_bwd4_kernel<2>);
     int n = 0;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess) {
         cudaLaunchConfig_t cfg;
@@ -831,7 +849,7 @@ int launch_bwd4(const SolveArgs& a, const V4Layout& v, const unsigned char* img,
     ba.s = a;
     ba.v = v;
     ba.img = img;
-    auto kern = v.chain ? ncde_bwd4_kernel<true> : ncde_bwd4_kernel<false>;
+    auto kern = v.chain == 0 ? ncde_bwd4_kernel<0> : (v.chain == 1 ? ncde_bwd4_kernel<1> : ncde_bwd4_kernel<2>);
     ANCDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem_total));
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute at[1];

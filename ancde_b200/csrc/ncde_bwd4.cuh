@@ -52,7 +52,7 @@ struct V4Layout {
     int dub;                        // floats of one tile's dU (| dU/da) block
     int act_ld;                     // floats of a saved-activation block staged in shared memory (z_s | h_1 .. h_n)
     int KP, HP;                     // hidden-layer buffers (see ncde_bwd.cu)
-    int chain;                      // 1: FP32 warp-synchronous hidden chain (all widths <= 32), 0: mma.sync
+    int chain;                      // hidden-layer mode of ncde_bwd4_kernel<HM>: 0 FP32 warp chain, 1 mma.sync, 2 FP32 one output per thread
     int chain_warps;                // warps that run the hidden layers (chain: one per sample; mma.sync: one per 16 inputs)
     int need_att;                   // timewise attention cotangent requested
     // shared-memory carve-up (byte offsets)

@@ -364,8 +364,15 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), _lib.launches_total() - launches0, prof
 
-    # ---- per-kernel timings (CUDA events around every library launch) from an eager pass; also counts the launches
+    # ---- per-kernel timings (CUDA events around every library launch) from an eager pass; also counts the launches.
+    # The weight-gradient kernels stay IN STREAM for this pass: on the library's side stream they share the GPU with the
+    # other network's recurrent backward, and an event pair around a kernel that waits for SMs measures the wait
+    # (hidden_wgrad_top 0.29 -> 1.9 ms, bwd_bottom 1.75 -> 2.3 ms), not the kernel.
+    from ancde_b200 import train as _train
+    _async = _train.ASYNC_WGRAD
+    _train.ASYNC_WGRAD = False
     _, launches_prof, prof = timed(lambda i: trainer.step(batches[i % n_res]), 3, max(3, args.warmup), profile=True)
+    _train.ASYNC_WGRAD = _async
     launches_per_step = launches_prof // 3
     prof_steps = 3
 
