@@ -54,25 +54,34 @@ struct V3Layout {
     // ---- shared memory ----
     int DUSTR, du_floats;           // dU[j][DUSTR] (DUSTR = NS + 4: conflict-free 128-bit reads by lanes with consecutive j)
     int tcol_h;                     // TMEM column of the hidden layers' accumulator (W_out tile t sits at column t*2*NS)
+    // ---- round 2: the W_out slice resident in TENSOR MEMORY (A operand of tcgen05.mma from TMEM), when the columns allow ----
+    int ts;                         // 1: W_out hi/lo tiles live in TMEM from column a_col on (tile t: KPo/2 columns; hi tiles, then lo)
+    int a_col;
+    int g_stage, sg_str;            // training: tanh outputs staged in shared memory [NS][sg_str] and written by TMA row copies
     // ---- buffers saved for the backward, in the streamed engine's layout with tiles of 8 samples (ncde_layout.cuh) ----
     int sv_ntiles, sv_act_floats, sv_off_h[ANCDE_MAX_LAYERS], sv_off_du, sv_off_duda, sv_DUS, sv_NCP, sv_C4;
 };
 
 struct V3Smem {
-    size_t img, act, du, k, kpart, times, bars, total;
+    size_t img, act, du, k, kpart, times, tout, bars, sg, total;
 };
 
 __host__ __device__ static inline V3Smem v3_smem(const V3Layout& lo)
 {
     V3Smem s;
     size_t o = 0;
-    s.img = o;    o += (size_t)lo.hidden_bytes + 2 * (size_t)lo.wo_mat_bytes;
+    s.img = o;    o += (size_t)lo.hidden_bytes + (lo.ts ? 0 : 2 * (size_t)lo.wo_mat_bytes);
     s.act = o;    o += 2 * (size_t)(lo.NS / 8) * lo.SBOa;                       // hi then lo
     s.du = o;     o += 2 * (size_t)lo.du_floats * 4;                            // double buffered by stage parity
     s.k = o;      o += 2 * (size_t)lo.Hd * (lo.NS + 4) * 4;                     // stage derivative [Hd][NS + 4], double buffered
     s.kpart = o;  o += (size_t)lo.ni_max * lo.nchunks * lo.NS * 4;
     s.times = o;  o += (size_t)pad4(lo.L) * 4;
+    s.tout = o;   o += (size_t)pad4(lo.n_out) * 4;
     s.bars = o;   o += 128;                                                     // mbarriers + TMEM base slot
+    s.sg = o;     o += lo.g_stage ? (size_t)lo.NS * lo.sg_str * 4 : 0;
+    // a hidden layer's A descriptor spans 128 rows: what it reads past the stored rows must stay inside the allocation
+    for (int l = 0; l < lo.n_hidden; ++l)
+        if ((size_t)lo.off_hlo[l] + 16 * (size_t)lo.SBOh[l] > o) o = (size_t)lo.off_hlo[l] + 16 * (size_t)lo.SBOh[l];
     s.total = (o + 15) & ~(size_t)15;
     return s;
 }

@@ -69,10 +69,12 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
     float* sK = reinterpret_cast<float*>(smem_raw + sm.k);
     float* sKpart = reinterpret_cast<float*>(smem_raw + sm.kpart);
     float* sTimes = reinterpret_cast<float*>(smem_raw + sm.times);
+    float* sTout = reinterpret_cast<float*>(smem_raw + sm.tout);    // requested output times (a global load per look-up cost ~600 cycles)
     uint64_t* bar_h = reinterpret_cast<uint64_t*>(smem_raw + sm.bars);          // hidden layers' accumulator ready
     uint64_t* bar_t = bar_h + 1;                                                // [V3_MAX_TILES] W_out tile t ready
     uint64_t* bar_k = bar_t + V3_MAX_TILES;                                     // [2] stage derivative of buffer b complete (transaction bytes)
     uint32_t* tslot = reinterpret_cast<uint32_t*>(bar_k + 2);
+    float* sG = reinterpret_cast<float*>(smem_raw + sm.sg);          // staged tanh outputs [NS][sg_str] (lo.g_stage)
     const int SBOa = lo.SBOa;
     const int KSTR = lo.NS + 4;                       // row stride of the stage-derivative buffers (conflict-free 128-bit reads)
     // activation operand (B of every product): MN-major, i.e. 8 consecutive SAMPLES of one feature k are contiguous, so
@@ -84,14 +86,19 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
         const uint4* srcH = reinterpret_cast<const uint4*>(p.img);
         uint4* dst = reinterpret_cast<uint4*>(sImg);
         for (int i = tid; i < lo.hidden_bytes / 16; i += NTHR) dst[i] = __ldg(srcH + i);
-        const uint4* srcW = reinterpret_cast<const uint4*>(p.img + lo.hidden_bytes + (size_t)rank * 2 * lo.wo_mat_bytes);
-        uint4* dstW = reinterpret_cast<uint4*>(sImg + lo.hidden_bytes);
-        for (int i = tid; i < 2 * lo.wo_mat_bytes / 16; i += NTHR) dstW[i] = __ldg(srcW + i);
+        if (!lo.ts) {
+            const uint4* srcW = reinterpret_cast<const uint4*>(p.img + lo.hidden_bytes + (size_t)rank * 2 * lo.wo_mat_bytes);
+            uint4* dstW = reinterpret_cast<uint4*>(sImg + lo.hidden_bytes);
+            for (int i = tid; i < 2 * lo.wo_mat_bytes / 16; i += NTHR) dstW[i] = __ldg(srcW + i);
+        }
+        if (lo.g_stage)         // padding channels of the staged rows are never written again: they stay zero
+            for (int i = tid; i < NS * lo.sg_str; i += NTHR) sG[i] = 0.f;
         uint4* za = reinterpret_cast<uint4*>(sActHi);
         for (int i = tid; i < 2 * (NS / 8) * SBOa / 16; i += NTHR) za[i] = make_uint4(0u, 0u, 0u, 0u);
         for (int i = tid; i < 2 * lo.du_floats; i += NTHR) sDU[i] = 0.f;
         for (int i = tid; i < 2 * Hd * KSTR; i += NTHR) sK[i] = 0.f;
         for (int i = tid; i < lo.L; i += NTHR) sTimes[i] = p.times[i];
+        for (int i = tid; i < lo.n_out; i += NTHR) sTout[i] = p.t_out[i];
         if (tid == 0) {
             mbar_init(bar_h, 1);
             for (int t = 0; t < V3_MAX_TILES; ++t) mbar_init(bar_t + t, 1);
@@ -106,6 +113,24 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tbase = *tslot;
     const uint32_t tlane = tbase + ((uint32_t)(32 * wq) << 16);     // this warp's lane quarter
+    if (lo.ts) {
+        // the W_out slice as the RESIDENT A operand in tensor memory: row m of a tile = TMEM lane m, 16 FP16 of the row (one k
+        // step) per 8 columns; read from the canonical K-major image (two 16-byte core-matrix rows per k step)
+        const int kst = lo.KPo >> 4, items = 2 * lo.mtiles * kst;
+        const unsigned char* srcW = p.img + lo.hidden_bytes + (size_t)rank * 2 * lo.wo_mat_bytes;
+        for (int it = wg; it < items; it += 4) {
+            const int mt = it / kst, ks = it - mt * kst;            // mt = matrix (hi, lo) * mtiles + tile
+            const int r = 128 * (mt % lo.mtiles) + 32 * wq + lane;
+            const unsigned char* q = srcW + (size_t)(mt / lo.mtiles) * lo.wo_mat_bytes + (size_t)(r >> 3) * lo.SBOo + (size_t)ks * 256 + (r & 7) * 16;
+            const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(q)), x1 = __ldg(reinterpret_cast<const uint4*>(q + 128));
+            const uint32_t rr[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            tmem_st8(tlane + (uint32_t)(lo.a_col + mt * (lo.KPo >> 1) + 8 * ks), rr);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
 
     // ---- control: dU[j][n] of a stage (spline derivative, attention product) for all NS samples, into `du`
     int cnt = 0;        // knots strictly below the current stage time (monotone)
@@ -347,6 +372,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
 #ifdef ANCDE_PHASE_TIMING
             if (tid == 64 && blockIdx.x == 0 && p.dbg) p.dbg[top ? 1 : 0] += clock64() - ctl_t0;
 #endif
+            if (lo.g_stage && warp == V3_THREADS / 32 - 1) bulk_wait_read0();     // the staged rows of the previous stage have left
             __syncthreads();
 
             // ---- (2) output layer slice x all samples (one commit per 128-row tile), tanh, contraction with dU
@@ -355,10 +381,19 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                     tc_fence_after();
                     const int ksteps = lo.KPo >> 4;
                     const uint32_t d = tbase + warp_u * 2 * NS;
+                    if (lo.ts) {
+                        const uint32_t tAhi = tbase + (uint32_t)(lo.a_col + warp_u * (lo.KPo >> 1));
+                        const uint32_t tAlo = tAhi + (uint32_t)(lo.mtiles * (lo.KPo >> 1));
 #pragma unroll 4
-                    for (int ks = 0; ks < ksteps; ++ks) umma_f16(d, dWhi + (uint64_t)(ks * 16), dBhi + (uint64_t)(ks * 16), idesc2, ks != 0);
+                        for (int ks = 0; ks < ksteps; ++ks) umma_f16_ts(d, tAhi + (uint32_t)(ks * 8), dBhi + (uint64_t)(ks * 16), idesc2, ks != 0);
 #pragma unroll 4
-                    for (int ks = 0; ks < ksteps; ++ks) umma_f16(d, dWlo + (uint64_t)(ks * 16), dBhi + (uint64_t)(ks * 16), idesc, true);
+                        for (int ks = 0; ks < ksteps; ++ks) umma_f16_ts(d, tAlo + (uint32_t)(ks * 8), dBhi + (uint64_t)(ks * 16), idesc, true);
+                    } else {
+#pragma unroll 4
+                        for (int ks = 0; ks < ksteps; ++ks) umma_f16(d, dWhi + (uint64_t)(ks * 16), dBhi + (uint64_t)(ks * 16), idesc2, ks != 0);
+#pragma unroll 4
+                        for (int ks = 0; ks < ksteps; ++ks) umma_f16(d, dWlo + (uint64_t)(ks * 16), dBhi + (uint64_t)(ks * 16), idesc, true);
+                    }
                     umma_commit(bar_t + warp_u);
                 }
             }
@@ -418,7 +453,14 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                         v[e] = valid ? g[e] * du[e] : 0.f;
                     }
                     PHX_MARK(2);
-                    if (training && vec_g) {
+                    if (lo.g_stage) {
+                        // staged: lanes with consecutive channels write consecutive words of the sample's row
+                        if (il < ni && j < lo.sv_C4) {
+                            float* gs = sG + n0 * lo.sg_str + il * lo.sv_C4 + j;
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) gs[e * lo.sg_str] = valid ? g[e] : 0.f;
+                        }
+                    } else if (training && vec_g) {
                         // tanh outputs in the streamed engine's layout [stage][sample][i*C4 + j]: 4x4 transposes over the 4 lanes
                         // that own 4 consecutive channels, so that a lane stores 4 channels of one sample (128-bit stores, 4
                         // samples x 128 contiguous bytes per warp instruction; scalar stores cost ~4x the store-issue time)
@@ -505,7 +547,17 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
             ph_t ^= 1;
             tc_fence_before();
             PH2_MARK(5);
+            if (lo.g_stage) fence_async_smem();
             __syncthreads();
+            if (lo.g_stage && warp == V3_THREADS / 32 - 1) {
+                // one TMA row copy per sample: this CTA's field rows are contiguous in [stage][sample][i*C4 + j]
+                const int64_t rows = (int64_t)lo.sv_ntiles * 8;
+                for (int n = lane; n < NS; n += 32)
+                    if (b0 + n < rows)
+                        bulk_s2g(p.save_G + ((int64_t)stage * rows + b0 + n) * lo.sv_NCP + i0 * lo.sv_C4, sG + n * lo.sg_str,
+                                 (uint32_t)(ni * lo.sv_C4 * 4));
+                bulk_commit();
+            }
 
             // ---- (3) scatter of the stage derivative: this CTA's field rows to every CTA of the cluster
             const int buf = stage & 1;
@@ -554,7 +606,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                     if (sc == rank) {
                         int jj = jout;
                         while (jj < lo.n_out) {
-                            const float tj = __ldg(p.t_out + jj);
+                            const float tj = sTout[jj];
                             if (!(t1 >= tj)) break;
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
@@ -579,7 +631,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
             }
             if (!const_cols_stable) write_const_cols();
             if (s == 3) {
-                while (jout < lo.n_out && t1 >= __ldg(p.t_out + jout)) ++jout;
+                while (jout < lo.n_out && t1 >= sTout[jout]) ++jout;
             }
             fence_async_smem();
             __syncthreads();
@@ -591,6 +643,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
     if (threadIdx.x == 0 && blockIdx.x == 0 && p.dbg)
         for (int i = 0; i < 8; ++i) p.dbg[40 + (top ? 8 : 0) + i] += phx_acc[i];
 #endif
+    if (lo.g_stage && warp == V3_THREADS / 32 - 1) bulk_wait0();
     tc_fence_before();
     cluster_arrive();     // nobody leaves while a peer may still address its shared memory
     cluster_wait();

@@ -1,5 +1,7 @@
 // Host side of the UMMA (tcgen05) NCDE forward: cluster / row tiling, the packed FP16 hi/lo operand images and the
 // packing kernel.
+#include <stdlib.h>
+
 #include "ncde3_common.cuh"
 
 namespace ancde {
@@ -71,18 +73,22 @@ int make_layout3(const ancde_ncde_desc* d, const NcdeLayout* st, V3Layout* lo)
         lo->ni_max = base + (extra ? 1 : 0);
         const int nblk = lo->ni_max * lo->nfull + (lo->rem ? (lo->ni_max + lo->ipb - 1) / lo->ipb : 0);
         lo->mtiles = (nblk + 3) / 4;
-        if (lo->mtiles > V3_MAX_TILES || (lo->mtiles + 1) * 2 * lo->NS > 512) continue;     // TMEM columns (hi and lo halves per tile)
+        if (lo->mtiles > V3_MAX_TILES) continue;
+        // TMEM columns: accumulators (hi and lo halves per tile), then either the hidden layers' accumulator or -- when
+        // they fit -- the W_out slice itself (the hidden layers' accumulator then shares tile 0's columns)
+        lo->ts = lo->mtiles * 2 * lo->NS + lo->mtiles * lo->KPo <= 512 && !getenv("ANCDE_FWD3_SS");
+        if (!lo->ts && (lo->mtiles + 1) * 2 * lo->NS > 512) continue;
+        lo->a_col = lo->mtiles * 2 * lo->NS;
+        lo->sg_str = st ? lo->ni_max * st->C4 : 0;
+        lo->g_stage = lo->ts && st && d->save_G && !getenv("ANCDE_FWD3_NOSTAGE");
         lo->wo_mat_bytes = 16 * lo->mtiles * lo->SBOo;
         lo->img_bytes = (int64_t)lo->hidden_bytes + (int64_t)CS * 2 * lo->wo_mat_bytes;
         lo->DUSTR = lo->NS + 4;
         lo->du_floats = pad4(d->C * lo->DUSTR);
-        lo->tcol_h = lo->mtiles * 2 * lo->NS;
+        lo->tcol_h = lo->ts ? 0 : lo->mtiles * 2 * lo->NS;
+        if (lo->g_stage && v3_smem(*lo).total > 227 * 1024) lo->g_stage = 0;
         if (v3_smem(*lo).total > 227 * 1024) continue;
-        // a hidden layer's A descriptor spans 128 rows: what it reads past the stored rows must stay inside the image
         bool ok = true;
-        const int img_cta = lo->hidden_bytes + 2 * lo->wo_mat_bytes;
-        for (int l = 0; l < d->n_hidden; ++l)
-            if (lo->off_hlo[l] + 16 * lo->SBOh[l] > img_cta) ok = false;
         // the RK4 state lives in registers: one thread per (field row, chunk of 8 samples)
         if (d->Hd * CS > V3_THREADS) ok = false;
         if (ok) return ANCDE_OK;

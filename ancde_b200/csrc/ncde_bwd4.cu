@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
     float* sMax = reinterpret_cast<float*>(smem_raw + v.o_max);
     int* sLp = reinterpret_cast<int*>(smem_raw + v.o_lp);
     float* sGst = reinterpret_cast<float*>(smem_raw + v.o_gst);              // staged tanh outputs [NS rows][GROW floats]
+    float* sTout = reinterpret_cast<float*>(smem_raw + v.o_tout);            // requested output times
     int4* sTab = reinterpret_cast<int4*>(smem_raw + v.o_tab);                // per run of 4 columns: {gbar row, dU index, G column, -}
 
     const int nks = v.ks_begin[rank + 1] - v.ks_begin[rank];
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
 
     // ---- prologue: resident operands, tables, barriers, tensor memory
     if (tid < NT) {
+        for (int i = tid; i < lo.n_out; i += NT) sTout[i] = p.s.t_out[i];
         if constexpr (CHAIN) {
             const float4* hs = reinterpret_cast<const float4*>(p.s.wpack + lo.off_hiddenb);
             float4* hd = reinterpret_cast<float4*>(smem_raw + v.o_hid);
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
         if (st_thr) {
             const int bg = b0 + sb;
             for (int j = jb; j >= 1; --j) {
-                const float tj = __ldg(p.s.t_out + j);
+                const float tj = sTout[j];
                 if (!(tj > t0)) break;
                 const float gz = (have_tile && bg < lo.B) ? __ldg(p.s.grad_z_out + ((int64_t)j * lo.B + bg) * Hd + si) : 0.f;
                 if (tj == t1) lam += gz;
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) ncde_bwd4_kernel(const __grid_c
                 }
             }
         }
-        while (jb >= 1 && __ldg(p.s.t_out + jb) > t0) --jb;
+        while (jb >= 1 && sTout[jb] > t0) --jb;
 
 #pragma unroll 1
         for (int s = 3; s >= 0; --s) {
@@ -716,6 +718,7 @@ int make_layout4(const ancde_ncde_desc* d, const NcdeLayout& st, bool need_att, 
                 v->o_lp = (int)o;      o = up(o + 8 * ANCDE_MAX_LAYERS * 4);
                 v->o_tab = (int)o;     o = up(o + (size_t)4 * v->PASSK * v->npass_max * 16);
                 v->o_gst = (int)o;     o = up(o + (size_t)v->NS * v->GROW * 4);
+                v->o_tout = (int)o;    o = up(o + (size_t)pad4(st.n_out) * 4);
                 v->smem_total = (int)o;
                 // the controls of the next stage are staged in the operand buffer
                 if ((size_t)CS * v->dub * 4 > (size_t)nslots * v->ring_bytes) continue;

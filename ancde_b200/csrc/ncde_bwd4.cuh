@@ -56,7 +56,7 @@ struct V4Layout {
     int chain_warps;                // warps that run the hidden layers (chain: one per sample; mma.sync: one per 16 inputs)
     int need_att;                   // timewise attention cotangent requested
     // shared-memory carve-up (byte offsets)
-    int o_bars, o_ring, o_hid, o_recv, o_recvatt, o_gall, o_du, o_act, o_zb, o_bd, o_max, o_lp, o_tab, o_gst;
+    int o_bars, o_ring, o_hid, o_recv, o_recvatt, o_gall, o_du, o_act, o_zb, o_bd, o_max, o_lp, o_tab, o_gst, o_tout;
     int smem_total;
 };
 

@@ -9,7 +9,8 @@ cfg = synthetic.CONFIGS[wl]
 torch.manual_seed(2021)
 model, _, _ = metamodel.model_from_config(cfg, file='ft')
 model = model.cuda()
-bt = synthetic.make_batch(wl, B=1024)
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+bt = synthetic.make_batch(wl, B=B)
 times = bt['times'].cuda()
 coeffs = ancde_b200.natural_cubic_spline_coeffs(times, bt['X'].cuda())
 fi = bt['final_index'].cuda()
