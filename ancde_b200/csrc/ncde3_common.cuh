@@ -57,7 +57,8 @@ struct V3Layout {
     // ---- round 2: the W_out slice resident in TENSOR MEMORY (A operand of tcgen05.mma from TMEM), when the columns allow ----
     int ts;                         // 1: W_out hi/lo tiles live in TMEM from column a_col on (tile t: KPo/2 columns; hi tiles, then lo)
     int a_col;
-    int g_stage, sg_str;            // training: tanh outputs staged in shared memory [NS][sg_str] and written by TMA row copies
+    int sg_str, C4, nip_log2;       // ts: tanh outputs staged in shared memory [NS][sg_str = ni_max*C4], C4 = C rounded up to 4; items of
+                                    // the contraction = (sample, field row < 2^nip_log2); dU is then kept as [NS][DUSTR = C4]
     // ---- buffers saved for the backward, in the streamed engine's layout with tiles of 8 samples (ncde_layout.cuh) ----
     int sv_ntiles, sv_act_floats, sv_off_h[ANCDE_MAX_LAYERS], sv_off_du, sv_off_duda, sv_DUS, sv_NCP, sv_C4;
 };
@@ -74,11 +75,11 @@ __host__ __device__ static inline V3Smem v3_smem(const V3Layout& lo)
     s.act = o;    o += 2 * (size_t)(lo.NS / 8) * lo.SBOa;                       // hi then lo
     s.du = o;     o += 2 * (size_t)lo.du_floats * 4;                            // double buffered by stage parity
     s.k = o;      o += 2 * (size_t)lo.Hd * (lo.NS + 4) * 4;                     // stage derivative [Hd][NS + 4], double buffered
-    s.kpart = o;  o += (size_t)lo.ni_max * lo.nchunks * lo.NS * 4;
+    s.kpart = o;  o += lo.ts ? 0 : (size_t)lo.ni_max * lo.nchunks * lo.NS * 4;
     s.times = o;  o += (size_t)pad4(lo.L) * 4;
     s.tout = o;   o += (size_t)pad4(lo.n_out) * 4;
     s.bars = o;   o += 128;                                                     // mbarriers + TMEM base slot
-    s.sg = o;     o += lo.g_stage ? (size_t)lo.NS * lo.sg_str * 4 : 0;
+    s.sg = o;     o += lo.ts ? (size_t)lo.NS * lo.sg_str * 4 : 0;
     // a hidden layer's A descriptor spans 128 rows: what it reads past the stored rows must stay inside the allocation
     for (int l = 0; l < lo.n_hidden; ++l)
         if ((size_t)lo.off_hlo[l] + 16 * (size_t)lo.SBOh[l] > o) o = (size_t)lo.off_hlo[l] + 16 * (size_t)lo.SBOh[l];

@@ -42,6 +42,9 @@ __device__ __forceinline__ void split_half(float x, __half& hi, __half& lo)
 
 constexpr int CTL_BATCH = 6;
 
+// TSM: the W_out slice lives in tensor memory, the tanh outputs of a stage are staged in shared memory [NS][sg_str] (one TMA
+// row copy per sample writes them out in training mode) and the contraction with dU reads them back from there.
+template <bool TSM>
 __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_constant__ V3Args p)
 {
     const V3Layout& lo = p.lo;
@@ -86,12 +89,12 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
         const uint4* srcH = reinterpret_cast<const uint4*>(p.img);
         uint4* dst = reinterpret_cast<uint4*>(sImg);
         for (int i = tid; i < lo.hidden_bytes / 16; i += NTHR) dst[i] = __ldg(srcH + i);
-        if (!lo.ts) {
+        if constexpr (!TSM) {
             const uint4* srcW = reinterpret_cast<const uint4*>(p.img + lo.hidden_bytes + (size_t)rank * 2 * lo.wo_mat_bytes);
             uint4* dstW = reinterpret_cast<uint4*>(sImg + lo.hidden_bytes);
             for (int i = tid; i < 2 * lo.wo_mat_bytes / 16; i += NTHR) dstW[i] = __ldg(srcW + i);
         }
-        if (lo.g_stage)         // padding channels of the staged rows are never written again: they stay zero
+        if constexpr (TSM)      // padding channels of the staged rows are never written again: they stay zero
             for (int i = tid; i < NS * lo.sg_str; i += NTHR) sG[i] = 0.f;
         uint4* za = reinterpret_cast<uint4*>(sActHi);
         for (int i = tid; i < 2 * (NS / 8) * SBOa / 16; i += NTHR) za[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tbase = *tslot;
     const uint32_t tlane = tbase + ((uint32_t)(32 * wq) << 16);     // this warp's lane quarter
-    if (lo.ts) {
+    if constexpr (TSM) {
         // the W_out slice as the RESIDENT A operand in tensor memory: row m of a tile = TMEM lane m, 16 FP16 of the row (one k
         // step) per 8 columns; read from the canonical K-major image (two 16-byte core-matrix rows per k step)
         const int kst = lo.KPo >> 4, items = 2 * lo.mtiles * kst;
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                         dU = __fadd_rn(__fmul_rn(dX, a), __fmul_rn(__fmul_rn(__fmul_rn(a, __fsub_rn(1.0f, a)), dX), hp));
                         duda = dX * (1.0f + (1.0f - 2.0f * a) * hp);
                     }
-                    if (j < C) du[j * lo.DUSTR + n] = dU;
+                    if (j < C) du[TSM ? n * lo.DUSTR + j : j * lo.DUSTR + n] = dU;
                     if (act && (n >> 3) == rank) {
                         const int di = (j >> 2) * lo.sv_DUS + (j & 3) * 8 + (n & 7);
                         act[lo.sv_off_du + di] = dU;
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
 #ifdef ANCDE_PHASE_TIMING
             if (tid == 64 && blockIdx.x == 0 && p.dbg) p.dbg[top ? 1 : 0] += clock64() - ctl_t0;
 #endif
-            if (lo.g_stage && warp == V3_THREADS / 32 - 1) bulk_wait_read0();     // the staged rows of the previous stage have left
+            if (TSM && training && warp == V3_THREADS / 32 - 1) bulk_wait_read0();     // the staged rows of the previous stage have left
             __syncthreads();
 
             // ---- (2) output layer slice x all samples (one commit per 128-row tile), tanh, contraction with dU
@@ -381,7 +384,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                     tc_fence_after();
                     const int ksteps = lo.KPo >> 4;
                     const uint32_t d = tbase + warp_u * 2 * NS;
-                    if (lo.ts) {
+                    if constexpr (TSM) {
                         const uint32_t tAhi = tbase + (uint32_t)(lo.a_col + warp_u * (lo.KPo >> 1));
                         const uint32_t tAlo = tAhi + (uint32_t)(lo.mtiles * (lo.KPo >> 1));
 #pragma unroll 4
@@ -429,6 +432,26 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                 mbar_spin(bar_t + t, ph_t);
                 tc_fence_after();
                 PHX_MARK(0);
+                if constexpr (TSM) {
+                    // tanh of the accumulator rows into the staged rows: lanes with consecutive channels write consecutive words
+                    const bool st_ok = il < ni && j < lo.C4;
+                    float* gs = sG + il * lo.C4 + j;
+                    for (int sl = 0; sl < nslab; ++sl) {
+                        const int n0 = 16 * sl;
+                        float v[16], v2[16];
+                        tmem_ld16x2(tlane + t * 2 * NS + n0, tlane + t * 2 * NS + NS + n0, v, v2);
+                        PHX_MARK(1);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] = valid ? tanh_scaled3(v[e] + v2[e], tanh_c) : 0.f;
+                        PHX_MARK(2);
+                        if (st_ok) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) gs[(n0 + e) * lo.sg_str] = v[e];
+                        }
+                        PHX_MARK(3);
+                    }
+                    continue;
+                }
                 for (int sl = 0; sl < nslab; ++sl) {
                     const int n0 = 16 * sl;
                     float v[16];
@@ -453,14 +476,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                         v[e] = valid ? g[e] * du[e] : 0.f;
                     }
                     PHX_MARK(2);
-                    if (lo.g_stage) {
-                        // staged: lanes with consecutive channels write consecutive words of the sample's row
-                        if (il < ni && j < lo.sv_C4) {
-                            float* gs = sG + n0 * lo.sg_str + il * lo.sv_C4 + j;
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) gs[e * lo.sg_str] = valid ? g[e] : 0.f;
-                        }
-                    } else if (training && vec_g) {
+                    if (training && vec_g) {
                         // tanh outputs in the streamed engine's layout [stage][sample][i*C4 + j]: 4x4 transposes over the 4 lanes
                         // that own 4 consecutive channels, so that a lane stores 4 channels of one sample (128-bit stores, 4
                         // samples x 128 contiguous bytes per warp instruction; scalar stores cost ~4x the store-issue time)
@@ -547,20 +563,44 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
             ph_t ^= 1;
             tc_fence_before();
             PH2_MARK(5);
-            if (lo.g_stage) fence_async_smem();
+            if constexpr (TSM) fence_async_smem();
             __syncthreads();
-            if (lo.g_stage && warp == V3_THREADS / 32 - 1) {
-                // one TMA row copy per sample: this CTA's field rows are contiguous in [stage][sample][i*C4 + j]
-                const int64_t rows = (int64_t)lo.sv_ntiles * 8;
-                for (int n = lane; n < NS; n += 32)
-                    if (b0 + n < rows)
-                        bulk_s2g(p.save_G + ((int64_t)stage * rows + b0 + n) * lo.sv_NCP + i0 * lo.sv_C4, sG + n * lo.sg_str,
-                                 (uint32_t)(ni * lo.sv_C4 * 4));
-                bulk_commit();
-            }
-
-            // ---- (3) scatter of the stage derivative: this CTA's field rows to every CTA of the cluster
             const int buf = stage & 1;
+            if constexpr (TSM) {
+                if (training && warp == V3_THREADS / 32 - 1) {
+                    // one TMA row copy per sample: this CTA's field rows are contiguous in [stage][sample][i*C4 + j]
+                    const int64_t rows = (int64_t)lo.sv_ntiles * 8;
+                    for (int n = lane; n < NS; n += 32)
+                        if (b0 + n < rows)
+                            bulk_s2g(p.save_G + ((int64_t)stage * rows + b0 + n) * lo.sv_NCP + i0 * lo.C4, sG + n * lo.sg_str,
+                                     (uint32_t)(ni * lo.C4 * 4));
+                    bulk_commit();
+                }
+                // ---- (3) contraction with dU from the staged rows (a thread per (sample, field row): lanes walk the field rows, 144-byte
+                // stride: conflict-free 128-bit reads) and scatter of the stage derivative to every CTA of the cluster
+                for (int item = tid; item < (NS << lo.nip_log2); item += NTHR) {
+                    const int il = item & ((1 << lo.nip_log2) - 1), n = item >> lo.nip_log2;
+                    if (il >= ni) continue;
+                    const float4* g4 = reinterpret_cast<const float4*>(sG + n * lo.sg_str + il * lo.C4);
+                    const float4* d4 = reinterpret_cast<const float4*>(du_cur + n * lo.DUSTR);
+                    float o0 = 0.f, o1 = 0.f;
+#pragma unroll 3
+                    for (int q = 0; q < (lo.C4 >> 2); ++q) {
+                        const float4 a = g4[q], b = d4[q];
+                        o0 = fmaf(a.x, b.x, o0); o1 = fmaf(a.y, b.y, o1);
+                        o0 = fmaf(a.z, b.z, o0); o1 = fmaf(a.w, b.w, o1);
+                    }
+                    const float o = o0 + o1;
+                    const int i = i0 + il;
+                    const uint32_t off = (uint32_t)(((buf * Hd + i) * KSTR + n) * 4);
+#pragma unroll
+                    for (int r = 0; r < V3_MAX_CS; ++r)
+                        if (r < CS) st_async_f32(sK_rank[r] + off, o, sK_rank[r] + bark_delta + buf * 8);
+                    const int bg = b0 + n;
+                    if (p.k_out && bg < B) p.k_out[((int64_t)stage * B + bg) * Hd + i] = o;
+                }
+            } else {
+            // ---- (3) scatter of the stage derivative: this CTA's field rows to every CTA of the cluster
             for (int item = tid; item < (ni << NSL); item += NTHR) {
                 const int il = item >> NSL, n = item & (NS - 1);
                 const float* pp = sKpart + (il * lo.nchunks) * NS + n;
@@ -573,6 +613,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                     if (r < CS) st_async_f32(sK_rank[r] + off, o, sK_rank[r] + bark_delta + buf * 8);
                 const int bg = b0 + n;
                 if (p.k_out && bg < B) p.k_out[((int64_t)stage * B + bg) * Hd + i] = o;
+            }
             }
             // Every CTA of the cluster sends its rows to everybody: buffer `buf` is complete when Hd*NS floats have landed.
             // No cluster barrier: a peer can only overwrite this buffer two stages later, after it has received OUR rows of
@@ -643,7 +684,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
     if (threadIdx.x == 0 && blockIdx.x == 0 && p.dbg)
         for (int i = 0; i < 8; ++i) p.dbg[40 + (top ? 8 : 0) + i] += phx_acc[i];
 #endif
-    if (lo.g_stage && warp == V3_THREADS / 32 - 1) bulk_wait0();
+    if (TSM && training && warp == V3_THREADS / 32 - 1) bulk_wait0();
     tc_fence_before();
     cluster_arrive();     // nobody leaves while a peer may still address its shared memory
     cluster_wait();
@@ -654,7 +695,8 @@ static int launch_fwd3_t(const V3Args& a, cudaStream_t stream)
 {
     const V3Layout& lo = a.lo;
     const size_t smem = v3_smem(lo).total;
-    ANCDE_CUDA(cudaFuncSetAttribute(ncde3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = lo.ts ? ncde3_fwd_kernel<true> : ncde3_fwd_kernel<false>;
+    ANCDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(lo.nclusters * lo.CS));
     cfg.blockDim = dim3(V3_THREADS);
@@ -669,7 +711,7 @@ static int launch_fwd3_t(const V3Args& a, cudaStream_t stream)
     cfg.numAttrs = 1;
     static const char* names[3] = {"ncde_fwd_plain", "ncde_fwd_bottom", "ncde_fwd_top"};
     prof_begin(names[lo.mode], stream);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, ncde3_fwd_kernel, a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
     prof_end(stream);
     count_launch();
     if (e != cudaSuccess) {

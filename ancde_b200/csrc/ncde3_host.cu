@@ -79,14 +79,21 @@ int make_layout3(const ancde_ncde_desc* d, const NcdeLayout* st, V3Layout* lo)
         lo->ts = lo->mtiles * 2 * lo->NS + lo->mtiles * lo->KPo <= 512 && !getenv("ANCDE_FWD3_SS");
         if (!lo->ts && (lo->mtiles + 1) * 2 * lo->NS > 512) continue;
         lo->a_col = lo->mtiles * 2 * lo->NS;
-        lo->sg_str = st ? lo->ni_max * st->C4 : 0;
-        lo->g_stage = lo->ts && st && d->save_G && !getenv("ANCDE_FWD3_NOSTAGE");
+        lo->C4 = pad4(d->C);
+        lo->sg_str = lo->ni_max * lo->C4;
+        lo->nip_log2 = ilog2(pow2ceil(lo->ni_max));
         lo->wo_mat_bytes = 16 * lo->mtiles * lo->SBOo;
         lo->img_bytes = (int64_t)lo->hidden_bytes + (int64_t)CS * 2 * lo->wo_mat_bytes;
-        lo->DUSTR = lo->NS + 4;
-        lo->du_floats = pad4(d->C * lo->DUSTR);
+        lo->DUSTR = lo->ts ? lo->C4 : lo->NS + 4;
+        lo->du_floats = lo->ts ? lo->NS * lo->C4 : pad4(d->C * lo->DUSTR);
         lo->tcol_h = lo->ts ? 0 : lo->mtiles * 2 * lo->NS;
-        if (lo->g_stage && v3_smem(*lo).total > 227 * 1024) lo->g_stage = 0;
+        if (lo->ts && v3_smem(*lo).total > 227 * 1024) {      // no room for the staged rows: weights from shared memory instead
+            if ((lo->mtiles + 1) * 2 * lo->NS > 512) continue;
+            lo->ts = 0;
+            lo->DUSTR = lo->NS + 4;
+            lo->du_floats = pad4(d->C * lo->DUSTR);
+            lo->tcol_h = lo->mtiles * 2 * lo->NS;
+        }
         if (v3_smem(*lo).total > 227 * 1024) continue;
         bool ok = true;
         // the RK4 state lives in registers: one thread per (field row, chunk of 8 samples)
