@@ -278,6 +278,15 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
     uint64_t hLo = umma_smem_desc(smem_u32(sImg) + lo.off_hlo[0], 128, (uint32_t)lo.SBOh[0]);
     const bool hidden_warp = wq < 2 && wg < nslab;                // warps that read the hidden layers' accumulator (warp 0 issues)
     uint32_t ph_h = 0, ph_t = 0;      // phase parities of bar_h / bar_t
+    // warps that neither read the hidden layers' accumulator, nor evaluate the control, nor hold RK4 state: they issue the TMA
+    // stores of the staged tanh outputs (every warp, when there is no such warp)
+    int tma_idx = -1, n_tma = 0;
+    for (int w = 0; w < NTHR / 32; ++w)
+        if ((w & 3) < 2 && (w >> 2) >= nslab && w * 32 >= Hd * CS) {
+            if (w == warp) tma_idx = n_tma;
+            ++n_tma;
+        }
+    if (n_tma == 0) { tma_idx = warp; n_tma = NTHR / 32; }
     int jout = 1;                     // next requested output time
     PH2_DECL();
 #ifdef ANCDE_PHASE_TIMING
@@ -375,7 +384,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
 #ifdef ANCDE_PHASE_TIMING
             if (tid == 64 && blockIdx.x == 0 && p.dbg) p.dbg[top ? 1 : 0] += clock64() - ctl_t0;
 #endif
-            if (TSM && training && warp == V3_THREADS / 32 - 1) bulk_wait_read0();     // the staged rows of the previous stage have left
+            if (TSM && training && tma_idx >= 0) bulk_wait_read0();     // the staged rows of the previous stage have left
             __syncthreads();
 
             // ---- (2) output layer slice x all samples (one commit per 128-row tile), tanh, contraction with dU
@@ -567,22 +576,16 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
             __syncthreads();
             const int buf = stage & 1;
             if constexpr (TSM) {
-                if (training && warp == V3_THREADS / 32 - 1) {
-                    // one TMA row copy per sample: this CTA's field rows are contiguous in [stage][sample][i*C4 + j]
-                    const int64_t rows = (int64_t)lo.sv_ntiles * 8;
-                    for (int n = lane; n < NS; n += 32)
-                        if (b0 + n < rows)
-                            bulk_s2g(p.save_G + ((int64_t)stage * rows + b0 + n) * lo.sv_NCP + i0 * lo.C4, sG + n * lo.sg_str,
-                                     (uint32_t)(ni * lo.C4 * 4));
-                    bulk_commit();
-                }
+                PHX_T0();
                 // ---- (3) contraction with dU from the staged rows (a thread per (sample, field row): lanes walk the field rows, 144-byte
                 // stride: conflict-free 128-bit reads) and scatter of the stage derivative to every CTA of the cluster
-                for (int item = tid; item < (NS << lo.nip_log2); item += NTHR) {
-                    const int il = item & ((1 << lo.nip_log2) - 1), n = item >> lo.nip_log2;
-                    if (il >= ni) continue;
-                    const float4* g4 = reinterpret_cast<const float4*>(sG + n * lo.sg_str + il * lo.C4);
-                    const float4* d4 = reinterpret_cast<const float4*>(du_cur + n * lo.DUSTR);
+                // (4 consecutive lanes = 4 consecutive samples of one field row: one 128-bit remote store per rank)
+                for (int item0 = 0; item0 < (NS << lo.nip_log2); item0 += NTHR) {
+                    const int item = item0 + tid;
+                    const int il = (item >> 2) & ((1 << lo.nip_log2) - 1), n = ((item >> (2 + lo.nip_log2)) << 2) | (item & 3);
+                    const bool ok = il < ni && n < NS;
+                    const float4* g4 = reinterpret_cast<const float4*>(sG + (ok ? n * lo.sg_str + il * lo.C4 : 0));
+                    const float4* d4 = reinterpret_cast<const float4*>(du_cur + (ok ? n * lo.DUSTR : 0));
                     float o0 = 0.f, o1 = 0.f;
 #pragma unroll 3
                     for (int q = 0; q < (lo.C4 >> 2); ++q) {
@@ -591,13 +594,31 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                         o0 = fmaf(a.z, b.z, o0); o1 = fmaf(a.w, b.w, o1);
                     }
                     const float o = o0 + o1;
+                    PHX_MARK(4);
+                    const float oa = __shfl_down_sync(0xffffffffu, o, 1), ob = __shfl_down_sync(0xffffffffu, o, 2),
+                                oc = __shfl_down_sync(0xffffffffu, o, 3);
                     const int i = i0 + il;
-                    const uint32_t off = (uint32_t)(((buf * Hd + i) * KSTR + n) * 4);
+                    if (ok && (lane & 3) == 0) {
+                        const uint32_t off = (uint32_t)(((buf * Hd + i) * KSTR + n) * 4);
 #pragma unroll
-                    for (int r = 0; r < V3_MAX_CS; ++r)
-                        if (r < CS) st_async_f32(sK_rank[r] + off, o, sK_rank[r] + bark_delta + buf * 8);
+                        for (int r = 0; r < V3_MAX_CS; ++r)
+                            if (r < CS) st_async_v4(sK_rank[r] + off, o, oa, ob, oc, sK_rank[r] + bark_delta + buf * 8);
+                    }
                     const int bg = b0 + n;
-                    if (p.k_out && bg < B) p.k_out[((int64_t)stage * B + bg) * Hd + i] = o;
+                    if (ok && p.k_out && bg < B) p.k_out[((int64_t)stage * B + bg) * Hd + i] = o;
+                }
+                PHX_MARK(5);
+                // the staged rows leave through one TMA row copy per sample (this CTA's field rows are contiguous in
+                // [stage][sample][i*C4 + j]).  Issuing a bulk copy costs its thread ~100 cycles and more when the queue is
+                // full (measured: 1.5 k cycles for two per warp), so warps that have nothing else to do until the next
+                // epilogue issue them -- off the critical path of the RK4 recurrence
+                if (training && tma_idx >= 0) {
+                    const int64_t rows = (int64_t)lo.sv_ntiles * 8;
+                    for (int n = tma_idx + n_tma * lane; n < NS; n += 32 * n_tma)
+                        if (b0 + n < rows)
+                            bulk_s2g(p.save_G + ((int64_t)stage * rows + b0 + n) * lo.sv_NCP + i0 * lo.C4, sG + n * lo.sg_str,
+                                     (uint32_t)(ni * lo.C4 * 4));
+                    bulk_commit();
                 }
             } else {
             // ---- (3) scatter of the stage derivative: this CTA's field rows to every CTA of the cluster
@@ -619,7 +640,9 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
             // No cluster barrier: a peer can only overwrite this buffer two stages later, after it has received OUR rows of
             // the next stage, which we send after the reads below.
             if (tid == 0) mbar_arrive_expect_tx(bar_k + buf, (uint32_t)(Hd * NS * 4));
+            PHX_MARK(6);
             if (state_thr) mbar_wait(bar_k + buf, (uint32_t)((stage >> 1) & 1));
+            PHX_MARK(7);
             PH2_MARK(6);
 
             // ---- (4) RK4 recurrence (rk4_alt_step_func); next stage input -> B operand of the first hidden layer
@@ -684,7 +707,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
     if (threadIdx.x == 0 && blockIdx.x == 0 && p.dbg)
         for (int i = 0; i < 8; ++i) p.dbg[40 + (top ? 8 : 0) + i] += phx_acc[i];
 #endif
-    if (TSM && training && warp == V3_THREADS / 32 - 1) bulk_wait0();
+    if (TSM && training && tma_idx >= 0) bulk_wait0();
     tc_fence_before();
     cluster_arrive();     // nobody leaves while a peer may still address its shared memory
     cluster_wait();

@@ -80,7 +80,7 @@ int make_layout3(const ancde_ncde_desc* d, const NcdeLayout* st, V3Layout* lo)
         if (!lo->ts && (lo->mtiles + 1) * 2 * lo->NS > 512) continue;
         lo->a_col = lo->mtiles * 2 * lo->NS;
         lo->C4 = pad4(d->C);
-        lo->sg_str = lo->ni_max * lo->C4;
+        lo->sg_str = ((lo->ni_max * lo->C4 - 8 + 31) / 32) * 32 + 8;     // = 8 (mod 32): conflict-free 128-bit reads of the contraction
         lo->nip_log2 = ilog2(pow2ceil(lo->ni_max));
         lo->wo_mat_bytes = 16 * lo->mtiles * lo->SBOo;
         lo->img_bytes = (int64_t)lo->hidden_bytes + (int64_t)CS * 2 * lo->wo_mat_bytes;

@@ -22,14 +22,6 @@
 
 namespace ancde {
 
-// 16 bytes into a peer CTA's shared memory, counted on the peer's mbarrier.
-__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float a, float b, float c, float d, uint32_t remote_mbar)
-{
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(remote_addr),
-                 "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)), "r"(remote_mbar)
-                 : "memory");
-}
-
 // Waits on an mbarrier: every thread suspends in mbarrier.try_wait.  (Measured alternative: one lane per warp
 // busy-polling test_wait while the others sit behind __syncwarp made every stage 4 k cycles SLOWER -- the polling warps
 // take issue slots and shared-memory bandwidth from the few warps that work in the latency-bound phases.)

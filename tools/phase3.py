@@ -37,6 +37,7 @@ for base, nm in ((16, 'fwd bottom'), (24, 'fwd top')):
     for i in range(8):
         print('  %d %-34s %9.0f' % (i, names[i], d[base + i] / stages))
     x = d[base + 24:base + 32]
+    print('  phase 6 detail: contraction %.0f, scatter %.0f, TMA issue %.0f, wait %.0f' % tuple(v / stages for v in x[4:8]))
     print('  out epilogue detail (warp 0): wait tile %.0f, tmem ld %.0f, dU + tanh %.0f, G store %.0f, butterfly %.0f, write %.0f' % tuple(v / stages for v in x[:6]))
 nl = cfg['nl'] if 'nl' in cfg else 4
 print('control (warp 2) cycles per stage: bottom %.0f top %.0f' % (d[0] / stages, d[1] / stages))
