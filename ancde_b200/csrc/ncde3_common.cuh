@@ -107,6 +107,25 @@ struct V3Args {
     long long* dbg;
 };
 
+// tanh(x) = 1 - 2 / (exp(2x) + 1), x = acc / weight-scale; |abs err| < 4e-7 (MUFU ex2 + rcp)
+__device__ __forceinline__ float tanh_scaled3(float acc, float c)
+{
+    float ex, r;
+    const float a = acc * c;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(a));
+    const float dd = ex + 1.0f;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(dd));
+    return fmaf(-2.0f, r, 1.0f);
+}
+
+__device__ __forceinline__ void split_half(float x, __half& hi, __half& lo)
+{
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+
+constexpr int CTL_BATCH = 6;        // control items a thread loads before the first use (one memory round trip per batch)
+
 // Returns ANCDE_OK and fills the layout when the shape is supported by this engine (quietly ANCDE_EUNSUPPORTED otherwise).
 int make_layout3(const ancde_ncde_desc* d, const NcdeLayout* streamed, V3Layout* lo);
 int pack_weights3(const ancde_ncde_desc* d, const V3Layout& lo, unsigned char* img, cudaStream_t stream);

@@ -23,24 +23,6 @@
 
 namespace ancde {
 
-// tanh(x) = 1 - 2 / (exp(2x) + 1), x = acc / weight-scale; |abs err| < 4e-7 (MUFU ex2 + rcp)
-__device__ __forceinline__ float tanh_scaled3(float acc, float c)
-{
-    float ex, r;
-    const float a = acc * c;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(a));
-    const float dd = ex + 1.0f;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(dd));
-    return fmaf(-2.0f, r, 1.0f);
-}
-
-__device__ __forceinline__ void split_half(float x, __half& hi, __half& lo)
-{
-    hi = __float2half_rn(x);
-    lo = __float2half_rn(x - __half2float(hi));
-}
-
-constexpr int CTL_BATCH = 6;
 
 // TSM: the W_out slice lives in tensor memory, the tanh outputs of a stage are staged in shared memory [NS][sg_str] (one TMA
 // row copy per sample writes them out in training mode) and the contraction with dU reads them back from there.
@@ -288,6 +270,16 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
         }
     if (n_tma == 0) { tma_idx = warp; n_tma = NTHR / 32; }
     int jout = 1;                     // next requested output time
+    // addresses that only depend on the stage number are carried along instead of being rebuilt on the critical path (every
+    // phase of a stage is a chain of dependent instructions of ONE warp at ~4 cycles each)
+    const int64_t act_stride = (int64_t)lo.sv_ntiles * lo.sv_act_floats;
+    float* act_run = save_mine ? p.save_act + (int64_t)my_tile * lo.sv_act_floats : nullptr;
+    const float* kk0 = sK + si * KSTR + 8 * sc;
+    // first (usually only) item of this thread in the contraction: field row, sample, offsets
+    const int c_il = (tid >> 2) & ((1 << lo.nip_log2) - 1), c_n = ((tid >> (2 + lo.nip_log2)) << 2) | (tid & 3);
+    const bool c_ok = c_il < ni && c_n < NS;
+    const int c_g = c_ok ? c_n * lo.sg_str + c_il * lo.C4 : 0, c_d = c_ok ? c_n * lo.DUSTR : 0;
+    const uint32_t c_off = (uint32_t)((((i0 + c_il) * KSTR) + c_n) * 4);
     PH2_DECL();
 #ifdef ANCDE_PHASE_TIMING
     long long phx_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, phx_t = 0;
@@ -306,7 +298,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
         for (int s = 0; s < 4; ++s) {
             const int stage = 4 * k + s;
             const bool have_next = stage + 1 < lo.n_stages;
-            float* act = save_mine ? p.save_act + ((int64_t)stage * lo.sv_ntiles + my_tile) * lo.sv_act_floats : nullptr;
+            float* act = act_run;                          // this stage's saved-activation block of my tile (or null)
+            if (save_mine) act_run += act_stride;
             const float* du_cur = sDU + (stage & 1) * lo.du_floats;
             float* du_next = sDU + ((stage + 1) & 1) * lo.du_floats;
             PH2_T0();
@@ -581,11 +574,20 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                 // stride: conflict-free 128-bit reads) and scatter of the stage derivative to every CTA of the cluster
                 // (4 consecutive lanes = 4 consecutive samples of one field row: one 128-bit remote store per rank)
                 for (int item0 = 0; item0 < (NS << lo.nip_log2); item0 += NTHR) {
-                    const int item = item0 + tid;
-                    const int il = (item >> 2) & ((1 << lo.nip_log2) - 1), n = ((item >> (2 + lo.nip_log2)) << 2) | (item & 3);
-                    const bool ok = il < ni && n < NS;
-                    const float4* g4 = reinterpret_cast<const float4*>(sG + (ok ? n * lo.sg_str + il * lo.C4 : 0));
-                    const float4* d4 = reinterpret_cast<const float4*>(du_cur + (ok ? n * lo.DUSTR : 0));
+                    int il = c_il, n = c_n, goff = c_g, doff = c_d;
+                    bool ok = c_ok;
+                    uint32_t off = c_off + (uint32_t)(buf * Hd * KSTR * 4);
+                    if (item0) {
+                        const int item = item0 + tid;
+                        il = (item >> 2) & ((1 << lo.nip_log2) - 1);
+                        n = ((item >> (2 + lo.nip_log2)) << 2) | (item & 3);
+                        ok = il < ni && n < NS;
+                        goff = ok ? n * lo.sg_str + il * lo.C4 : 0;
+                        doff = ok ? n * lo.DUSTR : 0;
+                        off = (uint32_t)(((buf * Hd + i0 + il) * KSTR + n) * 4);
+                    }
+                    const float4* g4 = reinterpret_cast<const float4*>(sG + goff);
+                    const float4* d4 = reinterpret_cast<const float4*>(du_cur + doff);
                     float o0 = 0.f, o1 = 0.f;
 #pragma unroll 3
                     for (int q = 0; q < (lo.C4 >> 2); ++q) {
@@ -599,7 +601,6 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
                                 oc = __shfl_down_sync(0xffffffffu, o, 3);
                     const int i = i0 + il;
                     if (ok && (lane & 3) == 0) {
-                        const uint32_t off = (uint32_t)(((buf * Hd + i) * KSTR + n) * 4);
 #pragma unroll
                         for (int r = 0; r < V3_MAX_CS; ++r)
                             if (r < CS) st_async_v4(sK_rank[r] + off, o, oa, ob, oc, sK_rank[r] + bark_delta + buf * 8);
@@ -646,9 +647,9 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
             PH2_MARK(6);
 
             // ---- (4) RK4 recurrence (rk4_alt_step_func); next stage input -> B operand of the first hidden layer
-            float* act_next = (save_mine && have_next) ? p.save_act + ((int64_t)(stage + 1) * lo.sv_ntiles + my_tile) * lo.sv_act_floats : nullptr;
+            float* act_next = have_next ? act_run : nullptr;       // (act_run already points at the next stage's block)
             if (state_thr) {
-                const float* kk = sK + (buf * Hd + si) * KSTR + 8 * sc;
+                const float* kk = kk0 + buf * (Hd * KSTR);
                 const float4 k0 = reinterpret_cast<const float4*>(kk)[0], k1 = reinterpret_cast<const float4*>(kk)[1];
                 const float o[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
                 const float third = 1.0f / 3.0f;

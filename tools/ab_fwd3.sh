@@ -1,8 +1,7 @@
-python -m pytest tests/test_gpu_ncde.py -m gpu -x -q 2>&1 | tail -3
-ANCDE_FWD3_SS=1 python -m pytest tests/test_gpu_ncde.py -m gpu -x -q 2>&1 | tail -2
+timeout 600 python -m pytest tests/test_gpu_ncde.py -m gpu -x -q 2>&1 | tail -3
 for v in "A=1"; do
   echo "== $v"
-  env $v python bench.py --steps 10 --warmup 3 --no-other-configs 2>/dev/null | tail -1 | python -c "
+  env $v timeout 300 python bench.py --steps 10 --warmup 3 --no-other-configs 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 print(d['value'], d['ms_per_step'], [(k['name'],k['avg_ms']) for k in d['kernels'][:4]])"
