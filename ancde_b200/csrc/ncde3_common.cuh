@@ -27,7 +27,7 @@ namespace ancde {
 
 constexpr int V3_MAX_CS = 8;
 constexpr int V3_THREADS = 512;
-constexpr int V3_MAX_TILES = 8;
+constexpr int V3_MAX_TILES = 16;
 constexpr float V3_WSCALE = 64.0f;          // weights are stored as fp16(64*W): keeps the lo halves out of the subnormals
 constexpr float V3_WSCALE_INV = 1.0f / 64.0f;
 
@@ -57,6 +57,10 @@ struct V3Layout {
     // ---- round 2: the W_out slice resident in TENSOR MEMORY (A operand of tcgen05.mma from TMEM), when the columns allow ----
     int ts;                         // 1: W_out hi/lo tiles live in TMEM from column a_col on (tile t: KPo/2 columns; hi tiles, then lo)
     int a_col;
+    // ---- single-CTA variant (ncde3_fwd1.cu): CS = 1, 8 samples per CTA, hidden layers (<= 32 units) as the FP32 warp chain of
+    // the streamed engine (its weights: c_hidden_floats floats at wpack[0], rows c_stride, see ncde_layout.cuh) ----
+    int chain1, c_hidden_floats, c_HP;
+    int c_off_w[ANCDE_MAX_LAYERS], c_off_b[ANCDE_MAX_LAYERS], c_stride[ANCDE_MAX_LAYERS];
     int sg_str, C4, nip_log2;       // ts: tanh outputs staged in shared memory [NS][sg_str = ni_max*C4], C4 = C rounded up to 4; items of
                                     // the contraction = (sample, field row < 2^nip_log2); dU is then kept as [NS][DUSTR = C4]
     // ---- buffers saved for the backward, in the streamed engine's layout with tiles of 8 samples (ncde_layout.cuh) ----
@@ -78,11 +82,33 @@ __host__ __device__ static inline V3Smem v3_smem(const V3Layout& lo)
     s.kpart = o;  o += lo.ts ? 0 : (size_t)lo.ni_max * lo.nchunks * lo.NS * 4;
     s.times = o;  o += (size_t)pad4(lo.L) * 4;
     s.tout = o;   o += (size_t)pad4(lo.n_out) * 4;
-    s.bars = o;   o += 128;                                                     // mbarriers + TMEM base slot
+    s.bars = o;   o += 256;                                                     // mbarriers + TMEM base slot
     s.sg = o;     o += lo.ts ? (size_t)lo.NS * lo.sg_str * 4 : 0;
     // a hidden layer's A descriptor spans 128 rows: what it reads past the stored rows must stay inside the allocation
     for (int l = 0; l < lo.n_hidden; ++l)
         if ((size_t)lo.off_hlo[l] + 16 * (size_t)lo.SBOh[l] > o) o = (size_t)lo.off_hlo[l] + 16 * (size_t)lo.SBOh[l];
+    s.total = (o + 15) & ~(size_t)15;
+    return s;
+}
+
+// Shared-memory carve-up of the single-CTA variant
+struct V3S1Smem {
+    size_t hw, lp, z, last, act, du, sg, times, tout, bars, total;
+};
+__host__ __device__ static inline V3S1Smem v3_s1_smem(const V3Layout& lo)
+{
+    V3S1Smem s;
+    size_t o = 0;
+    s.hw = o;     o += (size_t)pad4(lo.c_hidden_floats) * 4;
+    s.lp = o;     o += 8 * ANCDE_MAX_LAYERS * 4;
+    s.z = o;      o += 3 * (size_t)8 * lo.c_HP * 4;                             // stage input, ping, pong: [sample][c_HP]
+    s.last = o;   o += (size_t)pad4(lo.K * 8) * 4;                             // last hidden layer [unit][8]
+    s.act = o;    o += 2 * (size_t)lo.SBOa;                                    // B operand: hi (8 samples) then lo
+    s.du = o;     o += 2 * (size_t)8 * lo.C4 * 4;                              // [8][C4], double buffered by stage parity
+    s.sg = o;     o += (size_t)8 * lo.sg_str * 4;
+    s.times = o;  o += (size_t)pad4(lo.L) * 4;
+    s.tout = o;   o += (size_t)pad4(lo.n_out) * 4;
+    s.bars = o;   o += 256;
     s.total = (o + 15) & ~(size_t)15;
     return s;
 }
@@ -100,6 +126,7 @@ struct V3Args {
     const float* attention;
     const float* h_prime;
     const unsigned char* img;
+    const float* wpack;        // streamed engine's packed weights (the FP32 hidden block of the single-CTA variant)
     float* z_out;
     float* k_out;
     float* save_act;
@@ -130,6 +157,7 @@ constexpr int CTL_BATCH = 6;        // control items a thread loads before the f
 int make_layout3(const ancde_ncde_desc* d, const NcdeLayout* streamed, V3Layout* lo);
 int pack_weights3(const ancde_ncde_desc* d, const V3Layout& lo, unsigned char* img, cudaStream_t stream);
 int launch_fwd3(const ancde_ncde_desc* d, const V3Layout& lo, const unsigned char* img, cudaStream_t stream);
+int launch_fwd3_single(const V3Args& a, cudaStream_t stream);
 
 // Row r (0 .. 128*mtiles) of rank's slice -> field row i, control channel j; false for padding rows.
 __host__ __device__ static inline bool v3_row(const V3Layout& lo, int rank, int r, int* i, int* j)

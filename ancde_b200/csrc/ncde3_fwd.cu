@@ -718,6 +718,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd_kernel(const __grid_c
 static int launch_fwd3_t(const V3Args& a, cudaStream_t stream)
 {
     const V3Layout& lo = a.lo;
+    if (lo.chain1) return launch_fwd3_single(a, stream);
     const size_t smem = v3_smem(lo).total;
     auto kern = lo.ts ? ncde3_fwd_kernel<true> : ncde3_fwd_kernel<false>;
     ANCDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -757,6 +758,7 @@ int launch_fwd3(const ancde_ncde_desc* d, const V3Layout& lo, const unsigned cha
     a.times = d->times; a.t_out = d->t_out; a.cb = d->coeff_b; a.cc2 = d->coeff_c2; a.cd3 = d->coeff_d3;
     a.z0 = d->z0; a.attention = d->attention; a.h_prime = d->h_prime;
     a.img = img;
+    a.wpack = d->wpack;
     a.z_out = d->z_out; a.k_out = d->k_out; a.save_act = d->save_act; a.save_G = d->save_G;
     a.dbg = debug_buffer();
     return launch_fwd3_t(a, stream);

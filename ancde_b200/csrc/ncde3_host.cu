@@ -58,6 +58,40 @@ int make_layout3(const ancde_ncde_desc* d, const NcdeLayout* st, V3Layout* lo)
         lo->sv_off_duda = st->act_off_duda; lo->sv_DUS = st->DUS; lo->sv_NCP = st->NCP; lo->sv_C4 = st->C4;
         for (int l = 0; l < d->n_hidden; ++l) lo->sv_off_h[l] = st->act_off_h[l];
     }
+    // ---- single-CTA variant: narrow hidden layers run as the FP32 warp chain, the whole W_out lives in tensor memory
+    if (st && st->TS == 8 && !getenv("ANCDE_FWD3_NOSINGLE")) {
+        bool narrow = true;
+        for (int l = 0; l < d->n_hidden; ++l) narrow = narrow && d->width[l] <= 32;
+        if (narrow) {
+            V3Layout s1 = *lo;
+            s1.CS = 1; s1.NS = 8; s1.ns_log2 = 3;
+            s1.nclusters = (d->B + 7) / 8;
+            s1.i_begin[0] = 0;
+            for (int r = 0; r < V3_MAX_CS; ++r) s1.i_begin[r + 1] = d->Hd;
+            s1.ni_max = d->Hd;
+            const int nblk = d->Hd * s1.nfull + (s1.rem ? (d->Hd + s1.ipb - 1) / s1.ipb : 0);
+            s1.mtiles = (nblk + 3) / 4;
+            s1.ts = 1; s1.chain1 = 1;
+            s1.hidden_bytes = 0;
+            s1.a_col = s1.mtiles * 16;
+            s1.tcol_h = 0;
+            s1.C4 = pad4(d->C);
+            s1.sg_str = d->Hd * s1.C4;
+            if ((s1.sg_str / 4) % 2 == 0) s1.sg_str += 4;      // odd number of 16-byte units per row: conflict-free 128-bit reads over the samples
+            s1.nip_log2 = ilog2(pow2ceil(d->Hd));
+            s1.wo_mat_bytes = 16 * s1.mtiles * s1.SBOo;
+            s1.img_bytes = 2 * (int64_t)s1.wo_mat_bytes;
+            s1.DUSTR = s1.C4; s1.du_floats = 8 * s1.C4;
+            s1.KPa = s1.KPo; s1.SBOa = s1.KPa / 8 * 128;
+            s1.c_hidden_floats = st->hidden_floats; s1.c_HP = pad4(st->Hmax);
+            for (int l = 0; l < d->n_hidden; ++l) { s1.c_off_w[l] = st->off_w[l]; s1.c_off_b[l] = st->off_b[l]; s1.c_stride[l] = st->stride[l]; }
+            if (s1.mtiles <= V3_MAX_TILES && s1.mtiles * 16 + s1.mtiles * s1.KPo <= 512 && (8 << s1.nip_log2) <= V3_THREADS &&
+                v3_s1_smem(s1).total <= 227 * 1024) {
+                *lo = s1;
+                return ANCDE_OK;
+            }
+        }
+    }
     static const int cand[3] = {2, 4, 8};
     for (int c = 0; c < 3; ++c) {
         const int CS = cand[c];
@@ -108,6 +142,7 @@ struct Pack3Args {
     const float* W[ANCDE_MAX_LAYERS + 1];
     const float* bias[ANCDE_MAX_LAYERS + 1];
     unsigned char* img;
+    float* wpack;
 };
 
 __device__ __forceinline__ void put_hilo(unsigned char* hi_mat, unsigned char* lo_mat, int sbo, int r, int k, float v)
@@ -123,7 +158,18 @@ __global__ void pack_weights3_kernel(const __grid_constant__ Pack3Args a)
 {
     const V3Layout& lo = a.lo;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    for (int l = 0; l < lo.n_hidden; ++l) {
+    if (lo.chain1) {
+        // FP32 rows of the hidden layers where the streamed engine keeps them (pack_weights_kernel writes the same values)
+        for (int l = 0; l < lo.n_hidden; ++l) {
+            const int in = lo.in_dim[l], out = lo.width[l], S = lo.c_stride[l];
+            for (int idx = gtid; idx < out * S; idx += gsz) {
+                const int o = idx / S, k = idx - o * S;
+                a.wpack[lo.c_off_w[l] + idx] = (k < in) ? a.W[l][(int64_t)o * in + k] : 0.f;
+            }
+            for (int o = gtid; o < pad4(out); o += gsz) a.wpack[lo.c_off_b[l] + o] = (o < out) ? a.bias[l][o] : 0.f;
+        }
+    }
+    for (int l = 0; l < (lo.chain1 ? 0 : lo.n_hidden); ++l) {
         const int KP = lo.KPh[l], in = lo.in_dim[l], out = lo.width[l];
         for (int idx = gtid; idx < lo.rows_h[l] * KP; idx += gsz) {
             const int m = idx / KP, k = idx - m * KP;
@@ -157,6 +203,7 @@ int pack_weights3(const ancde_ncde_desc* d, const V3Layout& lo, unsigned char* i
         pa.bias[l] = d->bias[l];
     }
     pa.img = img;
+    pa.wpack = d->wpack;
     prof_begin("pack_weights", stream);
     pack_weights3_kernel<<<148, 256, 0, stream>>>(pa);
     prof_end(stream);

@@ -292,6 +292,11 @@ int engine_of(const ancde_ncde_desc* d)
     // (top network 49*35*49: 2.1 ms against 3.3 ms); below that the per-layer latency of the tensor-core round trip
     // (commit -> mbarrier -> tcgen05.ld, ~1.2 k cycles) outweighs it (bottom network 35*35*20: 2.2 ms against 1.8 ms)
     if ((int64_t)d->Hd * d->C * d->width[d->n_hidden - 1] >= 50000 && umma_layouts(d, &st, &l3)) return ANCDE_ENGINE_UMMA;
+    // round 2: networks with narrow hidden layers whose whole output layer fits one SM's tensor memory run on the single-CTA
+    // UMMA variant (ncde3_fwd1.cu; Sepsis bottom network 1.62 -> see DESIGN.md) once there are enough tiles of 8 samples to
+    // fill the GPU
+    if ((int64_t)d->Hd * d->C * d->width[d->n_hidden - 1] >= 15000 && d->B >= 8 * 100 && umma_layouts(d, &st, &l3) && l3.chain1)
+        return ANCDE_ENGINE_UMMA;
     return ANCDE_ENGINE_STREAMED;
 }
 // float offset of the UMMA operand image inside wpack (behind the streamed engine's packed weights, 16-byte aligned)
