@@ -14,13 +14,13 @@ namespace ancde {
 // cost hundreds of cycles on this critical path.
 //   sLp[8*l ..] = {ceil(in_dim / 4), width, row stride, off_w, off_b, act_off_h, -, -}
 // The last layer is also written as [unit][TS] (sLast): the operand layout of the output-layer loop.
-template <int TS>
+template <int TS, int SPW_ = (TS >= 2 ? 2 : 1)>
 __device__ __forceinline__ void hidden_chain(const int* __restrict__ sLp, int n_hidden, const float* __restrict__ sHW,
                                              const float* __restrict__ sInT, float* __restrict__ sT0,
                                              float* __restrict__ sT1, float* __restrict__ sLast,
                                              float* __restrict__ act, int HP, int warp, int NW, int lane)
 {
-    constexpr int SPW = (TS >= 2) ? 2 : 1;          // samples per chain warp (each weight load feeds SPW FMAs)
+    constexpr int SPW = SPW_;                       // samples per chain warp (each weight load feeds SPW FMAs)
     constexpr int NCW = TS / SPW;
     for (int cw = warp; cw < NCW; cw += NW) {
         const int s0 = cw * SPW;

@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd1_kernel(const __grid_
 {
     const V3Layout& lo = p.lo;
     constexpr int NTHR = V3_THREADS, NW = NTHR / 32, TS = 8;
-    constexpr int CHAIN_WARPS = TS / 2;                 // hidden_chain: a warp owns 2 samples
+    constexpr int SPWC = 1;                             // samples per chain warp
+    constexpr int CHAIN_WARPS = TS / SPWC;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
     const int wq = warp & 3, wg = warp >> 2;
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd1_kernel(const __grid_
     const int64_t g_rows = (int64_t)lo.sv_ntiles * 8;
     uint32_t ph_t = 0;
     int jout = 1;                     // next requested output time
+    PH2_DECL();
 
     for (int k = 0; k < lo.n_steps; ++k) {
         const float t0 = grid_time(k, lo.n_steps, p.t_start, p.t_end, p.step, p.grid);
@@ -219,20 +221,29 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd1_kernel(const __grid_
             if (save_mine) act_run += act_stride;
             const float* du_cur = sDU + (stage & 1) * (TS * C4);
             float* du_next = sDU + ((stage + 1) & 1) * (TS * C4);
+            PH2_T0();
 
             // ---- (1) hidden layers: FP32 warp chain; the last activation becomes the FP16 hi/lo B operand
             if (warp < CHAIN_WARPS) {
-                hidden_chain<TS>(sLp, lo.n_hidden, sHW, sInT, sT0, sT1, sLast, act, HP, warp, CHAIN_WARPS, lane);
+                hidden_chain<TS, SPWC>(sLp, lo.n_hidden, sHW, sInT, sT0, sT1, sLast, act, HP, warp, CHAIN_WARPS, lane);
                 __syncwarp();
-                const int s0 = 2 * warp;
+                const int s0 = SPWC * warp;
                 for (int o = lane; o < K; o += 32) {
-                    const float2 v = *reinterpret_cast<const float2*>(sLast + o * TS + s0);
-                    uint32_t hh, hl;
-                    split_pair(v.x, v.y, hh, hl);
-                    *reinterpret_cast<uint32_t*>(sActHi + act_off(s0, o)) = hh;
-                    *reinterpret_cast<uint32_t*>(sActLo + act_off(s0, o)) = hl;
+                    if (SPWC == 2) {
+                        const float2 v = *reinterpret_cast<const float2*>(sLast + o * TS + s0);
+                        uint32_t hh, hl;
+                        split_pair(v.x, v.y, hh, hl);
+                        *reinterpret_cast<uint32_t*>(sActHi + act_off(s0, o)) = hh;
+                        *reinterpret_cast<uint32_t*>(sActLo + act_off(s0, o)) = hl;
+                    } else {
+                        __half hh, hl;
+                        split_half(sLast[o * TS + s0], hh, hl);
+                        *reinterpret_cast<__half*>(sActHi + act_off(s0, o)) = hh;
+                        *reinterpret_cast<__half*>(sActLo + act_off(s0, o)) = hl;
+                    }
                 }
                 fence_async_smem();
+                PH2_MARK(0);
             } else {
                 // meanwhile: the previous stage's staged tanh rows leave through one TMA row copy per sample, and the control of the
                 // next stage is evaluated
@@ -245,6 +256,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd1_kernel(const __grid_
                 if (have_next) control(s == 3 ? k + 1 : k, s == 3 ? 0 : s + 1, du_next, tid - 32 * CHAIN_WARPS, NTHR - 32 * CHAIN_WARPS);
             }
             __syncthreads();
+            PH2_MARK(1);
 
             // ---- (2) W_out x [h_hi ; h_lo] per 128-row tile, tanh, rows staged in shared memory
             for (int t = warp_u; t < lo.mtiles; t += NW) {
@@ -261,6 +273,9 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd1_kernel(const __grid_
                 }
                 __syncwarp();
             }
+            PH2_MARK(2);
+            // (reading all tiles of a warp back behind one tcgen05.wait::ld was measured SLOWER, 1.41 -> 1.51 ms: the first tile's
+            // tanh no longer overlaps the products of the later ones)
             for (int t = wg; t < lo.mtiles; t += 4) {
                 const int blk = 4 * t + wq;
                 if (blk >= nblk) continue;
@@ -288,9 +303,11 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd1_kernel(const __grid_
                 }
             }
             ph_t ^= 1;
+            PH2_MARK(3);
             tc_fence_before();
             fence_async_smem();
             __syncthreads();
+            PH2_MARK(4);
 
             // ---- (3) contraction with dU from the staged rows, RK4 recurrence of this thread's state element
             if (c_ok) {
@@ -332,9 +349,12 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd1_kernel(const __grid_
             if (s == 3) {
                 while (jout < lo.n_out && t1 >= sTout[jout]) ++jout;
             }
+            PH2_MARK(5);
             __syncthreads();
+            PH2_MARK(6);
         }
     }
+    PH2_FLUSH(16 + (top ? 8 : 0));
     // the last stage's tanh rows
     if (training && warp == NW - 1) {
         if (lane < TS && b0 + lane < g_rows)

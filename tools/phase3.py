@@ -41,3 +41,8 @@ for base, nm in ((16, 'fwd bottom'), (24, 'fwd top')):
     print('  out epilogue detail (warp 0): wait tile %.0f, tmem ld %.0f, dU + tanh %.0f, G store %.0f, butterfly %.0f, write %.0f' % tuple(v / stages for v in x[:6]))
 nl = cfg['nl'] if 'nl' in cfg else 4
 print('control (warp 2) cycles per stage: bottom %.0f top %.0f' % (d[0] / stages, d[1] / stages))
+
+if d[16] and not d[23]:
+    nm1 = ['chain + operand', 'barrier (control, TMA)', 'mma issue', 'epilogue (wait, ld, tanh, stage)', 'fence + barrier', 'contraction + RK4', 'barrier']
+    print('single-CTA forward (bottom), thread 0: cycles per stage, total %.0f' % (sum(d[16:23]) / stages))
+    for i in range(7): print('  %d %-34s %9.0f' % (i, nm1[i], d[16 + i] / stages))
