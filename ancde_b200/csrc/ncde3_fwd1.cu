@@ -188,6 +188,11 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd1_kernel(const __grid_
     float ry = 0.f, rk1 = 0.f, rk2 = 0.f, rk3 = 0.f;
     const int64_t act_stride = (int64_t)lo.sv_ntiles * lo.sv_act_floats;
     float* act_run = save_mine ? p.save_act + (int64_t)my_tile * lo.sv_act_floats : nullptr;
+    // (addresses that only depend on the stage number are carried along, not rebuilt on the critical path)
+    const int64_t kout_stride = (int64_t)B * Hd;
+    float* kout_run = (p.k_out && c_ok && c_bg < B) ? p.k_out + (int64_t)c_bg * Hd + c_il : nullptr;
+    float* const zin_dst = sInT + c_n * HP + c_il;
+    const int act_idx = c_il * 8 + c_n;
     if (c_ok) {
         ry = (c_bg < B) ? __ldg(p.z0 + (int64_t)c_bg * Hd + c_il) : 0.f;
         if (c_bg < B) p.z_out[(int64_t)c_bg * Hd + c_il] = ry;                  // solution[0] = y0
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd1_kernel(const __grid_
                     o0 = fmaf(a.z, b.z, o0); o1 = fmaf(a.w, b.w, o1);
                 }
                 const float o = o0 + o1;
-                if (p.k_out && c_bg < B) p.k_out[((int64_t)stage * B + c_bg) * Hd + c_il] = o;
+                if (kout_run) { *kout_run = o; kout_run += kout_stride; }
                 const float third = 1.0f / 3.0f;
                 float zin;
                 if (s == 0) { rk1 = o; zin = fmaf(dt * third, o, ry); }                        // y + dt*k1/3
@@ -343,8 +348,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd1_kernel(const __grid_
                     ry = y1;
                     zin = y1;
                 }
-                sInT[c_n * HP + c_il] = zin;
-                if (have_next && act_run) act_run[c_il * 8 + c_n] = zin;
+                *zin_dst = zin;
+                if (have_next && act_run) act_run[act_idx] = zin;
             }
             if (s == 3) {
                 while (jout < lo.n_out && t1 >= sTout[jout]) ++jout;

@@ -1,4 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_ncde.py -m gpu -x -q 2>&1 | tail -5
+timeout 900 python -m pytest tests/test_gpu_ncde.py tests/test_gpu_bwd4.py -m gpu -x -q 2>&1 | tail -3
 for v in "A=1"; do
   echo "== $v"
   env $v timeout 300 python bench.py --steps 10 --warmup 3 --no-other-configs 2>/dev/null | tail -1 | python -c "

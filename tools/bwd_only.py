@@ -21,3 +21,12 @@ for _ in range(2):
     model(times, coeffs + extra, fi, 1.0, adjoint=False).sum().backward()
 torch.cuda.synchronize()
 print('ok', _lib.lib().ancde_debug_bwd4_launches())
+# wall time of the backward pass alone (CUDA events), 5 repetitions
+import statistics
+ts = []
+for _ in range(5):
+    out = model(times, coeffs + extra, fi, 1.0, adjoint=False).sum()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); out.backward(); e1.record(); torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+print('backward ms (median of 5): %.3f' % statistics.median(ts))
