@@ -1,11 +1,14 @@
-"""GPU parity of the tcgen05 (UMMA) kernels: the cluster forward engine (csrc/ncde3_fwd.cu) forced on EVERY golden shape
-it supports -- not only the large ones the library picks it for -- and the tcgen05 output-layer weight gradient
-(csrc/ncde_wgrad_umma.cu) against the mma.sync kernel and the reference's gradients.
+"""GPU parity of the tcgen05 (UMMA) kernels: the forward engine forced on EVERY golden shape it supports -- not only the
+large ones the library picks it for --, once with its single-CTA variant allowed (csrc/ncde3_fwd1.cu: narrow hidden
+layers as the FP32 warp chain, all of W_out in tensor memory) and once with the cluster kernel only (csrc/ncde3_fwd.cu),
+and the tcgen05 output-layer weight gradient (csrc/ncde_wgrad_umma.cu) against the mma.sync kernel and the reference's
+gradients.
 
 The shapes cover every row-block layout of the engine: C = 4 / 6 / 14 (several field rows per 32-lane block, butterfly
 over 4 / 8 / 16 lanes), C = 35 (full block + partial chunk) and both cluster sizes.  Bars as in test_gpu_ncde.py.
 """
 import ctypes
+import os
 
 import pytest
 import torch
@@ -28,8 +31,19 @@ def _forced(fn):
         solver.ENGINE = 0
 
 
+@pytest.fixture(params=['single_cta_allowed', 'cluster_only'])
+def umma_variant(request):
+    """The layout is made per call from the environment (development switch of csrc/ncde3_host.cu)."""
+    if request.param == 'cluster_only':
+        os.environ['ANCDE_FWD3_NOSINGLE'] = '1'
+    try:
+        yield request.param
+    finally:
+        os.environ.pop('ANCDE_FWD3_NOSINGLE', None)
+
+
 @pytest.mark.parametrize('case', DUAL_CASES)
-def test_umma_engine_forward_and_gradients_match_reference_golden(case):
+def test_umma_engine_forward_and_gradients_match_reference_golden(case, umma_variant):
     import ancde_b200
     g = dual_case(case)
     model = _build(g['cfg'], g['sd'])
@@ -54,7 +68,7 @@ def test_umma_engine_forward_and_gradients_match_reference_golden(case):
         assert rel_err(params[k].grad, ref) < GRAD_TOL, (case, k)
 
 
-def test_library_picks_the_umma_engine_for_the_sepsis_top_network_only():
+def test_library_picks_the_umma_engine_for_the_large_sepsis_networks():
     from ancde_b200 import _lib
     L = _lib.lib()
 
@@ -68,7 +82,10 @@ def test_library_picks_the_umma_engine_for_the_sepsis_top_network_only():
         return d
 
     assert L.ancde_ncde_engine(ctypes.byref(desc(35, 49, [49] * 4, _lib.MODE_TOP))) == _lib.ENGINE_UMMA
-    assert L.ancde_ncde_engine(ctypes.byref(desc(35, 35, [20] * 5, _lib.MODE_BOTTOM))) == _lib.ENGINE_STREAMED
+    # round 2: the bottom network (narrow hidden layers, W_out fits one SM's tensor memory) runs on the single-CTA variant
+    # once the batch fills the GPU with tiles of 8 samples
+    assert L.ancde_ncde_engine(ctypes.byref(desc(35, 35, [20] * 5, _lib.MODE_BOTTOM))) == _lib.ENGINE_UMMA
+    assert L.ancde_ncde_engine(ctypes.byref(desc(35, 35, [20] * 5, _lib.MODE_BOTTOM, B=256))) == _lib.ENGINE_STREAMED
     assert L.ancde_ncde_engine(ctypes.byref(desc(14, 12, [12] * 2, _lib.MODE_TOP))) == _lib.ENGINE_STREAMED
 
 
