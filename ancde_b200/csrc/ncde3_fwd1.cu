@@ -212,6 +212,33 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd1_kernel(const __grid_
     const int64_t g_rows = (int64_t)lo.sv_ntiles * 8;
     uint32_t ph_t = 0;
     int jout = 1;                     // next requested output time
+    // this lane's rows in the tiles its warp reads back (tile wg + 4u, lane quarter wq): offset of the row in a staged sample
+    // row (field row il, control channel j), -1 where the lane holds no row; computed once
+    constexpr int E_MAX = V3_MAX_TILES / 4;
+    int e_off[E_MAX], e_n = 0;
+    unsigned e_valid = 0;
+#pragma unroll
+    for (int u = 0; u < E_MAX; ++u) {
+        const int t = wg + 4 * u, blk = 4 * t + wq;
+        e_off[u] = -1;
+        if (t < lo.mtiles && blk < nblk) {
+            e_n = u + 1;
+            int il, j;
+            bool valid;
+            if (blk < Hd * lo.nfull) {
+                il = blk / lo.nfull;
+                j = 32 * (blk - il * lo.nfull) + lane;
+                valid = true;
+            } else {
+                const int q = blk - Hd * lo.nfull, jj = lane & (lo.seg - 1);
+                il = q * lo.ipb + (lane >> lo.seg_log2);
+                j = 32 * lo.nfull + jj;
+                valid = jj < lo.rem && il < Hd;
+            }
+            if (il < Hd && j < C4) e_off[u] = il * C4 + j;
+            if (valid) e_valid |= 1u << u;
+        }
+    }
     PH2_DECL();
 
     for (int k = 0; k < lo.n_steps; ++k) {
@@ -279,32 +306,32 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ncde3_fwd1_kernel(const __grid_
                 __syncwarp();
             }
             PH2_MARK(2);
-            // (reading all tiles of a warp back behind one tcgen05.wait::ld was measured SLOWER, 1.41 -> 1.51 ms: the first tile's
-            // tanh no longer overlaps the products of the later ones)
-            for (int t = wg; t < lo.mtiles; t += 4) {
-                const int blk = 4 * t + wq;
-                if (blk >= nblk) continue;
-                // identity of this lane's row: field row il, control channel j
-                int il, j;
-                bool valid;
-                if (blk < Hd * lo.nfull) {
-                    il = blk / lo.nfull;
-                    j = 32 * (blk - il * lo.nfull) + lane;
-                    valid = true;
-                } else {
-                    const int q = blk - Hd * lo.nfull, jj = lane & (lo.seg - 1);
-                    il = q * lo.ipb + (lane >> lo.seg_log2);
-                    j = 32 * lo.nfull + jj;
-                    valid = jj < lo.rem && il < Hd;
-                }
-                mbar_wait(bar_t + t, ph_t);
+            // This warp's tiles wg, wg + 4, ...: the tcgen05.ld of the next tile is in flight while the current one goes through tanh.
+            // (Reading all tiles back behind ONE tcgen05.wait::ld was measured slower, 1.41 -> 1.51 ms: the first tile's tanh no
+            // longer overlaps the products of the later ones.)
+            if (e_n > 0) {
+                uint32_t ra[16], rb[16];
+                mbar_wait(bar_t + wg, ph_t);
                 tc_fence_after();
-                float v[16];
-                tmem_ld16(tlane + (uint32_t)(16 * t), v);
-                if (il < Hd && j < C4) {
-                    float* gs = sG + il * C4 + j;
+                tmem_ld16_issue(tlane + (uint32_t)(16 * wg), ra);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) gs[e * lo.sg_str] = valid ? tanh_scaled3(v[e] + v[8 + e], tanh_c) : 0.f;
+                for (int u = 0; u < E_MAX; ++u) {
+                    if (u >= e_n) break;
+                    uint32_t (&cur)[16] = (u & 1) ? rb : ra;
+                    uint32_t (&nxt)[16] = (u & 1) ? ra : rb;
+                    tmem_ld16_wait(cur);
+                    if (u + 1 < e_n) {
+                        mbar_wait(bar_t + wg + 4 * (u + 1), ph_t);
+                        tc_fence_after();
+                        tmem_ld16_issue(tlane + (uint32_t)(16 * (wg + 4 * (u + 1))), nxt);
+                    }
+                    if (e_off[u] >= 0) {
+                        float* gs = sG + e_off[u];
+                        const bool valid = (e_valid >> u) & 1;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            gs[e * lo.sg_str] = valid ? tanh_scaled3(__uint_as_float(cur[e]) + __uint_as_float(cur[8 + e]), tanh_c) : 0.f;
+                    }
                 }
             }
             ph_t ^= 1;
