@@ -1,0 +1,247 @@
+// Hidden-layer weight gradients of the fused NCDE solve on the tcgen05 tensor cores (tiles of 8 samples, <= 4 layers).
+//
+//   dW_l[o][k] = sum over every (stage, sample) row r of  delta_l[r][o] * in_l[r][k],      db_l[o] = sum_r delta_l[r][o]
+//
+// delta_l (masked layer cotangents) and in_l (stage input for l = 0, previous activation otherwise) were left in the saved
+// activation blocks by the recurrent kernels as [unit][8 samples]: for a fixed unit the 8 samples of a tile are 8
+// consecutive elements of the REDUCTION index -- exactly one row of a K-major core matrix.  So a (unit, tile) item is two
+// 128-bit loads, an FP16 hi/lo split and two 128-bit stores, and per chunk of 16 rows (two tiles) and layer ONE
+// tcgen05.mma (M = 128, N = 128, K = 16) accumulates all four hi/lo quadrants
+//     [delta_hi ; delta_lo] (128 rows)  x  [in_hi | 1 ; in_lo] (128 columns)
+// in tensor memory (128 columns per layer, <= 4 layers = the 512 columns of an SM); the lo x lo quadrant is simply not read.
+// The bias gradient is the extra column in = 1.  delta is scaled by a power of two taken from max |gbar| (tracked by the
+// recurrent backward) so that the cotangents sit in FP16's range.  A CTA owns a contiguous range of chunks: raw blocks
+// arrive through a 3-stage TMA ring (two bulk copies per block: z | h_1..h_L and delta_1..delta_L), two operand buffers so
+// that the conversion of chunk c+1 overlaps the products of chunk c; at the end the accumulators are read back
+// (tcgen05.ld) and added to the torch-layout gradients with atomics.
+// The mma.sync kernel it replaces (ncde_wgrad.cu: 3xTF32, 0.29 + 0.19 ms for the two Sepsis networks) was issue bound.
+#include "mma_common.cuh"
+#include "umma.cuh"
+
+namespace ancde {
+
+struct HiddenGradPtrs { float* gW[ANCDE_MAX_LAYERS]; float* gB[ANCDE_MAX_LAYERS]; };
+
+constexpr int HU_THREADS = 512;
+constexpr int HU_TPC = 2;            // tiles of 8 samples per chunk = one K = 16 step
+constexpr int HU_STAGES = 3;         // TMA ring
+constexpr int HU_LBO = 128;          // bytes between the core matrices of the two tiles
+constexpr int HU_SBO = HU_TPC * HU_LBO;               // bytes between groups of 8 rows
+constexpr int HU_MAT = 16 * HU_SBO;  // one operand matrix: 128 rows
+constexpr int HU_MAXL = 4;
+
+__global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(const __grid_constant__ SolveArgs p,
+                                                                               const __grid_constant__ HiddenGradPtrs hp, int chunks_per_cta,
+                                                                               const unsigned* __restrict__ gmax_bits)
+{
+    constexpr int NT = HU_THREADS;
+    const NcdeLayout& lo = p.lo;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const int nl = lo.n_hidden;
+
+    // power-of-two scale that brings the largest stage cotangent to [1, 2): the layer cotangents are sums of such terms and
+    // stay far below FP16's 65504
+    float scale = 1.0f;
+    {
+        const float gm = __uint_as_float(__ldg(gmax_bits));
+        if (gm > 0.f) {
+            int e;
+            frexpf(gm, &e);                    // gm = f * 2^e, f in [0.5, 1)
+            scale = ldexpf(1.0f, 1 - e);
+        }
+    }
+
+    __shared__ __align__(8) uint64_t ld_bar[HU_STAGES];    // TMA completion of a ring stage
+    __shared__ __align__(8) uint64_t mma_bar[2];           // products that read operand buffer b have completed
+    __shared__ uint32_t tslot;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int zlen = lo.act_off_du;                                // floats: z_s | h_1 .. h_L
+    const int doff = lo.act_off_delta[0], dlen = lo.act_floats - doff;       // delta_1 .. delta_L
+    const int tile_floats = zlen + dlen;
+    const int stage_floats = HU_TPC * tile_floats;
+    float* sRaw = reinterpret_cast<float*>(smem_raw);
+    unsigned char* sOp = smem_raw + (size_t)HU_STAGES * stage_floats * 4;     // [2 buffers][layer][A, B][HU_MAT]
+    const int op_bytes = nl * 2 * HU_MAT;
+    // item table: {float offset of the 8 samples inside a raw tile, byte offset of the hi row in an operand buffer | scaled << 31}
+    int2* sTab = reinterpret_cast<int2*>(sOp + 2 * op_bytes);
+    int n_items = 0;
+    for (int l = 0; l < nl; ++l) n_items += lo.width[l] + lo.in_dim[l];
+
+    const int64_t nblocks = (int64_t)lo.n_stages * lo.ntiles;
+    const int64_t nchunks = (nblocks + HU_TPC - 1) / HU_TPC;
+    const int64_t c0 = (int64_t)blockIdx.x * chunks_per_cta;
+    int64_t c1 = c0 + chunks_per_cta;
+    if (c1 > nchunks) c1 = nchunks;
+    const int n_it = (c1 > c0) ? (int)(c1 - c0) : 0;
+
+    auto issue = [&](int64_t ch, int s) {          // warp 0: two bulk copies per existing block of the chunk
+        const int64_t blk0 = ch * HU_TPC;
+        int64_t nvalid = nblocks - blk0;
+        if (nvalid > HU_TPC) nvalid = HU_TPC;
+        if (lane == 0) mbar_arrive_expect_tx(ld_bar + s, (uint32_t)nvalid * (uint32_t)(tile_floats * 4));
+        __syncwarp();
+        if (lane < 2 * nvalid) {
+            const int t = lane >> 1;
+            const float* act = p.save_act + (blk0 + t) * lo.act_floats;
+            float* dst = sRaw + (size_t)s * stage_floats + (size_t)t * tile_floats;
+            if (lane & 1) bulk_g2s(dst + zlen, act + doff, (uint32_t)(dlen * 4), ld_bar + s);
+            else bulk_g2s(dst, act, (uint32_t)(zlen * 4), ld_bar + s);
+        }
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < HU_STAGES; ++s) mbar_init(ld_bar + s, 1);
+        mbar_init(mma_bar + 0, 1);
+        mbar_init(mma_bar + 1, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(&tslot, nl > 2 ? 512 : 256);
+    // operand buffers: zero (rows beyond a layer's units stay zero), the table
+    for (int i = tid; i < 2 * op_bytes / 16; i += NT) reinterpret_cast<uint4*>(sOp)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) {
+        int e = 0;
+        for (int l = 0; l < nl; ++l) {
+            for (int o = 0; o < lo.width[l]; ++o)            // A rows: delta_l, scaled
+                sTab[e++] = make_int2(zlen + lo.act_off_delta[l] - doff + o * 8,
+                                      (l * 2 * HU_MAT + (o >> 3) * HU_SBO + (o & 7) * 16) | (int)0x80000000);
+            const int in_off = (l == 0) ? 0 : lo.act_off_h[l - 1];
+            for (int k = 0; k < lo.in_dim[l]; ++k)           // B rows: in_l
+                sTab[e++] = make_int2(in_off + k * 8, l * 2 * HU_MAT + HU_MAT + (k >> 3) * HU_SBO + (k & 7) * 16);
+        }
+    }
+    __syncthreads();
+    // the bias column of every B matrix (row k = in_dim): ones in the hi half, both tiles, both buffers
+    if (tid < 2 * nl * HU_TPC) {
+        const int ob = tid / (nl * HU_TPC), r = tid - ob * nl * HU_TPC, l = r / HU_TPC, t = r - l * HU_TPC;
+        const int k = lo.in_dim[l];
+        uint4* dst = reinterpret_cast<uint4*>(sOp + ob * op_bytes + l * 2 * HU_MAT + HU_MAT + (k >> 3) * HU_SBO + t * HU_LBO + (k & 7) * 16);
+        const uint32_t one2 = 0x3C003C00u;                   // two FP16 ones
+        *dst = make_uint4(one2, one2, one2, one2);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tslot;
+
+    if (warp == 0)
+        for (int s = 0; s < HU_STAGES; ++s)
+            if (s < n_it) issue(c0 + s, s);
+
+    const uint32_t idesc = umma_idesc_f16(128, 128, false);
+    for (int it = 0; it < n_it; ++it) {
+        const int64_t ch = c0 + it;
+        const int s = it % HU_STAGES, ob = it & 1;
+        const float* sS = sRaw + (size_t)s * stage_floats;
+        unsigned char* sO = sOp + ob * op_bytes;
+        mbar_wait(ld_bar + s, (uint32_t)((it / HU_STAGES) & 1));
+        if (it >= 2) mbar_wait(mma_bar + ob, (uint32_t)(((it - 2) >> 1) & 1));       // the products of chunk it-2 have read this buffer
+        const int64_t blk_left = nblocks - ch * HU_TPC;          // tiles beyond the last block contribute zeros
+        // ---- (unit, tile) items -> FP16 hi/lo rows of the operands
+        for (int idx = tid; idx < HU_TPC * n_items; idx += NT) {
+            const int t = idx >= n_items ? 1 : 0, e = idx - t * n_items;
+            const int2 q = sTab[e];
+            float v[8];
+            if (t < blk_left) {
+                const float4 a = *reinterpret_cast<const float4*>(sS + t * tile_floats + q.x);
+                const float4 c = *reinterpret_cast<const float4*>(sS + t * tile_floats + q.x + 4);
+                const float f = q.y < 0 ? scale : 1.0f;
+                v[0] = a.x * f; v[1] = a.y * f; v[2] = a.z * f; v[3] = a.w * f; v[4] = c.x * f; v[5] = c.y * f; v[6] = c.z * f; v[7] = c.w * f;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = 0.f;
+            }
+            uint32_t hh[4], hl[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) split_pair(v[2 * u], v[2 * u + 1], hh[u], hl[u]);
+            unsigned char* dst = sO + (q.y & 0x7fffffff) + t * HU_LBO;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<uint4*>(dst + 8 * HU_SBO) = make_uint4(hl[0], hl[1], hl[2], hl[3]);      // the lo half: 64 rows down
+        }
+        fence_async_smem();
+        __syncthreads();
+        // ---- D_l += [delta_hi ; delta_lo] x [in_hi | 1 ; in_lo]^T over the 16 rows
+        if (warp_u == 1) {
+            if (elect_one()) {
+                tc_fence_after();
+#pragma unroll
+                for (int l = 0; l < HU_MAXL; ++l) {
+                    if (l < nl) {
+                        const uint64_t dA = umma_smem_desc(smem_u32(sO) + l * 2 * HU_MAT, HU_LBO, HU_SBO);
+                        const uint64_t dB = umma_smem_desc(smem_u32(sO) + l * 2 * HU_MAT + HU_MAT, HU_LBO, HU_SBO);
+                        umma_f16(tbase + l * 128, dA, dB, idesc, it != 0);
+                    }
+                }
+                umma_commit(mma_bar + ob);
+            }
+        }
+        if (warp == 0 && it + HU_STAGES < n_it) issue(ch + HU_STAGES, s);      // every thread has finished reading stage s
+    }
+
+    // ---- results: TMEM lane = accumulator row (this warp's quarter), 32 columns per warp group and layer
+    if (n_it > 0) {
+        for (int ob = 0; ob < 2; ++ob)
+            if (n_it > ob) mbar_wait(mma_bar + ob, (uint32_t)(((n_it - 1 - ob) >> 1) & 1));
+        tc_fence_after();
+        const float inv = 1.0f / scale;
+        const int wq = warp & 3, cg = warp >> 2;
+        const int m = 32 * wq + lane;
+        const bool lo_row = m >= 64;                 // rows 64.. hold delta_lo: only their product with in_hi (columns < 64) counts
+        const int o = lo_row ? m - 64 : m;
+        for (int l = 0; l < nl; ++l) {
+            const int N = lo.width[l], Kin = lo.in_dim[l];
+            float v[16], v2[16];
+            const uint32_t ta = tbase + ((uint32_t)(32 * wq) << 16) + l * 128 + 32 * cg;
+            tmem_ld16x2(ta, ta + 16, v, v2);
+            if (o < N && !(lo_row && cg >= 2)) {
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    const int n = 32 * cg + u, k = n & 63;
+                    const float val = (u < 16 ? v[u] : v2[u - 16]) * inv;
+                    if (k < Kin) atomicAdd(hp.gW[l] + (int64_t)o * Kin + k, val);
+                    else if (k == Kin && n < 64) atomicAdd(hp.gB[l] + o, val);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tbase, nl > 2 ? 512 : 256);
+}
+
+// true when this kernel takes the shape
+bool hidden_wgrad_umma_ok(const NcdeLayout& lo)
+{
+    if (lo.TS != 8 || lo.n_hidden < 1 || lo.n_hidden > HU_MAXL) return false;
+    for (int l = 0; l < lo.n_hidden; ++l)
+        if (lo.width[l] > 64 || lo.in_dim[l] + 1 > 64) return false;
+    if (lo.act_off_delta[0] < lo.act_off_du) return false;
+    return true;
+}
+
+int launch_hidden_wgrad_umma(const SolveArgs& a, const HiddenGradPtrs& hp, cudaStream_t stream)
+{
+    const NcdeLayout& lo = a.lo;
+    int n_items = 0;
+    for (int l = 0; l < lo.n_hidden; ++l) n_items += lo.width[l] + lo.in_dim[l];
+    const int tile_floats = lo.act_off_du + (lo.act_floats - lo.act_off_delta[0]);
+    const size_t smem = (size_t)HU_STAGES * HU_TPC * tile_floats * 4 + 2 * (size_t)lo.n_hidden * 2 * HU_MAT + (size_t)n_items * 8 + 128;
+    if (smem > 227 * 1024) return ANCDE_EUNSUPPORTED;
+    const int64_t nblocks = (int64_t)lo.n_stages * lo.ntiles;
+    const int64_t nchunks = (nblocks + HU_TPC - 1) / HU_TPC;
+    int64_t grid = 148;
+    if (grid > nchunks) grid = nchunks;
+    const int per = (int)((nchunks + grid - 1) / grid);
+    grid = (nchunks + per - 1) / per;
+    const unsigned* gmax = reinterpret_cast<const unsigned*>(a.wpack + lo.off_gscale);   // written by the recurrent backward
+    ANCDE_CUDA(cudaFuncSetAttribute(ncde_hidden_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const char* names[3] = {"ncde_hidden_wgrad_plain", "ncde_hidden_wgrad_bottom", "ncde_hidden_wgrad_top"};
+    prof_begin(names[lo.mode], stream);
+    ncde_hidden_wgrad_umma_kernel<<<(unsigned)grid, HU_THREADS, smem, stream>>>(a, hp, per, gmax);
+    prof_end(stream);
+    count_launch();
+    ANCDE_CUDA(cudaGetLastError());
+    return ANCDE_OK;
+}
+
+}  // namespace ancde

@@ -371,8 +371,19 @@ static int launch_hidden_wgrad_ts(const SolveArgs& a, const HiddenGradPtrs& hp, 
     return ANCDE_OK;
 }
 
+bool hidden_wgrad_umma_ok(const NcdeLayout& lo);
+int launch_hidden_wgrad_umma(const SolveArgs& a, const HiddenGradPtrs& hp, cudaStream_t stream);
+
 int launch_hidden_wgrad(const SolveArgs& a, const HiddenGradPtrs& hp, cudaStream_t stream)
 {
+    // round 2: tiles of 8 samples and <= 4 layers of <= 64 units go to the tcgen05 kernel (ncde_hidden_wgrad_umma.cu) unless
+    // ANCDE_HIDDEN_WGRAD_MMA=1 / ANCDE_HIDDEN_WGRAD_FP32=1 ask for the mma.sync / FP32 kernels (A/B timing, cross-check test)
+    static const bool legacy = (getenv("ANCDE_HIDDEN_WGRAD_MMA") && getenv("ANCDE_HIDDEN_WGRAD_MMA")[0] == '1') ||
+                               (getenv("ANCDE_HIDDEN_WGRAD_FP32") && getenv("ANCDE_HIDDEN_WGRAD_FP32")[0] == '1');
+    if (!legacy && hidden_wgrad_umma_ok(a.lo)) {
+        const int rc = launch_hidden_wgrad_umma(a, hp, stream);
+        if (rc != ANCDE_EUNSUPPORTED) return rc;
+    }
     switch (a.lo.TS) {
         case 8: return launch_hidden_wgrad_ts<8>(a, hp, stream);
         case 4: return launch_hidden_wgrad_ts<4>(a, hp, stream);
