@@ -10,10 +10,12 @@
 //     [delta_hi ; delta_lo] (128 rows)  x  [in_hi | 1 ; in_lo] (128 columns)
 // in tensor memory (128 columns per layer, <= 4 layers = the 512 columns of an SM); the lo x lo quadrant is simply not read.
 // The bias gradient is the extra column in = 1.  delta is scaled by a power of two taken from max |gbar| (tracked by the
-// recurrent backward) so that the cotangents sit in FP16's range.  A CTA owns a contiguous range of chunks: raw blocks
-// arrive through a 3-stage TMA ring (two bulk copies per block: z | h_1..h_L and delta_1..delta_L), two operand buffers so
-// that the conversion of chunk c+1 overlaps the products of chunk c; at the end the accumulators are read back
-// (tcgen05.ld) and added to the torch-layout gradients with atomics.
+// recurrent backward) so that the cotangents sit in FP16's range.  A CTA owns a contiguous range of chunks of 32 rows; the
+// items of a chunk are loaded straight into registers one chunk ahead (consecutive threads read consecutive 32-byte
+// pieces: the HBM latency is covered by registers -- a TMA ring of raw blocks in shared memory measured 0.21 ms for the
+// top network, per-chunk synchronisation bound); two operand buffers so that the conversion of chunk c+1 overlaps the
+// products of chunk c; at the end the accumulators are read back (tcgen05.ld) and added to the torch-layout gradients
+// with atomics.
 // The mma.sync kernel it replaces (ncde_wgrad.cu: 3xTF32, 0.29 + 0.19 ms for the two Sepsis networks) was issue bound.
 #include "mma_common.cuh"
 #include "umma.cuh"
@@ -23,8 +25,8 @@ namespace ancde {
 struct HiddenGradPtrs { float* gW[ANCDE_MAX_LAYERS]; float* gB[ANCDE_MAX_LAYERS]; };
 
 constexpr int HU_THREADS = 512;
-constexpr int HU_TPC = 2;            // tiles of 8 samples per chunk = one K = 16 step
-constexpr int HU_STAGES = 3;         // TMA ring
+constexpr int HU_TPC = 4;            // tiles of 8 samples per chunk = two K = 16 steps
+constexpr int HU_IPT = 4;            // (unit, tile) items per thread and chunk, loaded one chunk ahead into registers
 constexpr int HU_LBO = 128;          // bytes between the core matrices of the two tiles
 constexpr int HU_SBO = HU_TPC * HU_LBO;               // bytes between groups of 8 rows
 constexpr int HU_MAT = 16 * HU_SBO;  // one operand matrix: 128 rows
@@ -52,19 +54,11 @@ __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(c
         }
     }
 
-    __shared__ __align__(8) uint64_t ld_bar[HU_STAGES];    // TMA completion of a ring stage
     __shared__ __align__(8) uint64_t mma_bar[2];           // products that read operand buffer b have completed
     __shared__ uint32_t tslot;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int zlen = lo.act_off_du;                                // floats: z_s | h_1 .. h_L
-    const int doff = lo.act_off_delta[0], dlen = lo.act_floats - doff;       // delta_1 .. delta_L
-    const int tile_floats = zlen + dlen;
-    const int stage_floats = HU_TPC * tile_floats;
-    float* sRaw = reinterpret_cast<float*>(smem_raw);
-    unsigned char* sOp = smem_raw + (size_t)HU_STAGES * stage_floats * 4;     // [2 buffers][layer][A, B][HU_MAT]
+    unsigned char* sOp = smem_raw;                                          // [2 buffers][layer][A, B][HU_MAT]
     const int op_bytes = nl * 2 * HU_MAT;
-    // item table: {float offset of the 8 samples inside a raw tile, byte offset of the hi row in an operand buffer | scaled << 31}
-    int2* sTab = reinterpret_cast<int2*>(sOp + 2 * op_bytes);
     int n_items = 0;
     for (int l = 0; l < nl; ++l) n_items += lo.width[l] + lo.in_dim[l];
 
@@ -75,23 +69,43 @@ __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(c
     if (c1 > nchunks) c1 = nchunks;
     const int n_it = (c1 > c0) ? (int)(c1 - c0) : 0;
 
-    auto issue = [&](int64_t ch, int s) {          // warp 0: two bulk copies per existing block of the chunk
-        const int64_t blk0 = ch * HU_TPC;
-        int64_t nvalid = nblocks - blk0;
-        if (nvalid > HU_TPC) nvalid = HU_TPC;
-        if (lane == 0) mbar_arrive_expect_tx(ld_bar + s, (uint32_t)nvalid * (uint32_t)(tile_floats * 4));
-        __syncwarp();
-        if (lane < 2 * nvalid) {
-            const int t = lane >> 1;
-            const float* act = p.save_act + (blk0 + t) * lo.act_floats;
-            float* dst = sRaw + (size_t)s * stage_floats + (size_t)t * tile_floats;
-            if (lane & 1) bulk_g2s(dst + zlen, act + doff, (uint32_t)(dlen * 4), ld_bar + s);
-            else bulk_g2s(dst, act, (uint32_t)(zlen * 4), ld_bar + s);
+    // this thread's items of a chunk: item = tid + u * NT  ->  (tile t, entry e); source offset inside the saved block,
+    // destination of the hi row inside an operand buffer (bit 31: scaled, i.e. a delta row); the same for every chunk
+    int i_src[HU_IPT], i_dst[HU_IPT], i_tile[HU_IPT];
+#pragma unroll
+    for (int u = 0; u < HU_IPT; ++u) {
+        const int idx = tid + u * NT;
+        i_tile[u] = -1; i_src[u] = 0; i_dst[u] = 0;
+        if (idx < HU_TPC * n_items) {
+            const int t = idx / n_items, e = idx - t * n_items;
+            int l = 0, base = 0;
+            while (e >= base + lo.width[l] + lo.in_dim[l]) { base += lo.width[l] + lo.in_dim[l]; ++l; }
+            const int r = e - base;
+            i_tile[u] = t;
+            if (r < lo.width[l]) {                             // A rows: delta_l, scaled
+                i_src[u] = lo.act_off_delta[l] + r * 8;
+                i_dst[u] = (l * 2 * HU_MAT + (r >> 3) * HU_SBO + (r & 7) * 16 + t * HU_LBO) | (int)0x80000000;
+            } else {                                           // B rows: in_l
+                const int k = r - lo.width[l];
+                i_src[u] = ((l == 0) ? 0 : lo.act_off_h[l - 1]) + k * 8;
+                i_dst[u] = l * 2 * HU_MAT + HU_MAT + (k >> 3) * HU_SBO + (k & 7) * 16 + t * HU_LBO;
+            }
+        }
+    }
+    auto load_items = [&](int64_t ch, float4 (&g)[2 * HU_IPT]) {
+#pragma unroll
+        for (int u = 0; u < HU_IPT; ++u) {
+            g[2 * u] = g[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int64_t blk = ch * HU_TPC + i_tile[u];
+            if (i_tile[u] >= 0 && ch < c1 && blk < nblocks) {
+                const float4* src = reinterpret_cast<const float4*>(p.save_act + blk * lo.act_floats + i_src[u]);
+                g[2 * u] = __ldcs(src);
+                g[2 * u + 1] = __ldcs(src + 1);
+            }
         }
     };
 
     if (tid == 0) {
-        for (int s = 0; s < HU_STAGES; ++s) mbar_init(ld_bar + s, 1);
         mbar_init(mma_bar + 0, 1);
         mbar_init(mma_bar + 1, 1);
         mbar_fence_init();
@@ -99,17 +113,6 @@ __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(c
     if (warp == 1) tmem_alloc(&tslot, nl > 2 ? 512 : 256);
     // operand buffers: zero (rows beyond a layer's units stay zero), the table
     for (int i = tid; i < 2 * op_bytes / 16; i += NT) reinterpret_cast<uint4*>(sOp)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == 0) {
-        int e = 0;
-        for (int l = 0; l < nl; ++l) {
-            for (int o = 0; o < lo.width[l]; ++o)            // A rows: delta_l, scaled
-                sTab[e++] = make_int2(zlen + lo.act_off_delta[l] - doff + o * 8,
-                                      (l * 2 * HU_MAT + (o >> 3) * HU_SBO + (o & 7) * 16) | (int)0x80000000);
-            const int in_off = (l == 0) ? 0 : lo.act_off_h[l - 1];
-            for (int k = 0; k < lo.in_dim[l]; ++k)           // B rows: in_l
-                sTab[e++] = make_int2(in_off + k * 8, l * 2 * HU_MAT + HU_MAT + (k >> 3) * HU_SBO + (k & 7) * 16);
-        }
-    }
     __syncthreads();
     // the bias column of every B matrix (row k = in_dim): ones in the hi half, both tiles, both buffers
     if (tid < 2 * nl * HU_TPC) {
@@ -124,37 +127,28 @@ __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(c
     tc_fence_after();
     const uint32_t tbase = tslot;
 
-    if (warp == 0)
-        for (int s = 0; s < HU_STAGES; ++s)
-            if (s < n_it) issue(c0 + s, s);
-
     const uint32_t idesc = umma_idesc_f16(128, 128, false);
+    float4 g0[2 * HU_IPT];
+    load_items(c0, g0);
     for (int it = 0; it < n_it; ++it) {
         const int64_t ch = c0 + it;
-        const int s = it % HU_STAGES, ob = it & 1;
-        const float* sS = sRaw + (size_t)s * stage_floats;
+        const int ob = it & 1;
         unsigned char* sO = sOp + ob * op_bytes;
-        mbar_wait(ld_bar + s, (uint32_t)((it / HU_STAGES) & 1));
+        float4 g1[2 * HU_IPT];
+        load_items(ch + 1, g1);                              // one chunk ahead
         if (it >= 2) mbar_wait(mma_bar + ob, (uint32_t)(((it - 2) >> 1) & 1));       // the products of chunk it-2 have read this buffer
-        const int64_t blk_left = nblocks - ch * HU_TPC;          // tiles beyond the last block contribute zeros
-        // ---- (unit, tile) items -> FP16 hi/lo rows of the operands
-        for (int idx = tid; idx < HU_TPC * n_items; idx += NT) {
-            const int t = idx >= n_items ? 1 : 0, e = idx - t * n_items;
-            const int2 q = sTab[e];
-            float v[8];
-            if (t < blk_left) {
-                const float4 a = *reinterpret_cast<const float4*>(sS + t * tile_floats + q.x);
-                const float4 c = *reinterpret_cast<const float4*>(sS + t * tile_floats + q.x + 4);
-                const float f = q.y < 0 ? scale : 1.0f;
-                v[0] = a.x * f; v[1] = a.y * f; v[2] = a.z * f; v[3] = a.w * f; v[4] = c.x * f; v[5] = c.y * f; v[6] = c.z * f; v[7] = c.w * f;
-            } else {
+        // ---- (unit, tile) items -> FP16 hi/lo rows of the operands (tiles beyond the last block were loaded as zeros)
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = 0.f;
-            }
+        for (int u = 0; u < HU_IPT; ++u) {
+            if (i_tile[u] < 0) continue;
+            const float f = i_dst[u] < 0 ? scale : 1.0f;
+            const float4 a = g0[2 * u], c = g0[2 * u + 1];
             uint32_t hh[4], hl[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) split_pair(v[2 * u], v[2 * u + 1], hh[u], hl[u]);
-            unsigned char* dst = sO + (q.y & 0x7fffffff) + t * HU_LBO;
+            split_pair(a.x * f, a.y * f, hh[0], hl[0]);
+            split_pair(a.z * f, a.w * f, hh[1], hl[1]);
+            split_pair(c.x * f, c.y * f, hh[2], hl[2]);
+            split_pair(c.z * f, c.w * f, hh[3], hl[3]);
+            unsigned char* dst = sO + (i_dst[u] & 0x7fffffff);
             *reinterpret_cast<uint4*>(dst) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
             *reinterpret_cast<uint4*>(dst + 8 * HU_SBO) = make_uint4(hl[0], hl[1], hl[2], hl[3]);      // the lo half: 64 rows down
         }
@@ -169,13 +163,16 @@ __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(c
                     if (l < nl) {
                         const uint64_t dA = umma_smem_desc(smem_u32(sO) + l * 2 * HU_MAT, HU_LBO, HU_SBO);
                         const uint64_t dB = umma_smem_desc(smem_u32(sO) + l * 2 * HU_MAT + HU_MAT, HU_LBO, HU_SBO);
-                        umma_f16(tbase + l * 128, dA, dB, idesc, it != 0);
+#pragma unroll
+                        for (int ks = 0; ks < HU_TPC / 2; ++ks)      // a K = 16 step = two tiles = 2 * HU_LBO bytes = 16 descriptor units
+                            umma_f16(tbase + l * 128, dA + (uint64_t)(ks * 16), dB + (uint64_t)(ks * 16), idesc, (it | ks) != 0);
                     }
                 }
                 umma_commit(mma_bar + ob);
             }
         }
-        if (warp == 0 && it + HU_STAGES < n_it) issue(ch + HU_STAGES, s);      // every thread has finished reading stage s
+#pragma unroll
+        for (int e = 0; e < 2 * HU_IPT; ++e) g0[e] = g1[e];
     }
 
     // ---- results: TMEM lane = accumulator row (this warp's quarter), 32 columns per warp group and layer
@@ -224,9 +221,8 @@ int launch_hidden_wgrad_umma(const SolveArgs& a, const HiddenGradPtrs& hp, cudaS
     const NcdeLayout& lo = a.lo;
     int n_items = 0;
     for (int l = 0; l < lo.n_hidden; ++l) n_items += lo.width[l] + lo.in_dim[l];
-    const int tile_floats = lo.act_off_du + (lo.act_floats - lo.act_off_delta[0]);
-    const size_t smem = (size_t)HU_STAGES * HU_TPC * tile_floats * 4 + 2 * (size_t)lo.n_hidden * 2 * HU_MAT + (size_t)n_items * 8 + 128;
-    if (smem > 227 * 1024) return ANCDE_EUNSUPPORTED;
+    const size_t smem = 2 * (size_t)lo.n_hidden * 2 * HU_MAT + 128;
+    if (smem > 227 * 1024 || HU_TPC * n_items > HU_IPT * HU_THREADS) return ANCDE_EUNSUPPORTED;
     const int64_t nblocks = (int64_t)lo.n_stages * lo.ntiles;
     const int64_t nchunks = (nblocks + HU_TPC - 1) / HU_TPC;
     int64_t grid = 148;
