@@ -1,4 +1,5 @@
-// Hidden-layer weight gradients of the fused NCDE solve on the tcgen05 tensor cores (tiles of 8 samples, <= 4 layers).
+// Hidden-layer weight gradients of the fused NCDE solve on the tcgen05 tensor cores (tiles of 8 samples; the layers'
+// accumulators must fit the 512 columns of tensor memory: 128 per layer, 64 where in_dim + 1 <= 32).
 //
 //   dW_l[o][k] = sum over every (stage, sample) row r of  delta_l[r][o] * in_l[r][k],      db_l[o] = sum_r delta_l[r][o]
 //
@@ -8,7 +9,7 @@
 // 128-bit loads, an FP16 hi/lo split and two 128-bit stores, and per chunk of 16 rows (two tiles) and layer ONE
 // tcgen05.mma (M = 128, N = 128, K = 16) accumulates all four hi/lo quadrants
 //     [delta_hi ; delta_lo] (128 rows)  x  [in_hi | 1 ; in_lo] (128 columns)
-// in tensor memory (128 columns per layer, <= 4 layers = the 512 columns of an SM); the lo x lo quadrant is simply not read.
+// in tensor memory (N = 128 columns per layer, or 64 = [32 | 32] when in_dim + 1 <= 32); the lo x lo quadrant is simply not read.
 // The bias gradient is the extra column in = 1.  delta is scaled by a power of two taken from max |gbar| (tracked by the
 // recurrent backward) so that the cotangents sit in FP16's range.  A CTA owns a contiguous range of chunks of 32 rows; the
 // items of a chunk are loaded straight into registers one chunk ahead (consecutive threads read consecutive 32-byte
@@ -30,7 +31,7 @@ constexpr int HU_IPT = 4;            // (unit, tile) items per thread and chunk,
 constexpr int HU_LBO = 128;          // bytes between the core matrices of the two tiles
 constexpr int HU_SBO = HU_TPC * HU_LBO;               // bytes between groups of 8 rows
 constexpr int HU_MAT = 16 * HU_SBO;  // one operand matrix: 128 rows
-constexpr int HU_MAXL = 4;
+constexpr int HU_MAXL = ANCDE_MAX_LAYERS;
 
 __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(const __grid_constant__ SolveArgs p,
                                                                                const __grid_constant__ HiddenGradPtrs hp, int chunks_per_cta,
@@ -41,6 +42,15 @@ __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
     const int nl = lo.n_hidden;
+    // accumulator columns of layer l: [cb[l], cb[l] + nb[l]), in_hi | 1 in the first half, in_lo in the second
+    __shared__ int nb[HU_MAXL], cb[HU_MAXL];
+    int ncols = 0;
+    for (int l = 0; l < nl; ++l) {
+        const int w = (lo.in_dim[l] + 1 <= 32) ? 64 : 128;
+        if (tid == 0) { nb[l] = w; cb[l] = ncols; }
+        ncols += w;
+    }
+    const uint32_t tmem_cols = ncols <= 32 ? 32u : (ncols <= 64 ? 64u : (ncols <= 128 ? 128u : (ncols <= 256 ? 256u : 512u)));
 
     // power-of-two scale that brings the largest stage cotangent to [1, 2): the layer cotangents are sums of such terms and
     // stay far below FP16's 65504
@@ -88,7 +98,8 @@ __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(c
             } else {                                           // B rows: in_l
                 const int k = r - lo.width[l];
                 i_src[u] = ((l == 0) ? 0 : lo.act_off_h[l - 1]) + k * 8;
-                i_dst[u] = l * 2 * HU_MAT + HU_MAT + (k >> 3) * HU_SBO + (k & 7) * 16 + t * HU_LBO;
+                // (bit 30: narrow layer -- its lo rows sit 32 rows down, not 64)
+                i_dst[u] = (l * 2 * HU_MAT + HU_MAT + (k >> 3) * HU_SBO + (k & 7) * 16 + t * HU_LBO) | ((lo.in_dim[l] + 1 <= 32) ? 0x40000000 : 0);
             }
         }
     }
@@ -110,7 +121,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(c
         mbar_init(mma_bar + 1, 1);
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc(&tslot, nl > 2 ? 512 : 256);
+    if (warp == 1) tmem_alloc(&tslot, tmem_cols);
     // operand buffers: zero (rows beyond a layer's units stay zero), the table
     for (int i = tid; i < 2 * op_bytes / 16; i += NT) reinterpret_cast<uint4*>(sOp)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
@@ -127,7 +138,6 @@ __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(c
     tc_fence_after();
     const uint32_t tbase = tslot;
 
-    const uint32_t idesc = umma_idesc_f16(128, 128, false);
     float4 g0[2 * HU_IPT];
     load_items(c0, g0);
     for (int it = 0; it < n_it; ++it) {
@@ -148,9 +158,9 @@ __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(c
             split_pair(a.z * f, a.w * f, hh[1], hl[1]);
             split_pair(c.x * f, c.y * f, hh[2], hl[2]);
             split_pair(c.z * f, c.w * f, hh[3], hl[3]);
-            unsigned char* dst = sO + (i_dst[u] & 0x7fffffff);
+            unsigned char* dst = sO + (i_dst[u] & 0x3fffffff);
             *reinterpret_cast<uint4*>(dst) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-            *reinterpret_cast<uint4*>(dst + 8 * HU_SBO) = make_uint4(hl[0], hl[1], hl[2], hl[3]);      // the lo half: 64 rows down
+            *reinterpret_cast<uint4*>(dst + ((i_dst[u] & 0x40000000) ? 4 : 8) * HU_SBO) = make_uint4(hl[0], hl[1], hl[2], hl[3]);      // the lo half
         }
         fence_async_smem();
         __syncthreads();
@@ -165,7 +175,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(c
                         const uint64_t dB = umma_smem_desc(smem_u32(sO) + l * 2 * HU_MAT + HU_MAT, HU_LBO, HU_SBO);
 #pragma unroll
                         for (int ks = 0; ks < HU_TPC / 2; ++ks)      // a K = 16 step = two tiles = 2 * HU_LBO bytes = 16 descriptor units
-                            umma_f16(tbase + l * 128, dA + (uint64_t)(ks * 16), dB + (uint64_t)(ks * 16), idesc, (it | ks) != 0);
+                            umma_f16(tbase + cb[l], dA + (uint64_t)(ks * 16), dB + (uint64_t)(ks * 16), umma_idesc_f16(128, nb[l], false), (it | ks) != 0);
                     }
                 }
                 umma_commit(mma_bar + ob);
@@ -183,35 +193,41 @@ __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(c
         const float inv = 1.0f / scale;
         const int wq = warp & 3, cg = warp >> 2;
         const int m = 32 * wq + lane;
-        const bool lo_row = m >= 64;                 // rows 64.. hold delta_lo: only their product with in_hi (columns < 64) counts
+        const bool lo_row = m >= 64;                 // rows 64.. hold delta_lo: only their product with in_hi (first half) counts
         const int o = lo_row ? m - 64 : m;
         for (int l = 0; l < nl; ++l) {
-            const int N = lo.width[l], Kin = lo.in_dim[l];
-            float v[16], v2[16];
-            const uint32_t ta = tbase + ((uint32_t)(32 * wq) << 16) + l * 128 + 32 * cg;
-            tmem_ld16x2(ta, ta + 16, v, v2);
-            if (o < N && !(lo_row && cg >= 2)) {
+            const int N = lo.width[l], Kin = lo.in_dim[l], half = nb[l] >> 1;
+            for (int c16 = cg; c16 < (nb[l] >> 4); c16 += 4) {           // 16 columns at a time, the four warp groups in turn
+                float v[16];
+                tmem_ld16(tbase + ((uint32_t)(32 * wq) << 16) + cb[l] + 16 * c16, v);
+                const bool second = 16 * c16 >= half;                       // in_lo columns
+                if (o < N && !(lo_row && second)) {
 #pragma unroll
-                for (int u = 0; u < 32; ++u) {
-                    const int n = 32 * cg + u, k = n & 63;
-                    const float val = (u < 16 ? v[u] : v2[u - 16]) * inv;
-                    if (k < Kin) atomicAdd(hp.gW[l] + (int64_t)o * Kin + k, val);
-                    else if (k == Kin && n < 64) atomicAdd(hp.gB[l] + o, val);
+                    for (int u = 0; u < 16; ++u) {
+                        const int k = 16 * c16 + u - (second ? half : 0);
+                        const float val = v[u] * inv;
+                        if (k < Kin) atomicAdd(hp.gW[l] + (int64_t)o * Kin + k, val);
+                        else if (k == Kin && !second) atomicAdd(hp.gB[l] + o, val);
+                    }
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tbase, nl > 2 ? 512 : 256);
+    if (warp == 1) tmem_dealloc(tbase, tmem_cols);
 }
 
 // true when this kernel takes the shape
 bool hidden_wgrad_umma_ok(const NcdeLayout& lo)
 {
     if (lo.TS != 8 || lo.n_hidden < 1 || lo.n_hidden > HU_MAXL) return false;
-    for (int l = 0; l < lo.n_hidden; ++l)
+    int ncols = 0;
+    for (int l = 0; l < lo.n_hidden; ++l) {
         if (lo.width[l] > 64 || lo.in_dim[l] + 1 > 64) return false;
+        ncols += (lo.in_dim[l] + 1 <= 32) ? 64 : 128;
+    }
+    if (ncols > 512) return false;
     if (lo.act_off_delta[0] < lo.act_off_du) return false;
     return true;
 }
