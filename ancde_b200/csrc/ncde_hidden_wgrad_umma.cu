@@ -27,12 +27,14 @@ struct HiddenGradPtrs { float* gW[ANCDE_MAX_LAYERS]; float* gB[ANCDE_MAX_LAYERS]
 
 constexpr int HU_THREADS = 512;
 constexpr int HU_TPC = 4;            // tiles of 8 samples per chunk = two K = 16 steps
-constexpr int HU_IPT = 4;            // (unit, tile) items per thread and chunk, loaded one chunk ahead into registers
 constexpr int HU_LBO = 128;          // bytes between the core matrices of the two tiles
 constexpr int HU_SBO = HU_TPC * HU_LBO;               // bytes between groups of 8 rows
 constexpr int HU_MAT = 16 * HU_SBO;  // one operand matrix: 128 rows
 constexpr int HU_MAXL = ANCDE_MAX_LAYERS;
 
+// HU_IPT: (unit, tile) items per thread and chunk; DEEP: loaded two chunks ahead instead of one (few items per thread: the
+// bytes in flight decide the HBM rate)
+template <int HU_IPT, bool DEEP>
 __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(const __grid_constant__ SolveArgs p,
                                                                                const __grid_constant__ HiddenGradPtrs hp, int chunks_per_cta,
                                                                                const unsigned* __restrict__ gmax_bits)
@@ -138,14 +140,15 @@ __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(c
     tc_fence_after();
     const uint32_t tbase = tslot;
 
-    float4 g0[2 * HU_IPT];
+    float4 g0[2 * HU_IPT], g1[2 * HU_IPT], g2[DEEP ? 2 * HU_IPT : 1];
     load_items(c0, g0);
+    if (DEEP) load_items(c0 + 1, g1);
     for (int it = 0; it < n_it; ++it) {
         const int64_t ch = c0 + it;
         const int ob = it & 1;
         unsigned char* sO = sOp + ob * op_bytes;
-        float4 g1[2 * HU_IPT];
-        load_items(ch + 1, g1);                              // one chunk ahead
+        if constexpr (DEEP) load_items(ch + 2, reinterpret_cast<float4 (&)[2 * HU_IPT]>(g2));      // two chunks ahead
+        else load_items(ch + 1, g1);                              // one chunk ahead
         if (it >= 2) mbar_wait(mma_bar + ob, (uint32_t)(((it - 2) >> 1) & 1));       // the products of chunk it-2 have read this buffer
         // ---- (unit, tile) items -> FP16 hi/lo rows of the operands (tiles beyond the last block were loaded as zeros)
 #pragma unroll
@@ -182,7 +185,10 @@ __global__ void __launch_bounds__(HU_THREADS, 1) ncde_hidden_wgrad_umma_kernel(c
             }
         }
 #pragma unroll
-        for (int e = 0; e < 2 * HU_IPT; ++e) g0[e] = g1[e];
+        for (int e = 0; e < 2 * HU_IPT; ++e) {
+            g0[e] = g1[e];
+            if (DEEP) g1[e] = g2[e];
+        }
     }
 
     // ---- results: TMEM lane = accumulator row (this warp's quarter), 32 columns per warp group and layer
@@ -238,7 +244,8 @@ int launch_hidden_wgrad_umma(const SolveArgs& a, const HiddenGradPtrs& hp, cudaS
     int n_items = 0;
     for (int l = 0; l < lo.n_hidden; ++l) n_items += lo.width[l] + lo.in_dim[l];
     const size_t smem = 2 * (size_t)lo.n_hidden * 2 * HU_MAT + 128;
-    if (smem > 227 * 1024 || HU_TPC * n_items > HU_IPT * HU_THREADS) return ANCDE_EUNSUPPORTED;
+    if (smem > 227 * 1024 || HU_TPC * n_items > 4 * HU_THREADS) return ANCDE_EUNSUPPORTED;
+    const bool few = HU_TPC * n_items <= 2 * HU_THREADS;
     const int64_t nblocks = (int64_t)lo.n_stages * lo.ntiles;
     const int64_t nchunks = (nblocks + HU_TPC - 1) / HU_TPC;
     int64_t grid = 148;
@@ -246,10 +253,11 @@ int launch_hidden_wgrad_umma(const SolveArgs& a, const HiddenGradPtrs& hp, cudaS
     const int per = (int)((nchunks + grid - 1) / grid);
     grid = (nchunks + per - 1) / per;
     const unsigned* gmax = reinterpret_cast<const unsigned*>(a.wpack + lo.off_gscale);   // written by the recurrent backward
-    ANCDE_CUDA(cudaFuncSetAttribute(ncde_hidden_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = few ? ncde_hidden_wgrad_umma_kernel<2, true> : ncde_hidden_wgrad_umma_kernel<4, false>;
+    ANCDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const char* names[3] = {"ncde_hidden_wgrad_plain", "ncde_hidden_wgrad_bottom", "ncde_hidden_wgrad_top"};
     prof_begin(names[lo.mode], stream);
-    ncde_hidden_wgrad_umma_kernel<<<(unsigned)grid, HU_THREADS, smem, stream>>>(a, hp, per, gmax);
+    kern<<<(unsigned)grid, HU_THREADS, smem, stream>>>(a, hp, per, gmax);
     prof_end(stream);
     count_launch();
     ANCDE_CUDA(cudaGetLastError());
