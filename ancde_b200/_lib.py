@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get('ANCDE_LIB') or os.path.join(_HERE, 'libancde_b200.so'
 
 MAX_LAYERS = 8
 MODE_PLAIN, MODE_BOTTOM, MODE_TOP = 0, 1, 2
-ENGINE_STREAMED, ENGINE_UMMA = 1, 3
+ENGINE_STREAMED, ENGINE_UMMA, ENGINE_LANE = 1, 3, 4
 ABI_VERSION = 7
 
 _f32p = ctypes.POINTER(ctypes.c_float)

@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = ['api.cu', 'spline.cu', 'heads.cu', 'ncde_host.cu', 'ncde_fwd.cu', 'ncde_bwd.cu', 'ncde_bwd4.cu', 'ncde_wgrad.cu', 'ncde_wgrad_mma.cu', 'ncde_wgrad_umma.cu', 'ncde_hidden_wgrad_umma.cu', 'ncde3_host.cu', 'ncde3_fwd.cu', 'ncde3_fwd1.cu']
+SOURCES = ['api.cu', 'spline.cu', 'heads.cu', 'ncde_host.cu', 'ncde_fwd.cu', 'ncde_lane.cu', 'ncde_bwd.cu', 'ncde_bwd4.cu', 'ncde_wgrad.cu', 'ncde_wgrad_mma.cu', 'ncde_wgrad_umma.cu', 'ncde_hidden_wgrad_umma.cu', 'ncde3_host.cu', 'ncde3_fwd.cu', 'ncde3_fwd1.cu']
 LIB = os.path.join(HERE, 'libancde_b200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']

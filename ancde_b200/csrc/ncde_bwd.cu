@@ -21,6 +21,7 @@
 #include "mma_common.cuh"
 #include "bwd_hidden.cuh"
 #include "ncde_bwd4.cuh"
+#include "ncde_lane.cuh"
 
 namespace ancde {
 
@@ -790,6 +791,12 @@ extern "C" int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream_)
     if (rc != ANCDE_OK) return rc;
     rc = pack_weights(d, lo, stream);   // the packed weights of the forward may have been reused
     if (rc != ANCDE_OK) return rc;
+    if (engine_of(d) == ANCDE_ENGINE_LANE) {
+        // the latency regime: one warp per sample (ncde_lane.cu); same saved layout, same weight-gradient kernels
+        rc = launch_lane_bwd(a, stream);
+        if (rc != ANCDE_OK) return rc;
+        return launch_wgrads(d, a, stream);
+    }
     V4Layout v4;
     const int engine = bwd_engine_of(d, lo, &v4);
     if (engine < 0) {

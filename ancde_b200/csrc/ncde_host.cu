@@ -3,6 +3,7 @@
 #include "mma_common.cuh"
 #include "ncde3_common.cuh"
 #include "ncde_bwd4.cuh"
+#include "ncde_lane.cuh"
 
 namespace ancde {
 
@@ -210,7 +211,9 @@ int make_layout(const ancde_ncde_desc* d, NcdeLayout* lo)
                         "ncde: single_stage needs n_steps = n_out = 1 and a plain / bottom field (n_steps=%d n_out=%d mode=%d)",
                         d->n_steps, d->n_out, d->mode);
     int TS = d->samples_per_cta;
-    if (TS == 0 && engine_of(d) == ANCDE_ENGINE_UMMA) TS = 8;    // the UMMA forward saves in tiles of 8 samples
+    const int engine = engine_of(d);
+    if (engine == ANCDE_ENGINE_LANE) TS = 1;                      // the lane engine: one warp = one sample = one tile
+    if (TS == 0 && engine == ANCDE_ENGINE_UMMA) TS = 8;           // the UMMA forward saves in tiles of 8 samples
     if (TS == 0) {
         // the largest tile that still gives every SM work (148 SMs); weight reuse grows with TS.
         // The backward's shared-memory footprint grows with TS too, so shrink until it fits.
@@ -284,6 +287,12 @@ int engine_of(const ancde_ncde_desc* d)
     if (!d) return ANCDE_ENGINE_STREAMED;
     if (d->single_stage) return (d->engine == 0 || d->engine == ANCDE_ENGINE_STREAMED) ? ANCDE_ENGINE_STREAMED : -1;
     if (d->engine == ANCDE_ENGINE_STREAMED) return d->engine;
+    // round 2, the latency regime: one warp per sample (ncde_lane.cu) when there are too few samples to give every SM a tile
+    // of the streamed engine anyway (its own rule for one sample per CTA) -- measured on B200: UEA shape, 32 samples,
+    // 10.6 -> see DESIGN.md ms per training step
+    const bool lane_ts = d->samples_per_cta == 0 || d->samples_per_cta == 1;
+    if (d->engine == ANCDE_ENGINE_LANE) return (lane_ts && lane_shape_ok(d)) ? ANCDE_ENGINE_LANE : -1;
+    if (d->engine == 0 && lane_ts && d->B < 240 && lane_shape_ok(d)) return ANCDE_ENGINE_LANE;
     if (d->engine != 0 && d->engine != ANCDE_ENGINE_UMMA) return -1;
     NcdeLayout st;
     V3Layout l3;
@@ -339,7 +348,7 @@ static int64_t bwd4_img_floats(const ancde_ncde_desc* d, const NcdeLayout& st)
 
 extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
 {
-    if (engine_of(d) < 0) { set_error("ncde: this shape is not supported by the UMMA engine"); return -1; }
+    if (engine_of(d) < 0) { set_error("ncde: this shape is not supported by the requested engine"); return -1; }
     NcdeLayout lo;
     if (make_layout(d, &lo) != ANCDE_OK) return -1;
     if (engine_of(d) == ANCDE_ENGINE_UMMA) {
@@ -371,7 +380,8 @@ extern "C" int ancde_ncde_forward(const ancde_ncde_desc* d, void* stream_)
     ANCDE_CHECK_ARG((d->save_act == nullptr) == (d->save_G == nullptr), "ncde_forward: save_act and save_G go together");
     const int engine = engine_of(d);
     if (engine < 0) {
-        set_error("ncde_forward: this shape is not supported by the UMMA engine (state / hidden widths <= 63, C <= 128, backward tile of 8)");
+        set_error("ncde_forward: this shape is not supported by the requested engine (UMMA: state / hidden widths <= 63, C <= 128, backward "
+                  "tile of 8; lane: C <= 32 with C4 a power of two, widths <= 64, Hd * C4 <= 256, one sample per tile)");
         return ANCDE_EUNSUPPORTED;
     }
     NcdeLayout lo;
@@ -392,5 +402,6 @@ extern "C" int ancde_ncde_forward(const ancde_ncde_desc* d, void* stream_)
     if (rc != ANCDE_OK) return rc;
     rc = pack_weights(d, lo, stream);
     if (rc != ANCDE_OK) return rc;
+    if (engine == ANCDE_ENGINE_LANE) return launch_lane_fwd(a, stream);
     return launch_fwd(a, stream);
 }

@@ -82,6 +82,12 @@ int ancde_spline_coeffs_f64(const double* times, const double* X, double* a, dou
  *                          layout, so ancde_ncde_backward (streamed kernels) works on its output.  Chosen by default
  *                          (engine = 0) when the shape is supported and the output layer has >= 50 000 weights; state and hidden widths <= 63.   */
 #define ANCDE_ENGINE_UMMA     3
+/*   ANCDE_ENGINE_LANE      the latency regime (round 2): ONE WARP integrates one sample, forward and backward -- no CTA barrier
+ *                          inside the stage loop, the RK4 state in registers, FP32 FMA.  For small batches of small networks
+ *                          (UEA: 32 samples x 724 dependent stages): C <= 32 with pad4(C) a power of two, state and hidden
+ *                          widths <= 64, Hd * pad4(C) <= 256, samples_per_cta 0 or 1.  Chosen by default (engine = 0) for such
+ *                          shapes when B < 240.  Same saved layout (one sample per tile) and weight-gradient kernels.            */
+#define ANCDE_ENGINE_LANE     4
 
 typedef struct ancde_ncde_desc {
     /* ---- shapes ---- */
@@ -124,7 +130,7 @@ typedef struct ancde_ncde_desc {
     float* grad_bias[ANCDE_MAX_LAYERS + 1];
     float* grad_attention;     /* TOP, or NULL (adjoint-mode gradient flow): (att_L, B, att_C) accumulated into */
     int32_t samples_per_cta;   /* streamed engine only: 0 = let the library choose (8, 4, 2 or 1) */
-    int32_t engine;            /* 0 = library default; ANCDE_ENGINE_STREAMED or _UMMA (see above) */
+    int32_t engine;            /* 0 = library default; ANCDE_ENGINE_STREAMED, _UMMA or _LANE (see above) */
     int32_t single_stage;      /* 1 = evaluate only the vector field at (t_start, z0): k_out (1, B, Hd) = f(z0) dX/dt(t_start), the
                                 * building block of adaptive solvers driven from the host (dopri5).  n_steps = n_out = 1; streamed
                                 * engine.  Backward: grad_k_out (B, Hd) is the cotangent of k_out, grad_z_out is not read. */

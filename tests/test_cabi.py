@@ -81,6 +81,14 @@ def test_engine_resolution_runs_without_a_gpu():
     a = L.ancde_ncde_wpack_floats(ctypes.byref(desc(35, 49, [49] * 4, _lib.ENGINE_STREAMED)))
     b = L.ancde_ncde_wpack_floats(ctypes.byref(desc(35, 49, [49] * 4, _lib.ENGINE_UMMA)))
     assert b > a > 0
+    # round 2: small batches of small networks resolve to the lane engine (one warp per sample); it refuses what it cannot run
+    small = desc(6, 12, [12, 12])
+    small.B = 200
+    assert L.ancde_ncde_engine(ctypes.byref(small)) == _lib.ENGINE_LANE
+    assert L.ancde_ncde_wpack_floats(ctypes.byref(small)) > 0 and L.ancde_ncde_save_G_floats(ctypes.byref(small)) == 284 * 200 * 12 * 8
+    assert L.ancde_ncde_engine(ctypes.byref(desc(6, 12, [12, 12], _lib.ENGINE_LANE))) == _lib.ENGINE_LANE
+    assert L.ancde_ncde_engine(ctypes.byref(desc(35, 49, [49] * 4, _lib.ENGINE_LANE))) == -1     # pad4(C) = 36 does not divide 32
+    assert L.ancde_ncde_engine(ctypes.byref(desc(6, 12, [12, 80], _lib.ENGINE_LANE))) == -1      # a layer wider than 64
 
 
 def test_no_cpu_fallback():
