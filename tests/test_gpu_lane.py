@@ -95,26 +95,30 @@ def _seeded(workload, B):
 
 
 @pytest.mark.parametrize('workload,B', [('uea', 32), ('stock', 37), ('mujoco', 70), ('stock', 700)])
-def test_lane_engine_agrees_with_the_streamed_engine(workload, B):
-    """Same inputs, same weights, two engines: predictions and every gradient agree to FP32 summation order.  B = 700 runs
-    four warps per CTA with a ragged last CTA (forced: the library would not pick the lane engine at that size)."""
+def test_lane_engine_agrees_with_the_streamed_engine(workload, B, monkeypatch):
+    """Same inputs, same weights, two engines: predictions and every gradient agree to FP32 summation order -- for the
+    kernels specialised at compile time for the BASELINE networks AND for the same code with run-time bounds
+    (ANCDE_LANE_DYNAMIC=1, what any other supported shape runs).  B = 700 is forced: the library would not pick the lane
+    engine at that size."""
     import ancde_b200
     from ancde_b200 import _lib
     cfg, model, times, coeffs, fi = _seeded(workload, B)
     res = {}
-    for name, eng in (('lane', _lib.ENGINE_LANE), ('streamed', _lib.ENGINE_STREAMED)):
+    for name, eng in (('lane', _lib.ENGINE_LANE), ('lane_dynamic', _lib.ENGINE_LANE), ('streamed', _lib.ENGINE_STREAMED)):
         model.zero_grad(set_to_none=True)
+        monkeypatch.setenv('ANCDE_LANE_DYNAMIC', '1' if name == 'lane_dynamic' else '0')
         with forced_engine(eng):
             pred = model(times, coeffs, fi, 1.0, stream=cfg['stream'], adjoint=False)
             (pred * loss_weights(pred.shape).cuda()).sum().backward()
             torch.cuda.synchronize()
         res[name] = (pred.detach().clone(), ancde_b200.load_h_prime('lane_h_prime').clone(),
                      {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
-    assert rel_err(res['lane'][0], res['streamed'][0]) < 2e-5, workload
-    assert rel_err(res['lane'][1], res['streamed'][1]) < 2e-5, workload
-    assert res['lane'][2].keys() == res['streamed'][2].keys()
-    for k in res['lane'][2]:
-        assert rel_err(res['lane'][2][k], res['streamed'][2][k]) < 2e-4, (workload, k)
+    for name in ('lane', 'lane_dynamic'):
+        assert rel_err(res[name][0], res['streamed'][0]) < 2e-5, (workload, name)
+        assert rel_err(res[name][1], res['streamed'][1]) < 2e-5, (workload, name)
+        assert res[name][2].keys() == res['streamed'][2].keys()
+        for k in res[name][2]:
+            assert rel_err(res[name][2][k], res['streamed'][2][k]) < 2e-4, (workload, name, k)
 
 
 def test_library_picks_the_lane_engine_for_small_batches_of_small_networks():
