@@ -348,7 +348,10 @@ static int64_t bwd4_img_floats(const ancde_ncde_desc* d, const NcdeLayout& st)
 
 extern "C" int64_t ancde_ncde_wpack_floats(const ancde_ncde_desc* d)
 {
-    if (engine_of(d) < 0) { set_error("ncde: this shape is not supported by the requested engine"); return -1; }
+    if (engine_of(d) < 0) {
+        set_error("ncde: this shape is not supported by the requested engine (%s)", d->engine == ANCDE_ENGINE_LANE ? "lane" : "UMMA");
+        return -1;
+    }
     NcdeLayout lo;
     if (make_layout(d, &lo) != ANCDE_OK) return -1;
     if (engine_of(d) == ANCDE_ENGINE_UMMA) {

@@ -4,25 +4,31 @@
 // The streamed engine gives a tile of samples a CTA built for throughput and pays, per stage, a hidden-layer chain on ONE
 // warp whose every shared load is waited for, index arithmetic spread over a few dozen threads and two or three CTA
 // barriers: 5-7 k cycles per stage for a network of ~10 k FMAs.  With 32 samples there is nothing to overlap that
-// latency with.  Measured on B200 (ncu, UEA shape): a single warp issues one instruction every ~3.5 cycles whatever it
-// does, so the time of a stage is its longest per-warp instruction count -- the first version of this engine (one warp
-// per sample, ~2000 instructions per stage) was no faster than the streamed kernel.  Hence:
+// latency with.  What ncu showed on B200 (UEA shape; every state of this file was profiled): a warp that is alone on
+// its scheduler issues one instruction every 4-7 cycles WHATEVER it does (fixed-latency dependencies, shared-memory
+// round trips), so the time of a stage is the per-warp INSTRUCTION COUNT of its critical warp:
+//   * one warp per sample, every dot product unrolled with predicates (first version): ~2000 instructions per stage,
+//     no faster than the streamed kernel (UEA step 8.7 ms against 10.7);
+//   * a CTA per sample with layer tables in shared memory and run-time loop bounds: ~800 per warp and stage (8.4 ms);
+//   * the network STRUCTURE as compile-time constants (LaneStatic): 400-550 (5.2 ms);
+//   * shared-memory base addresses pinned in registers (the compiler rematerialised them from kernel parameters at
+//     every use: a third of the instructions) and units split over threads only above 4 pieces per thread: 4.65 ms.
 //
-//   ONE SMALL CTA PER SAMPLE, ONE THREAD PER OUTPUT-LAYER COLUMN (T = 32 * ceil(Hd * C4 / 32) threads, 1..8 warps on the
-//   SM's four schedulers), every phase spread over all T threads so that no warp executes more than a few hundred
-//   instructions per stage:
+//   ONE SMALL CTA PER SAMPLE, ONE THREAD PER OUTPUT-LAYER COLUMN (T = 32 * ceil(max(Hd * C4, widest layer) / 32) threads:
+//   1..8 warps on the SM's four schedulers), every phase spread over the threads it can use:
 //   * control (spline derivative, attention product): thread = column (i, j) evaluates ITS channel j from coefficients
 //     loaded a stage ahead                                    [cdeint_module.py:58-60,103-129; interpolate.py:261-303]
-//   * hidden ReLU layers: KP = T / units threads per unit split the dot product (128-bit pieces of the weight row and of
-//     the layer input in shared memory), log2(KP) shuffles      [vector_fields.py:205-216,237-247]
+//   * hidden ReLU layers: thread = unit, or KP threads per unit when a dot product has more than LANE_SPLIT 128-bit
+//     pieces per thread (weight row and layer input in shared memory, log2(KP) shuffles)
+//                                                             [vector_fields.py:205-216,237-247]
 //   * output layer: thread = column: full dot product, tanh, times dU of its channel; the contraction over j is
 //     log2(C4) shuffles inside groups of C4 lanes              [vector_fields.py:216-218, cdeint_module.py:61,133]
 //   * the RK4 recurrence (3/8 rule) of row i in registers, replicated over the C4 threads of the row
 //     [torchdiffeq rk4_alt_step_func]
-//   One CTA barrier per layer and one per stage (a __syncwarp when the CTA is a single warp).
+//   One CTA barrier per layer and one per stage (a __syncwarp when the CTA is a single warp: UEA's attention network).
 // The backward walks the stages in reverse with the same ownership: saved activations and tanh outputs of a stage arrive
 // by two TMA bulk copies on an mbarrier three stages ahead; the output layer's vector-Jacobian product runs with
-// KP = T / K threads per hidden unit over a padded copy of W_out^T [k][columns] (column-contiguous, conflict free) and
+// KP threads per hidden unit over a padded copy of W_out^T [k][columns] (column-contiguous, conflict free) and
 // the pre-activation cotangent broadcast from shared memory; hidden layers backwards as in the forward.
 // Both kernels read / write the streamed engine's TS = 1 layout (NcdeLayout), so the weight-gradient kernels and the
 // packed weights are shared.  C4 must divide 32 (C <= 32, C4 in {4, 8, 16, 32}), Hd * C4 <= 256, widths <= 64.
@@ -35,6 +41,9 @@ namespace ancde {
 
 namespace {
 
+#ifndef LANE_SPLIT
+#define LANE_SPLIT 4
+#endif
 constexpr int LANE_NBUF = 4;       // backward: stages of saved activations in flight
 constexpr int LANE_ML = ANCDE_MAX_LAYERS;
 
@@ -56,11 +65,9 @@ struct LaneLayer {
 __host__ __device__ constexpr int lane_pad4(int x) { return (x + 3) & ~3; }
 __host__ __device__ constexpr int lane_pad4odd(int x) { return 4 * (((x + 3) >> 2) | 1); }
 __host__ __device__ constexpr int lane_max(int a, int b) { return a > b ? a : b; }
-// threads of a CTA: one per output-layer column, at least four per unit of the widest layer, at least two warps
-__host__ __device__ constexpr int lane_threads_of(int NCP, int Hmax)
-{
-    return 32 * ((lane_max(lane_max(NCP, 4 * Hmax > 256 ? lane_max(256, Hmax) : 4 * Hmax), 64) + 31) / 32);
-}
+// threads of a CTA: one per output-layer column and at least one per unit of the widest layer -- a single warp (and
+// __syncwarp instead of CTA barriers) for the smallest networks
+__host__ __device__ constexpr int lane_threads_of(int NCP, int Hmax) { return 32 * ((lane_max(NCP, Hmax) + 31) / 32); }
 
 // The STRUCTURE of a network (layer count and widths, state size, padded channel count) as compile-time constants: every
 // loop bound, pieces-per-thread count and shuffle depth of the kernels folds, the layer loops unroll to exactly NL layers
@@ -110,11 +117,14 @@ __device__ __forceinline__ float lane_dot(const float* __restrict__ w, const flo
     return (a0 + a1) + (a2 + a3);
 }
 
-// log2 of the threads that share one unit of a layer of N units in a CTA of T threads (at most 8 per unit)
-__host__ __device__ inline int lane_kshift(int T, int N)
+// log2 of the threads that share one unit of a layer of N units whose dot products have nk4 128-bit pieces, in a CTA of T
+// threads.  A unit is split (one shuffle step per doubling) while a thread would have more than LANE_SPLIT pieces: measured on
+// B200, UEA shape (10 pieces per unit in the forward, 40 in the backward's output layer): thresholds 12 / 4 / 2 give
+// 5.05 / 4.67 / 4.65 ms per training step.
+__host__ __device__ constexpr int lane_kshift(int T, int N, int nk4)
 {
     int s = 0;
-    while (s < 3 && (N << (s + 1)) <= T) ++s;
+    while (s < 3 && (N << (s + 1)) <= T && (nk4 >> s) > LANE_SPLIT) ++s;
     return s;
 }
 
@@ -122,7 +132,7 @@ __host__ __device__ inline int lane_kshift(int T, int N)
 __device__ __forceinline__ LaneLayer lane_layer(int tid, int T, int N, int nk4, int stride)
 {
     LaneLayer L;
-    const int ksh = lane_kshift(T, N), KP = 1 << ksh;
+    const int ksh = lane_kshift(T, N, nk4), KP = 1 << ksh;
     const int o = tid >> ksh, part = tid & (KP - 1);
     const int oc = o < N ? o : N - 1;
     L.wofs = oc * stride + 4 * part;
@@ -143,6 +153,23 @@ __host__ __device__ inline int lane_wt_stride(int NCP, int kshift)
 {
     const int want = (4 << kshift) & 31;
     return NCP + ((want - NCP % 32) + 32) % 32;
+}
+
+// A shared-memory pointer the compiler must keep in a register: measured with ncu, a third of the instructions of a stage
+// were smem base addresses REMATERIALISED from kernel parameters at every use (the compiler considers that free).
+template <typename P>
+__device__ __forceinline__ P* lane_pin(P* p)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return reinterpret_cast<P*>(__cvta_shared_to_generic(a));
+}
+
+// CTA-wide synchronisation: a __syncwarp when the CTA is one warp (T folds to a constant for the static shapes)
+__device__ __forceinline__ void lane_sync(int T)
+{
+    if (T == 32) __syncwarp();
+    else __syncthreads();
 }
 
 struct LaneCtl { float b, c2, d3, a, hp, frac; };
@@ -242,6 +269,19 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
         }
     }
 
+    const float* pw[LANE_ML];
+    const float* px[LANE_ML];
+    float* po[LANE_ML];
+#pragma unroll
+    for (int l = 0; l < S::NL; ++l) {
+        pw[l] = px[l] = nullptr; po[l] = nullptr;
+        if (l < NL) {
+            pw[l] = lane_pin(sHW + ly[l].wofs);
+            px[l] = lane_pin(((l == 0) ? sIn : ((l & 1) ? sT0 : sT1)) + ly[l].xofs);
+            po[l] = lane_pin(((l & 1) ? sT1 : sT0) + (ly[l].out >= 0 ? ly[l].out : 0));
+        }
+    }
+
     const int tile = bg;
     const bool jvalid = j < lo.C;
     const bool wr = cv && j == 0;                            // the thread that writes row i
@@ -252,8 +292,10 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
     const int nk4o = (K + 3) >> 2;
     const bool saving = p.save_act != nullptr;
     const bool top = lo.mode == ANCDE_MODE_TOP;
-    const float* lastbuf = ((NL - 1) & 1) ? sT1 : sT0;
-    const float* wo_row = sWot + (size_t)(cv ? col : 0) * KPS;
+    const float* lastbuf = lane_pin(((NL - 1) & 1) ? sT1 : sT0);
+    const float* wo_row = lane_pin(sWot + (size_t)(cv ? col : 0) * KPS);
+    float* const sIn_i = lane_pin(sIn + (cv ? i : 0));
+    const float* const sTimesP = lane_pin(sTimes);
     const float bo = sBo[cv ? col : 0];
     // per-stage strides of the output pointers
     const size_t act_stride = (size_t)lo.ntiles * lo.act_floats, g_stride = (size_t)lo.ntiles * NCP, k_stride = (size_t)lo.B * Hd;
@@ -275,8 +317,8 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
     LaneCtl ctl;
     float t0 = grid_time(0, lo.n_steps, p.t_start, p.t_end, p.step, p.grid);
     float t1 = grid_time(1, lo.n_steps, p.t_start, p.t_end, p.step, p.grid);
-    lane_ctl_issue(p, sTimes, cnt, t0, 0, jvalid, obase, abase, hbase, ctl);
-    __syncthreads();
+    lane_ctl_issue(p, sTimesP, cnt, t0, 0, jvalid, obase, abase, hbase, ctl);
+    lane_sync(T);
 
     for (int k = 0; k < lo.n_steps; ++k) {
         const float dt = __fsub_rn(t1, t0);
@@ -292,7 +334,7 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
             if (have_next) {
                 if (top && ++mcall == lo.n_hp - 1) mcall = 0;
                 const float tsn = (s == 0) ? ts1 : (s == 1 ? ts2 : (s == 2 ? ts3 : t1));      // stage 0 of the next step is at its t0 = t1
-                lane_ctl_issue(p, sTimes, cnt, tsn, mcall, jvalid, obase, abase, hbase, ctl);
+                lane_ctl_issue(p, sTimesP, cnt, tsn, mcall, jvalid, obase, abase, hbase, ctl);
             }
             if (act && tid < C4) {
                 act[lo.act_off_du + duidx] = dU;
@@ -303,16 +345,16 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
 #pragma unroll
             for (int l = 0; l < S::NL; ++l) {
                 if (l < NL) {
-                    const float* in = (l == 0) ? sIn : ((l & 1) ? sT0 : sT1);
-                    float* out = (l & 1) ? sT1 : sT0;
-                    float acc = lane_dot(sHW + ly[l].wofs, in + ly[l].xofs, ly[l].step, ly[l].np, ly[l].npmin, ly[l].npmax);
-                    for (int m = 4; m < ly[l].step; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m >> 2);
+                    float acc = lane_dot(pw[l], px[l], ly[l].step, ly[l].np, ly[l].npmin, ly[l].npmax);
+                    const int kp = S::kStatic ? (1 << lane_kshift(S::T, S::width(l), ((l == 0 ? S::Hd : S::width(l > 0 ? l - 1 : 0)) + 3) >> 2))
+                                              : (ly[l].step >> 2);
+                    for (int m = 1; m < kp; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
                     if (ly[l].out >= 0) {
                         const float v = fmaxf(acc + ly[l].bias, 0.f);
-                        out[ly[l].out] = v;
+                        *po[l] = v;
                         if (act) act[ly[l].aofs] = v;
                     }
-                    __syncthreads();
+                    lane_sync(T);
                 }
             }
 
@@ -361,14 +403,14 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
                     zin = y1;
                 }
                 if (wr) {
-                    sIn[i] = zin;
+                    *sIn_i = zin;
                     if (act_next && have_next) act_next[i] = zin;
                 }
             }
             act = act_next;
             if (gsave) gsave += g_stride;
             if (kout) kout += k_stride;
-            __syncthreads();
+            lane_sync(T);
         }
         t0 = t1;
         t1 = t2;
@@ -391,7 +433,7 @@ __global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constan
     const int HP = pad4(S::kStatic ? S::Hmax : lo.Hmax);
     const int AF = lo.act_fwd_floats;
     const bool need_att = (lo.mode == ANCDE_MODE_TOP) && (p.grad_attention != nullptr);
-    const int kso = lane_kshift(T, K);                       // output layer backwards: 2^kso threads per hidden unit
+    const int kso = lane_kshift(T, K, NCP >> 2);             // output layer backwards: 2^kso threads per hidden unit
     const int SW = lane_wt_stride(NCP, kso);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -451,6 +493,26 @@ __global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constan
         }
     }
 
+    const float* pw[LANE_ML];
+    const float* px[LANE_ML];
+    float* po[LANE_ML];
+#pragma unroll
+    for (int l = 0; l < S::NL; ++l) {
+        pw[l] = px[l] = nullptr; po[l] = nullptr;
+        if (l < NL) {
+            pw[l] = lane_pin(sWtb + ly[l].wofs);
+            px[l] = lane_pin((((l + 1) & 1) ? sD1 : sD0) + ly[l].xofs);
+            po[l] = lane_pin((l == 0 ? sZb : ((l & 1) ? sD1 : sD0)) + (ly[l].out >= 0 ? ly[l].out : 0));
+        }
+    }
+    const float* const pwo = lane_pin(sWt + lyo.wofs);
+    const float* const pxo = lane_pin(sPre + lyo.xofs);
+    float* const poo = lane_pin(sDlast + (lyo.out >= 0 ? lyo.out : 0));
+    float* const sPre_c = lane_pin(sPre + (cv ? col : 0));
+    const float* const sZb_i = lane_pin(sZb + (cv ? i : 0));
+    const float* const sActP = lane_pin(sActBuf);
+    const float* const sGP = lane_pin(sGBuf + (cv ? col : 0));
+
     const int tile = bg;
     const bool wr = cv && j == 0;
     const int duidx = (j >> 2) * lo.DUS + (j & 3);
@@ -509,14 +571,13 @@ __global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constan
             if (wr) act[lo.act_off_gbar + i] = gv;           // for the weight-gradient kernels
             gmax = fmaxf(gmax, fabsf(gv));
             mbar_wait(bars + slot, (uint32_t)((r / LANE_NBUF) & 1));
-            const float* sAct = sActBuf + (size_t)slot * AF;
-            const float* sG = sGBuf + (size_t)slot * NCP;
+            const float* sAct = sActP + slot * AF;
 
             // ---- pre_bar = gbar * dU * (1 - G^2) of this thread's column; cotangent of dU for the attention
             {
-                const float g = cv ? sG[col] : 0.f;
+                const float g = cv ? sGP[slot * NCP] : 0.f;
                 const float dU = sAct[lo.act_off_du + duidx];
-                if (cv) sPre[col] = gv * dU * fmaf(-g, g, 1.0f);
+                if (cv) *sPre_c = gv * dU * fmaf(-g, g, 1.0f);
                 if (need_att) {
                     // dUbar[j] = sum_i gbar[i] G[i][j]: the rows of this warp by shuffles, the warps through shared memory
                     float a = gv * g * sAct[lo.act_off_duda + duidx];
@@ -524,7 +585,7 @@ __global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constan
                     if (lane < C4) sAtt[warp * C4 + lane] = a;
                 }
             }
-            __syncthreads();
+            lane_sync(T);
             if (need_att && tid < C4) {
                 float a = 0.f;
                 for (int w = 0; w < W; ++w) a += sAtt[w * C4 + tid];
@@ -542,40 +603,40 @@ __global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constan
 
             // ---- hbar[k] = sum_col W_out[col][k] pre_bar[col]: 2^kso threads per unit, then delta = hbar * relu'(h)
             {
-                float acc = lane_dot(sWt + lyo.wofs, sPre + lyo.xofs, lyo.step, lyo.np, lyo.npmin, lyo.npmax);
-                for (int m = 4; m < lyo.step; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m >> 2);
+                float acc = lane_dot(pwo, pxo, lyo.step, lyo.np, lyo.npmin, lyo.npmax);
+                for (int m = 1; m < (1 << kso); m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
                 if (lyo.out >= 0) {
                     const float v = (sAct[lyo_mask] > 0.f) ? acc : 0.f;
-                    sDlast[lyo.out] = v;
+                    *poo = v;
                     act[lyo.aofs] = v;
                 }
             }
-            __syncthreads();
+            lane_sync(T);
 
             // ---- hidden layers backwards: delta_{l-1} = (W_l^T delta_l) * relu'(h_{l-1}); the stage-input cotangent is W_0^T delta_0
 #pragma unroll
             for (int l = S::NL - 1; l >= 0; --l) {
                 if (l < NL) {
-                    const float* in = ((l + 1) & 1) ? sD1 : sD0;
-                    float* out = (l & 1) ? sD1 : sD0;
-                    float acc = lane_dot(sWtb + ly[l].wofs, in + ly[l].xofs, ly[l].step, ly[l].np, ly[l].npmin, ly[l].npmax);
-                    for (int m = 4; m < ly[l].step; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m >> 2);
+                    float acc = lane_dot(pw[l], px[l], ly[l].step, ly[l].np, ly[l].npmin, ly[l].npmax);
+                    const int kp = S::kStatic ? (1 << lane_kshift(S::T, l == 0 ? S::Hd : S::width(l > 0 ? l - 1 : 0), (S::width(l) + 3) >> 2))
+                                              : (ly[l].step >> 2);
+                    for (int m = 1; m < kp; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
                     if (ly[l].out >= 0) {
                         if (l > 0) {
                             const float v = (sAct[lmask[l]] > 0.f) ? acc : 0.f;
-                            out[ly[l].out] = v;
+                            *po[l] = v;
                             act[ly[l].aofs] = v;              // for the hidden weight-gradient kernel
                         } else {
-                            sZb[ly[l].out] = acc;             // cotangent of the stage input
+                            *po[l] = acc;                     // cotangent of the stage input (sZb)
                         }
                     }
-                    __syncthreads();
+                    lane_sync(T);
                 }
             }
 
             // ---- RK4 adjoint recurrence of row i
             {
-                const float v = cv ? sZb[i] : 0.f;
+                const float v = cv ? *sZb_i : 0.f;
                 if (s == 3) V4 = v;
                 else if (s == 2) V3 = v;
                 else if (s == 1) V2 = v;
@@ -604,7 +665,7 @@ size_t lane_fwd_smem(const NcdeLayout& lo)
 }
 size_t lane_bwd_smem(const NcdeLayout& lo, int T)
 {
-    const int SW = lane_wt_stride(lo.NCP, lane_kshift(T, lo.K));
+    const int SW = lane_wt_stride(lo.NCP, lane_kshift(T, lo.K, lo.NCP >> 2));
     size_t f = pad4(lo.hiddenb_floats) + (size_t)lo.K * SW + LANE_NBUF * ((size_t)lo.act_fwd_floats + lo.NCP) +
                lo.NCP + 3 * (size_t)pad4(lo.Hmax) + (size_t)(T / 32) * lo.C4;
     return f * 4 + LANE_NBUF * 8;

@@ -1,11 +1,11 @@
-"""GPU parity of the lane engine (csrc/ncde_lane.cu: one warp integrates one sample -- the latency regime of small
-batches of small networks, SURVEY section 7 "hard parts" / UEA B = 32).
+"""GPU parity of the lane engine (csrc/ncde_lane.cu: one small CTA per sample, one thread per output column -- the latency
+regime of small batches of small networks, SURVEY section 7 "hard parts" / UEA B = 32).
 
 * forced on every golden case of the unmodified reference: the shapes it must take (Stock, Mujoco, UEA: C4 = 8 / 16 / 4,
   hard elementwise and soft timewise attention) meet the north-star bars; the others are refused cleanly;
 * the streamed engine forced on the same small cases keeps ITS coverage (the library now picks the lane engine there);
 * both engines write the same saved layout: the lane engine against the streamed one on seeded batches at tight bars,
-  including batches with more than one warp per CTA and a ragged last CTA;
+  for the kernels specialised at compile time for the BASELINE networks and for the run-time-bounds code;
 * the CPU oracle on a seeded UEA batch of the BASELINE size (32 samples, 724 stages).
 """
 import ctypes
