@@ -175,12 +175,17 @@ __device__ __forceinline__ void lane_sync(int T)
 struct LaneCtl { float b, c2, d3, a, hp, frac; };
 
 // Global loads of the control of the stage at time ts (call counter m) for this thread's channel; consumed a stage later.
-__device__ __forceinline__ void lane_ctl_issue(const SolveArgs& p, const float* sTimes, int& cnt, float ts, int m, bool jvalid,
+// tknot = times[cnt] (+inf past the last knot) is carried in a register: the loop compares against it and only reloads when the
+// count advances -- a shared-memory round trip per comparison sat on every warp's critical path otherwise.
+__device__ __forceinline__ void lane_ctl_issue(const SolveArgs& p, const float* sTimes, int& cnt, float& tknot, float ts, int m, bool jvalid,
                                                int obase, int abase, int hbase, LaneCtl& r)
 {
     const NcdeLayout& lo = p.lo;
     // index = clamp(#(times < t) - 1, 0, L-2): the LEFT piece at a knot (interpolate.py:261-267)
-    while (cnt < lo.L && sTimes[cnt] < ts) ++cnt;
+    while (tknot < ts) {
+        ++cnt;
+        tknot = (cnt < lo.L) ? sTimes[cnt] : __int_as_float(0x7f800000);
+    }
     int idx = cnt - 1;
     idx = idx < 0 ? 0 : (idx > lo.L - 2 ? lo.L - 2 : idx);
     r.frac = __fsub_rn(ts, sTimes[idx]);
@@ -215,7 +220,8 @@ __device__ __forceinline__ void lane_ctl_finish(int mode, const LaneCtl& r, floa
 }
 
 // ---------------------------------------------------------------------------------------------------------- forward
-template <class S>
+// SAVE: training (save_act / save_G written) or inference -- a template parameter so that no store carries a null check
+template <class S, bool SAVE>
 __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constant__ SolveArgs p)
 {
     const NcdeLayout& lo = p.lo;
@@ -290,7 +296,6 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
     const int hbase = bg * lo.C + j;
     const int duidx = (j >> 2) * lo.DUS + (j & 3);           // du_index(j, 0, 1, DUS)
     const int nk4o = (K + 3) >> 2;
-    const bool saving = p.save_act != nullptr;
     const bool top = lo.mode == ANCDE_MODE_TOP;
     const float* lastbuf = lane_pin(((NL - 1) & 1) ? sT1 : sT0);
     const float* wo_row = lane_pin(sWot + (size_t)(cv ? col : 0) * KPS);
@@ -299,25 +304,28 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
     const float bo = sBo[cv ? col : 0];
     // per-stage strides of the output pointers
     const size_t act_stride = (size_t)lo.ntiles * lo.act_floats, g_stride = (size_t)lo.ntiles * NCP, k_stride = (size_t)lo.B * Hd;
-    float* act = saving ? p.save_act + (size_t)tile * lo.act_floats : nullptr;
-    float* gsave = p.save_G ? p.save_G + (size_t)tile * NCP + (cv ? col : 0) : nullptr;
-    float* kout = p.k_out ? p.k_out + (size_t)bg * Hd + (cv ? i : 0) : nullptr;
+    // running pointers (never dereferenced when the buffer is absent)
+    float* act = p.save_act + (size_t)tile * lo.act_floats;
+    float* gsave = p.save_G + (size_t)tile * NCP + (cv ? col : 0);
+    float* kout = p.k_out + (size_t)bg * Hd + (cv ? i : 0);
+    const bool have_kout = p.k_out != nullptr;
 
     float y = cv ? p.z0[(int64_t)bg * Hd + i] : 0.f;
     float k1 = 0.f, k2 = 0.f, k3 = 0.f;
     if (wr) {
         sIn[i] = y;
         p.z_out[(int64_t)bg * Hd + i] = y;                   // solution[0] = y0
-        if (saving) act[i] = y;
+        if (SAVE) act[i] = y;
     }
     int cnt = 0;        // knots strictly below the current stage time (monotone)
+    float tknot = sTimesP[0];
     int jout = 1;       // next requested output time
     float tout = (lo.n_out > 1) ? __ldg(p.t_out + 1) : 0.f;
     int mcall = 0;      // call counter of the stage whose control is being loaded, modulo n_hp - 1
     LaneCtl ctl;
     float t0 = grid_time(0, lo.n_steps, p.t_start, p.t_end, p.step, p.grid);
     float t1 = grid_time(1, lo.n_steps, p.t_start, p.t_end, p.step, p.grid);
-    lane_ctl_issue(p, sTimesP, cnt, t0, 0, jvalid, obase, abase, hbase, ctl);
+    lane_ctl_issue(p, sTimesP, cnt, tknot, t0, 0, jvalid, obase, abase, hbase, ctl);
     lane_sync(T);
 
     for (int k = 0; k < lo.n_steps; ++k) {
@@ -327,16 +335,16 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
 #pragma unroll 1
         for (int s = 0; s < 4; ++s) {
             const bool have_next = 4 * k + s + 1 < lo.n_stages;
-            float* act_next = act ? act + act_stride : nullptr;
+            float* act_next = act + act_stride;
             // (1) control of this stage from the registers loaded a stage ago; the loads of the next stage go out now
             float dU, duda;
             lane_ctl_finish(lo.mode, ctl, dU, duda);
             if (have_next) {
                 if (top && ++mcall == lo.n_hp - 1) mcall = 0;
                 const float tsn = (s == 0) ? ts1 : (s == 1 ? ts2 : (s == 2 ? ts3 : t1));      // stage 0 of the next step is at its t0 = t1
-                lane_ctl_issue(p, sTimesP, cnt, tsn, mcall, jvalid, obase, abase, hbase, ctl);
+                lane_ctl_issue(p, sTimesP, cnt, tknot, tsn, mcall, jvalid, obase, abase, hbase, ctl);
             }
-            if (act && tid < C4) {
+            if (SAVE && tid < C4) {
                 act[lo.act_off_du + duidx] = dU;
                 if (top) act[lo.act_off_duda + duidx] = duda;
             }
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
                     if (ly[l].out >= 0) {
                         const float v = fmaxf(acc + ly[l].bias, 0.f);
                         *po[l] = v;
-                        if (act) act[ly[l].aofs] = v;
+                        if (SAVE) act[ly[l].aofs] = v;
                     }
                     lane_sync(T);
                 }
@@ -364,7 +372,7 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
                 float g = 0.f;
                 if (cv) {
                     g = tanh_mufu(lane_dot(wo_row, lastbuf, 4, nk4o, nk4o, nk4o) + bo);
-                    if (gsave) *gsave = g;
+                    if (SAVE) *gsave = g;
                 }
                 ko = g * dU;
                 for (int m = 1; m < C4; m <<= 1) ko += __shfl_xor_sync(0xffffffffu, ko, m);
@@ -372,7 +380,7 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
 
             // (4) the RK4 recurrence of row i (rk4_alt_step_func)
             {
-                if (wr && kout) *kout = ko;
+                if (wr && have_kout) *kout = ko;
                 float zin;
                 if (s == 0) {
                     k1 = ko;
@@ -404,12 +412,12 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
                 }
                 if (wr) {
                     *sIn_i = zin;
-                    if (act_next && have_next) act_next[i] = zin;
+                    if (SAVE && have_next) act_next[i] = zin;
                 }
             }
             act = act_next;
-            if (gsave) gsave += g_stride;
-            if (kout) kout += k_stride;
+            gsave += g_stride;
+            kout += k_stride;
             lane_sync(T);
         }
         t0 = t1;
@@ -559,7 +567,7 @@ __global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constan
 
 #pragma unroll 1
         for (int s = 3; s >= 0; --s, ++r) {
-            const int slot = r % LANE_NBUF;
+            const int slot = r & (LANE_NBUF - 1);
             issue(r + LANE_NBUF - 1);                        // its slot was read last in stage r - 1, behind a barrier
             // ---- cotangent of the stage derivative k_{s+1} (transpose of rk4_alt_step_func)
             float gv;
@@ -570,7 +578,8 @@ __global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constan
             gv = cv ? gv : 0.f;
             if (wr) act[lo.act_off_gbar + i] = gv;           // for the weight-gradient kernels
             gmax = fmaxf(gmax, fabsf(gv));
-            mbar_wait(bars + slot, (uint32_t)((r / LANE_NBUF) & 1));
+            mbar_wait(bars + slot, (uint32_t)((r >> 2) & 1));
+            static_assert(LANE_NBUF == 4, "slot / parity arithmetic");
             const float* sAct = sActP + slot * AF;
 
             // ---- pre_bar = gbar * dU * (1 - G^2) of this thread's column; cotangent of dU for the attention
@@ -690,10 +699,10 @@ typedef LaneStatic<6, 8, 3, 8, 4, 4, 0> LaneStockBottom;       //      attention
 typedef LaneStatic<12, 16, 2, 12, 12, 0, 0> LaneMujocoTop;     // Mujoco: 14 channels
 typedef LaneStatic<14, 16, 3, 8, 4, 4, 0> LaneMujocoBottom;
 
-LaneKernel lane_kernel(const NcdeLayout& lo, bool bwd)
+LaneKernel lane_kernel(const NcdeLayout& lo, bool bwd, bool save)
 {
     const bool dyn_only = getenv("ANCDE_LANE_DYNAMIC") && getenv("ANCDE_LANE_DYNAMIC")[0] == '1';   // tests: the run-time-bounds code
-#define LANE_TRY(S) if (!dyn_only && lane_matches<S>(lo)) return bwd ? ncde_lane_bwd_kernel<S> : ncde_lane_fwd_kernel<S>
+#define LANE_TRY(S) if (!dyn_only && lane_matches<S>(lo)) return bwd ? ncde_lane_bwd_kernel<S> : (save ? ncde_lane_fwd_kernel<S, true> : ncde_lane_fwd_kernel<S, false>)
     LANE_TRY(LaneUeaTop);
     LANE_TRY(LaneUeaBottom);
     LANE_TRY(LaneStockTop);
@@ -701,7 +710,7 @@ LaneKernel lane_kernel(const NcdeLayout& lo, bool bwd)
     LANE_TRY(LaneMujocoTop);
     LANE_TRY(LaneMujocoBottom);
 #undef LANE_TRY
-    return bwd ? ncde_lane_bwd_kernel<LaneDyn> : ncde_lane_fwd_kernel<LaneDyn>;
+    return bwd ? ncde_lane_bwd_kernel<LaneDyn> : (save ? ncde_lane_fwd_kernel<LaneDyn, true> : ncde_lane_fwd_kernel<LaneDyn, false>);
 }
 
 int launch_lane(SolveArgs& a, bool bwd, cudaStream_t stream)
@@ -721,7 +730,7 @@ int launch_lane(SolveArgs& a, bool bwd, cudaStream_t stream)
         set_error("lane engine: needs %d threads and %zu bytes of shared memory per CTA", T, smem);
         return ANCDE_EUNSUPPORTED;
     }
-    void (*kern)(SolveArgs) = lane_kernel(lo, bwd);
+    void (*kern)(SolveArgs) = lane_kernel(lo, bwd, a.save_act != nullptr);
     ANCDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const char* fnames[3] = {"ncde_fwd_plain", "ncde_fwd_bottom", "ncde_fwd_top"};
     static const char* bnames[3] = {"ncde_bwd_plain", "ncde_bwd_bottom", "ncde_bwd_top"};
