@@ -212,7 +212,7 @@ int make_layout(const ancde_ncde_desc* d, NcdeLayout* lo)
                         d->n_steps, d->n_out, d->mode);
     int TS = d->samples_per_cta;
     const int engine = engine_of(d);
-    if (engine == ANCDE_ENGINE_LANE) TS = 1;                      // the lane engine: one warp = one sample = one tile
+    if (engine == ANCDE_ENGINE_LANE) TS = lane_choice(d);         // the lane engine: tiles of 1 sample, or 8 for large batches
     if (TS == 0 && engine == ANCDE_ENGINE_UMMA) TS = 8;           // the UMMA forward saves in tiles of 8 samples
     if (TS == 0) {
         // the largest tile that still gives every SM work (148 SMs); weight reuse grows with TS.
@@ -287,12 +287,10 @@ int engine_of(const ancde_ncde_desc* d)
     if (!d) return ANCDE_ENGINE_STREAMED;
     if (d->single_stage) return (d->engine == 0 || d->engine == ANCDE_ENGINE_STREAMED) ? ANCDE_ENGINE_STREAMED : -1;
     if (d->engine == ANCDE_ENGINE_STREAMED) return d->engine;
-    // round 2, the latency regime: one warp per sample (ncde_lane.cu) when there are too few samples to give every SM a tile
-    // of the streamed engine anyway (its own rule for one sample per CTA) -- measured on B200: UEA shape, 32 samples,
-    // 10.6 -> see DESIGN.md ms per training step
-    const bool lane_ts = d->samples_per_cta == 0 || d->samples_per_cta == 1;
-    if (d->engine == ANCDE_ENGINE_LANE) return (lane_ts && lane_shape_ok(d)) ? ANCDE_ENGINE_LANE : -1;
-    if (d->engine == 0 && lane_ts && d->B < 240 && lane_shape_ok(d)) return ANCDE_ENGINE_LANE;
+    // round 2, the latency regime and small networks at any batch size: one small CTA per sample (ncde_lane.cu; the choice
+    // and its measurements are in lane_choice)
+    if (d->engine == ANCDE_ENGINE_LANE) return lane_choice(d) > 0 ? ANCDE_ENGINE_LANE : -1;
+    if (d->engine == 0 && lane_choice(d) > 0) return ANCDE_ENGINE_LANE;
     if (d->engine != 0 && d->engine != ANCDE_ENGINE_UMMA) return -1;
     NcdeLayout st;
     V3Layout l3;

@@ -258,6 +258,28 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
     }
     __syncthreads();
 
+    // the saved layout: tiles of TS samples (1, or 8 for large batches: the tcgen05 weight-gradient kernels' layout), every
+    // sub-block [feature][TS]; this CTA's sample is slot sb of tile `tile`
+    const int TS = lo.TS, tile = bg / TS, sb = bg - tile * TS;
+    if (bg >= lo.B) {
+        // a slot of the last tile without a sample: the weight-gradient kernels read whole tiles, so it holds zeros
+        if (SAVE) {
+            for (int n = 0; n < lo.n_stages; ++n) {
+                float* a = p.save_act + ((size_t)n * lo.ntiles + tile) * lo.act_floats;
+                for (int q = tid; q < Hd; q += T) a[q * TS + sb] = 0.f;
+                for (int l = 0; l < lo.n_hidden; ++l)
+                    for (int q = tid; q < lo.width[l]; q += T) a[lo.act_off_h[l] + q * TS + sb] = 0.f;
+                for (int q = tid; q < C4; q += T) {
+                    a[lo.act_off_du + (q >> 2) * lo.DUS + (q & 3) * TS + sb] = 0.f;
+                    if (lo.mode == ANCDE_MODE_TOP) a[lo.act_off_duda + (q >> 2) * lo.DUS + (q & 3) * TS + sb] = 0.f;
+                }
+                float* g = p.save_G + (((size_t)n * lo.ntiles + tile) * TS + sb) * NCP;
+                for (int q = tid; q < NCP; q += T) g[q] = 0.f;
+            }
+        }
+        return;
+    }
+
     // this thread's share of every hidden layer
     LaneLayer ly[LANE_ML];
 #pragma unroll
@@ -270,7 +292,7 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
             ly[l].wofs += lo.off_w[l];
             if (ly[l].out >= 0) {
                 ly[l].bias = sHW[lo.off_b[l] + ly[l].out];
-                ly[l].aofs = lo.act_off_h[l] + ly[l].out;
+                ly[l].aofs = lo.act_off_h[l] + ly[l].out * TS + sb;
             }
         }
     }
@@ -288,13 +310,12 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
         }
     }
 
-    const int tile = bg;
     const bool jvalid = j < lo.C;
     const bool wr = cv && j == 0;                            // the thread that writes row i
     const int obase = bg * (lo.L - 1) * lo.C + j;
     const int abase = bg * lo.att_C + (lo.att_C == 1 ? 0 : j);
     const int hbase = bg * lo.C + j;
-    const int duidx = (j >> 2) * lo.DUS + (j & 3);           // du_index(j, 0, 1, DUS)
+    const int duidx = (j >> 2) * lo.DUS + (j & 3) * TS + sb;   // du_index(j, b, TS, DUS)
     const int nk4o = (K + 3) >> 2;
     const bool top = lo.mode == ANCDE_MODE_TOP;
     const float* lastbuf = lane_pin(((NL - 1) & 1) ? sT1 : sT0);
@@ -303,10 +324,10 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
     const float* const sTimesP = lane_pin(sTimes);
     const float bo = sBo[cv ? col : 0];
     // per-stage strides of the output pointers
-    const size_t act_stride = (size_t)lo.ntiles * lo.act_floats, g_stride = (size_t)lo.ntiles * NCP, k_stride = (size_t)lo.B * Hd;
+    const size_t act_stride = (size_t)lo.ntiles * lo.act_floats, g_stride = (size_t)lo.ntiles * TS * NCP, k_stride = (size_t)lo.B * Hd;
     // running pointers (never dereferenced when the buffer is absent)
     float* act = p.save_act + (size_t)tile * lo.act_floats;
-    float* gsave = p.save_G + (size_t)tile * NCP + (cv ? col : 0);
+    float* gsave = p.save_G + ((size_t)tile * TS + sb) * NCP + (cv ? col : 0);
     float* kout = p.k_out + (size_t)bg * Hd + (cv ? i : 0);
     const bool have_kout = p.k_out != nullptr;
 
@@ -315,7 +336,7 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
     if (wr) {
         sIn[i] = y;
         p.z_out[(int64_t)bg * Hd + i] = y;                   // solution[0] = y0
-        if (SAVE) act[i] = y;
+        if (SAVE) act[i * TS + sb] = y;
     }
     int cnt = 0;        // knots strictly below the current stage time (monotone)
     float tknot = sTimesP[0];
@@ -412,7 +433,7 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
                 }
                 if (wr) {
                     *sIn_i = zin;
-                    if (SAVE && have_next) act_next[i] = zin;
+                    if (SAVE && have_next) act_next[i * TS + sb] = zin;
                 }
             }
             act = act_next;
@@ -474,14 +495,26 @@ __global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constan
     }
     __syncthreads();
 
+    const int TS = lo.TS, tile = bg / TS, sb = bg - tile * TS;      // the saved layout, as in the forward
+    if (bg >= lo.B) {
+        // a slot of the last tile without a sample: zero cotangents for the weight-gradient kernels
+        for (int n = 0; n < lo.n_stages; ++n) {
+            float* a = p.save_act + ((size_t)n * lo.ntiles + tile) * lo.act_floats;
+            for (int q = tid; q < Hd; q += T) a[lo.act_off_gbar + q * TS + sb] = 0.f;
+            for (int l = 0; l < lo.n_hidden; ++l)
+                for (int q = tid; q < lo.width[l]; q += T) a[lo.act_off_delta[l] + q * TS + sb] = 0.f;
+        }
+        return;
+    }
+
     // this thread's share of the output layer (backwards: unit k of the last hidden layer <- all columns) and of every hidden layer
     // (backwards: input unit kin of layer l <- the layer's outputs); layer l reads its cotangent from D[(l+1) & 1], writes D[l & 1]
     LaneLayer lyo = lane_layer(tid, T, K, NCP >> 2, SW);
     float* const sDlast = (NL & 1) ? sD1 : sD0;
     int lyo_mask = 0;
     if (lyo.out >= 0) {
-        lyo_mask = lo.act_off_h[NL - 1] + lyo.out;
-        lyo.aofs = lo.act_off_delta[NL - 1] + lyo.out;
+        lyo_mask = lo.act_off_h[NL - 1] + lyo.out * TS + sb;
+        lyo.aofs = lo.act_off_delta[NL - 1] + lyo.out * TS + sb;
     }
     LaneLayer ly[LANE_ML];
     int lmask[LANE_ML];
@@ -495,8 +528,8 @@ __global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constan
             ly[l] = lane_layer(tid, T, IN, (N + 3) >> 2, S::kStatic ? lane_pad4odd(N) : lo.tstride[l]);
             ly[l].wofs += lo.off_wt[l] - lo.off_hiddenb;
             if (ly[l].out >= 0 && l > 0) {
-                lmask[l] = lo.act_off_h[l - 1] + ly[l].out;
-                ly[l].aofs = lo.act_off_delta[l - 1] + ly[l].out;
+                lmask[l] = lo.act_off_h[l - 1] + ly[l].out * TS + sb;
+                ly[l].aofs = lo.act_off_delta[l - 1] + ly[l].out * TS + sb;
             }
         }
     }
@@ -521,9 +554,8 @@ __global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constan
     const float* const sActP = lane_pin(sActBuf);
     const float* const sGP = lane_pin(sGBuf + (cv ? col : 0));
 
-    const int tile = bg;
     const bool wr = cv && j == 0;
-    const int duidx = (j >> 2) * lo.DUS + (j & 3);
+    const int duidx = (j >> 2) * lo.DUS + (j & 3) * TS + sb;
     const int NS = lo.n_stages;
     const size_t act_stride = (size_t)lo.ntiles * lo.act_floats;
     // saved activations (forward part of the block) and tanh outputs of reverse stage r = NS - 1 - n -> ring slot r % NBUF
@@ -532,7 +564,7 @@ __global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constan
             const int n = NS - 1 - r, slot = r % LANE_NBUF;
             mbar_arrive_expect_tx(bars + slot, (uint32_t)((AF + NCP) * 4));
             bulk_g2s(sActBuf + (size_t)slot * AF, p.save_act + ((int64_t)n * lo.ntiles + tile) * lo.act_floats, (uint32_t)(AF * 4), bars + slot);
-            bulk_g2s(sGBuf + (size_t)slot * NCP, p.save_G + ((int64_t)n * lo.ntiles + tile) * NCP, (uint32_t)(NCP * 4), bars + slot);
+            bulk_g2s(sGBuf + (size_t)slot * NCP, p.save_G + (((int64_t)n * lo.ntiles + tile) * TS + sb) * NCP, (uint32_t)(NCP * 4), bars + slot);
         }
     };
     for (int r = 0; r < LANE_NBUF - 1; ++r) issue(r);
@@ -576,7 +608,7 @@ __global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constan
             else if (s == 1) gv = dt * (0.375f * lam - V4 + V3);
             else gv = dt * (0.125f * lam + V4 + (V2 - V3) * (1.0f / 3.0f));
             gv = cv ? gv : 0.f;
-            if (wr) act[lo.act_off_gbar + i] = gv;           // for the weight-gradient kernels
+            if (wr) act[lo.act_off_gbar + i * TS + sb] = gv;    // for the weight-gradient kernels
             gmax = fmaxf(gmax, fabsf(gv));
             mbar_wait(bars + slot, (uint32_t)((r >> 2) & 1));
             static_assert(LANE_NBUF == 4, "slot / parity arithmetic");
@@ -716,8 +748,8 @@ LaneKernel lane_kernel(const NcdeLayout& lo, bool bwd, bool save)
 int launch_lane(SolveArgs& a, bool bwd, cudaStream_t stream)
 {
     const NcdeLayout& lo = a.lo;
-    if (lo.TS != 1) {
-        set_error("lane engine: needs one sample per tile (got %d)", lo.TS);
+    if (lo.TS != 1 && lo.TS != 8) {
+        set_error("lane engine: saves in tiles of 1 or 8 samples (got %d)", lo.TS);
         return ANCDE_EINVAL;
     }
     if ((int64_t)lo.B * (lo.L - 1) * lo.C >= ((int64_t)1 << 31) - lo.C) {
@@ -735,7 +767,7 @@ int launch_lane(SolveArgs& a, bool bwd, cudaStream_t stream)
     static const char* fnames[3] = {"ncde_fwd_plain", "ncde_fwd_bottom", "ncde_fwd_top"};
     static const char* bnames[3] = {"ncde_bwd_plain", "ncde_bwd_bottom", "ncde_bwd_top"};
     prof_begin(bwd ? bnames[lo.mode] : fnames[lo.mode], stream);
-    kern<<<lo.B, T, smem, stream>>>(a);
+    kern<<<lo.ntiles * lo.TS, T, smem, stream>>>(a);      // one CTA per slot of the saved layout (slots past B hold zeros)
     prof_end(stream);
     count_launch();
     ANCDE_CUDA(cudaGetLastError());
@@ -760,6 +792,32 @@ bool lane_shape_ok(const ancde_ncde_desc* d)
     const int K = d->width[d->n_hidden - 1];
     const int64_t bytes = 4 * (hidden + (int64_t)d->Hd * C4 * (8 * ((K + 7) / 8) + 37) + d->L + 4096);
     return bytes <= 200 * 1024;
+}
+
+// Samples per tile of the saved layout when the lane engine runs this descriptor (1 or 8), 0 when it does not.
+//   * small batches (B < 240, the streamed engine's own "one sample per CTA" regime): tiles of one sample;
+//   * larger batches of the small networks: tiles of 8 samples -- the layout of the tcgen05 weight-gradient kernels.  Measured
+//     on B200 at B = 1024 (recurrent kernels, lane against streamed): Google Stock 0.44 against 1.22 ms, UEA 8.8 against
+//     15.6 ms, Mujoco 0.92 against 1.12 ms -- a CTA per sample keeps 4-7 CTAs resident per SM where the streamed engine has one
+//     latency-bound CTA of 8 samples.  Restricted to the measured range: output layer <= 8192 weights, <= 80 KB of
+//     shared memory per CTA of the forward.
+int lane_choice(const ancde_ncde_desc* d)
+{
+    if (!lane_shape_ok(d)) return 0;
+    const int spc = d->samples_per_cta;
+    if (d->engine == ANCDE_ENGINE_LANE) {
+        if (spc == 1 || spc == 8) return spc;
+        return spc == 0 ? (d->B < 240 ? 1 : 8) : 0;
+    }
+    if (d->engine != 0) return 0;
+    if ((spc == 0 || spc == 1) && d->B < 240) return 1;
+    if ((spc == 0 || spc == 8) && d->B >= 240) {
+        const int C4 = pad4(d->C), K = d->width[d->n_hidden - 1];
+        int64_t f = (int64_t)d->Hd * C4 * (8 * ((K + 7) / 8) + 5) + d->L + 256;
+        for (int l = 0; l < d->n_hidden; ++l) f += (int64_t)d->width[l] * (pad4odd(l == 0 ? d->Hd : d->width[l - 1]) + 1);
+        if ((int64_t)d->Hd * C4 * K <= 8192 && 4 * f <= 80 * 1024) return 8;
+    }
+    return 0;
 }
 
 int launch_lane_fwd(SolveArgs a, cudaStream_t stream) { return launch_lane(a, false, stream); }

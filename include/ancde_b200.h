@@ -82,11 +82,13 @@ int ancde_spline_coeffs_f64(const double* times, const double* X, double* a, dou
  *                          layout, so ancde_ncde_backward (streamed kernels) works on its output.  Chosen by default
  *                          (engine = 0) when the shape is supported and the output layer has >= 50 000 weights; state and hidden widths <= 63.   */
 #define ANCDE_ENGINE_UMMA     3
-/*   ANCDE_ENGINE_LANE      the latency regime (round 2): ONE WARP integrates one sample, forward and backward -- no CTA barrier
- *                          inside the stage loop, the RK4 state in registers, FP32 FMA.  For small batches of small networks
- *                          (UEA: 32 samples x 724 dependent stages): C <= 32 with pad4(C) a power of two, state and hidden
- *                          widths <= 64, Hd * pad4(C) <= 256, samples_per_cta 0 or 1.  Chosen by default (engine = 0) for such
- *                          shapes when B < 240.  Same saved layout (one sample per tile) and weight-gradient kernels.            */
+/*   ANCDE_ENGINE_LANE      small networks (round 2): ONE SMALL CTA integrates one sample, forward and backward -- a thread per
+ *                          output-layer column, the RK4 state in registers, FP32 FMA; the latency regime of small batches (UEA:
+ *                          32 samples x 724 dependent stages) and, with 4-7 CTAs resident per SM, large batches of small networks.
+ *                          C <= 32 with pad4(C) a power of two, state and hidden widths <= 64, Hd * pad4(C) <= 256.  Saves in tiles
+ *                          of 1 sample (B < 240) or 8 samples (larger batches: the tcgen05 weight-gradient kernels' layout);
+ *                          samples_per_cta 0, 1 or 8.  Chosen by default (engine = 0) for such shapes when B < 240, and for B >= 240
+ *                          when the output layer has <= 8192 weights.                                                            */
 #define ANCDE_ENGINE_LANE     4
 
 typedef struct ancde_ncde_desc {

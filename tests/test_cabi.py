@@ -73,7 +73,8 @@ def test_engine_resolution_runs_without_a_gpu():
         return d
 
     assert L.ancde_ncde_engine(ctypes.byref(desc(35, 49, [49] * 4))) == _lib.ENGINE_UMMA
-    assert L.ancde_ncde_engine(ctypes.byref(desc(6, 12, [12, 12]))) == _lib.ENGINE_STREAMED
+    assert L.ancde_ncde_engine(ctypes.byref(desc(6, 12, [12, 12]))) == _lib.ENGINE_LANE         # a small network, at any batch size
+    assert L.ancde_ncde_engine(ctypes.byref(desc(20, 49, [49] * 4))) == _lib.ENGINE_STREAMED       # 49 * 20 * 49 weights: not small
     assert L.ancde_ncde_engine(ctypes.byref(desc(6, 12, [12, 12], _lib.ENGINE_UMMA))) == _lib.ENGINE_UMMA
     assert L.ancde_ncde_engine(ctypes.byref(desc(69, 69, [20] * 5, _lib.ENGINE_UMMA))) == -1      # state wider than 63
     assert L.ancde_ncde_engine(ctypes.byref(desc(35, 49, [49] * 4, 2))) == -1      # the removed round-1 cluster engine
@@ -86,6 +87,9 @@ def test_engine_resolution_runs_without_a_gpu():
     small.B = 200
     assert L.ancde_ncde_engine(ctypes.byref(small)) == _lib.ENGINE_LANE
     assert L.ancde_ncde_wpack_floats(ctypes.byref(small)) > 0 and L.ancde_ncde_save_G_floats(ctypes.byref(small)) == 284 * 200 * 12 * 8
+    big = desc(6, 12, [12, 12])
+    big.B = 1021                      # tiles of 8 samples for large batches: 128 tiles, the last one with 3 empty slots
+    assert L.ancde_ncde_save_G_floats(ctypes.byref(big)) == 284 * 128 * 8 * 12 * 8
     assert L.ancde_ncde_engine(ctypes.byref(desc(6, 12, [12, 12], _lib.ENGINE_LANE))) == _lib.ENGINE_LANE
     assert L.ancde_ncde_engine(ctypes.byref(desc(35, 49, [49] * 4, _lib.ENGINE_LANE))) == -1     # pad4(C) = 36 does not divide 32
     assert L.ancde_ncde_engine(ctypes.byref(desc(6, 12, [12, 80], _lib.ENGINE_LANE))) == -1      # a layer wider than 64

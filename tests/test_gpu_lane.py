@@ -94,12 +94,12 @@ def _seeded(workload, B):
     return cfg, model, times, coeffs, fi
 
 
-@pytest.mark.parametrize('workload,B', [('uea', 32), ('stock', 37), ('mujoco', 70), ('stock', 700)])
+@pytest.mark.parametrize('workload,B', [('uea', 32), ('stock', 37), ('mujoco', 70), ('stock', 700), ('mujoco', 251), ('uea', 243)])
 def test_lane_engine_agrees_with_the_streamed_engine(workload, B, monkeypatch):
     """Same inputs, same weights, two engines: predictions and every gradient agree to FP32 summation order -- for the
     kernels specialised at compile time for the BASELINE networks AND for the same code with run-time bounds
-    (ANCDE_LANE_DYNAMIC=1, what any other supported shape runs).  B = 700 is forced: the library would not pick the lane
-    engine at that size."""
+    (ANCDE_LANE_DYNAMIC=1, what any other supported shape runs).  Batches of 240 samples and more save in tiles of 8 samples
+    (the layout of the tcgen05 weight-gradient kernels); 700, 251 and 243 leave 4, 5 and 5 empty slots in the last tile."""
     import ancde_b200
     from ancde_b200 import _lib
     cfg, model, times, coeffs, fi = _seeded(workload, B)
@@ -137,7 +137,9 @@ def test_library_picks_the_lane_engine_for_small_batches_of_small_networks():
 
     assert L.ancde_ncde_engine(ctypes.byref(desc(4, 40, [40] * 3, _lib.MODE_TOP, 32))) == _lib.ENGINE_LANE
     assert L.ancde_ncde_engine(ctypes.byref(desc(4, 4, [10, 20, 20, 20], _lib.MODE_BOTTOM, 32))) == _lib.ENGINE_LANE
-    assert L.ancde_ncde_engine(ctypes.byref(desc(4, 40, [40] * 3, _lib.MODE_TOP, 1024))) == _lib.ENGINE_STREAMED
+    assert L.ancde_ncde_engine(ctypes.byref(desc(4, 40, [40] * 3, _lib.MODE_TOP, 1024))) == _lib.ENGINE_LANE       # tiles of 8 samples
+    assert L.ancde_ncde_engine(ctypes.byref(desc(4, 40, [40] * 3, _lib.MODE_TOP, 1024, spc=4))) == _lib.ENGINE_STREAMED
+    assert L.ancde_ncde_engine(ctypes.byref(desc(20, 49, [49] * 4, _lib.MODE_TOP, 1024))) == _lib.ENGINE_STREAMED   # 48 k weights
     assert L.ancde_ncde_engine(ctypes.byref(desc(4, 40, [40] * 3, _lib.MODE_TOP, 32, spc=8))) == _lib.ENGINE_STREAMED
     assert L.ancde_ncde_engine(ctypes.byref(desc(35, 49, [49] * 4, _lib.MODE_TOP, 32))) != _lib.ENGINE_LANE   # C4 = 36
 

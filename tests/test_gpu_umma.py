@@ -86,7 +86,7 @@ def test_library_picks_the_umma_engine_for_the_large_sepsis_networks():
     # once the batch fills the GPU with tiles of 8 samples
     assert L.ancde_ncde_engine(ctypes.byref(desc(35, 35, [20] * 5, _lib.MODE_BOTTOM))) == _lib.ENGINE_UMMA
     assert L.ancde_ncde_engine(ctypes.byref(desc(35, 35, [20] * 5, _lib.MODE_BOTTOM, B=256))) == _lib.ENGINE_STREAMED
-    assert L.ancde_ncde_engine(ctypes.byref(desc(14, 12, [12] * 2, _lib.MODE_TOP))) == _lib.ENGINE_STREAMED
+    assert L.ancde_ncde_engine(ctypes.byref(desc(14, 12, [12] * 2, _lib.MODE_TOP))) == _lib.ENGINE_LANE      # small networks: the lane engine
 
 
 def test_tcgen05_weight_gradient_agrees_with_the_mma_sync_kernel():
