@@ -58,6 +58,8 @@ struct LaneLayer {
     int np;        // its pieces (threads beyond the last unit recompute the last unit and do not write)
     int npmin, npmax;   // bounds of np over the threads of a unit (compile-time constants for a static shape)
     int out;       // unit index when this thread writes the unit's result (part 0), else -1
+    bool warp_on;  // this thread's WARP holds at least one unit of the layer (warp-uniform): the others only meet at the barrier --
+                   // with 4-7 CTAs per SM (large batches) the kernels are issue bound and idle warps' instructions are not free
     int aofs;      // where that result goes in the saved-activation block
     float bias;
 };
@@ -142,6 +144,7 @@ __device__ __forceinline__ LaneLayer lane_layer(int tid, int T, int N, int nk4, 
     L.npmax = (nk4 + KP - 1) >> ksh;
     L.np = part < nk4 ? (nk4 - part + KP - 1) >> ksh : 0;
     L.out = (o < N && part == 0) ? o : -1;
+    L.warp_on = (tid & ~31) < (N << ksh);
     L.aofs = 0;
     L.bias = 0.f;
     return L;
@@ -220,8 +223,11 @@ __device__ __forceinline__ void lane_ctl_finish(int mode, const LaneCtl& r, floa
 }
 
 // ---------------------------------------------------------------------------------------------------------- forward
-// SAVE: training (save_act / save_G written) or inference -- a template parameter so that no store carries a null check
-template <class S, bool SAVE>
+// SAVE: training (save_act / save_G written) or inference -- a template parameter so that no store carries a null check.
+// SKIP: warps that hold no unit of a layer skip its body (large batches: several CTAs per SM, issue bound -- Mujoco at B = 1024
+// 1.15 -> 1.07 ms per step); in the latency regime the extra branches cost more than they save (UEA 4.56 -> 4.79 ms), so the
+// tiles-of-one-sample kernels are compiled without them.
+template <class S, bool SAVE, bool SKIP>
 __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constant__ SolveArgs p)
 {
     const NcdeLayout& lo = p.lo;
@@ -374,14 +380,16 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
 #pragma unroll
             for (int l = 0; l < S::NL; ++l) {
                 if (l < NL) {
-                    float acc = lane_dot(pw[l], px[l], ly[l].step, ly[l].np, ly[l].npmin, ly[l].npmax);
-                    const int kp = S::kStatic ? (1 << lane_kshift(S::T, S::width(l), ((l == 0 ? S::Hd : S::width(l > 0 ? l - 1 : 0)) + 3) >> 2))
-                                              : (ly[l].step >> 2);
-                    for (int m = 1; m < kp; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
-                    if (ly[l].out >= 0) {
-                        const float v = fmaxf(acc + ly[l].bias, 0.f);
-                        *po[l] = v;
-                        if (SAVE) act[ly[l].aofs] = v;
+                    if (!SKIP || ly[l].warp_on) {
+                        float acc = lane_dot(pw[l], px[l], ly[l].step, ly[l].np, ly[l].npmin, ly[l].npmax);
+                        const int kp = S::kStatic ? (1 << lane_kshift(S::T, S::width(l), ((l == 0 ? S::Hd : S::width(l > 0 ? l - 1 : 0)) + 3) >> 2))
+                                                  : (ly[l].step >> 2);
+                        for (int m = 1; m < kp; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+                        if (ly[l].out >= 0) {
+                            const float v = fmaxf(acc + ly[l].bias, 0.f);
+                            *po[l] = v;
+                            if (SAVE) act[ly[l].aofs] = v;
+                        }
                     }
                     lane_sync(T);
                 }
@@ -447,7 +455,7 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
 }
 
 // --------------------------------------------------------------------------------------------------------- backward
-template <class S>
+template <class S, bool SKIP>
 __global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constant__ SolveArgs p)
 {
     const NcdeLayout& lo = p.lo;
@@ -644,12 +652,14 @@ __global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constan
 
             // ---- hbar[k] = sum_col W_out[col][k] pre_bar[col]: 2^kso threads per unit, then delta = hbar * relu'(h)
             {
-                float acc = lane_dot(pwo, pxo, lyo.step, lyo.np, lyo.npmin, lyo.npmax);
-                for (int m = 1; m < (1 << kso); m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
-                if (lyo.out >= 0) {
-                    const float v = (sAct[lyo_mask] > 0.f) ? acc : 0.f;
-                    *poo = v;
-                    act[lyo.aofs] = v;
+                if (!SKIP || lyo.warp_on) {
+                    float acc = lane_dot(pwo, pxo, lyo.step, lyo.np, lyo.npmin, lyo.npmax);
+                    for (int m = 1; m < (1 << kso); m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+                    if (lyo.out >= 0) {
+                        const float v = (sAct[lyo_mask] > 0.f) ? acc : 0.f;
+                        *poo = v;
+                        act[lyo.aofs] = v;
+                    }
                 }
             }
             lane_sync(T);
@@ -658,17 +668,19 @@ __global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constan
 #pragma unroll
             for (int l = S::NL - 1; l >= 0; --l) {
                 if (l < NL) {
-                    float acc = lane_dot(pw[l], px[l], ly[l].step, ly[l].np, ly[l].npmin, ly[l].npmax);
-                    const int kp = S::kStatic ? (1 << lane_kshift(S::T, l == 0 ? S::Hd : S::width(l > 0 ? l - 1 : 0), (S::width(l) + 3) >> 2))
-                                              : (ly[l].step >> 2);
-                    for (int m = 1; m < kp; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
-                    if (ly[l].out >= 0) {
-                        if (l > 0) {
-                            const float v = (sAct[lmask[l]] > 0.f) ? acc : 0.f;
-                            *po[l] = v;
-                            act[ly[l].aofs] = v;              // for the hidden weight-gradient kernel
-                        } else {
-                            *po[l] = acc;                     // cotangent of the stage input (sZb)
+                    if (!SKIP || ly[l].warp_on) {
+                        float acc = lane_dot(pw[l], px[l], ly[l].step, ly[l].np, ly[l].npmin, ly[l].npmax);
+                        const int kp = S::kStatic ? (1 << lane_kshift(S::T, l == 0 ? S::Hd : S::width(l > 0 ? l - 1 : 0), (S::width(l) + 3) >> 2))
+                                                  : (ly[l].step >> 2);
+                        for (int m = 1; m < kp; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+                        if (ly[l].out >= 0) {
+                            if (l > 0) {
+                                const float v = (sAct[lmask[l]] > 0.f) ? acc : 0.f;
+                                *po[l] = v;
+                                act[ly[l].aofs] = v;              // for the hidden weight-gradient kernel
+                            } else {
+                                *po[l] = acc;                     // cotangent of the stage input (sZb)
+                            }
                         }
                     }
                     lane_sync(T);
@@ -733,8 +745,12 @@ typedef LaneStatic<14, 16, 3, 8, 4, 4, 0> LaneMujocoBottom;
 
 LaneKernel lane_kernel(const NcdeLayout& lo, bool bwd, bool save)
 {
+    const bool big = lo.TS != 1;          // several CTAs per SM: idle warps skip the layer bodies
     const bool dyn_only = getenv("ANCDE_LANE_DYNAMIC") && getenv("ANCDE_LANE_DYNAMIC")[0] == '1';   // tests: the run-time-bounds code
-#define LANE_TRY(S) if (!dyn_only && lane_matches<S>(lo)) return bwd ? ncde_lane_bwd_kernel<S> : (save ? ncde_lane_fwd_kernel<S, true> : ncde_lane_fwd_kernel<S, false>)
+#define LANE_PICK(S) (bwd ? (big ? ncde_lane_bwd_kernel<S, true> : ncde_lane_bwd_kernel<S, false>)                                   \
+                          : (save ? (big ? ncde_lane_fwd_kernel<S, true, true> : ncde_lane_fwd_kernel<S, true, false>)              \
+                                  : (big ? ncde_lane_fwd_kernel<S, false, true> : ncde_lane_fwd_kernel<S, false, false>)))
+#define LANE_TRY(S) if (!dyn_only && lane_matches<S>(lo)) return LANE_PICK(S)
     LANE_TRY(LaneUeaTop);
     LANE_TRY(LaneUeaBottom);
     LANE_TRY(LaneStockTop);
@@ -742,7 +758,7 @@ LaneKernel lane_kernel(const NcdeLayout& lo, bool bwd, bool save)
     LANE_TRY(LaneMujocoTop);
     LANE_TRY(LaneMujocoBottom);
 #undef LANE_TRY
-    return bwd ? ncde_lane_bwd_kernel<LaneDyn> : (save ? ncde_lane_fwd_kernel<LaneDyn, true> : ncde_lane_fwd_kernel<LaneDyn, false>);
+    return LANE_PICK(LaneDyn);
 }
 
 int launch_lane(SolveArgs& a, bool bwd, cudaStream_t stream)
