@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
     float* sTimes = sp; sp += pad4(lo.L);
     float* sIn = sp;   sp += HP;                            // stage input
     float* sT0 = sp;   sp += HP;                            // activations ping / pong
-    float* sT1 = sp;
+    float* sT1 = sp;   sp += HP;
+    float* sDU = sp;                                        // SKIP: the control increment of the stage, from warp 0 (32 floats)
 
     {
         const float4* src = reinterpret_cast<const float4*>(p.wpack);
@@ -364,16 +365,23 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
             const bool have_next = 4 * k + s + 1 < lo.n_stages;
             float* act_next = act + act_stride;
             // (1) control of this stage from the registers loaded a stage ago; the loads of the next stage go out now
-            float dU, duda;
-            lane_ctl_finish(lo.mode, ctl, dU, duda);
-            if (have_next) {
-                if (top && ++mcall == lo.n_hp - 1) mcall = 0;
-                const float tsn = (s == 0) ? ts1 : (s == 1 ? ts2 : (s == 2 ? ts3 : t1));      // stage 0 of the next step is at its t0 = t1
-                lane_ctl_issue(p, sTimesP, cnt, tknot, tsn, mcall, jvalid, obase, abase, hbase, ctl);
-            }
-            if (SAVE && tid < C4) {
-                act[lo.act_off_du + duidx] = dU;
-                if (top) act[lo.act_off_duda + duidx] = duda;
+            // (SKIP, large batches: only warp 0 evaluates it -- the C4 channels are all it takes -- and hands dU over through
+            // shared memory; the hidden layers' barriers lie between its store and the other warps' load)
+            float dU = 0.f, duda = 0.f;
+            if (!SKIP || tid < 32) {
+                lane_ctl_finish(lo.mode, ctl, dU, duda);
+                if (have_next) {
+                    if (top && ++mcall == lo.n_hp - 1) mcall = 0;
+                    const float tsn = (s == 0) ? ts1 : (s == 1 ? ts2 : (s == 2 ? ts3 : t1));      // stage 0 of the next step is at its t0 = t1
+                    lane_ctl_issue(p, sTimesP, cnt, tknot, tsn, mcall, jvalid, obase, abase, hbase, ctl);
+                }
+                if (tid < C4) {
+                    if (SKIP) sDU[tid] = dU;
+                    if (SAVE) {
+                        act[lo.act_off_du + duidx] = dU;
+                        if (top) act[lo.act_off_duda + duidx] = duda;
+                    }
+                }
             }
 
             // (2) hidden layers: KP threads per unit, one CTA barrier per layer
@@ -403,6 +411,7 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
                     g = tanh_mufu(lane_dot(wo_row, lastbuf, 4, nk4o, nk4o, nk4o) + bo);
                     if (SAVE) *gsave = g;
                 }
+                if (SKIP) dU = sDU[j];
                 ko = g * dU;
                 for (int m = 1; m < C4; m <<= 1) ko += __shfl_xor_sync(0xffffffffu, ko, m);
             }
@@ -713,7 +722,7 @@ int lane_threads(const NcdeLayout& lo) { return lane_threads_of(lo.NCP, lo.Hmax)
 
 size_t lane_fwd_smem(const NcdeLayout& lo)
 {
-    size_t f = pad4(lo.hidden_floats) + lo.NCP + (size_t)lo.NCP * lo.KPS + pad4(lo.L) + 3 * (size_t)pad4(lo.Hmax);
+    size_t f = pad4(lo.hidden_floats) + lo.NCP + (size_t)lo.NCP * lo.KPS + pad4(lo.L) + 3 * (size_t)pad4(lo.Hmax) + 32;
     return f * 4;
 }
 size_t lane_bwd_smem(const NcdeLayout& lo, int T)
