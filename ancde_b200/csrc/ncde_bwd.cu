@@ -791,8 +791,9 @@ extern "C" int ancde_ncde_backward(const ancde_ncde_desc* d, void* stream_)
     if (rc != ANCDE_OK) return rc;
     rc = pack_weights(d, lo, stream);   // the packed weights of the forward may have been reused
     if (rc != ANCDE_OK) return rc;
-    if (engine_of(d) == ANCDE_ENGINE_LANE) {
-        // the latency regime: one warp per sample (ncde_lane.cu); same saved layout, same weight-gradient kernels
+    if (engine_of(d) == ANCDE_ENGINE_LANE && g_force_bwd_engine == 0) {
+        // small networks: one small CTA per sample (ncde_lane.cu); same saved layout, same weight-gradient kernels (a backward
+        // kernel forced through ancde_debug_force_bwd_engine runs on the lane forward's saves: the layouts are the same)
         rc = launch_lane_bwd(a, stream);
         if (rc != ANCDE_OK) return rc;
         return launch_wgrads(d, a, stream);

@@ -754,7 +754,7 @@ typedef LaneStatic<14, 16, 3, 8, 4, 4, 0> LaneMujocoBottom;
 
 LaneKernel lane_kernel(const NcdeLayout& lo, bool bwd, bool save)
 {
-    const bool big = lo.TS != 1;          // several CTAs per SM: idle warps skip the layer bodies
+    const bool big = lo.B >= 240;         // several CTAs per SM: idle warps skip the layer bodies, control from warp 0
     const bool dyn_only = getenv("ANCDE_LANE_DYNAMIC") && getenv("ANCDE_LANE_DYNAMIC")[0] == '1';   // tests: the run-time-bounds code
 #define LANE_PICK(S) (bwd ? (big ? ncde_lane_bwd_kernel<S, true> : ncde_lane_bwd_kernel<S, false>)                                   \
                           : (save ? (big ? ncde_lane_fwd_kernel<S, true, true> : ncde_lane_fwd_kernel<S, true, false>)              \
@@ -820,23 +820,25 @@ bool lane_shape_ok(const ancde_ncde_desc* d)
 }
 
 // Samples per tile of the saved layout when the lane engine runs this descriptor (1 or 8), 0 when it does not.
-//   * small batches (B < 240, the streamed engine's own "one sample per CTA" regime): tiles of one sample;
-//   * larger batches of the small networks: tiles of 8 samples -- the layout of the tcgen05 weight-gradient kernels.  Measured
-//     on B200 at B = 1024 (recurrent kernels, lane against streamed): Google Stock 0.44 against 1.22 ms, UEA 8.8 against
-//     15.6 ms, Mujoco 0.92 against 1.12 ms -- a CTA per sample keeps 4-7 CTAs resident per SM where the streamed engine has one
-//     latency-bound CTA of 8 samples.  Restricted to the measured range: output layer <= 8192 weights, <= 80 KB of
-//     shared memory per CTA of the forward.
+//   * Tiles of 8 samples -- the layout of the tcgen05 weight-gradient kernels -- unless the caller asks for tiles of one: measured
+//     on B200 with the same recurrent kernels, UEA (B = 32) 4.69 -> 4.42 ms and Google Stock (B = 200) 0.64 -> 0.57 ms per step
+//     (the mma.sync weight-gradient kernels of the one-sample layout take 50-100 us each for this little work); at B = 1024 the
+//     one-sample layout costs UEA 9.6 ms of weight gradients.
+//   * Small batches (B < 240, the streamed engine's own "one sample per CTA" regime): always the lane engine.
+//   * Larger batches of the small networks: measured at B = 1024 (recurrent kernels, lane against streamed): Google Stock 0.44
+//     against 1.22 ms, UEA 8.8 against 15.6 ms, Mujoco 0.92 against 1.12 ms -- a CTA per sample keeps 4-7 CTAs resident per SM
+//     where the streamed engine has one latency-bound CTA of 8 samples.  Restricted to the measured range: output layer <= 8192
+//     weights, <= 80 KB of shared memory per CTA of the forward.
 int lane_choice(const ancde_ncde_desc* d)
 {
     if (!lane_shape_ok(d)) return 0;
     const int spc = d->samples_per_cta;
-    if (d->engine == ANCDE_ENGINE_LANE) {
-        if (spc == 1 || spc == 8) return spc;
-        return spc == 0 ? (d->B < 240 ? 1 : 8) : 0;
-    }
+    if (spc != 0 && spc != 1 && spc != 8) return 0;
+    const int ts = spc ? spc : 8;
+    if (d->engine == ANCDE_ENGINE_LANE) return ts;
     if (d->engine != 0) return 0;
-    if ((spc == 0 || spc == 1) && d->B < 240) return 1;
-    if ((spc == 0 || spc == 8) && d->B >= 240) {
+    if (d->B < 240) return ts;
+    if (spc != 1) {
         const int C4 = pad4(d->C), K = d->width[d->n_hidden - 1];
         int64_t f = (int64_t)d->Hd * C4 * (8 * ((K + 7) / 8) + 5) + d->L + 256;
         for (int l = 0; l < d->n_hidden; ++l) f += (int64_t)d->width[l] * (pad4odd(l == 0 ? d->Hd : d->width[l - 1]) + 1);

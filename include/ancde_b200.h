@@ -86,8 +86,8 @@ int ancde_spline_coeffs_f64(const double* times, const double* X, double* a, dou
  *                          output-layer column, the RK4 state in registers, FP32 FMA; the latency regime of small batches (UEA:
  *                          32 samples x 724 dependent stages) and, with 4-7 CTAs resident per SM, large batches of small networks.
  *                          C <= 32 with pad4(C) a power of two, state and hidden widths <= 64, Hd * pad4(C) <= 256.  Saves in tiles
- *                          of 1 sample (B < 240) or 8 samples (larger batches: the tcgen05 weight-gradient kernels' layout);
- *                          samples_per_cta 0, 1 or 8.  Chosen by default (engine = 0) for such shapes when B < 240, and for B >= 240
+ *                          of 8 samples (the tcgen05 weight-gradient kernels' layout; samples_per_cta 0 or 8) or of 1 sample
+ *                          (samples_per_cta 1).  Chosen by default (engine = 0) for such shapes when B < 240, and for B >= 240
  *                          when the output layer has <= 8192 weights.                                                            */
 #define ANCDE_ENGINE_LANE     4
 

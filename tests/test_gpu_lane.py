@@ -67,6 +67,25 @@ def test_lane_engine_forward_and_gradients_match_reference_golden(case):
     assert worst < GRAD_TOL, (case, worst)
 
 
+@pytest.mark.parametrize('case', ['stock', 'uea', 'mujoco_soft_tw'])
+def test_lane_engine_with_tiles_of_one_sample(case):
+    """The lane engine saves in tiles of 8 samples by default (the tcgen05 weight-gradient kernels' layout); tiles of one sample
+    (samples_per_cta = 1, the mma.sync weight-gradient kernels) stay supported and meet the same bars."""
+    from ancde_b200 import _lib, solver
+    g = dual_case(case)
+    model = _build(g['cfg'], g['sd'])
+    solver.FORCE_SAMPLES_PER_CTA = 1
+    try:
+        with forced_engine(_lib.ENGINE_LANE):
+            pred = _run(model, g)
+    finally:
+        solver.FORCE_SAMPLES_PER_CTA = 0
+    assert rel_err(pred, g['pred']) < FWD_TOL, case
+    params = dict(model.named_parameters())
+    for k, ref in g['grads'].items():
+        assert rel_err(params[k].grad, ref) < GRAD_TOL, (case, k)
+
+
 @pytest.mark.parametrize('case', sorted(MUST_SUPPORT))
 def test_streamed_engine_keeps_its_coverage_on_the_small_shapes(case):
     from ancde_b200 import _lib
@@ -98,8 +117,8 @@ def _seeded(workload, B):
 def test_lane_engine_agrees_with_the_streamed_engine(workload, B, monkeypatch):
     """Same inputs, same weights, two engines: predictions and every gradient agree to FP32 summation order -- for the
     kernels specialised at compile time for the BASELINE networks AND for the same code with run-time bounds
-    (ANCDE_LANE_DYNAMIC=1, what any other supported shape runs).  Batches of 240 samples and more save in tiles of 8 samples
-    (the layout of the tcgen05 weight-gradient kernels); 700, 251 and 243 leave 4, 5 and 5 empty slots in the last tile."""
+    (ANCDE_LANE_DYNAMIC=1, what any other supported shape runs).  The engine saves in tiles of 8 samples (the layout of the tcgen05
+    weight-gradient kernels); 37, 70, 700, 251 and 243 samples leave 3, 2, 4, 5 and 5 empty slots in the last tile."""
     import ancde_b200
     from ancde_b200 import _lib
     cfg, model, times, coeffs, fi = _seeded(workload, B)
@@ -140,7 +159,10 @@ def test_library_picks_the_lane_engine_for_small_batches_of_small_networks():
     assert L.ancde_ncde_engine(ctypes.byref(desc(4, 40, [40] * 3, _lib.MODE_TOP, 1024))) == _lib.ENGINE_LANE       # tiles of 8 samples
     assert L.ancde_ncde_engine(ctypes.byref(desc(4, 40, [40] * 3, _lib.MODE_TOP, 1024, spc=4))) == _lib.ENGINE_STREAMED
     assert L.ancde_ncde_engine(ctypes.byref(desc(20, 49, [49] * 4, _lib.MODE_TOP, 1024))) == _lib.ENGINE_STREAMED   # 48 k weights
-    assert L.ancde_ncde_engine(ctypes.byref(desc(4, 40, [40] * 3, _lib.MODE_TOP, 32, spc=8))) == _lib.ENGINE_STREAMED
+    assert L.ancde_ncde_engine(ctypes.byref(desc(4, 40, [40] * 3, _lib.MODE_TOP, 32, spc=8))) == _lib.ENGINE_LANE
+    assert L.ancde_ncde_engine(ctypes.byref(desc(4, 40, [40] * 3, _lib.MODE_TOP, 32, spc=1))) == _lib.ENGINE_LANE
+    assert L.ancde_ncde_engine(ctypes.byref(desc(4, 40, [40] * 3, _lib.MODE_TOP, 32, spc=2))) == _lib.ENGINE_STREAMED
+    assert L.ancde_ncde_engine(ctypes.byref(desc(4, 40, [40] * 3, _lib.MODE_TOP, 1024, spc=1))) == _lib.ENGINE_STREAMED
     assert L.ancde_ncde_engine(ctypes.byref(desc(35, 49, [49] * 4, _lib.MODE_TOP, 32))) != _lib.ENGINE_LANE   # C4 = 36
 
 
