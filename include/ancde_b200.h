@@ -28,7 +28,7 @@ extern "C" {
 
 #define ANCDE_MAX_LAYERS 8      /* hidden (ReLU) layers in a vector-field MLP */
 
-/* ABI version; bumped when a struct below changes.  7: head / tail / regulariser entry points.  6: ancde_ncde_desc gained `grid`.  5: ancde_ncde_desc gained single_stage, grad_k_out (ABI 5) and
+/* ABI version; bumped when a struct below changes (the engine value ANCDE_ENGINE_LANE of round 2 changed none).  7: head / tail / regulariser entry points.  6: ancde_ncde_desc gained `grid`.  5: ancde_ncde_desc gained single_stage, grad_k_out (ABI 5) and
  * async_wgrad (ABI 4, with ancde_ncde_join). */
 int ancde_abi_version(void);
 
@@ -131,7 +131,7 @@ typedef struct ancde_ncde_desc {
     float* grad_W[ANCDE_MAX_LAYERS + 1];      /* accumulated into (caller zeroes), same layout as W */
     float* grad_bias[ANCDE_MAX_LAYERS + 1];
     float* grad_attention;     /* TOP, or NULL (adjoint-mode gradient flow): (att_L, B, att_C) accumulated into */
-    int32_t samples_per_cta;   /* streamed engine only: 0 = let the library choose (8, 4, 2 or 1) */
+    int32_t samples_per_cta;   /* samples per tile of the saved layout: 0 = let the library choose; streamed engine 8, 4, 2 or 1; lane engine 8 or 1 */
     int32_t engine;            /* 0 = library default; ANCDE_ENGINE_STREAMED, _UMMA or _LANE (see above) */
     int32_t single_stage;      /* 1 = evaluate only the vector field at (t_start, z0): k_out (1, B, Hd) = f(z0) dX/dt(t_start), the
                                 * building block of adaptive solvers driven from the host (dopri5).  n_steps = n_out = 1; streamed
