@@ -59,7 +59,7 @@ struct LaneLayer {
     int npmin, npmax;   // bounds of np over the threads of a unit (compile-time constants for a static shape)
     int out;       // unit index when this thread writes the unit's result (part 0), else -1
     bool warp_on;  // this thread's WARP holds at least one unit of the layer (warp-uniform): the others only meet at the barrier --
-                   // with 4-7 CTAs per SM (large batches) the kernels are issue bound and idle warps' instructions are not free
+                   // with several CTAs per SM (large batches) idle warps' instructions are not free
     int aofs;      // where that result goes in the saved-activation block
     float bias;
 };
@@ -224,7 +224,7 @@ __device__ __forceinline__ void lane_ctl_finish(int mode, const LaneCtl& r, floa
 
 // ---------------------------------------------------------------------------------------------------------- forward
 // SAVE: training (save_act / save_G written) or inference -- a template parameter so that no store carries a null check.
-// SKIP: warps that hold no unit of a layer skip its body (large batches: several CTAs per SM, issue bound -- Mujoco at B = 1024
+// SKIP: warps that hold no unit of a layer skip its body (large batches: several CTAs per SM share the issue slots -- Mujoco at B = 1024
 // 1.15 -> 1.07 ms per step); in the latency regime the extra branches cost more than they save (UEA 4.56 -> 4.79 ms), so the
 // tiles-of-one-sample kernels are compiled without them.
 template <class S, bool SAVE, bool SKIP>
