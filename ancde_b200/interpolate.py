@@ -11,11 +11,13 @@ import torch
 from . import _lib
 
 
-def natural_cubic_spline_coeffs(t, X):
+def natural_cubic_spline_coeffs(t, X, out=None):
     """Coefficients of the natural cubic spline through X (reference: interpolate.py:159-226).
 
     t: (L,) strictly increasing float tensor.  X: (..., L, C) float tensor, NaN = missing.
     Returns (a, b, two_c, three_d), each (..., L-1, C) in X's dtype, on X's device.
+    `out` (not in the reference): four preallocated contiguous tensors of that shape and dtype to write into -- an input pipeline
+    that refills the static buffers of a captured training step (bench.py's end-to-end leg) needs no extra copy.
     """
     if not t.is_floating_point():
         raise ValueError("t and X must both be floating point/")
@@ -38,7 +40,14 @@ def natural_cubic_spline_coeffs(t, X):
     N = Xc.size(0)
     tf32 = 1 if (X.dtype == torch.float64 and t.dtype != torch.float64) else 0
     tc = t.detach().to(device=X.device, dtype=X.dtype).contiguous()
-    outs = [torch.empty(N, L - 1, C, dtype=X.dtype, device=X.device) for _ in range(4)]
+    if out is not None:
+        out = tuple(out)
+        if len(out) != 4 or any(o.dtype != X.dtype or o.device != X.device or not o.is_contiguous() or
+                                tuple(o.shape) != tuple(batch) + (L - 1, C) for o in out):
+            raise ValueError("out must be four contiguous tensors of shape %s, X's dtype and device" % (tuple(batch) + (L - 1, C),))
+        outs = [o.view(N, L - 1, C) for o in out]
+    else:
+        outs = [torch.empty(N, L - 1, C, dtype=X.dtype, device=X.device) for _ in range(4)]
     if N > 0:
         L_ = _lib.lib()
         with torch.cuda.device(X.device):
