@@ -98,3 +98,24 @@ def test_errors_match_reference():
     out = ancde_b200.natural_cubic_spline_coeffs(t, torch.randn(0, 4, 3).cuda())      # empty batch
     assert out[0].shape == (0, 3, 3)
 
+
+
+def test_out_argument_writes_the_same_coefficients_in_place():
+    """`out=` (not in the reference; used by the input pipeline of a captured training step): same values, written into the
+    caller's tensors; a wrong shape / dtype is refused."""
+    import ancde_b200
+    torch.manual_seed(3)
+    t = torch.arange(9.).cuda()
+    X = torch.randn(5, 9, 4, device='cuda')
+    X[torch.rand(5, 9, 4, device='cuda') < 0.4] = float('nan')
+    ref = ancde_b200.natural_cubic_spline_coeffs(t, X)
+    out = tuple(torch.full((5, 8, 4), 7.0, device='cuda') for _ in range(4))
+    got = ancde_b200.natural_cubic_spline_coeffs(t, X, out=out)
+    torch.cuda.synchronize()
+    for r, o, g in zip(ref, out, got):
+        assert g.data_ptr() == o.data_ptr()
+        assert torch.equal(r, o)
+    with pytest.raises(ValueError):
+        ancde_b200.natural_cubic_spline_coeffs(t, X, out=tuple(torch.empty(5, 8, 3, device='cuda') for _ in range(4)))
+    with pytest.raises(ValueError):
+        ancde_b200.natural_cubic_spline_coeffs(t, X, out=tuple(torch.empty(5, 8, 4, device='cuda', dtype=torch.float64) for _ in range(4)))
