@@ -30,8 +30,10 @@
 // by two TMA bulk copies on an mbarrier three stages ahead; the output layer's vector-Jacobian product runs with
 // KP threads per hidden unit over a padded copy of W_out^T [k][columns] (column-contiguous, conflict free) and
 // the pre-activation cotangent broadcast from shared memory; hidden layers backwards as in the forward.
-// Both kernels read / write the streamed engine's TS = 1 layout (NcdeLayout), so the weight-gradient kernels and the
-// packed weights are shared.  C4 must divide 32 (C <= 32, C4 in {4, 8, 16, 32}), Hd * C4 <= 256, widths <= 64.
+// Both kernels read / write the streamed engine's saved layout (NcdeLayout: tiles of 8 samples -- what the tcgen05 weight-gradient
+// kernels take -- or of 1 sample on request; a CTA owns one slot of a tile, slots without a sample are zero-filled), so the
+// weight-gradient kernels and the packed weights are shared.  For large batches (B >= 240: several CTAs per SM) idle warps skip the
+// layer bodies and only warp 0 evaluates the control (template parameter SKIP).  C4 must divide 32 (C <= 32, C4 in {4, 8, 16, 32}), Hd * C4 <= 256, widths <= 64.
 #include "ncde_lane.cuh"
 #include "pipeline.cuh"
 
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
 {
     const NcdeLayout& lo = p.lo;
     const int tid = threadIdx.x, T = S::kStatic ? S::T : (int)blockDim.x;
-    const int bg = blockIdx.x;                              // this CTA's sample = its tile (TS = 1)
+    const int bg = blockIdx.x;                              // this CTA's sample (slot bg % TS of tile bg / TS of the saved layout)
     const int NL = S::kStatic ? S::NL : lo.n_hidden;
     const int Hd = S::kStatic ? S::Hd : lo.Hd, C4 = S::kStatic ? S::C4 : lo.C4, NCP = S::kStatic ? S::NCP : lo.NCP;
     const int K = S::kStatic ? S::K : lo.K;
