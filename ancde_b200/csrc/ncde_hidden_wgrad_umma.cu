@@ -18,6 +18,8 @@
 // products of chunk c; at the end the accumulators are read back (tcgen05.ld) and added to the torch-layout gradients
 // with atomics.
 // The mma.sync kernel it replaces (ncde_wgrad.cu: 3xTF32, 0.29 + 0.19 ms for the two Sepsis networks) was issue bound.
+#include <cstdlib>
+
 #include "mma_common.cuh"
 #include "umma.cuh"
 
@@ -248,9 +250,15 @@ int launch_hidden_wgrad_umma(const SolveArgs& a, const HiddenGradPtrs& hp, cudaS
     const bool few = HU_TPC * n_items <= 2 * HU_THREADS;
     const int64_t nblocks = (int64_t)lo.n_stages * lo.ntiles;
     const int64_t nchunks = (nblocks + HU_TPC - 1) / HU_TPC;
+    // Every CTA ends with one atomic per weight (its accumulators are partial sums over its rows): with few rows (small batches of
+    // small networks) 148 CTAs spend longer on 148 x (weights) contended atomics than on their rows, so a CTA gets at least
+    // `min_per` chunks of 32 rows.  Measured on B200 (min_per 1 / 8 / 32 / 128): UEA B = 32 4.41 / 4.15 / 4.14 / 4.21 ms per step,
+    // Stock B = 200 0.57 / 0.54 / 0.55 / 0.61, Mujoco B = 1024 1.05 / 1.05 / 1.03 / 1.08; the Sepsis batch has 62 chunks per CTA anyway.
+    static const int min_per = getenv("ANCDE_HWGRAD_MIN_CHUNKS") ? atoi(getenv("ANCDE_HWGRAD_MIN_CHUNKS")) : 16;
     int64_t grid = 148;
     if (grid > nchunks) grid = nchunks;
-    const int per = (int)((nchunks + grid - 1) / grid);
+    int per = (int)((nchunks + grid - 1) / grid);
+    if (per < min_per) per = min_per;
     grid = (nchunks + per - 1) / per;
     const unsigned* gmax = reinterpret_cast<const unsigned*>(a.wpack + lo.off_gscale);   // written by the recurrent backward
     auto kern = few ? ncde_hidden_wgrad_umma_kernel<2, true> : ncde_hidden_wgrad_umma_kernel<4, false>;
