@@ -77,9 +77,11 @@ __host__ __device__ constexpr int lane_threads_of(int NCP, int Hmax) { return 32
 // loop bound, pieces-per-thread count and shuffle depth of the kernels folds, the layer loops unroll to exactly NL layers
 // and the dot products to straight-line code.  Instantiated for the networks of the BASELINE configurations the engine
 // serves (UEA, Google Stock, Mujoco); any other supported shape runs the same code with run-time bounds (LaneDyn).
-template <int HD, int CC4, int NL_, int W0, int W1, int W2, int W3>
+// MB: CTAs per SM the large-batch kernels are compiled for (a register cap; 1 = none)
+template <int HD, int CC4, int NL_, int W0, int W1, int W2, int W3, int MB = 1>
 struct LaneStatic {
     static constexpr bool kStatic = true;
+    static constexpr int kMinBlocksBig = MB;
     static constexpr int Hd = HD, C4 = CC4, NL = NL_, NCP = HD * CC4;
     __host__ __device__ static constexpr int width(int l) { return l == 0 ? W0 : (l == 1 ? W1 : (l == 2 ? W2 : W3)); }
     static constexpr int K = width(NL_ - 1);
@@ -88,6 +90,7 @@ struct LaneStatic {
 };
 struct LaneDyn {
     static constexpr bool kStatic = false;
+    static constexpr int kMinBlocksBig = 1;
     static constexpr int Hd = 0, C4 = 0, NL = LANE_ML, NCP = 0, K = 0, Hmax = 0, T = 0;
     __host__ __device__ static constexpr int width(int) { return 0; }
 };
@@ -230,7 +233,7 @@ __device__ __forceinline__ void lane_ctl_finish(int mode, const LaneCtl& r, floa
 // 1.15 -> 1.07 ms per step); in the latency regime the extra branches cost more than they save (UEA 4.56 -> 4.79 ms), so the
 // tiles-of-one-sample kernels are compiled without them.
 template <class S, bool SAVE, bool SKIP>
-__global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constant__ SolveArgs p)
+__global__ void __launch_bounds__(256, SKIP ? S::kMinBlocksBig : 1) ncde_lane_fwd_kernel(const __grid_constant__ SolveArgs p)
 {
     const NcdeLayout& lo = p.lo;
     const int tid = threadIdx.x, T = S::kStatic ? S::T : (int)blockDim.x;
@@ -467,7 +470,7 @@ __global__ void __launch_bounds__(256) ncde_lane_fwd_kernel(const __grid_constan
 
 // --------------------------------------------------------------------------------------------------------- backward
 template <class S, bool SKIP>
-__global__ void __launch_bounds__(256) ncde_lane_bwd_kernel(const __grid_constant__ SolveArgs p)
+__global__ void __launch_bounds__(256, SKIP ? S::kMinBlocksBig : 1) ncde_lane_bwd_kernel(const __grid_constant__ SolveArgs p)
 {
     const NcdeLayout& lo = p.lo;
     const int tid = threadIdx.x, T = S::kStatic ? S::T : (int)blockDim.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
@@ -751,8 +754,10 @@ typedef LaneStatic<40, 4, 3, 40, 40, 40, 0> LaneUeaTop;        // UEA: h = hh = 
 typedef LaneStatic<4, 4, 4, 10, 20, 20, 20> LaneUeaBottom;     //      attention 20 / 10
 typedef LaneStatic<12, 8, 2, 12, 12, 0, 0> LaneStockTop;       // Google Stock: h = hh = 12, 2 layers, 6 channels
 typedef LaneStatic<6, 8, 3, 8, 4, 4, 0> LaneStockBottom;       //      attention 4 / 8
-typedef LaneStatic<12, 16, 2, 12, 12, 0, 0> LaneMujocoTop;     // Mujoco: 14 channels
-typedef LaneStatic<14, 16, 3, 8, 4, 4, 0> LaneMujocoBottom;
+// Mujoco (14 channels) runs at B = 1024: 64 registers = four CTAs per SM put its attention network's forward in two waves of CTAs
+// instead of three (1.05 -> 1.02 ms per step); the same cap costs the UEA networks 27 % in spills at that batch size
+typedef LaneStatic<12, 16, 2, 12, 12, 0, 0, 4> LaneMujocoTop;
+typedef LaneStatic<14, 16, 3, 8, 4, 4, 0, 4> LaneMujocoBottom;
 
 LaneKernel lane_kernel(const NcdeLayout& lo, bool bwd, bool save)
 {
